@@ -1,0 +1,721 @@
+"""Load-time model compiler: ``assets/trex.urdf`` -> flat model blob.
+
+The URDF is read through the reference's own parser (``tools/urdf_parsing.py``,
+``Urdf.from_string`` :237-239, ``UrdfJoint.from_element`` :49-59,
+``UrdfInertial.from_element`` :77-86) via :mod:`reference_loader`.  Two parser
+defects are worked around here and nowhere else:
+
+* ``tools/urdf_parsing.py:82`` reads the mass from a non-existent attribute so
+  every link parses with mass 0.0 -> ``<mass value>`` is read directly;
+* ``<dynamics damping>`` is dropped by the parser -> read directly.
+
+Two granularities are produced:
+
+``full``   base + 132 links in pybullet's link order (DFS pre-order, children
+           in joint file order), link frames = URDF *inertial* frames, fixed
+           joints kept as 0-DoF links.  This is what ``oracle/trex_oracle.c``
+           simulates (a restatement of Bullet's btMultiBody pipeline).
+``merged`` fixed joints folded: 26 rigid bodies / 31 DoF.  Body frame of a
+           revolute body = its URDF joint frame re-oriented so the joint axis is
+           the local +z axis; body 0 keeps the base link's inertial frame so the
+           base state is exactly pybullet's base state.  This is what the CUDA
+           kernels simulate.
+
+Contact geometry is *reference-undefined* (the URDF has no ``<collision>``;
+SURVEY.md section 8a-N2): a fixed set of candidate contact points per body is
+derived here from the visual meshes and used identically by kernels and oracle.
+"""
+from __future__ import annotations
+
+import dataclasses
+import json
+import os
+from collections import OrderedDict, defaultdict
+from xml.etree import ElementTree
+
+import numpy as np
+from scipy.spatial.transform import Rotation
+
+from . import model_blob
+from .reference_loader import find_tools_dir, load_urdf_parsing
+
+# ---------------------------------------------------------------------------
+# Name mapping N1: the env addresses joints/links by the
+# names of an older URDF (trex_env.py:81-87, trex_robot.py:316).
+# ---------------------------------------------------------------------------
+
+
+def map_legacy_joint_name(name: str) -> str:
+    """``femur_L_joint`` -> ``joint_femur_left`` (trex_env.py:81-87 vs trex.urdf:1020)."""
+    if name.startswith("joint_"):
+        return name
+    if name.endswith("_joint"):
+        core = name[: -len("_joint")]
+        if core.endswith("_L"):
+            core = core[:-2] + "_left"
+        elif core.endswith("_R"):
+            core = core[:-2] + "_right"
+        return "joint_" + core
+    return name
+
+
+def map_legacy_link_name(name: str) -> str:
+    """``atlas_axis_link`` -> ``link_atlas_axis`` (trex_robot.py:316 vs trex.urdf:2413)."""
+    if name.startswith("link_"):
+        return name
+    if name.endswith("_link"):
+        core = name[: -len("_link")]
+        if core.endswith("_L"):
+            core = core[:-2] + "_left"
+        elif core.endswith("_R"):
+            core = core[:-2] + "_right"
+        return "link_" + core
+    return name
+
+
+HEAD_LINK_NAME = "link_atlas_axis"  # trex_robot.py:316 after N1
+
+# Solver / engine constants.  Everything tagged [RECALL] restates pybullet /
+# Bullet defaults from knowledge of the Bullet3 sources;
+# pybullet is not vendored in the reference nor installable here, so these are
+# parameters of the model blob rather than hard-coded literals.
+DEFAULT_PARAMS = OrderedDict(
+    [
+        ("time_step", 0.01),  # trex_env.py:54 (divided by substeps at :71)
+        ("solver_iterations", 300.0),  # trex_env.py:57 (divided at :72)
+        ("num_substeps", 5.0),  # trex_env.py:18
+        ("gravity", 9.81),  # trex_env.py:20,117
+        ("motor_kp", 5.0e-3),  # trex_robot.py:421
+        ("motor_kd", 0.1),  # trex_robot.py:398  sqrt(2*1.0*kp)
+        ("motor_max_torque", 3.0e5),  # trex_robot.py:260
+        ("linear_damping", 0.04),  # [RECALL] btMultiBody default
+        ("angular_damping", 0.04),  # [RECALL] btMultiBody default
+        ("max_coordinate_velocity", 100.0),  # [RECALL] btMultiBody default
+        ("erp", 0.2),  # [RECALL] btContactSolverInfo::m_erp (non-contact rows)
+        ("contact_erp", 0.08),  # [RECALL] pybullet sets m_erp2 = 0.08
+        ("split_impulse_threshold", -0.04),  # [RECALL] m_splitImpulsePenetrationThreshold
+        ("linear_slop", 1.0e-5),  # [RECALL] pybullet sets m_linearSlop = 1e-5
+        ("residual_threshold", 1.0e-7),  # [RECALL] m_leastSquaresResidualThreshold
+        ("warmstart_factor", 0.1),  # [RECALL] pybullet sets m_warmstartingFactor = 0.1
+        ("friction", 0.25),  # [RECALL] 0.5 (link) * 0.5 (floor), product combine
+        ("contact_breaking_threshold", 0.02),  # [RECALL] gContactBreakingThreshold
+        ("floor_height", 0.0005),  # assets/floor.urdf:21 box 0.001 thick centred at 0
+        ("limit_max_impulse", 100.0),  # [RECALL] btMultiBodyConstraint::m_maxAppliedImpulse default
+        ("reset_height", 3.0),  # trex_env.py:105
+        ("reward_target_height", 2.5),  # trex_env.py:189
+    ]
+)
+
+# Starting crouch, trex_env.py:81-87 with N1 applied.
+STARTING_CONFIGURATION = OrderedDict(
+    [
+        ("joint_femur_left", -0.6),
+        ("joint_tibia_left", 0.4),
+        ("joint_tarsometatarsus_left", -1.2),
+        ("joint_femur_right", -0.6),
+        ("joint_tibia_right", 0.4),
+        ("joint_tarsometatarsus_right", -1.2),
+    ]
+)
+
+# Candidate contact points per merged body (keyed by the body's root link with
+# the ``link_`` prefix and side suffix removed).  The link set is the one the
+# orphaned hulls in assets/collisions/ cover.
+# value = (count, "lower" | "all"): directions considered at the reset pose.
+CONTACT_POINT_PLAN = {
+    "vertebrae_sacral": (6, "all"),
+    "tibia": (1, "lower"),
+    "tarsometatarsus": (2, "lower"),
+    "toe_02_a": (2, "lower"),
+    "toe_02_b": (2, "lower"),
+    "toe_03_a": (2, "lower"),
+    "toe_03_c": (2, "lower"),
+    "toe_04_a": (2, "lower"),
+    "toe_04_d": (2, "lower"),
+    "vertebra_cervical_09": (1, "lower"),
+    "vertebra_cervical_03": (1, "lower"),
+    "cranium": (4, "all"),
+    "vertebra_caudal_02": (2, "lower"),
+    "vertebra_caudal_10": (2, "lower"),
+    "vertebra_caudal_24": (2, "lower"),
+}
+MAX_CONTACT_CANDIDATES = 64
+
+
+def _rot_z_to(axis: np.ndarray) -> np.ndarray:
+    """Rotation matrix A with A @ z = axis (axis is a unit vector)."""
+    axis = axis / np.linalg.norm(axis)
+    z = np.array([0.0, 0.0, 1.0])
+    c = float(z @ axis)
+    if c > 1.0 - 1e-12:
+        return np.eye(3)
+    if c < -1.0 + 1e-12:
+        return np.diag([1.0, -1.0, -1.0])
+    v = np.cross(z, axis)
+    s = np.linalg.norm(v)
+    vx = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    return np.eye(3) + vx + vx @ vx * ((1 - c) / (s * s))
+
+
+def _bullet_quicksort_equal_keys(n: int) -> list:
+    """Permutation Bullet's ``btAlignedObjectArray::quickSort`` applies to ``n``
+    elements whose sort keys are all equal.
+
+    [RECALL] ``btMultiBodyDynamicsWorld::solveConstraints`` quick-sorts the
+    constraint array by island id each step; all constraints of the one
+    multibody share an island, the predicate is a strict ``<`` and the Hoare
+    partition swaps on ties, so the (unstable) sort permutes the array
+    deterministically.  The non-contact rows are solved in this order.
+    """
+    a = list(range(n))
+
+    def qs(lo, hi):
+        i, j = lo, hi
+        while True:
+            # all keys equal: neither inner while loop advances
+            if i <= j:
+                a[i], a[j] = a[j], a[i]
+                i += 1
+                j -= 1
+            if not (i <= j):
+                break
+        if lo < j:
+            qs(lo, j)
+        if i < hi:
+            qs(i, hi)
+
+    if n > 1:
+        qs(0, n - 1)
+    return a
+
+
+@dataclasses.dataclass
+class CompiledModel:
+    sections: "OrderedDict[str, np.ndarray]"
+    meta: dict
+
+    def blob(self) -> bytes:
+        return model_blob.pack(self.sections)
+
+    def __getitem__(self, k):
+        return self.sections[k]
+
+
+def _load_obj_vertices(path: str) -> np.ndarray:
+    vs = []
+    with open(path, "r") as f:
+        for line in f:
+            if line.startswith("v "):
+                p = line.split()
+                vs.append((float(p[1]), float(p[2]), float(p[3])))
+    return np.asarray(vs, dtype=np.float64).reshape(-1, 3)
+
+
+_DIRS26 = np.array(
+    [
+        (x, y, z)
+        for x in (-1, 0, 1)
+        for y in (-1, 0, 1)
+        for z in (-1, 0, 1)
+        if (x, y, z) != (0, 0, 0)
+    ],
+    dtype=np.float64,
+)
+_DIRS26 /= np.linalg.norm(_DIRS26, axis=1, keepdims=True)
+
+
+def _select_contact_points(world_pts: np.ndarray, count: int, mode: str) -> list:
+    """Pick ``count`` vertex indices: the lowest point at the reset pose first,
+    then farthest-point sampling among support points of 26 fixed directions
+    (lower hemisphere only for ``mode == 'lower'``)."""
+    dirs = _DIRS26 if mode == "all" else _DIRS26[_DIRS26[:, 2] <= 1e-9]
+    pool = []
+    for d in dirs:
+        idx = int(np.argmax(world_pts @ d))
+        if idx not in pool:
+            pool.append(idx)
+    first = int(np.argmin(world_pts[:, 2]))
+    chosen = [first]
+    while len(chosen) < count:
+        best, best_d = None, -1.0
+        for idx in pool:
+            if idx in chosen:
+                continue
+            dmin = min(np.linalg.norm(world_pts[idx] - world_pts[c]) for c in chosen)
+            if dmin > best_d + 1e-12:
+                best, best_d = idx, dmin
+        if best is None or best_d < 1e-6:
+            break
+        chosen.append(best)
+    return chosen
+
+
+def compile_model(
+    urdf_path: str,
+    *,
+    inertia_source: str = "urdf",
+    with_contacts: bool = True,
+    params: dict | None = None,
+) -> CompiledModel:
+    """Compile ``urdf_path`` (normally ``<reference>/assets/trex.urdf``).
+
+    ``inertia_source``: ``"urdf"`` uses the ``<inertia>`` tensors of the file
+    (pybullet ``URDF_USE_INERTIA_FROM_FILE``); ``"bullet_default"`` restates
+    what pybullet does with default ``loadURDF`` flags on a link without a
+    collision shape [RECALL, SURVEY.md H6 / Appendix A.1]: the diagonal becomes
+    that of a box with half extents = the 0.001 m collision margin.
+    """
+    tools_dir = find_tools_dir(urdf_path)
+    up = load_urdf_parsing(tools_dir)
+    with open(urdf_path, "r") as f:
+        text = f.read()
+    urdf = up.Urdf.from_string(text)  # tools/urdf_parsing.py:237
+    et = ElementTree.fromstring(text)
+
+    # --- parser defect work-arounds --------------------
+    link_mass = {}
+    for ln in et.findall("link"):
+        m = ln.find("inertial/mass")
+        link_mass[ln.get("name")] = float(m.get("value")) if m is not None else 0.0
+    joint_damping = {}
+    for jn in et.findall("joint"):
+        d = jn.find("dynamics")
+        joint_damping[jn.get("name")] = float(d.get("damping", 0.0)) if d is not None else 0.0
+
+    roots = urdf.root_link_names  # tools/urdf_parsing.py:133
+    if len(roots) != 1:
+        raise ValueError("expected a single root link, got %r" % (roots,))
+    root = roots[0]
+
+    # --- pybullet link order: DFS pre-order, children in joint file order -----
+    children = defaultdict(list)
+    for j in urdf.joints.values():
+        children[j.parent_name].append(j)
+    order = []
+
+    def dfs(link_name):
+        for j in children.get(link_name, []):
+            order.append(j)
+            dfs(j.child_name)
+
+    dfs(root)
+    n_links = len(order)
+    link_names = [root] + [j.child_name for j in order]  # index 0 = base, i+1 = link i
+    link_index = {n: i - 1 for i, n in enumerate(link_names)}  # base = -1
+    joint_names = [j.name for j in order]
+
+    def rin(name):
+        return urdf.links[name].inertia.origin.rotation.as_matrix()
+
+    def cin(name):
+        return np.asarray(urdf.links[name].inertia.origin.translation, dtype=np.float64)
+
+    def principal(name):
+        I = np.asarray(urdf.links[name].inertia.inertia, dtype=np.float64)
+        off = abs(I[0, 1]) + abs(I[0, 2]) + abs(I[1, 2])
+        if off > 0:
+            raise ValueError("link %s: non-diagonal <inertia> not supported" % name)
+        return np.array([I[0, 0], I[1, 1], I[2, 2]])
+
+    full_parent = np.zeros(n_links, np.int32)
+    full_jtype = np.zeros(n_links, np.int32)
+    full_dof = -np.ones(n_links, np.int32)
+    full_mass = np.zeros(n_links + 1)
+    full_inertia = np.zeros((n_links + 1, 3))
+    full_rot0 = np.zeros((n_links, 9))
+    full_axis = np.zeros((n_links, 3))
+    full_d = np.zeros((n_links, 3))
+    full_e = np.zeros((n_links, 3))
+    full_lower = np.zeros(n_links)
+    full_upper = np.zeros(n_links)
+    full_damping = np.zeros(n_links)
+
+    def inertia_of(name):
+        m = link_mass[name]
+        if inertia_source == "urdf":
+            return principal(name)
+        if inertia_source == "bullet_default":
+            h = 0.001  # gUrdfDefaultCollisionMargin, empty btCompoundShape AABB [RECALL]
+            l2 = (2 * h) ** 2
+            v = m / 12.0 * (l2 + l2)
+            return np.array([v, v, v])
+        raise ValueError("inertia_source must be 'urdf' or 'bullet_default'")
+
+    full_mass[0] = link_mass[root]
+    full_inertia[0] = inertia_of(root)
+    n_dof = 0
+    for i, j in enumerate(order):
+        p, c = j.parent_name, j.child_name
+        full_parent[i] = link_index[p]
+        rj = j.origin.rotation.as_matrix()
+        xj = np.asarray(j.origin.translation, dtype=np.float64)
+        full_rot0[i] = (rin(c).T @ rj.T @ rin(p)).reshape(-1)
+        full_d[i] = rin(c).T @ cin(c)
+        full_e[i] = rin(p).T @ (xj - cin(p))
+        full_mass[i + 1] = link_mass[c]
+        full_inertia[i + 1] = inertia_of(c)
+        full_damping[i] = joint_damping.get(j.name, 0.0)
+        if j.type == "revolute":
+            full_jtype[i] = 1
+            full_dof[i] = n_dof
+            n_dof += 1
+            a = np.asarray(j.axis, dtype=np.float64)
+            a = a / np.linalg.norm(a)
+            full_axis[i] = rin(c).T @ a
+            full_lower[i] = j.limits.position[0]
+            full_upper[i] = j.limits.position[1]
+        elif j.type != "fixed":
+            raise ValueError("joint %s: unsupported type %s" % (j.name, j.type))
+
+    # --- zero-pose link frames (base URDF link frame at identity) -------------
+    W_R = {root: np.eye(3)}
+    W_x = {root: np.zeros(3)}
+    for j in order:
+        rp, xp = W_R[j.parent_name], W_x[j.parent_name]
+        W_R[j.child_name] = rp @ j.origin.rotation.as_matrix()
+        W_x[j.child_name] = xp + rp @ np.asarray(j.origin.translation, dtype=np.float64)
+
+    # --- merged bodies ----------------------------------------------------------
+    body_of_link = {root: 0}
+    body_root = [root]
+    body_parent = [-1]
+    body_joint = [None]
+    for j in order:
+        if j.type == "revolute":
+            body_of_link[j.child_name] = len(body_root)
+            body_root.append(j.child_name)
+            body_parent.append(body_of_link[j.parent_name])
+            body_joint.append(j)
+        else:
+            body_of_link[j.child_name] = body_of_link[j.parent_name]
+    nb = len(body_root)
+
+    # body frames in the zero-pose "world" (base URDF link frame)
+    B_R = [W_R[root] @ rin(root)]
+    B_x = [W_x[root] + W_R[root] @ cin(root)]
+    for b in range(1, nb):
+        j = body_joint[b]
+        a = np.asarray(j.axis, dtype=np.float64)
+        B_R.append(W_R[j.child_name] @ _rot_z_to(a))
+        B_x.append(W_x[j.child_name].copy())
+
+    mb_parent = np.asarray(body_parent, np.int32)
+    mb_E0 = np.zeros((nb, 9))
+    mb_r0 = np.zeros((nb, 3))
+    mb_E0[0] = np.eye(3).reshape(-1)
+    for b in range(1, nb):
+        p = body_parent[b]
+        mb_E0[b] = (B_R[p].T @ B_R[b]).reshape(-1)  # child axes in parent coordinates
+        mb_r0[b] = B_R[p].T @ (B_x[b] - B_x[p])  # child origin in parent coordinates
+
+    mb_mass = np.zeros(nb)
+    mb_mc = np.zeros((nb, 3))
+    mb_I = np.zeros((nb, 3, 3))
+    mb_damp_rot = np.zeros((nb, 3, 3))
+    mb_nlinks = np.zeros(nb, np.int32)
+    task_body, task_r, task_m = [], [], []
+    for idx, name in enumerate(link_names):
+        b = body_of_link[name]
+        m = full_mass[idx]
+        Rk = B_R[b].T @ (W_R[name] @ rin(name))
+        pk = B_R[b].T @ (W_x[name] + W_R[name] @ cin(name) - B_x[b])
+        Ik = Rk @ np.diag(full_inertia[idx]) @ Rk.T
+        mb_mass[b] += m
+        mb_mc[b] += m * pk
+        mb_I[b] += Ik + m * ((pk @ pk) * np.eye(3) - np.outer(pk, pk))
+        mb_damp_rot[b] += Ik
+        mb_nlinks[b] += 1
+        task_body.append(b)
+        task_r.append(pk)
+        task_m.append(m)
+
+    def sym6(M):
+        return np.array([M[0, 0], M[0, 1], M[0, 2], M[1, 1], M[1, 2], M[2, 2]])
+
+    mb_lower = np.zeros(nb)
+    mb_upper = np.zeros(nb)
+    mb_damping = np.zeros(nb)
+    mb_link = -np.ones(nb, np.int32)  # pybullet link index of the body's joint
+    for b in range(1, nb):
+        j = body_joint[b]
+        mb_lower[b] = j.limits.position[0]
+        mb_upper[b] = j.limits.position[1]
+        mb_damping[b] = joint_damping.get(j.name, 0.0)
+        mb_link[b] = link_index[j.child_name]
+
+    # name-sorted revolute joints = action / observation order (trex_robot.py:311-314;
+    # pybullet returns names as bytes: a bytes-wise sort == str sort for ASCII)
+    rev = [(body_joint[b].name, b) for b in range(1, nb)]
+    rev_sorted = sorted(rev, key=lambda t: t[0].encode())
+    obs_body = np.asarray([b for _, b in rev_sorted], np.int32)  # obs slot k -> body index
+    obs_dof = obs_body - 1  # merged joint dof index (0..24) == full revolute dof index
+
+    start_q = np.zeros(nb)  # per body
+    for jn, val in STARTING_CONFIGURATION.items():
+        for b in range(1, nb):
+            if body_joint[b].name == jn:
+                start_q[b] = val
+
+    # head point: COM of link_atlas_axis (trex_robot.py:330-335: getLinkState()[0])
+    hb = body_of_link[HEAD_LINK_NAME]
+    head_p = B_R[hb].T @ (W_x[HEAD_LINK_NAME] + W_R[HEAD_LINK_NAME] @ cin(HEAD_LINK_NAME) - B_x[hb])
+    head_link = link_index[HEAD_LINK_NAME]
+
+    # --- reset-pose FK (for contact-point selection and golden numbers) ---------
+    def body_world_poses(q_body, base_R=np.eye(3), base_x=np.array([0.0, 0.0, 3.0])):
+        R = [base_R]
+        x = [base_x]
+        for b in range(1, nb):
+            p = body_parent[b]
+            c, s = np.cos(q_body[b]), np.sin(q_body[b])
+            Rz = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+            R.append(R[p] @ mb_E0[b].reshape(3, 3) @ Rz)
+            x.append(x[p] + R[p] @ mb_r0[b])
+        return R, x
+
+    RW, XW = body_world_poses(start_q)
+
+    # --- contact candidates -------------------------------------------------------
+    cand_body, cand_p, cand_link, cand_local = [], [], [], []
+    mesh_stats = {}
+    asset_dir = os.path.dirname(os.path.abspath(urdf_path))
+    lowest_vertex_z = None
+    if with_contacts:
+        body_pts = defaultdict(list)
+        for ln in et.findall("link"):
+            name = ln.get("name")
+            b = body_of_link[name]
+            for vis in ln.findall("visual"):
+                mesh = vis.find("geometry/mesh")
+                if mesh is None:
+                    continue
+                path = os.path.join(asset_dir, mesh.get("filename"))
+                if not os.path.isfile(path):
+                    continue
+                org = vis.find("origin")
+                xyz = np.array([float(v) for v in org.get("xyz").split()]) if org is not None else np.zeros(3)
+                rpy = [float(v) for v in org.get("rpy").split()] if org is not None else [0, 0, 0]
+                Rv = Rotation.from_euler("xyz", rpy).as_matrix()  # tools/urdf_parsing.py:267-269
+                v = _load_obj_vertices(path)
+                if v.size == 0:
+                    continue
+                vl = v @ Rv.T + xyz  # link frame
+                vw0 = vl @ W_R[name].T + W_x[name]  # zero-pose world
+                vb = (vw0 - B_x[b]) @ B_R[b]  # body frame
+                body_pts[b].append(vb)
+        for b in range(nb):
+            if b in body_pts:
+                pts = np.concatenate(body_pts[b], axis=0)
+                zw = (pts @ RW[b].T + XW[b])[:, 2]
+                lo = float(zw.min())
+                lowest_vertex_z = lo if lowest_vertex_z is None else min(lowest_vertex_z, lo)
+        for b in range(nb):
+            key = body_root[b][len("link_"):]
+            for suf in ("_left", "_right"):
+                if key.endswith(suf):
+                    key = key[: -len(suf)]
+            if key not in CONTACT_POINT_PLAN or b not in body_pts:
+                continue
+            count, mode = CONTACT_POINT_PLAN[key]
+            pts = np.concatenate(body_pts[b], axis=0)
+            wpts = pts @ RW[b].T + XW[b]
+            for idx in _select_contact_points(wpts, count, mode):
+                cand_body.append(b)
+                cand_p.append(pts[idx])
+        if len(cand_body) > MAX_CONTACT_CANDIDATES:
+            raise ValueError("too many contact candidates")
+        # oracle view: attach each point to the body's root link, in that link's inertial frame
+        for b, p in zip(cand_body, cand_p):
+            name = body_root[b]
+            pw0 = B_x[b] + B_R[b] @ p
+            Rl = W_R[name] @ rin(name)
+            xl = W_x[name] + W_R[name] @ cin(name)
+            cand_link.append(link_index[name])
+            cand_local.append(Rl.T @ (pw0 - xl))
+
+    # --- non-contact constraint order [RECALL] ------------------------------------
+    # creation order: one joint-limit constraint per revolute link (added while the
+    # URDF is converted, link order), then one motor per revolute link.
+    # id k in [0,25): limit of dof k ; id 25+k: motor of dof k.
+    n_rev = nb - 1
+    perm = _bullet_quicksort_equal_keys(2 * n_rev)
+    noncontact_order = np.asarray(perm, np.int32)
+
+    p = OrderedDict(DEFAULT_PARAMS)
+    if params:
+        for k, v in params.items():
+            if k not in p:
+                raise KeyError("unknown model parameter %r" % k)
+            p[k] = float(v)
+
+    S = OrderedDict()
+    S["param_values"] = np.asarray(list(p.values()), dtype=np.float64)
+    S["full_n_links"] = np.asarray([n_links], np.int32)
+    S["full_parent"] = full_parent
+    S["full_jtype"] = full_jtype
+    S["full_dof"] = full_dof
+    S["full_mass"] = full_mass
+    S["full_inertia"] = full_inertia.reshape(-1)
+    S["full_rot0"] = full_rot0.reshape(-1)
+    S["full_axis"] = full_axis.reshape(-1)
+    S["full_d"] = full_d.reshape(-1)
+    S["full_e"] = full_e.reshape(-1)
+    S["full_lower"] = full_lower
+    S["full_upper"] = full_upper
+    S["full_damping"] = full_damping
+    S["full_head_link"] = np.asarray([head_link], np.int32)
+    S["full_start_q"] = np.asarray(
+        [start_q[body_of_link[j.child_name]] if j.type == "revolute" else 0.0 for j in order]
+    )
+    S["full_cand_link"] = np.asarray(cand_link, np.int32).reshape(-1)
+    S["full_cand_local"] = np.asarray(cand_local, np.float64).reshape(-1)
+    S["noncontact_order"] = noncontact_order
+    S["obs_dof"] = obs_dof.astype(np.int32)
+    S["mb_n_bodies"] = np.asarray([nb], np.int32)
+    S["mb_parent"] = mb_parent
+    S["mb_link"] = mb_link
+    S["mb_E0"] = mb_E0.reshape(-1)
+    S["mb_r0"] = mb_r0.reshape(-1)
+    S["mb_mass"] = mb_mass
+    S["mb_mc"] = mb_mc.reshape(-1)
+    S["mb_I"] = np.stack([sym6(M) for M in mb_I]).reshape(-1)
+    S["mb_damp_rot"] = np.stack([sym6(M) for M in mb_damp_rot]).reshape(-1)
+    S["mb_lower"] = mb_lower
+    S["mb_upper"] = mb_upper
+    S["mb_damping"] = mb_damping
+    S["mb_start_q"] = start_q
+    S["mb_head_body"] = np.asarray([hb], np.int32)
+    S["mb_head_p"] = head_p
+    S["mb_task_body"] = np.asarray(task_body, np.int32)
+    S["mb_task_r"] = np.asarray(task_r).reshape(-1)
+    S["mb_task_m"] = np.asarray(task_m)
+    S["mb_cand_body"] = np.asarray(cand_body, np.int32).reshape(-1)
+    S["mb_cand_p"] = np.asarray(cand_p, np.float64).reshape(-1)
+
+    # golden numbers
+    total_mass = float(full_mass.sum())
+    com = sum(
+        mb_mass[b] * XW[b] + RW[b] @ mb_mc[b] for b in range(nb)
+    ) / total_mass
+    head_w = XW[hb] + RW[hb] @ head_p
+    meta = {
+        "urdf": os.path.basename(urdf_path),
+        "inertia_source": inertia_source,
+        "root_link": root,
+        "n_links": n_links,
+        "n_bodies": nb,
+        "n_dof": n_dof,
+        "link_names": link_names,
+        "joint_names": joint_names,
+        "body_root_links": body_root,
+        "body_joint_names": [None] + [body_joint[b].name for b in range(1, nb)],
+        "body_n_links": mb_nlinks.tolist(),
+        "obs_joint_names": [n for n, _ in rev_sorted],
+        "obs_pybullet_link_index": [int(mb_link[b]) for _, b in rev_sorted],
+        "head_link": HEAD_LINK_NAME,
+        "head_pybullet_link_index": int(head_link),
+        "param_names": list(p.keys()),
+        "params": dict(p),
+        "starting_configuration": dict(STARTING_CONFIGURATION),
+        "contact_candidate_bodies": [int(b) for b in cand_body],
+        "golden": {
+            "total_mass": total_mass,
+            "links_mass_excluding_base": float(full_mass[1:].sum()),
+            "reset_head_position": head_w.tolist(),
+            "reset_com": com.tolist(),
+            "reset_lowest_vertex_z": lowest_vertex_z,
+        },
+    }
+    return CompiledModel(S, meta)
+
+
+# ---------------------------------------------------------------------------
+# Checked-in compiled model (the GPU box has no /root/reference)
+# ---------------------------------------------------------------------------
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+BLOB_PATH = os.path.join(DATA_DIR, "trex_model.blob")
+META_PATH = os.path.join(DATA_DIR, "trex_model.json")
+TOPOLOGY_HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "trex_topology.h")
+
+
+def load_builtin() -> CompiledModel:
+    with open(BLOB_PATH, "rb") as f:
+        sections = model_blob.unpack(f.read())
+    with open(META_PATH, "r") as f:
+        meta = json.load(f)
+    return CompiledModel(sections, meta)
+
+
+def with_params(model: CompiledModel, **overrides) -> CompiledModel:
+    """Copy of ``model`` with some ``param_values`` replaced."""
+    names = model.meta["param_names"]
+    vals = model.sections["param_values"].copy()
+    params = dict(model.meta["params"])
+    for k, v in overrides.items():
+        vals[names.index(k)] = float(v)
+        params[k] = float(v)
+    sections = OrderedDict(model.sections)
+    sections["param_values"] = vals
+    meta = dict(model.meta)
+    meta["params"] = params
+    return CompiledModel(sections, meta)
+
+
+def emit_topology_header(model: CompiledModel) -> str:
+    """C header with the merged tree as compile-time constants.
+
+    The kernels unroll over the 26-body tree with static register allocation, so
+    the topology is baked in; ``trex_create`` verifies that the blob it is given
+    matches these constants and fails loudly otherwise.
+    """
+    S = model.sections
+    nb = int(S["mb_n_bodies"][0])
+    parent = S["mb_parent"].tolist()
+    depth = [0] * nb
+    for b in range(1, nb):
+        depth[b] = depth[parent[b]] + 1
+    order = S["noncontact_order"].tolist()
+    tb = S["mb_task_body"].tolist()
+
+    def arr(name, vals, ty="int"):
+        return "static constexpr %s %s[%d] = {%s};" % (ty, name, len(vals), ", ".join(str(v) for v in vals))
+
+    lines = [
+        "// GENERATED by trex_gym_b200/model_compiler.py (emit_topology_header) -- do not edit.",
+        "// Merged T-rex tree (fixed joints folded) as compile-time constants.",
+        "#pragma once",
+        "namespace trex_topo {",
+        "static constexpr int NB = %d;      // rigid bodies (body 0 = floating base)" % nb,
+        "static constexpr int NJ = %d;      // revolute joints, joint j drives body j+1" % (nb - 1),
+        "static constexpr int NDOF = %d;    // 6 + NJ" % (nb + 5),
+        "static constexpr int MAX_DEPTH = %d;" % max(depth),
+        "static constexpr int N_TASKS = %d;   // original URDF links (per-link damping)" % len(tb),
+        "static constexpr int N_CAND = %d;    // contact candidate points" % len(S["mb_cand_body"]),
+        arr("PARENT", parent),
+        arr("DEPTH", depth),
+        arr("NONCONTACT_ORDER", order),
+        arr("OBS_DOF", S["obs_dof"].tolist()),
+        "}  // namespace trex_topo",
+        "",
+    ]
+    return "\n".join(lines)
+
+
+def write_builtin(model: CompiledModel) -> None:
+    os.makedirs(DATA_DIR, exist_ok=True)
+    with open(BLOB_PATH, "wb") as f:
+        f.write(model.blob())
+    with open(META_PATH, "w") as f:
+        json.dump(model.meta, f, indent=1, sort_keys=True)
+    with open(TOPOLOGY_HEADER, "w") as f:
+        f.write(emit_topology_header(model))
+
+
+if __name__ == "__main__":  # python -m trex_gym_b200.model_compiler [urdf]
+    import sys
+
+    path = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/assets/trex.urdf"
+    mdl = compile_model(path)
+    write_builtin(mdl)
+    print(json.dumps(mdl.meta["golden"], indent=1))
+    print("bodies", mdl.meta["n_bodies"], "links", mdl.meta["n_links"], "candidates", len(mdl["mb_cand_body"]))
