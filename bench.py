@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the trex-gym hot path at 65,536 envs/GPU (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+One "step" = one TrexBulletEnv.step (5 fused physics substeps + obs + reward + done) over the whole
+batch of synthetic random actions.  One process per GPU (torchrun for N > 1); environments shard
+across ranks with NO step-path communication (weak scaling); NCCL is used only for the barrier and
+the max-over-ranks of the device time.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65536
+B_ALG = 909.0  # algorithmic HBM bytes per env-step
+# algorithmic FLOPs per env-step (frozen planning constants)
+C_ABA, C_RESP, C_ROW, C_INT, C_OBS, N_B = 500.0, 1900.0, 90.0, 200.0, 150.0, 26.0
+
+
+def f_alg(n_sub, mean_iters, mean_contacts, mean_limit_rows=0.0):
+    R = 25.0 + mean_limit_rows + 3.0 * mean_contacts
+    return n_sub * (N_B * C_ABA + R * C_RESP + mean_iters * R * C_ROW + C_INT) + C_OBS
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    p = [x.strip() for x in line.split(",")]
+                    if len(p) >= 9:
+                        self.samples.append(p)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for p in self.samples:
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def oracle_workers(n_threads, steps_per_worker, warmup, seed=0, preroll=0):
+    """The reference algorithm (oracle port of pybullet's pipeline) on host cores: one double-precision
+    environment per worker thread (the reference is one env per process), same action distribution."""
+    from oracle.oracle import Oracle
+    from trex_gym_b200.model_compiler import load_builtin
+
+    model = load_builtin()
+    blob = model.blob()
+    lo = model["mb_lower"][1:][model["obs_dof"]]
+    hi = model["mb_upper"][1:][model["obs_dof"]]
+    orcs = [Oracle(blob) for _ in range(n_threads)]
+    acts = []
+    for w in range(n_threads):
+        rng = np.random.Generator(np.random.Philox(key=seed + w))
+        acts.append(rng.uniform(lo, hi, size=(warmup + steps_per_worker, 25)))
+        orcs[w].reset()
+    times = [0.0] * n_threads
+
+    def work(w):
+        if preroll:
+            rng = np.random.Generator(np.random.Philox(key=10_000 + seed + w))
+            orcs[w].run(rng.uniform(lo, hi, size=(preroll, 25)), want_obs=False)
+        orcs[w].run(acts[w][:warmup], want_obs=False)
+        t0 = time.perf_counter()
+        orcs[w].run(acts[w][warmup:], want_obs=False)
+        times[w] = time.perf_counter() - t0
+
+    ths = [threading.Thread(target=work, args=(w,)) for w in range(n_threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.perf_counter() - t0
+    mean_iters = float(np.mean([o.total_iterations / max(1, o.total_substeps) for o in orcs]))
+    return n_threads * steps_per_worker / max(times), max(times), wall, mean_iters
+
+
+def run_reference(args):
+    rank, world, local = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    per_step = 16  # env-steps per worker per bench "step": a bounded sample of the 65,536-env batch
+    total_steps = per_step * args.steps
+    value, tmax, wall, mean_iters = oracle_workers(cores, total_steps, per_step * args.warmup, preroll=args.preroll)
+    sample = "%d worker threads x %d env-steps each (one double-precision env per worker, random actions after %d untimed pre-roll steps)" % (cores, total_steps, args.preroll)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec at 65,536 envs/GPU", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tmax / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "65,536 envs/GPU, random actions (configs[2]); reference arm = bounded sample of %d env-steps per step on host cores" % (cores * per_step),
+                   "num_substeps": 5, "solver_iterations": 60, "mean_solver_iterations": mean_iters},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of pybullet's algorithm (oracle/trex_oracle.c), not pybullet: pybullet is not installable here"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+
+    from trex_gym_b200 import _native
+    from trex_gym_b200.sim import TrexBatchSim
+
+    rank, world, local = dist_setup(args.gpus)
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    sim = TrexBatchSim(n, device=local, contacts=not args.no_contacts, num_substeps=args.substeps,
+                       max_episode_steps=args.horizon, warps_per_block=args.warps_per_block)
+    env_offset = rank * n
+    ring = 8
+    acts = [sim.random_actions(step=t, seed=0, env_offset=env_offset) for t in range(ring)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # untimed pre-roll: bring the batch from the reset pose (0.25 m above the floor) to its steady regime
+    for t in range(args.preroll):
+        sim.step(sim.random_actions(step=1_000_000 + t, seed=0, env_offset=env_offset, out=acts[0]))
+    acts[0] = sim.random_actions(step=0, seed=0, env_offset=env_offset, out=acts[0])
+
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    for t in range(args.warmup):
+        sim.step(acts[t % ring])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = sim.kernel_launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    it_sum = ct_sum = 0.0
+    for k in range(args.steps):
+        flush.fill_(float(k))  # L2 flush between timed steps (not timed)
+        evs[k][0].record()
+        sim.step(acts[(args.warmup + k) % ring])
+        evs[k][1].record()
+    barrier()
+    launches = sim.kernel_launches - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    st = sim.stats()
+    it_sum, ct_sum = st["mean_solver_iterations"], st["mean_contacts"]
+    t_ms = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if use_dist:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t_ms.item())
+    value = world * n * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer entry point ("e2e") ----------------------------------
+    h_act = [a.cpu().pin_memory() for a in acts]
+    h_obs = torch.empty(n, 75, dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(max(1, args.warmup)):
+        sim.step_host(h_act[t % ring], h_obs, h_rew, h_done)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        sim.step_host(h_act[k % ring], h_obs, h_rew, h_done)  # H2D actions, step, D2H obs/reward/done, sync
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if use_dist:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(t_e.item())
+    sampler.stop()
+    clocks = sampler.summary()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        tf = _native.ctypes.c_double(0.0)
+        _native.check(_native.lib().trex_measure_fp32_peak(local, _native.ctypes.byref(tf)), "trex_measure_fp32_peak")
+        fp32_peak = float(tf.value)
+        kernel_ms = dev_ms / args.steps  # one launch of trex_step_kernel per step (rank 0's own device time)
+        flops = f_alg(sim.num_substeps, it_sum, ct_sum) * n
+        achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
+        hbm_gbs = B_ALG * n / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "env-steps/sec at 65,536 envs/GPU", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%d envs/GPU, random actions U(low,high) Philox-keyed by (seed,global env,step), %s (BASELINE.json configs[2])"
+                                   % (n, "derived floor-contact points" if not args.no_contacts else "literal collision-less URDF (free fall)"),
+                       "envs_per_gpu": n, "num_substeps": sim.num_substeps, "solver_iterations": int(300 / sim.num_substeps),
+                       "mean_solver_iterations": it_sum, "mean_contacts_per_env": ct_sum, "horizon": args.horizon, "preroll_steps": args.preroll,
+                       "l2": "flushed between timed steps (256 MiB fill, untimed); steps timed individually with CUDA events",
+                       "parallelism": "envs sharded over %d GPU(s), no step-path collective" % world},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 25 * 4, "d2h_bytes_per_step": n * (75 * 4 + 4 + 1)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak if fp32_peak else None,
+                         "traffic": None, "kernel": "trex_step_kernel", "kernel_ms": kernel_ms,
+                         "peak_source": "measured in this run: register-resident FFMA microbenchmark (trex_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
+                         "flops_per_env_step": f_alg(sim.num_substeps, it_sum, ct_sum),
+                         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "bytes_per_env_step": B_ALG, "peak_source": hbm_src}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = len(os.sched_getaffinity(0))
+            steps_pw = 400
+            v, tmax, wall, mi = oracle_workers(cores, steps_pw, 20, preroll=args.preroll)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": "%d worker threads x %d env-steps (one f64 env each, same action distribution), %.1f s" % (cores, steps_pw, wall),
+                                    "mean_solver_iterations": mi,
+                                    "note": "CPU restatement of pybullet's algorithm (oracle/), not pybullet"}
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--substeps", type=int, default=5)
+    ap.add_argument("--horizon", type=int, default=0, help="max episode steps (0 = reference behaviour: never terminate)")
+    ap.add_argument("--no-contacts", action="store_true", help="literal reference URDF (no collision shapes)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warps-per-block", type=int, default=0)
+    ap.add_argument("--preroll", type=int, default=100, help="untimed env-steps from the reset state before warm-up, so the batch is in its steady regime (on the floor, in contact)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

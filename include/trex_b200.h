@@ -1,0 +1,128 @@
+/*
+ * trex_b200.h -- C ABI of libtrex_b200.so: a batched, B200-native replacement for the
+ * trex-gym hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference is pure Python over pybullet and has no FFI of its own for this path; each
+ * entry point below names the reference interface (file:line under /root/reference) whose
+ * work it replaces.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Buffers are ROW-MAJOR PER ENVIRONMENT ("one record per env"): action [N][25], obs [N][75],
+ * reward [N], done [N], state [N][TREX_STATE_DIM].  One warp steps one environment, lane k
+ * touches element k of the record, so a record is one coalesced burst.  Joint order of
+ * action/obs is the reference's: revolute joints sorted by name (trex_robot.py:311-314).
+ *
+ * Ownership: the caller (PyTorch) owns action/obs/reward/done/state buffers and passes raw
+ * device pointers; the library owns the uploaded model and its internal environment records
+ * and never allocates, frees or retains caller memory.  All launches are asynchronous on the
+ * caller's stream (a cudaStream_t passed as void*; NULL = default stream); only
+ * trex_get_stats, trex_step_host and trex_reset_host synchronise.
+ *
+ * Errors: 0 = success, negative = error; trex_last_error() returns the thread-local message.
+ * Calls on one handle are not re-entrant.
+ */
+#ifndef TREX_B200_H
+#define TREX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TREX_NUM_JOINTS 25   /* action width; trex_robot.py:413-422 */
+#define TREX_OBS_DIM 75      /* q | qd | applied motor torque; trex_robot.py:359-365 */
+#define TREX_STATE_DIM 160   /* floats per environment record, layout below */
+#define TREX_AUX_DIM 8
+
+/* environment record (float32), identical to the oracle's state vector for [0,152):
+ *   [0:3]   base COM position (world)            getBasePositionAndOrientation, trex_robot.py:322-328
+ *   [3:7]   base quaternion x,y,z,w (base->world)
+ *   [7:10]  base angular velocity (world)   [10:13] base linear velocity (world)
+ *   [13:38] joint position, pybullet link order  [38:63] joint velocity
+ *   [63:88] applied motor torque of the last substep
+ *   [88:152] cached normal impulse per contact candidate (solver warm start)
+ *   [152] steps in the current episode  [153] episodes started  [154] NaN-guard resets  */
+
+#define TREX_OK 0
+#define TREX_ERR_INVALID (-1)
+#define TREX_ERR_CUDA (-2)
+#define TREX_ERR_MODEL (-3)
+
+typedef struct trex_handle trex_handle;
+
+typedef struct trex_config {
+  int32_t num_substeps;      /* trex_env.py:18 NUM_SUBSTEPS (5); dt = 0.01/n, iterations = int(300/n)  (:71-73) */
+  float distance_weight;     /* trex_env.py:42 */
+  float energy_weight;       /* trex_env.py:43 */
+  float drift_weight;        /* trex_env.py:44 */
+  int32_t max_episode_steps; /* 0 = never terminate, the reference behaviour (trex_env.py:183-184) */
+  int32_t enable_contacts;   /* 1 = floor contact on the derived candidate points; 0 = the literal
+                                collision-less URDF of the reference (free fall) */
+  int32_t reset_mode;        /* 0 = reference reset pose (trex_env.py:81-87,105-109) */
+  uint32_t seed;
+  int32_t reserved[8];
+} trex_config;
+
+typedef struct trex_stats {
+  int64_t env_steps;         /* environment steps executed since creation */
+  int64_t episodes;          /* episodes started (resets) */
+  int64_t nan_resets;        /* environments reset by the NaN guard */
+  double mean_solver_iterations; /* PGS iterations per substep, last step */
+  double mean_contacts;      /* active contact points per environment, last step */
+  int64_t contact_overflow;  /* contact points dropped (more than the per-env capacity), last step */
+} trex_stats;
+
+/* Replaces TrexBulletEnv.__init__ + loadURDF (trex_env.py:39-96, trex_robot.py:47-56) for n_envs
+ * environments on CUDA device `device`.  model_blob = bytes produced by
+ * trex_gym_b200.model_compiler (URDF parsed by the reference's tools/urdf_parsing.py:237-239). */
+int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t device, const trex_config* cfg,
+                trex_handle** out);
+void trex_destroy(trex_handle* h);
+
+/* TrexBulletEnv.reset (trex_env.py:98-122): reset pose, zero-gain motors, one physics step, obs.
+ * mask_dev: optional uint8[N] on the device; only environments with mask != 0 are reset and have
+ * their obs row written.  obs_dev may be NULL. */
+int trex_reset(trex_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* TrexBulletEnv.step (trex_env.py:128-154) for all environments: clip, n substeps of
+ * (set_actions; stepSimulation) (trex_robot.py:413-422), observations (trex_robot.py:359-365),
+ * reward (trex_env.py:186-196), done (trex_env.py:183-184; plus optional horizon / NaN guard with
+ * VecEnv-style auto-reset: a done environment is reset and its obs row is the reset observation). */
+int trex_step(trex_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+              void* stream);
+
+/* Same step with HOST buffers (the reference-facing call: numpy in, numpy out): copies the
+ * actions to the device, steps, copies obs/reward/done back and synchronises. */
+int trex_step_host(trex_handle* h, const float* action_host, float* obs_host, float* reward_host,
+                   uint8_t* done_host);
+int trex_reset_host(trex_handle* h, float* obs_host);
+
+/* Simulator-state checkpoint / parity hooks: copy the environment records out / in (device pointers). */
+int trex_get_state(trex_handle* h, float* state_dev, void* stream);
+int trex_set_state(trex_handle* h, const float* state_dev, void* stream);
+/* per-env diagnostics of the last step: head xyz (trex_robot.py:330-335), the three penalty terms
+ * logged at trex_env.py:193-195 (lifting, station keeping, energy), PGS iterations, contacts. */
+int trex_get_aux(trex_handle* h, float* aux_dev, void* stream);
+
+/* action/observation limits in name-sorted joint order (trex_robot.py:337-357, 424-433); host pointers */
+int trex_get_joint_limits(trex_handle* h, float* lower25_host, float* upper25_host);
+
+/* Synthetic benchmark input: action[i][k] ~ U(lower_k, upper_k) from a counter-based generator keyed by
+ * (seed, env_offset + i, step), so streams do not depend on the number of GPUs. */
+int trex_fill_random_actions(trex_handle* h, float* action_dev, uint32_t seed, uint64_t step, int64_t env_offset,
+                             void* stream);
+
+int trex_get_stats(trex_handle* h, trex_stats* out); /* synchronises the device */
+/* Measurement aid (no reference counterpart): register-resident FFMA microbenchmark, best of 5, in
+ * TFLOP/s -- the FP32 CUDA-core roofline denominator for this path.  Synchronises. */
+int trex_measure_fp32_peak(int32_t device, double* tflops_out);
+int64_t trex_kernel_launches(const trex_handle* h);  /* kernels launched by this handle so far */
+int32_t trex_num_envs(const trex_handle* h);
+const char* trex_last_error(void);
+const char* trex_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""The PRODUCT kernel source (trex_gym_b200/csrc/trex_core.h) executed lane-for-lane on the CPU through
+tests/emu (32-wide host structs instead of warp registers) and compared with the CPU oracle.
+This is how the kernel arithmetic is covered in the GPU-less container; the real GPU runs are in
+test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from conftest import STATE_BLOCKS, rel_err
+
+
+@pytest.fixture(scope="module")
+def emu_cls():
+    from emu import EmuEnv
+
+    return EmuEnv
+
+
+def _oracle(model, **kw):
+    from oracle.oracle import Oracle
+
+    return Oracle(model.blob(), **kw)
+
+
+def test_reset_matches_oracle(model, emu_cls):
+    e, o = emu_cls(model.blob()), _oracle(model)
+    eo, oo = e.reset(), o.reset()
+    assert np.abs(eo - oo).max() < 1e-6
+    assert np.abs(e.get_state(o.num_candidates) - o.get_state()).max() < 1e-6
+    assert e.rec[153] == 1.0 and e.rec[152] == 0.0  # one episode started, zero steps
+
+
+def test_per_step_parity_contact_free(model, emu_cls, action_limits):
+    lo, hi = action_limits
+    e, o = emu_cls(model.blob(), contacts=False), _oracle(model, contacts=False)
+    e.reset()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for t in range(25):
+        a = rng.uniform(lo, hi)
+        o.set_state(e.get_state(o.num_candidates))
+        oobs, orew = o.step(a)
+        eobs, erew, done = e.step(a)
+        so, se = o.get_state(), e.get_state(o.num_candidates)
+        for k, sl in STATE_BLOCKS.items():
+            worst = max(worst, rel_err(so[sl], se[sl]))
+        assert abs(orew - erew) < 2e-5 * max(1.0, abs(orew))
+        assert np.abs(oobs - eobs).max() < 2e-5 * max(1.0, np.abs(oobs).max())
+        assert not done
+        assert e.aux[6] == 300  # 5 substeps x 60 iterations (the solver never reaches 1e-7 here)
+    assert worst < 2e-5, worst
+
+
+def test_per_substep_parity_with_contacts(model, emu_cls, action_limits):
+    from trex_gym_b200.model_compiler import with_params
+
+    lo, hi = action_limits
+    sub = with_params(model, time_step=0.002, solver_iterations=60)
+    e, o = emu_cls(sub.blob(), num_substeps=1), _oracle(sub, num_substeps=1)
+    e.reset()
+    rng = np.random.default_rng(5)
+    errs, n_contact = [], 0
+    a = rng.uniform(lo, hi)
+    for t in range(220):
+        if t % 5 == 0:
+            a = rng.uniform(lo, hi)
+        o.set_state(e.get_state(o.num_candidates))
+        o.step(a)
+        e.step(a)
+        so, se = o.get_state(), e.get_state(o.num_candidates)
+        errs.append(max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()))
+        n_contact += o.last_num_contacts > 0
+        assert int(e.aux[7]) == o.last_num_contacts
+    errs = np.asarray(errs)
+    assert n_contact > 60
+    assert np.percentile(errs, 50) < 2e-5 and np.percentile(errs, 99) < 2e-3, (np.percentile(errs, 50), errs.max())
+
+
+def test_standing_drop_matches_oracle_qualitatively(model, emu_cls):
+    """Free-running (no re-seeding) hold-pose drop: both land on the feet and stand at the same height."""
+    e, o = emu_cls(model.blob()), _oracle(model)
+    hold = o.reset()[:25].copy()
+    e.reset()
+    for _ in range(120):
+        o.step(hold)
+        e.step(hold)
+    so, se = o.get_state(), e.get_state(o.num_candidates)
+    assert abs(so[2] - se[2]) < 0.02 and abs(se[2] - 2.19) < 0.1
+    assert int(e.aux[7]) >= 6
+
+
+def test_reward_bit_exact_from_outputs(model, emu_cls, action_limits):
+    lo, hi = action_limits
+    e = emu_cls(model.blob(), reward_weights=(200.0, 1e-6, 1.0))
+    e.reset()
+    rng = np.random.default_rng(1)
+    f = np.float32
+    for t in range(10):
+        obs, rew, _ = e.step(rng.uniform(lo, hi))
+        power = f(0)
+        for k in range(25):
+            power = f(power + f(abs(f(obs[25 + k] * obs[50 + k]))))
+        x, y, z = e.aux[0], e.aux[1], e.aux[2]
+        dz = f(f(2.5) - z)
+        lifting = f(f(200.0) * f(dz * dz))
+        station = f(f(1.0) * f(f(x * x) + f(y * y)))
+        energy = f(f(1e-6) * power)
+        assert f(f(-lifting - station) - energy) == f(rew)
+        assert e.aux[3] == lifting and e.aux[4] == station and e.aux[5] == energy
+
+
+def test_horizon_auto_reset(model, emu_cls, action_limits):
+    lo, hi = action_limits
+    e = emu_cls(model.blob(), max_episode_steps=3)
+    reset_obs = e.reset()
+    rng = np.random.default_rng(2)
+    dones = []
+    for t in range(7):
+        obs, rew, done = e.step(rng.uniform(lo, hi))
+        dones.append(done)
+        if done:
+            assert np.array_equal(obs, reset_obs)
+    assert dones == [False, False, True, False, False, True, False]
+    assert e.rec[153] == 3.0 and e.rec[154] == 0.0
+
+
+def test_nan_guard_resets(model, emu_cls):
+    e = emu_cls(model.blob())
+    reset_obs = e.reset()
+    e.rec[40] = np.nan
+    obs, rew, done = e.step(np.zeros(25))
+    assert done and np.array_equal(obs, reset_obs) and e.rec[154] == 1.0
+
+
+def test_substep_sweep(model, emu_cls, action_limits):
+    lo, hi = action_limits
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 8):
+        e, o = emu_cls(model.blob(), num_substeps=n), _oracle(model, num_substeps=n)
+        e.reset()
+        for t in range(3):
+            a = rng.uniform(lo, hi)
+            o.set_state(e.get_state(o.num_candidates))
+            o.step(a)
+            e.step(a)
+            so, se = o.get_state(), e.get_state(o.num_candidates)
+            assert max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()) < 2e-3
+        assert e.aux[6] == n * int(300 / n)
+
+
+def test_shared_slab_fits_ten_warps_per_sm(emu_cls):
+    from emu import lib
+
+    assert lib().emu_shared_bytes() <= 24 * 1024
+    assert lib().emu_state_stride() == 160

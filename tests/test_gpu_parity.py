@@ -1,0 +1,283 @@
+"""GPU parity: the CUDA path (through the C ABI) against the double-precision CPU oracle.
+
+PARITY UNPINNED: the oracle restates pybullet from recall (oracle/trex_oracle.h); these tests
+prove kernel == oracle, the oracle itself is pinned only by the analytic KATs.
+
+Stated FP32 tolerances (relative to the largest magnitude of the state block, per env step of
+5 substeps, oracle re-seeded with the kernel's pre-step state):
+  contact-free steps : 2e-5     steps with floor contact : 2e-3
+"""
+import numpy as np
+import pytest
+
+from conftest import STATE_BLOCKS, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_FREE = 2e-5
+TOL_CONTACT = 2e-3
+
+
+def _oracle(model, **kw):
+    from oracle.oracle import Oracle
+
+    return Oracle(model.blob(), **kw)
+
+
+def _sim(model, n, **kw):
+    from trex_gym_b200.sim import TrexBatchSim
+
+    return TrexBatchSim(n, device=0, model=model, **kw)
+
+
+def _core(state_row, ncand):
+    s = np.asarray(state_row, np.float64)
+    return np.concatenate([s[:88], s[88:88 + ncand]])
+
+
+def test_library_loaded_and_version():
+    from trex_gym_b200 import _native
+
+    assert b"sm_100a" in _native.lib().trex_version()
+
+
+def test_reset_matches_oracle(model):
+    sim = _sim(model, 8)
+    o = _oracle(model)
+    oobs = o.reset()
+    obs = sim.reset().cpu().numpy()
+    st = sim.get_state().cpu().numpy()
+    for e in range(8):
+        assert np.abs(obs[e] - oobs).max() < 1e-6
+        assert np.abs(_core(st[e], o.num_candidates) - o.get_state()).max() < 1e-6
+    # analytic KAT: one free-fall substep from rest
+    assert abs(st[0, 12] - (-9.81 * 0.002)) < 1e-7
+    assert abs(st[0, 2] - (3.0 - 9.81 * 0.002 ** 2)) < 1e-6
+
+
+def _parity_campaign(model, contacts, n, n_check, steps, n_sub=5, model_for_sub=None):
+    """Step a batch with random actions; for a subset of envs re-seed the oracle with the kernel's
+    pre-step state every step and collect the per-step relative error of every state block."""
+    import torch
+
+    mdl = model_for_sub if model_for_sub is not None else model
+    sim = _sim(mdl, n, contacts=contacts, num_substeps=n_sub)
+    # per-env perturbation of the reset state: q0 += U(-0.05, 0.05) clipped to limits, seed = env id
+    st = sim.get_state().cpu().numpy()
+    qlo, qhi = model["mb_lower"][1:], model["mb_upper"][1:]
+    for e in range(n):
+        r = np.random.default_rng(e)
+        st[e, 13:38] = np.clip(st[e, 13:38] + r.uniform(-0.05, 0.05, 25), qlo, qhi)
+    sim.set_state(torch.from_numpy(st).cuda())
+    o = _oracle(mdl, contacts=contacts, num_substeps=n_sub)
+    nc = o.num_candidates
+    errs = {k: [] for k in STATE_BLOCKS}
+    rew_err, n_contact_steps = [], 0
+    for t in range(steps):
+        pre = sim.get_state().cpu().numpy()
+        act = sim.random_actions(step=t, seed=0)
+        obs, rew, done = sim.step(act)
+        post = sim.get_state().cpu().numpy()
+        a = act.cpu().numpy()
+        rew = rew.cpu().numpy()
+        assert not done.any().item()
+        for e in range(0, n, n // n_check):
+            o.set_state(_core(pre[e], nc))
+            oobs, orew = o.step(a[e].astype(np.float64))
+            so = o.get_state()
+            n_contact_steps += o.last_num_contacts > 0
+            for k, sl in STATE_BLOCKS.items():
+                errs[k].append(rel_err(so[sl], post[e, sl]))
+            rew_err.append(abs(orew - rew[e]) / max(1.0, abs(orew)))
+    return {k: np.asarray(v) for k, v in errs.items()}, np.asarray(rew_err), n_contact_steps
+
+
+def _report(tag, errs, rew_err):
+    allv = np.max(np.stack(list(errs.values())), axis=0)
+    print("%s: n=%d  p50 %.2e  p90 %.2e  p99 %.2e  max %.2e | per block max %s | reward max %.2e" % (
+        tag, allv.size, np.percentile(allv, 50), np.percentile(allv, 90), np.percentile(allv, 99), allv.max(),
+        {k: "%.1e" % v.max() for k, v in errs.items()}, rew_err.max()))
+    return allv
+
+
+def test_per_step_parity_contact_free(model):
+    """BASELINE.json configs[1] on the literal reference model (no collision shapes => free fall):
+    4,096 envs, per-step state delta vs the oracle on 64 of them, every step.  Tolerance 2e-5."""
+    errs, rew_err, _ = _parity_campaign(model, False, 4096, 64, 40)
+    allv = _report("contact-free per env-step", errs, rew_err)
+    assert allv.max() < TOL_FREE
+    assert rew_err.max() < 10 * TOL_FREE
+
+
+def test_per_substep_parity_with_contacts(model):
+    """With floor contact, per PHYSICS step (one stepSimulation of 2 ms, 60 PGS iterations): the
+    cleanest measure of arithmetic agreement.  The solver is far from converged under random
+    actions (residual >> 1), so FP32 round-off is amplified; the bound is on percentiles."""
+    from trex_gym_b200.model_compiler import with_params
+
+    sub = with_params(model, time_step=0.002, solver_iterations=60)
+    errs, rew_err, n_contact = _parity_campaign(model, True, 4096, 64, 100, n_sub=1, model_for_sub=sub)
+    allv = _report("contact per physics substep", errs, rew_err)
+    assert n_contact > 500
+    assert np.percentile(allv, 50) < 2e-5
+    assert np.percentile(allv, 99) < 2e-3
+    assert allv.max() < 0.1
+
+
+def test_per_step_parity_with_contacts(model):
+    """BASELINE.json configs[1] with the derived contact geometry: per env-step (5 substeps)."""
+    errs, rew_err, n_contact = _parity_campaign(model, True, 4096, 64, 40)
+    allv = _report("contact per env-step", errs, rew_err)
+    assert n_contact > 200
+    assert np.percentile(allv, 50) < 1e-4
+    assert np.percentile(allv, 99) < 2e-2
+    assert np.isfinite(allv).all()
+
+
+def test_rollout_divergence_100_steps(model, action_limits):
+    """Free-running 100-step divergence kernel vs oracle (reported; loose bound: chaotic under contact)."""
+    n = 16
+    sim = _sim(model, n, contacts=False)
+    orcs = [_oracle(model, contacts=False) for _ in range(n)]
+    for o in orcs:
+        o.reset()
+    div = []
+    for t in range(100):
+        act = sim.random_actions(step=t, seed=1)
+        sim.step(act)
+        a = act.cpu().numpy().astype(np.float64)
+        st = sim.get_state().cpu().numpy()
+        d = 0.0
+        for e, o in enumerate(orcs):
+            o.step(a[e])
+            so = o.get_state()
+            d = max(d, rel_err(so[13:38], st[e, 13:38]), rel_err(so[0:3], st[e, 0:3]))
+        div.append(d)
+    print("contact-free 100-step divergence: step10 %.2e step50 %.2e step100 %.2e" % (div[9], div[49], div[99]))
+    assert div[9] < 1e-4
+    assert np.isfinite(div[99])
+
+
+def test_reward_bit_exact_from_outputs(model):
+    """Reward recomputed in FP32 from the kernel's own outputs (same op order as trex_env.py:186-196)."""
+    sim = _sim(model, 256, distance_weight=200.0, energy_weight=1e-6, drift_weight=1.0)  # trex_train.py:66
+    f = np.float32
+    for t in range(20):
+        obs, rew, done = sim.step(sim.random_actions(step=t, seed=3))
+        obs, rew, aux = obs.cpu().numpy(), rew.cpu().numpy(), sim.aux().cpu().numpy()
+        for e in range(256):
+            power = f(0)
+            for k in range(25):
+                power = f(power + f(abs(f(obs[e, 25 + k] * obs[e, 50 + k]))))
+            x, y, z = aux[e, 0], aux[e, 1], aux[e, 2]
+            dz = f(f(2.5) - z)
+            lifting = f(f(200.0) * f(dz * dz))
+            station = f(f(1.0) * f(f(x * x) + f(y * y)))
+            energy = f(f(1e-6) * power)
+            expect = f(f(-lifting - station) - energy)
+            assert expect == rew[e], (t, e, expect, rew[e])
+            assert aux[e, 3] == lifting and aux[e, 4] == station and aux[e, 5] == energy
+        assert not done.any()
+
+
+def test_done_flags_and_auto_reset(model):
+    """Reference never terminates (trex_env.py:183-184); with a horizon every env is done exactly at
+    the horizon, auto-reset, and returns the reset observation (VecEnv semantics)."""
+    sim = _sim(model, 64, max_episode_steps=5)
+    reset_obs = sim.reset().clone()
+    for t in range(12):
+        obs, rew, done = sim.step(sim.random_actions(step=t))
+        d = done.cpu().numpy()
+        if (t + 1) % 5 == 0:
+            assert d.all()
+            assert (obs == reset_obs).all().item()
+        else:
+            assert not d.any()
+    s = sim.stats()
+    assert s["episodes"] == 64 * 4  # create + explicit reset + 2 horizons
+    assert s["nan_resets"] == 0
+    sim2 = _sim(model, 64)
+    for t in range(12):
+        _, _, done = sim2.step(sim2.random_actions(step=t))
+        assert not done.any().item()
+
+
+def test_state_roundtrip_and_env_independence(model):
+    import torch
+
+    sim = _sim(model, 128)
+    for t in range(5):
+        sim.step(sim.random_actions(step=t))
+    st = sim.get_state().clone()
+    # environment 0's state copied everywhere, identical actions -> bitwise identical results
+    st2 = st[0:1].repeat(128, 1).contiguous()
+    sim.set_state(st2)
+    assert (sim.get_state() == st2).all().item()
+    a = sim.random_actions(step=99)[0:1].repeat(128, 1).contiguous()
+    obs, rew, _ = sim.step(a)
+    assert (obs == obs[0:1]).all().item() and (rew == rew[0]).all().item()
+    assert (sim.get_state() == sim.get_state()[0:1]).all().item()
+
+
+def test_random_actions_keyed_by_global_env(model, action_limits):
+    lo, hi = action_limits
+    a = _sim(model, 64).random_actions(step=7, seed=5, env_offset=0).cpu().numpy()
+    b = _sim(model, 32).random_actions(step=7, seed=5, env_offset=32).cpu().numpy()
+    assert (a[32:] == b).all()
+    assert (a >= lo.astype(np.float32) - 1e-6).all() and (a <= hi.astype(np.float32) + 1e-6).all()
+    assert np.abs(a.mean(0) - (lo + hi) / 2).max() < 0.6
+
+
+def test_step_host_equals_device_step(model):
+    s1, s2 = _sim(model, 96), _sim(model, 96)
+    for t in range(3):
+        act = s1.random_actions(step=t)
+        obs, rew, done = s1.step(act)
+        hobs, hrew, hdone = s2.step_host(act.cpu().numpy())
+        assert (obs.cpu().numpy() == hobs).all() and (rew.cpu().numpy() == hrew).all() and (done.cpu().numpy() == hdone).all()
+
+
+def test_gym_surface(model):
+    from trex_gym_b200 import TrexBulletEnv, TrexVecEnv
+
+    env = TrexBulletEnv(urdf_path=None, model=model)
+    assert env.action_space.shape == (25,) and env.observation_space.shape == (75,)
+    o = _oracle(model)
+    oobs = o.reset()
+    obs = env.reset()
+    assert len(obs) == 75 and np.abs(np.asarray(obs) - oobs).max() < 1e-6
+    a = env.action_space.sample()
+    obs, rew, done, info = env.step(a)
+    oobs2, orew = o.step(a.astype(np.float64))
+    assert done is False and info == {}
+    assert np.abs(np.asarray(obs) - oobs2).max() < 1e-3 * max(1.0, np.abs(oobs2).max())
+    assert abs(rew - orew) < 1e-3 * max(1.0, abs(orew))
+    assert len(env.model._revolute_joint_indices) == 25 and abs(env.model._total_mass - 4834.866376) < 1e-3
+    assert np.allclose(env.model.get_head_position(), o.head_position(), atol=1e-4)
+    with pytest.raises(ValueError):
+        env.step(np.zeros(24))
+    venv = TrexVecEnv(32, model=model)
+    vobs = venv.reset()
+    assert tuple(vobs.shape) == (32, 75)
+    vobs, vrew, vdone, _ = venv.step(np.zeros((32, 25), np.float32))
+    assert tuple(vrew.shape) == (32,) and not vdone.any().item()
+
+
+def test_substep_sweep_matches_oracle(model):
+    """BASELINE.json configs[4]: num_substeps 1..8, dt = 0.01/n, iterations = int(300/n) (trex_env.py:71-72)."""
+    for n_sub in (1, 2, 3, 8):
+        sim = _sim(model, 4, num_substeps=n_sub)
+        o = _oracle(model, num_substeps=n_sub)
+        o.reset()
+        sim.reset()
+        nc = o.num_candidates
+        for t in range(3):
+            pre = sim.get_state().cpu().numpy()
+            act = sim.random_actions(step=t, seed=n_sub)
+            sim.step(act)
+            post = sim.get_state().cpu().numpy()
+            o.set_state(_core(pre[0], nc))
+            o.step(act[0].cpu().numpy().astype(np.float64))
+            so = o.get_state()
+            for k, sl in STATE_BLOCKS.items():
+                assert rel_err(so[sl], post[0, sl]) < TOL_CONTACT, (n_sub, k)

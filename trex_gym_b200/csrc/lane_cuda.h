@@ -1,0 +1,76 @@
+// lane_cuda.h -- native sm_100a backend of the lane-vector vocabulary used by trex_core.h.
+//
+// trex_core.h is written once against a tiny SPMD vocabulary (vf/vi/vb = "one value per
+// lane of the warp that owns this environment").  Here, on the device, a vf is simply the
+// thread's own float register and the collective operations are warp shuffles / votes.
+// tests/emu/lane_emu.h provides the same vocabulary as 32-wide host structs so that the
+// *identical* kernel source can be executed lane-for-lane on a CPU in the test-suite
+// (there is no GPU in the build container).  The emulator is test infrastructure only: it
+// is not compiled into libtrex_b200.so and there is no CPU fallback in the product.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TREX_FN __device__ __forceinline__
+#define TREX_UNROLL _Pragma("unroll")
+#define TREX_FULL 0xffffffffu
+
+typedef float vf;
+typedef int vi;
+typedef bool vb;
+
+TREX_FN vi lane_id() { return (int)(threadIdx.x & 31u); }
+TREX_FN vf vbroadcast(float x) { return x; }
+TREX_FN vf sel(vb p, vf a, vf b) { return p ? a : b; }
+TREX_FN vi seli(vb p, vi a, vi b) { return p ? a : b; }
+TREX_FN vf shfl(vf x, int src) { return __shfl_sync(TREX_FULL, x, src); }
+TREX_FN vf shflv(vf x, vi src) { return __shfl_sync(TREX_FULL, x, src); }
+TREX_FN vf shfl_xor(vf x, int m) { return __shfl_xor_sync(TREX_FULL, x, m); }
+TREX_FN float lane_value(vf x, int lane) { return __shfl_sync(TREX_FULL, x, lane); }
+TREX_FN int lane_value_i(vi x, int lane) { return __shfl_sync(TREX_FULL, x, lane); }
+TREX_FN uint32_t vballot(vb p) { return __ballot_sync(TREX_FULL, p); }
+TREX_FN bool vany(vb p) { return __any_sync(TREX_FULL, p); }
+TREX_FN void warp_sync() { __syncwarp(); }
+
+// butterfly reductions: every lane ends with the same bits (fixed association order)
+TREX_FN vf warp_sum(vf x) {
+  TREX_UNROLL for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m);
+  return x;
+}
+TREX_FN vf warp_max(vf x) {
+  TREX_UNROLL for (int m = 16; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(TREX_FULL, x, m));
+  return x;
+}
+
+// memory (global or shared): per-lane index
+TREX_FN vf ld(const float* p, vi idx) { return p[idx]; }
+TREX_FN vf ldg_ro(const float* p, vi idx) { return __ldg(p + idx); }
+TREX_FN vf ld_if(const float* p, vi idx, vb pred, float dflt) { return pred ? p[idx] : dflt; }
+TREX_FN void st(float* p, vi idx, vf v) { p[idx] = v; }
+TREX_FN void st_if(float* p, vi idx, vf v, vb pred) { if (pred) p[idx] = v; }
+TREX_FN void st_u8_if(uint8_t* p, vi idx, vi v, vb pred) { if (pred) p[idx] = (uint8_t)v; }
+// uniform (same address on every lane) loads
+TREX_FN float ldu(const float* p, int idx) { return p[idx]; }
+TREX_FN int ldui(const int* p, int idx) { return p[idx]; }
+
+TREX_FN vf vfma(vf a, vf b, vf c) { return fmaf(a, b, c); }
+TREX_FN vf vsqrt(vf x) { return sqrtf(x); }
+TREX_FN vf vabs(vf x) { return fabsf(x); }
+TREX_FN vf vmin(vf a, vf b) { return fminf(a, b); }
+TREX_FN vf vmax(vf a, vf b) { return fmaxf(a, b); }
+TREX_FN vf vsin(vf x) { return sinf(x); }
+TREX_FN vf vcos(vf x) { return cosf(x); }
+TREX_FN vf vdiv(vf a, vf b) { return a / b; }
+TREX_FN vb visnan(vf x) { return !(fabsf(x) <= 3.0e38f); }  // NaN or inf
+TREX_FN vi vf2i_bits(vf x) { return __float_as_int(x); }
+TREX_FN vf vi2f_bits(vi x) { return __int_as_float(x); }
+TREX_FN vf vi2f(vi x) { return (float)x; }
+
+TREX_FN vi ldi(const int* p, vi idx) { return p[idx]; }
+TREX_FN void sti_if(int* p, vi idx, vi v, vb pred) { if (pred) p[idx] = v; }
+TREX_FN vi rank_below(uint32_t mask) { return __popc(mask & ((1u << (threadIdx.x & 31u)) - 1u)); }
+TREX_FN int popc_u(uint32_t m) { return __popc(m); }
+// non-contracted arithmetic (the reward must be reproducible bit-for-bit from the outputs)
+TREX_FN float fmul_rn(float a, float b) { return __fmul_rn(a, b); }
+TREX_FN float fadd_rn(float a, float b) { return __fadd_rn(a, b); }
+TREX_FN vf vmul_rn(vf a, vf b) { return __fmul_rn(a, b); }

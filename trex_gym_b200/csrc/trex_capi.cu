@@ -1,0 +1,411 @@
+// trex_capi.cu -- sm_100a kernels + the C ABI declared in include/trex_b200.h.
+//
+// One warp per environment; see trex_core.h for the algorithm and the lane mapping.
+// There is no CPU path in this library: every entry point launches CUDA kernels.
+#include "lane_cuda.h"
+#include "trex_core.h"
+#include "trex_model.h"
+
+#include "../../include/trex_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#define TREX_STR2(x) #x
+#define TREX_STR(x) TREX_STR2(x)
+
+static_assert(TREX_STATE_DIM == TREX_STATE_STRIDE, "state record size");
+static_assert(TREX_AUX_DIM == TREX_AUX_STRIDE, "aux record size");
+static_assert(trex::F_COUNT == 32, "float field table");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof g_err, fmt, detail);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                 \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) return fail(TREX_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// step / reset kernel: WARPS environments per CTA, one warp each, warp-private shared slab.
+//   mode 0: TrexBulletEnv.step for every environment
+//   mode 1: TrexBulletEnv.reset for environments with mask[env] != 0 (or all when mask == nullptr)
+// ------------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+trex_step_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
+                 const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
+                 float* __restrict__ state, const float* __restrict__ action, float* __restrict__ obs,
+                 float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ aux,
+                 const uint8_t* __restrict__ mask, int n_envs, int mode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * WARPS + warp;
+  if (env >= n_envs) return;
+  if (mode == 1 && mask != nullptr && mask[env] == 0) return;
+  trex::WarpShared& S = slabs[warp];
+  float* rec = state + (size_t)env * TREX_STATE_STRIDE;
+  trex::env_step(P, mdl, mdli, tasks, cand_p, cand_lane, S, rec,
+                 mode == 0 ? action + (size_t)env * trex::NJ : nullptr,
+                 obs ? obs + (size_t)env * (3 * trex::NJ) : nullptr,
+                 (mode == 0 && reward) ? reward + env : nullptr,
+                 (mode == 0 && done) ? done + env : nullptr,
+                 aux ? aux + (size_t)env * TREX_AUX_STRIDE : nullptr, mode == 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic actions: Philox4x32-10, key (seed, 0x5eed), counter (env lo, env hi, step lo, step hi ^ block)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+trex_random_action_kernel(float* __restrict__ action, const float* __restrict__ lower, const float* __restrict__ upper,
+                          uint32_t seed, uint64_t step, int64_t env_offset, int n_envs) {
+  // one thread per (env, block of 4 joints): 7 blocks cover 25 joints
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = idx / 7, blk = idx % 7;
+  if (env >= n_envs) return;
+  const uint64_t genv = (uint64_t)(env_offset + env);
+  uint32_t c[4] = {(uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)blk << 24)};
+  philox4x32_10(c, seed, 0x5eedu);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int j = blk * 4 + k;
+    if (j < trex::NJ) {
+      const float u = (float)(c[k] >> 8) * (1.0f / 16777216.0f);  // [0,1)
+      action[(size_t)env * trex::NJ + j] = lower[j] + (upper[j] - lower[j]) * u;
+    }
+  }
+}
+
+// FP32 FFMA peak microbenchmark (register resident, 8 independent chains per thread): the
+// roofline denominator for this path (MEASURED_PEAKS.json has no FP32 figure).
+__global__ void __launch_bounds__(256)
+trex_ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f, x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f,
+        x7 = x0 + 7.0f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+struct DevStats {
+  double steps, episodes, nan_resets, iters, contacts, overflow;
+};
+
+__global__ void __launch_bounds__(256)
+trex_stats_kernel(const float* __restrict__ state, const float* __restrict__ aux, int n_envs, DevStats* out) {
+  double ep = 0, nn = 0, it = 0, ct = 0, ov = 0;
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n_envs; env += gridDim.x * blockDim.x) {
+    const float* rec = state + (size_t)env * TREX_STATE_STRIDE;
+    ep += rec[trex::ST_EPISODE];
+    nn += rec[trex::ST_NANRESETS];
+    it += aux[(size_t)env * TREX_AUX_STRIDE + 6];
+    const float cv = aux[(size_t)env * TREX_AUX_STRIDE + 7];
+    const float o = floorf(cv / 1000.0f);
+    ov += o;
+    ct += cv - 1000.0f * o;
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    ep += __shfl_xor_sync(0xffffffffu, ep, m); nn += __shfl_xor_sync(0xffffffffu, nn, m);
+    it += __shfl_xor_sync(0xffffffffu, it, m); ct += __shfl_xor_sync(0xffffffffu, ct, m);
+    ov += __shfl_xor_sync(0xffffffffu, ov, m);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out->episodes, ep); atomicAdd(&out->nan_resets, nn); atomicAdd(&out->iters, it);
+    atomicAdd(&out->contacts, ct); atomicAdd(&out->overflow, ov);
+  }
+}
+
+}  // namespace
+
+struct trex_handle {
+  int device = 0;
+  int n_envs = 0;
+  int warps_per_block = 1;
+  trex_host::ModelTables T;
+  trex_host::EnvConfig C;
+  trex::Uniform P;
+  float *d_mdl = nullptr, *d_tasks = nullptr, *d_cand_p = nullptr, *d_state = nullptr, *d_aux = nullptr;
+  float *d_lower = nullptr, *d_upper = nullptr;
+  int *d_mdli = nullptr, *d_cand_lane = nullptr;
+  // staging for the host-buffer entry points
+  float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
+  uint8_t* d_done = nullptr;
+  DevStats* d_stats = nullptr;
+  int64_t launches = 0;
+  int64_t env_steps = 0;
+};
+
+namespace {
+
+template <int WARPS>
+int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
+                int mode, cudaStream_t st) {
+  const size_t smem = sizeof(trex::WarpShared) * WARPS;
+  static bool configured[16] = {false};
+  if (!configured[h->device & 15]) {
+    CUDA_TRY(cudaFuncSetAttribute(trex_step_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(trex_step_kernel<WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    configured[h->device & 15] = true;
+  }
+  const int grid = (h->n_envs + WARPS - 1) / WARPS;
+  trex_step_kernel<WARPS><<<grid, 32 * WARPS, smem, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+                                                          h->d_state, action, obs, reward, done, h->d_aux, mask, h->n_envs, mode);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return TREX_OK;
+}
+
+int dispatch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
+                  int mode, cudaStream_t st) {
+  switch (h->warps_per_block) {
+    case 1: return launch_step<1>(h, action, obs, reward, done, mask, mode, st);
+    case 2: return launch_step<2>(h, action, obs, reward, done, mask, mode, st);
+    case 3: return launch_step<3>(h, action, obs, reward, done, mask, mode, st);
+    case 4: return launch_step<4>(h, action, obs, reward, done, mask, mode, st);
+    default: return fail(TREX_ERR_INVALID, "warps_per_block must be 1..4%s");
+  }
+}
+
+template <class Tp>
+int upload(Tp** dst, const std::vector<Tp>& src) {
+  CUDA_TRY(cudaMalloc((void**)dst, src.size() * sizeof(Tp)));
+  CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+  return TREX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* trex_last_error(void) { return g_err; }
+const char* trex_version(void) { return "trex_b200 0.1 (sm_100a, warp-per-environment, KMAX=" TREX_STR(TREX_KMAX) ")"; }
+
+int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t device, const trex_config* cfg,
+                trex_handle** out) {
+  if (!out) return fail(TREX_ERR_INVALID, "out is NULL%s");
+  *out = nullptr;
+  if (!model_blob || n_envs <= 0) return fail(TREX_ERR_INVALID, "model_blob is NULL or n_envs <= 0%s");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(TREX_ERR_CUDA, "no CUDA device available (%s); libtrex_b200 has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(TREX_ERR_INVALID, "device index out of range%s");
+  CUDA_TRY(cudaSetDevice(device));
+  trex_handle* h = new (std::nothrow) trex_handle();
+  if (!h) return fail(TREX_ERR_INVALID, "out of host memory%s");
+  h->device = device;
+  h->n_envs = n_envs;
+  if (!trex_host::build_tables(model_blob, bytes, h->T, trex::F_COUNT, trex::IF_COUNT)) {
+    int rc = fail(TREX_ERR_MODEL, "model blob rejected: %s", h->T.err.c_str());
+    delete h;
+    return rc;
+  }
+  if (cfg) {
+    h->C.num_substeps = cfg->num_substeps > 0 ? cfg->num_substeps : 5;
+    h->C.distance_weight = cfg->distance_weight; h->C.energy_weight = cfg->energy_weight; h->C.drift_weight = cfg->drift_weight;
+    h->C.max_episode_steps = cfg->max_episode_steps; h->C.enable_contacts = cfg->enable_contacts;
+    h->C.reset_mode = cfg->reset_mode; h->C.seed = cfg->seed;
+    if (cfg->reserved[0] >= 1 && cfg->reserved[0] <= 4) h->warps_per_block = cfg->reserved[0];
+  }
+  trex_host::fill_uniform(h->T, h->C, h->P);
+  int rc;
+#define TRY(x) if ((rc = (x)) != TREX_OK) { trex_destroy(h); return rc; }
+  TRY(upload(&h->d_mdl, h->T.mdl)); TRY(upload(&h->d_mdli, h->T.mdli)); TRY(upload(&h->d_tasks, h->T.tasks));
+  TRY(upload(&h->d_cand_p, h->T.cand_p)); TRY(upload(&h->d_cand_lane, h->T.cand_lane));
+  {
+    std::vector<float> lo(h->T.lower_sorted, h->T.lower_sorted + trex::NJ), hi(h->T.upper_sorted, h->T.upper_sorted + trex::NJ);
+    TRY(upload(&h->d_lower, lo)); TRY(upload(&h->d_upper, hi));
+  }
+#undef TRY
+#define CTRY(expr) { cudaError_t _e = (expr); if (_e != cudaSuccess) { int r_ = fail(TREX_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); trex_destroy(h); return r_; } }
+  const size_t N = (size_t)n_envs;
+  CTRY(cudaMalloc((void**)&h->d_state, N * TREX_STATE_STRIDE * sizeof(float)));
+  CTRY(cudaMemset(h->d_state, 0, N * TREX_STATE_STRIDE * sizeof(float)));
+  CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
+  CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
+  CTRY(cudaMalloc((void**)&h->d_action, N * trex::NJ * sizeof(float)));
+  CTRY(cudaMalloc((void**)&h->d_obs, N * 3 * trex::NJ * sizeof(float)));
+  CTRY(cudaMalloc((void**)&h->d_reward, N * sizeof(float)));
+  CTRY(cudaMalloc((void**)&h->d_done, N));
+  CTRY(cudaMalloc((void**)&h->d_stats, sizeof(DevStats)));
+#undef CTRY
+  // all environments start from the reference reset (TrexBulletEnv.__init__ calls reset(), trex_env.py:92)
+  rc = trex_reset(h, nullptr, nullptr, nullptr);
+  if (rc != TREX_OK) { trex_destroy(h); return rc; }
+  {
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e2 != cudaSuccess) { int r_ = fail(TREX_ERR_CUDA, "initial reset failed: %s", cudaGetErrorString(e2)); trex_destroy(h); return r_; }
+  }
+  *out = h;
+  return TREX_OK;
+}
+
+void trex_destroy(trex_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_mdl); cudaFree(h->d_mdli); cudaFree(h->d_tasks); cudaFree(h->d_cand_p); cudaFree(h->d_cand_lane);
+  cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_action);
+  cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_stats);
+  delete h;
+}
+
+int trex_reset(trex_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return dispatch_step(h, nullptr, obs_dev, nullptr, nullptr, mask_dev, 1, (cudaStream_t)stream);
+}
+
+int trex_step(trex_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
+  if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
+  if (!action_dev) return fail(TREX_ERR_INVALID, "action is NULL%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = dispatch_step(h, action_dev, obs_dev, reward_dev, done_dev, nullptr, 0, (cudaStream_t)stream);
+  if (rc == TREX_OK) h->env_steps += h->n_envs;
+  return rc;
+}
+
+int trex_step_host(trex_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host) {
+  if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
+  if (!action_host) return fail(TREX_ERR_INVALID, "action is NULL%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t N = (size_t)h->n_envs;
+  CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, N * trex::NJ * sizeof(float), cudaMemcpyHostToDevice, 0));
+  int rc = dispatch_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, nullptr, 0, 0);
+  if (rc != TREX_OK) return rc;
+  h->env_steps += h->n_envs;
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs, N * 3 * trex::NJ * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->d_done, N, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return TREX_OK;
+}
+
+int trex_reset_host(trex_handle* h, float* obs_host) {
+  if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = dispatch_step(h, nullptr, h->d_obs, nullptr, nullptr, nullptr, 1, 0);
+  if (rc != TREX_OK) return rc;
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs, (size_t)h->n_envs * 3 * trex::NJ * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return TREX_OK;
+}
+
+int trex_get_state(trex_handle* h, float* state_dev, void* stream) {
+  if (!h || !state_dev) return fail(TREX_ERR_INVALID, "NULL argument%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(state_dev, h->d_state, (size_t)h->n_envs * TREX_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return TREX_OK;
+}
+
+int trex_set_state(trex_handle* h, const float* state_dev, void* stream) {
+  if (!h || !state_dev) return fail(TREX_ERR_INVALID, "NULL argument%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(h->d_state, state_dev, (size_t)h->n_envs * TREX_STATE_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return TREX_OK;
+}
+
+int trex_get_aux(trex_handle* h, float* aux_dev, void* stream) {
+  if (!h || !aux_dev) return fail(TREX_ERR_INVALID, "NULL argument%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(aux_dev, h->d_aux, (size_t)h->n_envs * TREX_AUX_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return TREX_OK;
+}
+
+int trex_get_joint_limits(trex_handle* h, float* lower25_host, float* upper25_host) {
+  if (!h || !lower25_host || !upper25_host) return fail(TREX_ERR_INVALID, "NULL argument%s");
+  memcpy(lower25_host, h->T.lower_sorted, sizeof(float) * trex::NJ);
+  memcpy(upper25_host, h->T.upper_sorted, sizeof(float) * trex::NJ);
+  return TREX_OK;
+}
+
+int trex_fill_random_actions(trex_handle* h, float* action_dev, uint32_t seed, uint64_t step, int64_t env_offset, void* stream) {
+  if (!h || !action_dev) return fail(TREX_ERR_INVALID, "NULL argument%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int total = h->n_envs * 7;
+  trex_random_action_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(action_dev, h->d_lower, h->d_upper, seed, step,
+                                                                                     env_offset, h->n_envs);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return TREX_OK;
+}
+
+int trex_get_stats(trex_handle* h, trex_stats* out) {
+  if (!h || !out) return fail(TREX_ERR_INVALID, "NULL argument%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), 0));
+  trex_stats_kernel<<<296, 256>>>(h->d_state, h->d_aux, h->n_envs, h->d_stats);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  DevStats s;
+  CUDA_TRY(cudaMemcpy(&s, h->d_stats, sizeof s, cudaMemcpyDeviceToHost));
+  out->env_steps = h->env_steps;
+  out->episodes = (int64_t)s.episodes;
+  out->nan_resets = (int64_t)s.nan_resets;
+  out->mean_solver_iterations = s.iters / ((double)h->n_envs * h->P.n_sub);
+  out->mean_contacts = s.contacts / (double)h->n_envs;
+  out->contact_overflow = (int64_t)s.overflow;
+  return TREX_OK;
+}
+
+int trex_measure_fp32_peak(int32_t device, double* tflops_out) {
+  if (!tflops_out) return fail(TREX_ERR_INVALID, "NULL argument%s");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float* buf = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&buf, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    trex_ffma_peak_kernel<<<blocks, threads>>>(buf, iters, 0.999f, 0.001f);
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+  *tflops_out = best;
+  return TREX_OK;
+}
+
+int64_t trex_kernel_launches(const trex_handle* h) { return h ? h->launches : 0; }
+int32_t trex_num_envs(const trex_handle* h) { return h ? h->n_envs : 0; }
+
+}  // extern "C"

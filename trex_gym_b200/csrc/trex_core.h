@@ -1,0 +1,974 @@
+// trex_core.h -- the T-rex environment step, one WARP per environment.
+//
+// Replaces, for the 26-body merged T-rex tree, everything the reference does per
+// TrexBulletEnv.step / reset:
+//   /root/reference/trex_gym/trex_env.py:128-154 (step), :98-122 (reset), :186-196 (reward)
+//   /root/reference/trex_gym/trex_robot.py:359-365 (observations), :377-422 (motor targets)
+//   pybullet.stepSimulation (external; semantics restated in SURVEY.md Appendix A)
+//
+// Mapping (B200: 32-wide warps, everything in registers + a ~23 KB per-warp shared slab):
+//   lane L in [0,25)   joint L  = rigid body L+1 = generalised velocity index 6+L
+//   lane 25            floating base body; lanes 25..30 own base velocity coordinates 0..5
+//   lane 31            spare
+// * tree passes (kinematics, bias forces, articulated inertias, accelerations) run
+//   level-synchronously: a lane is a body, parents/children talk through warp shuffles;
+// * the inverse joint-space inertia is built column-per-lane (31 unit-impulse passes run
+//   concurrently, one per lane, reading the per-body data as shared-memory broadcasts).
+//   M^-1 is symmetric, so lane d ends up holding exactly the coefficients it needs to
+//   update "its" velocity coordinate in the projected Gauss-Seidel sweep;
+// * PGS rows are solved in Bullet's order; a row update is one shuffle + one FMA per lane
+//   for the 25 motor rows and a butterfly reduction + FMA for contact rows.
+//
+// Written against the lane vocabulary of lane_cuda.h (device) / tests/emu/lane_emu.h
+// (host emulation for the CPU test-suite).  All control flow is warp-uniform.
+#pragma once
+#include "trex_topology.h"
+
+#ifndef TREX_KMAX
+#define TREX_KMAX 24  // max simultaneously active contact points per environment
+#endif
+#define TREX_NCAND_MAX 64
+#define TREX_MAX_ROUNDS 12
+#define TREX_STATE_STRIDE 160  // floats per environment record (see include/trex_b200.h)
+#define TREX_AUX_STRIDE 8
+
+namespace trex {
+
+using trex_topo::NB;
+using trex_topo::NJ;
+using trex_topo::MAX_DEPTH;
+
+// ---- per-lane model table: float fields, layout [field][32] -----------------------------
+enum {
+  F_E0 = 0,        // 9: child axes in parent coordinates at q=0 (row major)
+  F_R0 = 9,        // 3: child origin in parent coordinates
+  F_MASS = 12,     // 1
+  F_MC = 13,       // 3: first mass moment (mass * COM) in body coordinates
+  F_I = 16,        // 6: rotational inertia about the body origin xx,xy,xz,yy,yz,zz
+  F_DROT = 22,     // 6: sum_k R_k diag(I_k) R_k^T over the URDF links of the body (angular damping)
+  F_LOWER = 28,
+  F_UPPER = 29,
+  F_JDAMP = 30,
+  F_STARTQ = 31,
+  F_COUNT = 32
+};
+// ---- per-lane model table: int fields, layout [field][32] -------------------------------
+enum {
+  IF_PARENT_LANE = 0,  // lane of the parent body (25 for children of the base; own lane for base/spare)
+  IF_DEPTH = 1,        // tree depth of the body (0 base, -1 for lanes without a body)
+  IF_ANC_MASK = 2,     // bit L set <=> body of lane L is this body or one of its ancestors (base excluded)
+  IF_CHILDREN = 3,     // 4 x 6 bits: lanes of the children (63 = none)
+  IF_OBS_SLOT = 4,     // name-sorted observation/action slot of this joint
+  IF_DAMP_LANE = 5,    // lane of the body whose URDF links this lane evaluates for link damping
+  IF_DAMP_CONTRIB = 6, // 4 x 6 bits: lanes whose partial damping wrench belongs to this body (63 = none)
+  IF_COUNT = 8
+};
+
+struct Uniform {
+  float dt, g, kp, kd, max_impulse, k_lin, k_ang, maxvel, erp, contact_erp, split_thresh, slop;
+  float resid_thresh, warm, mu, breaking, floor_z, limit_max_impulse, reset_z, target_h;
+  float w_dist, w_energy, w_drift;
+  float head_p[3];
+  float r0[NB][3];  // static-index copy of F_R0 (body index, not lane)
+  int iters, n_sub, max_episode_steps, head_lane, n_cand, n_rounds, contacts_on, reset_mode;
+  unsigned seed;
+};
+
+// per-warp shared memory slab
+struct WarpShared {
+  float E[9][32];     // parent -> body rotation, per body lane
+  float U[6][32];     // IA * S
+  float invD[32];
+  float Rw[9][32];    // world -> body rotation
+  float xw[3][32];    // body origin, world
+  float part[6][32];  // link-damping partial wrenches / scratch
+  float lam_cache[TREX_NCAND_MAX];
+  float cpos[TREX_KMAX][4];  // active contact point (world) + pad
+  int ccand[TREX_KMAX];      // candidate index of the active contact
+  int clane[TREX_KMAX];      // body lane of the active contact
+  float J[3 * TREX_KMAX][32];   // rows: 3*c + {0 normal, 1 t1, 2 t2}, indexed by LANE
+  float dV[3 * TREX_KMAX][32];
+};
+
+TREX_FN constexpr int SI(int i, int j) {  // upper-triangular index of a symmetric 6x6
+  return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
+}
+TREX_FN constexpr int body_lane(int b) { return b == 0 ? 25 : b - 1; }
+
+struct EnvRegs {
+  vf q, qd, tgt, tau;  // joint lanes
+  float pos[3], quat[4], om[3], vl[3];  // floating base (uniform across lanes)
+};
+
+struct StepStats {
+  int iters;     // PGS iterations executed (summed over substeps)
+  int contacts;  // active contact points (last substep)
+  int overflow;  // contact points dropped because more than TREX_KMAX were active
+};
+
+#define MDL(f) ldg_ro(mdl, lane + (f) * 32)
+#define MDLI(f) ldi(mdli, lane + (f) * 32)
+
+TREX_FN vf clampv(vf x, float lo, float hi) { return vmin(vmax(x, lo), hi); }
+TREX_FN float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// world -> base rotation from the base -> world quaternion (x,y,z,w)
+TREX_FN void quat_to_Rb(const float q[4], float Rb[9]) {
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  const float s = 2.0f / (x * x + y * y + z * z + w * w);
+  // base->world matrix M; Rb = M^T
+  Rb[0] = 1.0f - s * (y * y + z * z); Rb[3] = s * (x * y - w * z);        Rb[6] = s * (x * z + w * y);
+  Rb[1] = s * (x * y + w * z);        Rb[4] = 1.0f - s * (x * x + z * z); Rb[7] = s * (y * z - w * x);
+  Rb[2] = s * (x * z - w * y);        Rb[5] = s * (y * z + w * x);        Rb[8] = 1.0f - s * (x * x + y * y);
+}
+
+// local joint rotation: E = (E0 * Rz(q))^T  (parent coordinates -> body coordinates)
+TREX_FN void local_rotation(const float* mdl, vi lane, vf q, vf E[9]) {
+  const vf c = vcos(q), s = vsin(q);
+  vf e0[9];
+  TREX_UNROLL for (int k = 0; k < 9; k++) e0[k] = MDL(F_E0 + k);
+  E[0] = c * e0[0] + s * e0[1]; E[1] = c * e0[3] + s * e0[4]; E[2] = c * e0[6] + s * e0[7];
+  E[3] = c * e0[1] - s * e0[0]; E[4] = c * e0[4] - s * e0[3]; E[5] = c * e0[7] - s * e0[6];
+  E[6] = e0[2]; E[7] = e0[5]; E[8] = e0[8];
+}
+
+// Level-synchronous forward kinematics (+ optional spatial velocities in body coordinates).
+template <bool WITH_VEL>
+TREX_FN void forward_pass(const float* mdl, const int* mdli, vi lane, const EnvRegs& R, const float Rb[9],
+                          const vf E[9], vf Rw[9], vf xw[3], vf v[6]) {
+  const vi plane = MDLI(IF_PARENT_LANE);
+  const vi depth = MDLI(IF_DEPTH);
+  vf r0[3];
+  TREX_UNROLL for (int k = 0; k < 3; k++) r0[k] = MDL(F_R0 + k);
+  TREX_UNROLL for (int k = 0; k < 9; k++) Rw[k] = vbroadcast(Rb[k]);
+  TREX_UNROLL for (int k = 0; k < 3; k++) xw[k] = vbroadcast(R.pos[k]);
+  if (WITH_VEL) {
+    TREX_UNROLL for (int i = 0; i < 3; i++) {
+      v[i] = vbroadcast(Rb[3 * i] * R.om[0] + Rb[3 * i + 1] * R.om[1] + Rb[3 * i + 2] * R.om[2]);
+      v[3 + i] = vbroadcast(Rb[3 * i] * R.vl[0] + Rb[3 * i + 1] * R.vl[1] + Rb[3 * i + 2] * R.vl[2]);
+    }
+  }
+  for (int d = 1; d <= MAX_DEPTH; d++) {
+    const vb at = depth == d;
+    vf pR[9], px[3];
+    TREX_UNROLL for (int k = 0; k < 9; k++) pR[k] = shflv(Rw[k], plane);
+    TREX_UNROLL for (int k = 0; k < 3; k++) px[k] = shflv(xw[k], plane);
+    TREX_UNROLL for (int i = 0; i < 3; i++)
+      TREX_UNROLL for (int j = 0; j < 3; j++) {
+        const vf t = E[3 * i] * pR[j] + E[3 * i + 1] * pR[3 + j] + E[3 * i + 2] * pR[6 + j];
+        Rw[3 * i + j] = sel(at, t, Rw[3 * i + j]);
+      }
+    TREX_UNROLL for (int j = 0; j < 3; j++) {
+      const vf t = px[j] + pR[j] * r0[0] + pR[3 + j] * r0[1] + pR[6 + j] * r0[2];
+      xw[j] = sel(at, t, xw[j]);
+    }
+    if (WITH_VEL) {
+      vf pv[6];
+      TREX_UNROLL for (int k = 0; k < 6; k++) pv[k] = shflv(v[k], plane);
+      // linear velocity of the child origin in parent coordinates: v_p + w_p x r
+      const vf lx = pv[3] + (pv[1] * r0[2] - pv[2] * r0[1]);
+      const vf ly = pv[4] + (pv[2] * r0[0] - pv[0] * r0[2]);
+      const vf lz = pv[5] + (pv[0] * r0[1] - pv[1] * r0[0]);
+      TREX_UNROLL for (int i = 0; i < 3; i++) {
+        vf wa = E[3 * i] * pv[0] + E[3 * i + 1] * pv[1] + E[3 * i + 2] * pv[2];
+        const vf la = E[3 * i] * lx + E[3 * i + 1] * ly + E[3 * i + 2] * lz;
+        if (i == 2) wa = wa + R.qd;
+        v[i] = sel(at, wa, v[i]);
+        v[3 + i] = sel(at, la, v[3 + i]);
+      }
+    }
+  }
+}
+
+// inverse of a symmetric positive definite 6x6 given as SI()-packed upper triangle (uniform math)
+TREX_FN void spd6_inverse(const float a[21], float inv[21]) {
+  float L[6][6];
+  TREX_UNROLL for (int j = 0; j < 6; j++) {
+    float s = a[SI(j, j)];
+    TREX_UNROLL for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+    const float d = sqrtf(s);
+    const float id = 1.0f / d;
+    L[j][j] = d;
+    TREX_UNROLL for (int i = j + 1; i < 6; i++) {
+      float t = a[SI(i, j)];
+      TREX_UNROLL for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+      L[i][j] = t * id;
+    }
+  }
+  float Li[6][6];  // inverse of L (lower triangular)
+  TREX_UNROLL for (int j = 0; j < 6; j++) {
+    Li[j][j] = 1.0f / L[j][j];
+    TREX_UNROLL for (int i = j + 1; i < 6; i++) {
+      float t = 0.0f;
+      TREX_UNROLL for (int k = j; k < i; k++) t -= L[i][k] * Li[k][j];
+      Li[i][j] = t / L[i][i];
+    }
+  }
+  TREX_UNROLL for (int i = 0; i < 6; i++)
+    TREX_UNROLL for (int j = i; j < 6; j++) {
+      float t = 0.0f;
+      TREX_UNROLL for (int k = j; k < 6; k++) t += Li[k][i] * Li[k][j];
+      inv[SI(i, j)] = t;
+    }
+}
+
+// child -> parent transform of an articulated inertia (SI packed, child coordinates) and a
+// spatial force.  E: parent->child rotation, r: child origin in parent coordinates.
+//   I_p = X^T I X ,  f_p = X^T f ,  X = [[E, 0], [-E [r]x, E]]
+TREX_FN void to_parent(const vf E[9], const vf r[3], const vf Ia[21], const vf pa[6], vf Ip[21], vf pp[6]) {
+  // blocks in child coordinates
+  vf A[3][3], B[3][3], M[3][3];
+  TREX_UNROLL for (int i = 0; i < 3; i++)
+    TREX_UNROLL for (int j = 0; j < 3; j++) {
+      A[i][j] = Ia[SI(i, j)];
+      B[i][j] = Ia[SI(i, 3 + j)];
+      M[i][j] = Ia[SI(3 + i, 3 + j)];
+    }
+  // rotate into parent axes: K' = E^T K E
+  vf T[3][3], Ar[3][3], Br[3][3], Mr[3][3];
+#define ROT_BLOCK(K, Kr)                                                                         \
+  TREX_UNROLL for (int i = 0; i < 3; i++)                                                        \
+    TREX_UNROLL for (int j = 0; j < 3; j++) T[i][j] = K[i][0] * E[j] + K[i][1] * E[3 + j] + K[i][2] * E[6 + j]; \
+  TREX_UNROLL for (int i = 0; i < 3; i++)                                                        \
+    TREX_UNROLL for (int j = 0; j < 3; j++) Kr[i][j] = E[i] * T[0][j] + E[3 + i] * T[1][j] + E[6 + i] * T[2][j];
+  ROT_BLOCK(A, Ar)
+  ROT_BLOCK(B, Br)
+  ROT_BLOCK(M, Mr)
+#undef ROT_BLOCK
+  // K = [r]x Mr ; Bp = Br + K ; Ap = Ar + [r]x Br^T + ([r]x Bp^T)^T
+  vf K[3][3], C[3][3], Dm[3][3], Bp[3][3];
+  TREX_UNROLL for (int j = 0; j < 3; j++) {
+    K[0][j] = r[1] * Mr[2][j] - r[2] * Mr[1][j];
+    K[1][j] = r[2] * Mr[0][j] - r[0] * Mr[2][j];
+    K[2][j] = r[0] * Mr[1][j] - r[1] * Mr[0][j];
+  }
+  TREX_UNROLL for (int i = 0; i < 3; i++)
+    TREX_UNROLL for (int j = 0; j < 3; j++) Bp[i][j] = Br[i][j] + K[i][j];
+  TREX_UNROLL for (int j = 0; j < 3; j++) {  // C = [r]x Br^T ; Dm = [r]x Bp^T
+    C[0][j] = r[1] * Br[j][2] - r[2] * Br[j][1];
+    C[1][j] = r[2] * Br[j][0] - r[0] * Br[j][2];
+    C[2][j] = r[0] * Br[j][1] - r[1] * Br[j][0];
+    Dm[0][j] = r[1] * Bp[j][2] - r[2] * Bp[j][1];
+    Dm[1][j] = r[2] * Bp[j][0] - r[0] * Bp[j][2];
+    Dm[2][j] = r[0] * Bp[j][1] - r[1] * Bp[j][0];
+  }
+  TREX_UNROLL for (int i = 0; i < 3; i++)
+    TREX_UNROLL for (int j = i; j < 3; j++) {
+      Ip[SI(i, j)] = Ar[i][j] + C[i][j] + Dm[j][i];
+      Ip[SI(3 + i, 3 + j)] = Mr[i][j];
+    }
+  TREX_UNROLL for (int i = 0; i < 3; i++)
+    TREX_UNROLL for (int j = 0; j < 3; j++) Ip[SI(i, 3 + j)] = Bp[i][j];
+  // force: f' = E^T f ; n' = E^T n + r x f'
+  vf fn[3], ff[3];
+  TREX_UNROLL for (int i = 0; i < 3; i++) {
+    fn[i] = E[i] * pa[0] + E[3 + i] * pa[1] + E[6 + i] * pa[2];
+    ff[i] = E[i] * pa[3] + E[3 + i] * pa[4] + E[6 + i] * pa[5];
+  }
+  pp[0] = fn[0] + (r[1] * ff[2] - r[2] * ff[1]);
+  pp[1] = fn[1] + (r[2] * ff[0] - r[0] * ff[2]);
+  pp[2] = fn[2] + (r[0] * ff[1] - r[1] * ff[0]);
+  pp[3] = ff[0]; pp[4] = ff[1]; pp[5] = ff[2];
+}
+
+// ------------------------------------------------------------------------------------------
+// One pybullet stepSimulation for the environment owned by this warp.
+// kp/kd/max_imp: motor settings of this substep (zero during the reset step).
+// ------------------------------------------------------------------------------------------
+TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+                     const int* cand_lane, WarpShared& S, EnvRegs& R, float kp, float kd, float max_imp,
+                     StepStats& stats) {
+  const vi lane = lane_id();
+  const vb is_joint = lane < NJ;
+  const vb is_base = lane == 25;
+  const vi plane = MDLI(IF_PARENT_LANE);
+  const vi depth = MDLI(IF_DEPTH);
+  const vi anc = MDLI(IF_ANC_MASK);
+  const float dt = P.dt;
+
+  float Rb[9];
+  quat_to_Rb(R.quat, Rb);
+
+  // ---- 1-2. kinematics and velocities ---------------------------------------------------
+  vf E[9];
+  local_rotation(mdl, lane, R.q, E);
+  TREX_UNROLL for (int k = 0; k < 9; k++) E[k] = sel(is_base, vbroadcast(Rb[k]), E[k]);
+  vf Rw[9], xw[3], v[6];
+  forward_pass<true>(mdl, mdli, lane, R, Rb, E, Rw, xw, v);
+  TREX_UNROLL for (int k = 0; k < 9; k++) { st(S.E[k], lane, E[k]); st(S.Rw[k], lane, Rw[k]); }
+  TREX_UNROLL for (int k = 0; k < 3; k++) st(S.xw[k], lane, xw[k]);
+
+  // ---- 3. bias forces: p = v x* (I v) - gravity wrench + angular damping ------------------
+  const vf mass = MDL(F_MASS);
+  vf mc[3], I3[6];
+  TREX_UNROLL for (int k = 0; k < 3; k++) mc[k] = MDL(F_MC + k);
+  TREX_UNROLL for (int k = 0; k < 6; k++) I3[k] = MDL(F_I + k);
+  vf pA[6];
+  {
+    const vf wx = v[0], wy = v[1], wz = v[2], lx = v[3], ly = v[4], lz = v[5];
+    // n = I w + mc x v ; f = m v - mc x w
+    const vf nx = I3[0] * wx + I3[1] * wy + I3[2] * wz + (mc[1] * lz - mc[2] * ly);
+    const vf ny = I3[1] * wx + I3[3] * wy + I3[4] * wz + (mc[2] * lx - mc[0] * lz);
+    const vf nz = I3[2] * wx + I3[4] * wy + I3[5] * wz + (mc[0] * ly - mc[1] * lx);
+    const vf fx = mass * lx - (mc[1] * wz - mc[2] * wy);
+    const vf fy = mass * ly - (mc[2] * wx - mc[0] * wz);
+    const vf fz = mass * lz - (mc[0] * wy - mc[1] * wx);
+    pA[0] = (wy * nz - wz * ny) + (ly * fz - lz * fy);
+    pA[1] = (wz * nx - wx * nz) + (lz * fx - lx * fz);
+    pA[2] = (wx * ny - wy * nx) + (lx * fy - ly * fx);
+    pA[3] = wy * fz - wz * fy;
+    pA[4] = wz * fx - wx * fz;
+    pA[5] = wx * fy - wy * fx;
+    // gravity as an external force on every body: world (0,0,-g) in body coordinates = -g * Rw[:,2]
+    const vf gx = -P.g * Rw[2], gy = -P.g * Rw[5], gz = -P.g * Rw[8];
+    pA[0] -= mc[1] * gz - mc[2] * gy;
+    pA[1] -= mc[2] * gx - mc[0] * gz;
+    pA[2] -= mc[0] * gy - mc[1] * gx;
+    pA[3] -= mass * gx; pA[4] -= mass * gy; pA[5] -= mass * gz;
+    // angular damping of every URDF link of the body: (sum R I R^T) w (k + k|w|)
+    vf dr[6];
+    TREX_UNROLL for (int k = 0; k < 6; k++) dr[k] = MDL(F_DROT + k);
+    const vf wn = vsqrt(wx * wx + wy * wy + wz * wz);
+    const vf ka = P.k_ang + P.k_ang * wn;
+    pA[0] += (dr[0] * wx + dr[1] * wy + dr[2] * wz) * ka;
+    pA[1] += (dr[1] * wx + dr[3] * wy + dr[4] * wz) * ka;
+    pA[2] += (dr[2] * wx + dr[4] * wy + dr[5] * wz) * ka;
+  }
+  // ---- 4. linear damping, evaluated at the COM of every original URDF link -----------------
+  {
+    const vi dl = MDLI(IF_DAMP_LANE);
+    vf bv[6];
+    TREX_UNROLL for (int k = 0; k < 6; k++) bv[k] = shflv(v[k], dl);
+    vf acc[6];
+    TREX_UNROLL for (int k = 0; k < 6; k++) acc[k] = 0.0f;
+    for (int rd = 0; rd < P.n_rounds; rd++) {
+      const float* t = tasks + rd * 4 * 32;
+      const vf rx = ldg_ro(t, lane), ry = ldg_ro(t, lane + 32), rz = ldg_ro(t, lane + 64), m = ldg_ro(t, lane + 96);
+      const vf cx = bv[3] + (bv[1] * rz - bv[2] * ry);
+      const vf cy = bv[4] + (bv[2] * rx - bv[0] * rz);
+      const vf cz = bv[5] + (bv[0] * ry - bv[1] * rx);
+      const vf sc = m * (P.k_lin + P.k_lin * vsqrt(cx * cx + cy * cy + cz * cz));
+      const vf fx = cx * sc, fy = cy * sc, fz = cz * sc;
+      acc[0] += ry * fz - rz * fy;
+      acc[1] += rz * fx - rx * fz;
+      acc[2] += rx * fy - ry * fx;
+      acc[3] += fx; acc[4] += fy; acc[5] += fz;
+    }
+    warp_sync();
+    TREX_UNROLL for (int k = 0; k < 6; k++) st(S.part[k], lane, acc[k]);
+    warp_sync();
+    const vi contrib = MDLI(IF_DAMP_CONTRIB);
+    TREX_UNROLL for (int s = 0; s < 4; s++) {
+      const vi cl = (contrib >> (6 * s)) & 63;
+      const vb ok = cl != 63;
+      const vi cls = seli(ok, cl, lane);
+      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, ld(S.part[k], cls), 0.0f);
+    }
+    warp_sync();
+  }
+
+  // Coriolis term c = v x (S qd), S = z rotation: only 4 non-zero components
+  const vf c0 = R.qd * v[1], c1 = -(R.qd * v[0]), c3 = R.qd * v[4], c4 = -(R.qd * v[3]);
+  // explicit joint damping torque (pybullet adds -damping*qd before each step)
+  const vf tau_j = -(MDL(F_JDAMP) * R.qd);
+
+  // ---- 5. inward pass: articulated inertias ---------------------------------------------------
+  vf IA[21];
+  TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] = 0.0f;
+  IA[SI(0, 0)] = I3[0]; IA[SI(0, 1)] = I3[1]; IA[SI(0, 2)] = I3[2];
+  IA[SI(1, 1)] = I3[3]; IA[SI(1, 2)] = I3[4]; IA[SI(2, 2)] = I3[5];
+  IA[SI(0, 4)] = -mc[2]; IA[SI(0, 5)] = mc[1];
+  IA[SI(1, 3)] = mc[2];  IA[SI(1, 5)] = -mc[0];
+  IA[SI(2, 3)] = -mc[1]; IA[SI(2, 4)] = mc[0];
+  IA[SI(3, 3)] = mass; IA[SI(4, 4)] = mass; IA[SI(5, 5)] = mass;
+  vf r0[3];
+  TREX_UNROLL for (int k = 0; k < 3; k++) r0[k] = MDL(F_R0 + k);
+  const vi children = MDLI(IF_CHILDREN);
+  vf U[6], invD = 0.0f, uu = 0.0f;
+  TREX_UNROLL for (int k = 0; k < 6; k++) U[k] = 0.0f;
+  for (int d = MAX_DEPTH; d >= 1; d--) {
+    const vb at = depth == d;
+    // U = IA S, D = S^T U, u = tau - S^T pA      (S = unit z rotation)
+    vf Ut[6];
+    Ut[0] = IA[SI(0, 2)]; Ut[1] = IA[SI(1, 2)]; Ut[2] = IA[SI(2, 2)];
+    Ut[3] = IA[SI(2, 3)]; Ut[4] = IA[SI(2, 4)]; Ut[5] = IA[SI(2, 5)];
+    const vf Dt = Ut[2];
+    const vf iD = sel(Dt >= 1.1920929e-7f, vdiv(1.0f, Dt), 0.0f);
+    const vf ut = tau_j - pA[2];
+    TREX_UNROLL for (int k = 0; k < 6; k++) U[k] = sel(at, Ut[k], U[k]);
+    invD = sel(at, iD, invD);
+    uu = sel(at, ut, uu);
+    // Ia = IA - U U^T / D
+    vf Ia[21];
+    TREX_UNROLL for (int i = 0; i < 6; i++)
+      TREX_UNROLL for (int j = i; j < 6; j++) Ia[SI(i, j)] = IA[SI(i, j)] - (Ut[i] * iD) * Ut[j];
+    // pa = pA + Ia c + U u / D
+    vf pa[6];
+    const vf s = ut * iD;
+    TREX_UNROLL for (int i = 0; i < 6; i++)
+      pa[i] = pA[i] + (Ia[SI(i, 0)] * c0 + Ia[SI(i, 1)] * c1 + Ia[SI(i, 3)] * c3 + Ia[SI(i, 4)] * c4) + Ut[i] * s;
+    vf Ip[21], pp[6];
+    to_parent(E, r0, Ia, pa, Ip, pp);
+    // parents (depth d-1) gather from their children (all at depth d)
+    const vb parent_now = depth == (d - 1);
+    TREX_UNROLL for (int sidx = 0; sidx < 4; sidx++) {
+      const vi cl = (children >> (6 * sidx)) & 63;
+      const vb ok = parent_now && (cl != 63);
+      const vi cls = seli(ok, cl, lane);
+      TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] += sel(ok, shflv(Ip[k], cls), 0.0f);
+      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, shflv(pp[k], cls), 0.0f);
+    }
+  }
+  TREX_UNROLL for (int k = 0; k < 6; k++) st(S.U[k], lane, U[k]);
+  st(S.invD, lane, invD);
+
+  // ---- 6. base acceleration --------------------------------------------------------------------
+  float ia0[21], ia0inv[21], pA0[6], a0[6];
+  TREX_UNROLL for (int k = 0; k < 21; k++) ia0[k] = lane_value(IA[k], 25);
+  TREX_UNROLL for (int k = 0; k < 6; k++) pA0[k] = lane_value(pA[k], 25);
+  spd6_inverse(ia0, ia0inv);
+  TREX_UNROLL for (int i = 0; i < 6; i++) {
+    float t = 0.0f;
+    TREX_UNROLL for (int j = 0; j < 6; j++) t += ia0inv[SI(i, j)] * pA0[j];
+    a0[i] = -t;
+  }
+
+  // ---- 7. outward pass: accelerations -------------------------------------------------------------
+  vf a[6];
+  TREX_UNROLL for (int k = 0; k < 6; k++) a[k] = vbroadcast(a0[k]);
+  vf qdd = 0.0f;
+  for (int d = 1; d <= MAX_DEPTH; d++) {
+    const vb at = depth == d;
+    vf ap[6];
+    TREX_UNROLL for (int k = 0; k < 6; k++) ap[k] = shflv(a[k], plane);
+    const vf lx = ap[3] + (ap[1] * r0[2] - ap[2] * r0[1]);
+    const vf ly = ap[4] + (ap[2] * r0[0] - ap[0] * r0[2]);
+    const vf lz = ap[5] + (ap[0] * r0[1] - ap[1] * r0[0]);
+    vf an[6];
+    TREX_UNROLL for (int i = 0; i < 3; i++) {
+      an[i] = E[3 * i] * ap[0] + E[3 * i + 1] * ap[1] + E[3 * i + 2] * ap[2];
+      an[3 + i] = E[3 * i] * lx + E[3 * i + 1] * ly + E[3 * i + 2] * lz;
+    }
+    an[0] += c0; an[1] += c1; an[3] += c3; an[4] += c4;
+    const vf dd = (uu - (U[0] * an[0] + U[1] * an[1] + U[2] * an[2] + U[3] * an[3] + U[4] * an[4] + U[5] * an[5])) * invD;
+    an[2] += dd;
+    qdd = sel(at, dd, qdd);
+    TREX_UNROLL for (int k = 0; k < 6; k++) a[k] = sel(at, an[k], a[k]);
+  }
+
+  // ---- 8. velocities += dt * acceleration, each coordinate clamped (btMultiBody::applyDeltaVeeMultiDof) ----
+  R.qd = sel(is_joint, clampv(R.qd + dt * qdd, -P.maxvel, P.maxvel), 0.0f);
+  {
+    const float wb[3] = {Rb[0] * R.om[0] + Rb[1] * R.om[1] + Rb[2] * R.om[2], Rb[3] * R.om[0] + Rb[4] * R.om[1] + Rb[5] * R.om[2],
+                         Rb[6] * R.om[0] + Rb[7] * R.om[1] + Rb[8] * R.om[2]};
+    const float vb_[3] = {Rb[0] * R.vl[0] + Rb[1] * R.vl[1] + Rb[2] * R.vl[2], Rb[3] * R.vl[0] + Rb[4] * R.vl[1] + Rb[5] * R.vl[2],
+                          Rb[6] * R.vl[0] + Rb[7] * R.vl[1] + Rb[8] * R.vl[2]};
+    const float al[3] = {a0[3] + (wb[1] * vb_[2] - wb[2] * vb_[1]), a0[4] + (wb[2] * vb_[0] - wb[0] * vb_[2]),
+                         a0[5] + (wb[0] * vb_[1] - wb[1] * vb_[0])};
+    TREX_UNROLL for (int j = 0; j < 3; j++) {
+      const float wd = Rb[j] * a0[0] + Rb[3 + j] * a0[1] + Rb[6 + j] * a0[2];
+      const float vd = Rb[j] * al[0] + Rb[3 + j] * al[1] + Rb[6 + j] * al[2];
+      R.om[j] = clampf(R.om[j] + dt * wd, -P.maxvel, P.maxvel);
+      R.vl[j] = clampf(R.vl[j] + dt * vd, -P.maxvel, P.maxvel);
+    }
+  }
+  warp_sync();
+
+  // ---- 9. M^-1, one column per lane (btMultiBody::calcAccelerationDeltasMultiDof for unit impulses) ----
+  vf col[trex_topo::NDOF];
+  {
+    // (a) inward along this lane's own ancestor path
+    vf z[6];
+    TREX_UNROLL for (int k = 0; k < 6; k++) z[k] = sel(is_joint, U[k] * invD, 0.0f);
+    vf Ydep[MAX_DEPTH + 1];
+    TREX_UNROLL for (int dd = 0; dd <= MAX_DEPTH; dd++) Ydep[dd] = sel(is_joint && (depth == dd), 1.0f, 0.0f);
+    vi cur = lane;
+    for (int s = 0; s < MAX_DEPTH; s++) {
+      const vb active = is_joint && ((depth - s) >= 1);
+      const vi cs = seli(active, cur, lane);
+      vf Ec[9], rc[3];
+      TREX_UNROLL for (int k = 0; k < 9; k++) Ec[k] = ld(S.E[k], cs);
+      TREX_UNROLL for (int k = 0; k < 3; k++) rc[k] = ldg_ro(mdl, cs + (F_R0 + k) * 32);
+      vf fn[3], ff[3];
+      TREX_UNROLL for (int i = 0; i < 3; i++) {
+        fn[i] = Ec[i] * z[0] + Ec[3 + i] * z[1] + Ec[6 + i] * z[2];
+        ff[i] = Ec[i] * z[3] + Ec[3 + i] * z[4] + Ec[6 + i] * z[5];
+      }
+      vf zn[6];
+      zn[0] = fn[0] + (rc[1] * ff[2] - rc[2] * ff[1]);
+      zn[1] = fn[1] + (rc[2] * ff[0] - rc[0] * ff[2]);
+      zn[2] = fn[2] + (rc[0] * ff[1] - rc[1] * ff[0]);
+      zn[3] = ff[0]; zn[4] = ff[1]; zn[5] = ff[2];
+      const vi par = ldi(mdli, cs + IF_PARENT_LANE * 32);
+      const vb par_joint = active && (par != 25);
+      const vi ps = seli(par_joint, par, lane);
+      // at a joint parent: Y = -S^T z ; z += U * Y / D
+      const vf Yp = -zn[2];
+      const vf sc = Yp * ld(S.invD, ps);
+      TREX_UNROLL for (int k = 0; k < 6; k++) {
+        const vf up = ld(S.U[k], ps);
+        z[k] = sel(active, sel(par_joint, zn[k] + up * sc, zn[k]), z[k]);
+      }
+      const vi pd = depth - s - 1;
+      TREX_UNROLL for (int dd = 1; dd <= MAX_DEPTH; dd++) Ydep[dd] = sel(par_joint && (pd == dd), Yp, Ydep[dd]);
+      cur = seli(active, par, cur);
+    }
+    // base-coordinate lanes: unit torque / force on the base, rotated into base coordinates
+    {
+      const vi kk = lane - 25;
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        // column kk of Rb
+        const vf rk = sel(kk == 0 || kk == 3, vbroadcast(Rb[3 * k]), sel(kk == 1 || kk == 4, vbroadcast(Rb[3 * k + 1]), vbroadcast(Rb[3 * k + 2])));
+        const vb isw = (lane >= 25) && (lane < 28);
+        const vb isv = (lane >= 28) && (lane < 31);
+        z[k] = sel(isw, -rk, sel(is_joint, z[k], 0.0f));
+        z[3 + k] = sel(isv, -rk, sel(is_joint, z[3 + k], 0.0f));
+      }
+    }
+    // (b) base: a0 = -IA0^-1 z
+    vf ab[NB][6];
+    TREX_UNROLL for (int i = 0; i < 6; i++) {
+      vf t = 0.0f;
+      TREX_UNROLL for (int j = 0; j < 6; j++) t += ia0inv[SI(i, j)] * z[j];
+      ab[0][i] = -t;
+    }
+    // (c) outward over the whole tree (static topology -> static registers)
+    TREX_UNROLL for (int b = 1; b < NB; b++) {
+      const int p = trex_topo::parent_of(b);
+      const int bl = b - 1;
+      float Eb[9], Ub[6];
+      TREX_UNROLL for (int k = 0; k < 9; k++) Eb[k] = ldu(S.E[k], bl);
+      TREX_UNROLL for (int k = 0; k < 6; k++) Ub[k] = ldu(S.U[k], bl);
+      const float iDb = ldu(S.invD, bl);
+      const float rx = P.r0[b][0], ry = P.r0[b][1], rz = P.r0[b][2];
+      const vf lx = ab[p][3] + (ab[p][1] * rz - ab[p][2] * ry);
+      const vf ly = ab[p][4] + (ab[p][2] * rx - ab[p][0] * rz);
+      const vf lz = ab[p][5] + (ab[p][0] * ry - ab[p][1] * rx);
+      TREX_UNROLL for (int i = 0; i < 3; i++) {
+        ab[b][i] = Eb[3 * i] * ab[p][0] + Eb[3 * i + 1] * ab[p][1] + Eb[3 * i + 2] * ab[p][2];
+        ab[b][3 + i] = Eb[3 * i] * lx + Eb[3 * i + 1] * ly + Eb[3 * i + 2] * lz;
+      }
+      const vf Yb = sel(((anc >> bl) & 1) != 0, Ydep[trex_topo::depth_of(b)], 0.0f);
+      const vf dd = (Yb - (Ub[0] * ab[b][0] + Ub[1] * ab[b][1] + Ub[2] * ab[b][2] + Ub[3] * ab[b][3] + Ub[4] * ab[b][4] + Ub[5] * ab[b][5])) * iDb;
+      ab[b][2] += dd;
+      col[6 + bl] = dd;
+    }
+    TREX_UNROLL for (int j = 0; j < 3; j++) {
+      col[j] = Rb[j] * ab[0][0] + Rb[3 + j] * ab[0][1] + Rb[6 + j] * ab[0][2];
+      col[3 + j] = Rb[j] * ab[0][3] + Rb[3 + j] * ab[0][4] + Rb[6 + j] * ab[0][5];
+    }
+  }
+
+  // ---- 10. constraint rows -------------------------------------------------------------------------
+  // this lane's own velocity coordinate and diagonal of M^-1
+  vf uown = R.qd;
+  vf dself = 0.0f;
+  TREX_UNROLL for (int k = 0; k < 3; k++) {
+    uown = sel(lane == 25 + k, vbroadcast(R.om[k]), uown);
+    uown = sel(lane == 28 + k, vbroadcast(R.vl[k]), uown);
+  }
+  uown = sel(lane == 31, 0.0f, uown);
+  TREX_UNROLL for (int g = 0; g < trex_topo::NDOF; g++) {
+    const int ln = g < 6 ? 25 + g : g - 6;
+    dself = sel(lane == ln, col[g], dself);
+  }
+  // joint rows: J = +-e_j so the response is +-column j and J M^-1 J^T = M^-1[j][j]
+  const vf jdi = sel(is_joint && (dself > 1.1920929e-7f), vdiv(1.0f, dself), 0.0f);
+  // motor (btMultiBodyJointMotor): target velocity kp*(target-q)/dt + qd + kd*(0-qd), impulse in [-max,max]
+  const vf vt = kp * (R.tgt - R.q) / dt + R.qd + kd * (0.0f - R.qd);
+  const vf rhs_m = (vt - R.qd) * jdi;
+  vf lam_m = 0.0f;
+  // joint limits (btMultiBodyJointLimitConstraint): a row only while the limit is violated
+  const vf lower = MDL(F_LOWER), upper = MDL(F_UPPER);
+  const vf pen_lo = R.q - lower, pen_hi = upper - R.q;
+  const vb act_lo = is_joint && !(pen_lo > 0.0f);
+  const vb act_hi = is_joint && !(pen_hi > 0.0f);
+  // shallow violations (> split threshold) keep the velocity part only
+  const vf rhs_lo = sel(pen_lo > P.split_thresh, (-R.qd) * jdi, (-pen_lo * P.erp / dt + (-R.qd)) * jdi);
+  const vf rhs_hi = sel(pen_hi > P.split_thresh, (R.qd) * jdi, (-pen_hi * P.erp / dt + (R.qd)) * jdi);
+  vf lam_lo = 0.0f, lam_hi = 0.0f;
+  const uint32_t mask_lo = vballot(act_lo), mask_hi = vballot(act_hi);
+
+  // contacts: candidate points against the floor plane
+  int n_act = 0;
+  vf c_lam[3], c_rhs[3], c_jdi[3];  // lane s holds the scalars of active contact s (normal, t1, t2)
+  TREX_UNROLL for (int k = 0; k < 3; k++) { c_lam[k] = 0.0f; c_rhs[k] = 0.0f; c_jdi[k] = 0.0f; }
+  vf dv = 0.0f;  // this lane's coordinate of the accumulated delta velocity
+  if (P.contacts_on) {
+    TREX_UNROLL for (int half = 0; half < 2; half++) {
+      const vi ci = lane + 32 * half;
+      const vb valid = ci < P.n_cand;
+      const vi cis = seli(valid, ci, 0);
+      const vi bl = ldi(cand_lane, cis);
+      const vf px = ldg_ro(cand_p, cis), py = ldg_ro(cand_p, cis + TREX_NCAND_MAX), pz = ldg_ro(cand_p, cis + 2 * TREX_NCAND_MAX);
+      // world point = xw + Rw^T p
+      const vf wx = ld(S.xw[0], bl) + ld(S.Rw[0], bl) * px + ld(S.Rw[3], bl) * py + ld(S.Rw[6], bl) * pz;
+      const vf wy = ld(S.xw[1], bl) + ld(S.Rw[1], bl) * px + ld(S.Rw[4], bl) * py + ld(S.Rw[7], bl) * pz;
+      const vf wz = ld(S.xw[2], bl) + ld(S.Rw[2], bl) * px + ld(S.Rw[5], bl) * py + ld(S.Rw[8], bl) * pz;
+      const vb active = valid && ((wz - P.floor_z) < P.breaking);
+      const uint32_t am = vballot(active);
+      // slot = n_act + rank among active lanes
+      vi rank;
+      rank = rank_below(am) + n_act;
+      const vb keep = active && (rank < TREX_KMAX);
+      const vi slot = seli(keep, rank, 0);
+      st_if(&S.cpos[0][0], slot * 4 + 0, wx, keep);
+      st_if(&S.cpos[0][0], slot * 4 + 1, wy, keep);
+      st_if(&S.cpos[0][0], slot * 4 + 2, wz, keep);
+      sti_if(S.ccand, slot, ci, keep);
+      sti_if(S.clane, slot, bl, keep);
+      // contact points that left the manifold lose their cached impulse
+      st_if(S.lam_cache, cis, 0.0f, valid && !keep);
+      const int cnt = popc_u(am);
+      if (n_act + cnt > TREX_KMAX) stats.overflow += n_act + cnt - TREX_KMAX;
+      n_act = (n_act + cnt > TREX_KMAX) ? TREX_KMAX : n_act + cnt;
+    }
+    warp_sync();
+    // axis of this lane's joint in world coordinates and its origin
+    const vf ax = Rw[6], ay = Rw[7], az = Rw[8];
+    for (int c = 0; c < n_act; c++) {
+      const float Px = ldu(&S.cpos[0][0], 4 * c), Py = ldu(&S.cpos[0][0], 4 * c + 1), Pz = ldu(&S.cpos[0][0], 4 * c + 2);
+      const int cl = ldui(S.clane, c);
+      const int cc = ldui(S.ccand, c);
+      // which joints move this point: ancestors-or-self of its body
+      const int ancb = cl == 25 ? 0 : lane_value_i(anc, cl);
+      const vb moves = is_joint && (((vi(ancb) >> lane) & 1) != 0);
+      // d(point velocity)/d(qd_lane) = axis x (P - origin)
+      const vf ex = Px - xw[0], ey = Py - xw[1], ez = Pz - xw[2];
+      vf jx = sel(moves, ay * ez - az * ey, 0.0f);
+      vf jy = sel(moves, az * ex - ax * ez, 0.0f);
+      vf jz = sel(moves, ax * ey - ay * ex, 0.0f);
+      // base coordinates: angular (P - x_base) x dir, linear dir
+      const float bx = Px - R.pos[0], by = Py - R.pos[1], bz = Pz - R.pos[2];
+      // rows: 0 normal (0,0,1) ; 1 t1 (0,-1,0) ; 2 t2 (1,0,0)      [btPlaneSpace1 of (0,0,1)]
+      vf Jn = jz, J1 = -jy, J2 = jx;
+      // (P-x) x (0,0,1) = (by, -bx, 0) ; (P-x) x (0,-1,0) = (bz, 0, -bx) ; (P-x) x (1,0,0) = (0, bz, -by)
+      Jn = sel(lane == 25, by, sel(lane == 26, -bx, sel(lane == 30, 1.0f, Jn)));
+      J1 = sel(lane == 25, bz, sel(lane == 27, -bx, sel(lane == 29, -1.0f, J1)));
+      J2 = sel(lane == 26, bz, sel(lane == 27, -by, sel(lane == 28, 1.0f, J2)));
+      const vf Jr[3] = {Jn, J1, J2};
+      // response dV = M^-1 J^T : this lane's coordinate = <own column, J>
+      warp_sync();
+      TREX_UNROLL for (int k = 0; k < 3; k++) st(S.part[k], lane, Jr[k]);
+      warp_sync();
+      vf dVr[3];
+      TREX_UNROLL for (int k = 0; k < 3; k++) dVr[k] = 0.0f;
+      TREX_UNROLL for (int g = 0; g < trex_topo::NDOF; g++) {
+        const int ln = g < 6 ? 25 + g : g - 6;
+        TREX_UNROLL for (int k = 0; k < 3; k++) dVr[k] = vfma(col[g], vbroadcast(ldu(S.part[k], ln)), dVr[k]);
+      }
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        dVr[k] = sel(lane == 31, 0.0f, dVr[k]);
+        st(S.J[3 * c + k], lane, Jr[k]);
+        st(S.dV[3 * c + k], lane, dVr[k]);
+      }
+      // J M^-1 J^T and J u
+      float dd[3], rel[3];
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        dd[k] = lane_value(warp_sum(Jr[k] * dVr[k]), 0);
+        rel[k] = lane_value(warp_sum(Jr[k] * uown), 0);
+      }
+      const float dist = Pz - P.floor_z;
+      const float pen = dist + P.slop;
+      float jd[3], rh[3];
+      TREX_UNROLL for (int k = 0; k < 3; k++) jd[k] = dd[k] > 1.1920929e-7f ? 1.0f / dd[k] : 0.0f;
+      {
+        float poserr = 0.0f, velerr = -rel[0];
+        if (pen > 0.0f) velerr -= pen / dt; else poserr = -pen * P.contact_erp / dt;
+        rh[0] = (poserr + velerr) * jd[0];
+      }
+      rh[1] = -rel[1] * jd[1];
+      rh[2] = -rel[2] * jd[2];
+      const float warm = ldu(S.lam_cache, cc) * P.warm;
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        c_rhs[k] = sel(lane == c, vbroadcast(rh[k]), c_rhs[k]);
+        c_jdi[k] = sel(lane == c, vbroadcast(jd[k]), c_jdi[k]);
+      }
+      c_lam[0] = sel(lane == c, vbroadcast(warm), c_lam[0]);
+      dv = vfma(dVr[0], vbroadcast(warm), dv);
+    }
+  }
+  warp_sync();
+
+  // ---- 11. projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration) --------------------
+  int it_done = 0;
+  const float lim_hi = P.limit_max_impulse;
+  for (int it = 0; it < P.iters; it++) {
+    vf resid = 0.0f;  // per lane: max over the rows this lane owns of (delta impulse / jacDiagABInv)^2
+#define TREX_JOINT_ROW(ID)                                                                          \
+    {                                                                                                  \
+      constexpr int id = (ID);                                                                         \
+      constexpr int j = id < NJ ? id : id - NJ;                                                        \
+      if (id < NJ) { /* limit constraint of joint id: lower row then upper row */                      \
+        if ((mask_lo >> j) & 1u) {                                                                     \
+          vf dl = rhs_lo - dv * jdi;                                                                   \
+          const vf sum = lam_lo + dl;                                                                  \
+          const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                                 \
+          dl = nl - lam_lo;                                                                            \
+          const float dlu = lane_value(dl, j);                                                         \
+          const vb own = lane == j;                                                                    \
+          lam_lo = sel(own, nl, lam_lo);                                                               \
+          resid = sel(own, vmax(resid, (dl * dself) * (dl * dself)), resid);                           \
+          dv = vfma(col[6 + j], vbroadcast(dlu), dv);                                                  \
+        }                                                                                              \
+        if ((mask_hi >> j) & 1u) {                                                                     \
+          vf dl = rhs_hi + dv * jdi;                                                                   \
+          const vf sum = lam_hi + dl;                                                                  \
+          const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                                 \
+          dl = nl - lam_hi;                                                                            \
+          const float dlu = lane_value(dl, j);                                                         \
+          const vb own = lane == j;                                                                    \
+          lam_hi = sel(own, nl, lam_hi);                                                               \
+          resid = sel(own, vmax(resid, (dl * dself) * (dl * dself)), resid);                           \
+          dv = vfma(col[6 + j], vbroadcast(-dlu), dv);                                                 \
+        }                                                                                              \
+      } else { /* motor of joint id-NJ */                                                              \
+        vf dl = rhs_m - dv * jdi;                                                                      \
+        const vf sum = lam_m + dl;                                                                     \
+        const vf nl = vmin(vmax(sum, -max_imp), max_imp);                                              \
+        dl = nl - lam_m;                                                                               \
+        const float dlu = lane_value(dl, j);                                                           \
+        const vb own = lane == j;                                                                      \
+        lam_m = sel(own, nl, lam_m);                                                                   \
+        resid = sel(own, vmax(resid, (dl * dself) * (dl * dself)), resid);                             \
+        dv = vfma(col[6 + j], vbroadcast(dlu), dv);                                                    \
+      }                                                                                                \
+    }
+#define R_(k) TREX_JOINT_ROW(trex_topo::noncontact_order(k))
+    if (it & 1) {
+      R_(0) R_(1) R_(2) R_(3) R_(4) R_(5) R_(6) R_(7) R_(8) R_(9) R_(10) R_(11) R_(12) R_(13) R_(14) R_(15) R_(16)
+      R_(17) R_(18) R_(19) R_(20) R_(21) R_(22) R_(23) R_(24) R_(25) R_(26) R_(27) R_(28) R_(29) R_(30) R_(31) R_(32)
+      R_(33) R_(34) R_(35) R_(36) R_(37) R_(38) R_(39) R_(40) R_(41) R_(42) R_(43) R_(44) R_(45) R_(46) R_(47) R_(48) R_(49)
+    } else {
+      R_(49) R_(48) R_(47) R_(46) R_(45) R_(44) R_(43) R_(42) R_(41) R_(40) R_(39) R_(38) R_(37) R_(36) R_(35) R_(34) R_(33)
+      R_(32) R_(31) R_(30) R_(29) R_(28) R_(27) R_(26) R_(25) R_(24) R_(23) R_(22) R_(21) R_(20) R_(19) R_(18) R_(17) R_(16)
+      R_(15) R_(14) R_(13) R_(12) R_(11) R_(10) R_(9) R_(8) R_(7) R_(6) R_(5) R_(4) R_(3) R_(2) R_(1) R_(0)
+    }
+#undef R_
+#undef TREX_JOINT_ROW
+    // normal contact rows
+    for (int c = 0; c < n_act; c++) {
+      const vf jdv = warp_sum(ld(S.J[3 * c], lane) * dv);
+      vf dl = c_rhs[0] - jdv * c_jdi[0];
+      const vf sum = c_lam[0] + dl;
+      const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
+      dl = nl - c_lam[0];
+      const vb own = lane == c;
+      const float dlu = lane_value(dl, c);
+      c_lam[0] = sel(own, nl, c_lam[0]);
+      const vf dvel = sel(c_jdi[0] != 0.0f, vdiv(dl, c_jdi[0]), 0.0f);
+      resid = sel(own, vmax(resid, dvel * dvel), resid);
+      dv = vfma(ld(S.dV[3 * c], lane), vbroadcast(dlu), dv);
+    }
+    // friction rows, implicit cone (resolveConeFrictionConstraintRows); both rows read dv before either writes
+    for (int c = 0; c < n_act; c++) {
+      const vf jA = warp_sum(ld(S.J[3 * c + 1], lane) * dv);
+      const vf jB = warp_sum(ld(S.J[3 * c + 2], lane) * dv);
+      const vf lim = P.mu * c_lam[0];
+      vf dB = c_rhs[2] - jB * c_jdi[2];
+      const vf sumB = c_lam[2] + dB;
+      vf dA = c_rhs[1] - jA * c_jdi[1];
+      const vf sumA = c_lam[1] + dA;
+      // |lim*sin(atan2(sumA,sumB))| , |lim*cos(atan2(sumA,sumB))| without the trigonometry
+      const vf nn = vsqrt(sumA * sumA + sumB * sumB);
+      const vb nz = nn > 0.0f;
+      const vf clipA = sel(nz, vabs(lim * vdiv(sumA, sel(nz, nn, 1.0f))), 0.0f);
+      const vf clipB = sel(nz, vabs(lim * vdiv(sumB, sel(nz, nn, 1.0f))), vabs(lim));
+      const vf nA = vmin(vmax(sumA, -clipA), clipA);
+      const vf nB = vmin(vmax(sumB, -clipB), clipB);
+      dA = nA - c_lam[1];
+      dB = nB - c_lam[2];
+      const vb own = lane == c;
+      const float dAu = lane_value(dA, c), dBu = lane_value(dB, c);
+      c_lam[1] = sel(own, nA, c_lam[1]);
+      c_lam[2] = sel(own, nB, c_lam[2]);
+      const vf dvel = sel(c_jdi[1] != 0.0f, vdiv(dA, c_jdi[1]), 0.0f) + sel(c_jdi[2] != 0.0f, vdiv(dB, c_jdi[2]), 0.0f);
+      resid = sel(own, vmax(resid, dvel * dvel), resid);
+      dv = vfma(ld(S.dV[3 * c + 1], lane), vbroadcast(dAu), dv);
+      dv = vfma(ld(S.dV[3 * c + 2], lane), vbroadcast(dBu), dv);
+    }
+    it_done = it + 1;
+    const float rmax = lane_value(warp_max(resid), 0);
+    if (rmax <= P.resid_thresh || it >= P.iters - 1) break;
+  }
+  stats.iters += it_done;
+  stats.contacts = n_act;
+
+  // ---- 12. velocities += dv (clamped); impulses written back ------------------------------------------------
+  R.qd = sel(is_joint, clampv(R.qd + dv, -P.maxvel, P.maxvel), 0.0f);
+  TREX_UNROLL for (int k = 0; k < 3; k++) {
+    R.om[k] = clampf(R.om[k] + lane_value(dv, 25 + k), -P.maxvel, P.maxvel);
+    R.vl[k] = clampf(R.vl[k] + lane_value(dv, 28 + k), -P.maxvel, P.maxvel);
+  }
+  R.tau = sel(is_joint, vdiv(lam_m, dt), 0.0f);  // appliedJointMotorTorque = impulse / dt
+  if (P.contacts_on) {
+    vi cc = 0;
+    {
+      const vb has = lane < n_act;
+      cc = ldi(S.ccand, seli(has, lane, 0));
+      st_if(S.lam_cache, cc, c_lam[0], has);
+    }
+  }
+  warp_sync();
+
+  // ---- 13. positions with the NEW velocities (btMultiBody::stepPositionsMultiDof) ------------------------------
+  TREX_UNROLL for (int k = 0; k < 3; k++) R.pos[k] += dt * R.vl[k];
+  {
+    float fAngle = sqrtf(R.om[0] * R.om[0] + R.om[1] * R.om[1] + R.om[2] * R.om[2]);
+    if (fAngle * dt > 0.78539816339744831f) fAngle = 0.78539816339744831f / dt;
+    float sc;
+    if (fAngle < 0.001f) sc = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * fAngle * fAngle;
+    else sc = sinf(0.5f * fAngle * dt) / fAngle;
+    const float ax = R.om[0] * sc, ay = R.om[1] * sc, az = R.om[2] * sc, aw = cosf(fAngle * dt * 0.5f);
+    const float x = R.quat[0], y = R.quat[1], z = R.quat[2], w = R.quat[3];
+    const float nx = aw * x + ax * w + ay * z - az * y;
+    const float ny = aw * y - ax * z + ay * w + az * x;
+    const float nz = aw * z + ax * y - ay * x + az * w;
+    const float nw = aw * w - ax * x - ay * y - az * z;
+    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    R.quat[0] = nx * inv; R.quat[1] = ny * inv; R.quat[2] = nz * inv; R.quat[3] = nw * inv;
+  }
+  R.q = sel(is_joint, R.q + dt * R.qd, 0.0f);
+}
+
+
+// environment record offsets (floats), see include/trex_b200.h
+enum { ST_POS = 0, ST_QUAT = 3, ST_OM = 7, ST_VL = 10, ST_Q = 13, ST_QD = 38, ST_TAU = 63, ST_LAM = 88,
+       ST_STEP = 152, ST_EPISODE = 153, ST_NANRESETS = 154 };
+
+TREX_FN void load_env(const float* rec, vi lane, WarpShared& S, EnvRegs& R) {
+  const vb is_joint = lane < NJ;
+  const vi js = seli(is_joint, lane, 0);
+  R.q = ld_if(rec, js + ST_Q, is_joint, 0.0f);
+  R.qd = ld_if(rec, js + ST_QD, is_joint, 0.0f);
+  R.tau = ld_if(rec, js + ST_TAU, is_joint, 0.0f);
+  R.tgt = 0.0f;
+  TREX_UNROLL for (int k = 0; k < 3; k++) { R.pos[k] = ldu(rec, ST_POS + k); R.om[k] = ldu(rec, ST_OM + k); R.vl[k] = ldu(rec, ST_VL + k); }
+  TREX_UNROLL for (int k = 0; k < 4; k++) R.quat[k] = ldu(rec, ST_QUAT + k);
+  st(S.lam_cache, lane, ld(rec, lane + ST_LAM));
+  st(S.lam_cache, lane + 32, ld(rec, lane + (ST_LAM + 32)));
+  warp_sync();
+}
+
+TREX_FN void store_env(float* rec, vi lane, WarpShared& S, const EnvRegs& R) {
+  const vb is_joint = lane < NJ;
+  const vi js = seli(is_joint, lane, 0);
+  st_if(rec, js + ST_Q, R.q, is_joint);
+  st_if(rec, js + ST_QD, R.qd, is_joint);
+  st_if(rec, js + ST_TAU, R.tau, is_joint);
+  // base state: lanes 0..12 each write one float
+  vf bs = 0.0f;
+  TREX_UNROLL for (int k = 0; k < 3; k++) {
+    bs = sel(lane == ST_POS + k, vbroadcast(R.pos[k]), bs);
+    bs = sel(lane == ST_OM + k, vbroadcast(R.om[k]), bs);
+    bs = sel(lane == ST_VL + k, vbroadcast(R.vl[k]), bs);
+  }
+  TREX_UNROLL for (int k = 0; k < 4; k++) bs = sel(lane == ST_QUAT + k, vbroadcast(R.quat[k]), bs);
+  st_if(rec, lane, bs, lane < 13);
+  warp_sync();
+  st(rec, lane + ST_LAM, ld(S.lam_cache, lane));
+  st(rec, lane + (ST_LAM + 32), ld(S.lam_cache, lane + 32));
+}
+
+// TrexRobot.reset / reset_configuration (trex_robot.py:39-65, 300-309)
+TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared& S, EnvRegs& R) {
+  const vb is_joint = lane < NJ;
+  R.q = sel(is_joint, MDL(F_STARTQ), 0.0f);
+  R.qd = 0.0f; R.tau = 0.0f; R.tgt = 0.0f;
+  R.pos[0] = 0.0f; R.pos[1] = 0.0f; R.pos[2] = P.reset_z;
+  R.quat[0] = 0.0f; R.quat[1] = 0.0f; R.quat[2] = 0.0f; R.quat[3] = 1.0f;
+  TREX_UNROLL for (int k = 0; k < 3; k++) { R.om[k] = 0.0f; R.vl[k] = 0.0f; }
+  st(S.lam_cache, lane, 0.0f);
+  st(S.lam_cache, lane + 32, 0.0f);
+  warp_sync();
+}
+
+// One TrexBulletEnv.step (trex_env.py:128-154) or reset (trex_env.py:98-122) for this warp's environment.
+//   action : 25 floats, name-sorted joint order (trex_robot.py:311-314), or nullptr when force_reset
+//   obs    : 75 floats  q | qd | applied motor torque  (trex_robot.py:359-365)
+//   aux    : TREX_AUX_STRIDE floats: head xyz, lifting/station/energy penalties, PGS iterations, contacts
+TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+                      const int* cand_lane, WarpShared& S, float* rec, const float* action, float* obs, float* reward,
+                      uint8_t* done, float* aux, bool force_reset) {
+  const vi lane = lane_id();
+  const vb is_joint = lane < NJ;
+  const vi slot = seli(is_joint, MDLI(IF_OBS_SLOT), 0);
+  EnvRegs R;
+  load_env(rec, lane, S, R);
+  float step_count = ldu(rec, ST_STEP), episode = ldu(rec, ST_EPISODE), nan_resets = ldu(rec, ST_NANRESETS);
+  StepStats stats;
+  stats.iters = 0; stats.contacts = 0; stats.overflow = 0;
+  bool is_done = false;
+  float rew = 0.0f, head[3] = {0.0f, 0.0f, 0.0f}, terms[3] = {0.0f, 0.0f, 0.0f};
+
+  if (!force_reset) {
+    // np.clip(action, low, high)  (trex_env.py:147); targets held for all substeps (:148-150)
+    const vf a = ld_if(action, slot, is_joint, 0.0f);
+    R.tgt = vmin(vmax(a, MDL(F_LOWER)), MDL(F_UPPER));
+    for (int s = 0; s < P.n_sub; s++) substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, stats);
+    step_count += 1.0f;
+
+    // reward (trex_env.py:186-196): head-link COM in world, total |qd * tau| in sorted-joint order
+    float Rb[9];
+    quat_to_Rb(R.quat, Rb);
+    vf E[9], Rw[9], xw[3], vdummy[6];
+    local_rotation(mdl, lane, R.q, E);
+    forward_pass<false>(mdl, mdli, lane, R, Rb, E, Rw, xw, vdummy);
+    TREX_UNROLL for (int j = 0; j < 3; j++)
+      head[j] = lane_value(xw[j] + Rw[j] * P.head_p[0] + Rw[3 + j] * P.head_p[1] + Rw[6 + j] * P.head_p[2], P.head_lane);
+    warp_sync();
+    st_if(S.part[0], slot, vabs(vmul_rn(R.qd, R.tau)), is_joint);
+    warp_sync();
+    float power = 0.0f;
+    for (int k = 0; k < NJ; k++) power = fadd_rn(power, ldu(S.part[0], k));
+    const float dz = fadd_rn(P.target_h, -head[2]);
+    terms[0] = fmul_rn(P.w_dist, fmul_rn(dz, dz));                                           // lifting
+    terms[1] = fmul_rn(P.w_drift, fadd_rn(fmul_rn(head[0], head[0]), fmul_rn(head[1], head[1])));  // station keeping
+    terms[2] = fmul_rn(P.w_energy, power);                                                   // energy
+    rew = fadd_rn(fadd_rn(-terms[0], -terms[1]), -terms[2]);
+    warp_sync();
+
+    // termination: the reference never terminates (trex_env.py:183-184); optional horizon + NaN guard
+    const bool bad = vany(visnan(R.q) || visnan(R.qd)) || !(fabsf(R.pos[0]) + fabsf(R.pos[1]) + fabsf(R.pos[2]) <= 3.0e38f) ||
+                     !(fabsf(R.quat[0]) + fabsf(R.quat[3]) <= 3.0e38f) || !(fabsf(R.om[0]) + fabsf(R.om[1]) + fabsf(R.om[2]) <= 3.0e38f);
+    if (bad) nan_resets += 1.0f;
+    is_done = bad || (P.max_episode_steps > 0 && step_count >= (float)P.max_episode_steps);
+  }
+
+  if (force_reset || is_done) {
+    // TrexBulletEnv.reset: reset pose, zero-gain zero-force motors, ONE physics step (trex_env.py:120)
+    reset_pose(P, mdl, lane, S, R);
+    StepStats rs;
+    rs.iters = 0; rs.contacts = 0; rs.overflow = 0;
+    substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, 0.0f, 0.0f, 0.0f, rs);
+    step_count = 0.0f;
+    episode += 1.0f;
+  }
+
+  // observations q | qd | tau in name-sorted joint order
+  if (obs) {
+    st_if(obs, slot, R.q, is_joint);
+    st_if(obs, slot + NJ, R.qd, is_joint);
+    st_if(obs, slot + 2 * NJ, R.tau, is_joint);
+  }
+  store_env(rec, lane, S, R);
+  vf meta = 0.0f;
+  meta = sel(lane == 0, vbroadcast(step_count), meta);
+  meta = sel(lane == 1, vbroadcast(episode), meta);
+  meta = sel(lane == 2, vbroadcast(nan_resets), meta);
+  st_if(rec, lane + ST_STEP, meta, lane < 3);
+  if (reward) st_if(reward, lane, vbroadcast(rew), lane == 0);
+  if (done) st_u8_if(done, lane, vi(is_done ? 1 : 0), lane == 0);
+  if (aux) {
+    vf ax = 0.0f;
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      ax = sel(lane == k, vbroadcast(head[k]), ax);
+      ax = sel(lane == 3 + k, vbroadcast(terms[k]), ax);
+    }
+    ax = sel(lane == 6, vbroadcast((float)stats.iters), ax);
+    ax = sel(lane == 7, vbroadcast((float)(stats.contacts + 1000 * stats.overflow)), ax);
+    st_if(aux, lane, ax, lane < TREX_AUX_STRIDE);
+  }
+}
+
+}  // namespace trex

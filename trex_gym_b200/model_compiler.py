@@ -677,13 +677,21 @@ def emit_topology_header(model: CompiledModel) -> str:
     order = S["noncontact_order"].tolist()
     tb = S["mb_task_body"].tolist()
 
-    def arr(name, vals, ty="int"):
-        return "static constexpr %s %s[%d] = {%s};" % (ty, name, len(vals), ", ".join(str(v) for v in vals))
+    def fn(name, vals):
+        return (
+            "TREX_TOPO_FN int %s(int i) { constexpr int T[%d] = {%s}; return T[i]; }"
+            % (name, len(vals), ", ".join(str(v) for v in vals))
+        )
 
     lines = [
         "// GENERATED by trex_gym_b200/model_compiler.py (emit_topology_header) -- do not edit.",
         "// Merged T-rex tree (fixed joints folded) as compile-time constants.",
         "#pragma once",
+        "#ifdef __CUDACC__",
+        "#define TREX_TOPO_FN __host__ __device__ constexpr",
+        "#else",
+        "#define TREX_TOPO_FN constexpr",
+        "#endif",
         "namespace trex_topo {",
         "static constexpr int NB = %d;      // rigid bodies (body 0 = floating base)" % nb,
         "static constexpr int NJ = %d;      // revolute joints, joint j drives body j+1" % (nb - 1),
@@ -691,10 +699,10 @@ def emit_topology_header(model: CompiledModel) -> str:
         "static constexpr int MAX_DEPTH = %d;" % max(depth),
         "static constexpr int N_TASKS = %d;   // original URDF links (per-link damping)" % len(tb),
         "static constexpr int N_CAND = %d;    // contact candidate points" % len(S["mb_cand_body"]),
-        arr("PARENT", parent),
-        arr("DEPTH", depth),
-        arr("NONCONTACT_ORDER", order),
-        arr("OBS_DOF", S["obs_dof"].tolist()),
+        fn("parent_of", parent),
+        fn("depth_of", depth),
+        fn("noncontact_order", order),
+        fn("obs_dof", S["obs_dof"].tolist()),
         "}  // namespace trex_topo",
         "",
     ]

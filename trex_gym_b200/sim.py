@@ -1,0 +1,175 @@
+"""Batched T-rex simulator: thin Python host over the C ABI, torch tensors as zero-copy buffers.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in
+``libtrex_b200.so`` (``csrc/trex_core.h``).  Requires a CUDA device: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from .model_compiler import CompiledModel, load_builtin
+
+
+class TrexBatchSim:
+    """``num_envs`` independent T-rex environments on one GPU, one warp each.
+
+    Buffers are one row per environment: ``action [N,25]``, ``obs [N,75]``, ``reward [N]``,
+    ``done [N]`` (uint8), ``state [N,160]`` (layout: ``include/trex_b200.h``).  Joint order
+    of action/obs = revolute joints sorted by name (trex_robot.py:311-314).
+    """
+
+    def __init__(self, num_envs: int, device: int | str | torch.device = 0, model: CompiledModel | None = None,
+                 num_substeps: int = 5, distance_weight: float = 1.0, energy_weight: float = 0.005,
+                 drift_weight: float = 0.002, max_episode_steps: int = 0, contacts: bool = True,
+                 seed: int = 0, warps_per_block: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("trex_gym_b200 needs a CUDA device (no CPU fallback)")
+        dev = torch.device(device if not isinstance(device, int) else "cuda:%d" % device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        self.device = dev
+        self.num_envs = int(num_envs)
+        self.model = model if model is not None else load_builtin()
+        self._L = _native.lib()
+        cfg = _native.TrexConfig()
+        cfg.num_substeps = int(num_substeps)
+        cfg.distance_weight = float(distance_weight)
+        cfg.energy_weight = float(energy_weight)
+        cfg.drift_weight = float(drift_weight)
+        cfg.max_episode_steps = int(max_episode_steps)
+        cfg.enable_contacts = int(bool(contacts))
+        cfg.reset_mode = 0
+        cfg.seed = int(seed) & 0xFFFFFFFF
+        if warps_per_block:
+            cfg.reserved[0] = int(warps_per_block)
+        blob = self.model.blob()
+        h = ctypes.c_void_p()
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        _native.check(self._L.trex_create(blob, len(blob), self.num_envs, idx, ctypes.byref(cfg), ctypes.byref(h)),
+                      "trex_create")
+        self._h = h
+        self.num_substeps = int(num_substeps)
+        with torch.cuda.device(dev):
+            self.obs = torch.zeros(self.num_envs, _native.OBS_DIM, device=dev, dtype=torch.float32)
+            self.reward = torch.zeros(self.num_envs, device=dev, dtype=torch.float32)
+            self.done = torch.zeros(self.num_envs, device=dev, dtype=torch.uint8)
+        lo = np.zeros(_native.NUM_JOINTS, np.float32)
+        hi = np.zeros(_native.NUM_JOINTS, np.float32)
+        _native.check(self._L.trex_get_joint_limits(self._h, lo.ctypes.data, hi.ctypes.data), "trex_get_joint_limits")
+        self.action_low, self.action_high = lo, hi
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.trex_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_tensor(self, t: torch.Tensor, shape, dtype, name):
+        if not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) \
+                or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s" % (name, dtype, tuple(shape), self.device))
+
+    # -- the hot path -------------------------------------------------------------------------
+    def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        """``TrexBulletEnv.reset`` (trex_env.py:98-122) for all (or the masked) environments."""
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if mask.shape != (self.num_envs,):
+                raise ValueError("mask must have shape (num_envs,)")
+            mp = ctypes.c_void_p(mask.data_ptr())
+        _native.check(self._L.trex_reset(self._h, mp, ctypes.c_void_p(self.obs.data_ptr()), self._stream()), "trex_reset")
+        return self.obs
+
+    def step(self, action: torch.Tensor):
+        """``TrexBulletEnv.step`` (trex_env.py:128-154) for every environment; returns views of the
+        simulator-owned ``obs``, ``reward``, ``done`` tensors (overwritten by the next call)."""
+        self._check_tensor(action, (self.num_envs, _native.NUM_JOINTS), torch.float32, "action")
+        _native.check(
+            self._L.trex_step(self._h, ctypes.c_void_p(action.data_ptr()), ctypes.c_void_p(self.obs.data_ptr()),
+                              ctypes.c_void_p(self.reward.data_ptr()), ctypes.c_void_p(self.done.data_ptr()), self._stream()),
+            "trex_step")
+        return self.obs, self.reward, self.done
+
+    def step_into(self, action: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
+        """Step writing into caller-provided buffers (e.g. slices of a rollout buffer)."""
+        self._check_tensor(action, (self.num_envs, _native.NUM_JOINTS), torch.float32, "action")
+        self._check_tensor(obs, (self.num_envs, _native.OBS_DIM), torch.float32, "obs")
+        self._check_tensor(reward, (self.num_envs,), torch.float32, "reward")
+        self._check_tensor(done, (self.num_envs,), torch.uint8, "done")
+        _native.check(
+            self._L.trex_step(self._h, ctypes.c_void_p(action.data_ptr()), ctypes.c_void_p(obs.data_ptr()),
+                              ctypes.c_void_p(reward.data_ptr()), ctypes.c_void_p(done.data_ptr()), self._stream()),
+            "trex_step")
+
+    def step_host(self, action: np.ndarray | torch.Tensor, obs=None, reward=None, done=None):
+        """Host-buffer step (numpy or pinned CPU tensors in, numpy / CPU tensors out): H2D copy of the
+        actions, step, D2H copy of obs/reward/done, synchronise.  This is the end-to-end call."""
+        def ptr(x):
+            return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        if isinstance(action, np.ndarray):
+            action = np.ascontiguousarray(action, np.float32)
+        if tuple(action.shape) != (self.num_envs, _native.NUM_JOINTS):
+            raise ValueError("action must have shape (num_envs, 25)")
+        if obs is None:
+            obs = np.empty((self.num_envs, _native.OBS_DIM), np.float32)
+        if reward is None:
+            reward = np.empty(self.num_envs, np.float32)
+        if done is None:
+            done = np.empty(self.num_envs, np.uint8)
+        _native.check(self._L.trex_step_host(self._h, ctypes.c_void_p(ptr(action)), ctypes.c_void_p(ptr(obs)),
+                                             ctypes.c_void_p(ptr(reward)), ctypes.c_void_p(ptr(done))), "trex_step_host")
+        return obs, reward, done
+
+    def reset_host(self) -> np.ndarray:
+        obs = np.empty((self.num_envs, _native.OBS_DIM), np.float32)
+        _native.check(self._L.trex_reset_host(self._h, ctypes.c_void_p(obs.ctypes.data)), "trex_reset_host")
+        return obs
+
+    # -- state / diagnostics -----------------------------------------------------------------------
+    def get_state(self) -> torch.Tensor:
+        s = torch.empty(self.num_envs, _native.STATE_DIM, device=self.device, dtype=torch.float32)
+        _native.check(self._L.trex_get_state(self._h, ctypes.c_void_p(s.data_ptr()), self._stream()), "trex_get_state")
+        return s
+
+    def set_state(self, state: torch.Tensor) -> None:
+        self._check_tensor(state, (self.num_envs, _native.STATE_DIM), torch.float32, "state")
+        _native.check(self._L.trex_set_state(self._h, ctypes.c_void_p(state.data_ptr()), self._stream()), "trex_set_state")
+
+    def aux(self) -> torch.Tensor:
+        """[N,8]: head xyz, lifting / station-keeping / energy penalties (trex_env.py:193-195), PGS
+        iterations of the last step, active contacts."""
+        a = torch.empty(self.num_envs, _native.AUX_DIM, device=self.device, dtype=torch.float32)
+        _native.check(self._L.trex_get_aux(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()), "trex_get_aux")
+        return a
+
+    def random_actions(self, step: int, seed: int = 0, env_offset: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        """U(low, high) actions from Philox keyed by (seed, env_offset + env, step)."""
+        if out is None:
+            out = torch.empty(self.num_envs, _native.NUM_JOINTS, device=self.device, dtype=torch.float32)
+        self._check_tensor(out, (self.num_envs, _native.NUM_JOINTS), torch.float32, "out")
+        _native.check(self._L.trex_fill_random_actions(self._h, ctypes.c_void_p(out.data_ptr()), int(seed) & 0xFFFFFFFF,
+                                                       int(step), int(env_offset), self._stream()), "trex_fill_random_actions")
+        return out
+
+    def stats(self) -> dict:
+        s = _native.TrexStats()
+        _native.check(self._L.trex_get_stats(self._h, ctypes.byref(s)), "trex_get_stats")
+        return {f: getattr(s, f) for f, _ in _native.TrexStats._fields_}
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.trex_kernel_launches(self._h))
