@@ -46,10 +46,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
         self.samples = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -59,10 +59,10 @@ class ClockSampler(threading.Thread):
                         self.samples.append(p)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
 
     def summary(self):

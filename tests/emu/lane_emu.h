@@ -10,6 +10,7 @@
 
 #define TREX_FN static inline
 #define TREX_UNROLL
+#define TREX_ROLLED
 #define TREX_EMU 1
 
 struct vb {
@@ -140,3 +141,8 @@ TREX_FN int popc_u(uint32_t m) { return __builtin_popcount(m); }
 TREX_FN float fmul_rn(float a, float b) { return a * b; }
 TREX_FN float fadd_rn(float a, float b) { return a + b; }
 TREX_FN vf vmul_rn(const vf& a, const vf& b) { return a * b; }
+TREX_FN int ctz_u(uint32_t m) { return __builtin_ctz(m); }
+TREX_FN int clz_u(uint32_t m) { return __builtin_clz(m); }
+TREX_FN vf vrsqrt(const vf& x) { vf r; for (int l = 0; l < 32; l++) r.v[l] = 1.0f / sqrtf(x.v[l]); return r; }
+TREX_FN void stb(unsigned char* p, const vi& idx, const vi& v) { for (int l = 0; l < 32; l++) p[idx.v[l]] = (unsigned char)v.v[l]; }
+TREX_FN vi ldb(const unsigned char* p, const vi& idx) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)p[idx.v[l]]; return r; }

@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libtrex_b200.so")
+LIB_PATH = os.environ.get("TREX_LIB", os.path.join(CSRC, "libtrex_b200.so"))
 
 NUM_JOINTS = 25
 OBS_DIM = 75

@@ -13,6 +13,7 @@
 
 #define TREX_FN __device__ __forceinline__
 #define TREX_UNROLL _Pragma("unroll")
+#define TREX_ROLLED _Pragma("unroll 1")
 #define TREX_FULL 0xffffffffu
 
 typedef float vf;
@@ -74,3 +75,8 @@ TREX_FN int popc_u(uint32_t m) { return __popc(m); }
 TREX_FN float fmul_rn(float a, float b) { return __fmul_rn(a, b); }
 TREX_FN float fadd_rn(float a, float b) { return __fadd_rn(a, b); }
 TREX_FN vf vmul_rn(vf a, vf b) { return __fmul_rn(a, b); }
+TREX_FN int ctz_u(uint32_t m) { return __ffs((int)m) - 1; }
+TREX_FN int clz_u(uint32_t m) { return __clz((int)m); }
+TREX_FN vf vrsqrt(vf x) { return rsqrtf(x); }
+TREX_FN void stb(unsigned char* p, vi idx, vi v) { p[idx] = (unsigned char)v; }
+TREX_FN vi ldb(const unsigned char* p, vi idx) { return (int)p[idx]; }

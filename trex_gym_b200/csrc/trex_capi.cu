@@ -14,6 +14,9 @@
 
 #include <new>
 
+#ifndef TREX_MIN_BLOCKS
+#define TREX_MIN_BLOCKS 14
+#endif
 #define TREX_STR2(x) #x
 #define TREX_STR(x) TREX_STR2(x)
 
@@ -41,7 +44,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 //   mode 1: TrexBulletEnv.reset for environments with mask[env] != 0 (or all when mask == nullptr)
 // ------------------------------------------------------------------------------------------------
 template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS)
+__global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
 trex_step_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
                  const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
                  float* __restrict__ state, const float* __restrict__ action, float* __restrict__ obs,
@@ -147,7 +150,7 @@ trex_stats_kernel(const float* __restrict__ state, const float* __restrict__ aux
 struct trex_handle {
   int device = 0;
   int n_envs = 0;
-  int warps_per_block = 1;
+  int warps_per_block = 2;
   trex_host::ModelTables T;
   trex_host::EnvConfig C;
   trex::Uniform P;

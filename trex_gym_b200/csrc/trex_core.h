@@ -25,7 +25,10 @@
 #include "trex_topology.h"
 
 #ifndef TREX_KMAX
-#define TREX_KMAX 24  // max simultaneously active contact points per environment
+#define TREX_KMAX 20  // max simultaneously active contact points per environment
+#endif
+#ifndef TREX_PGS_UNROLL
+#define TREX_PGS_UNROLL TREX_ROLLED
 #endif
 #define TREX_NCAND_MAX 64
 #define TREX_MAX_ROUNDS 12
@@ -61,6 +64,7 @@ enum {
   IF_OBS_SLOT = 4,     // name-sorted observation/action slot of this joint
   IF_DAMP_LANE = 5,    // lane of the body whose URDF links this lane evaluates for link damping
   IF_DAMP_CONTRIB = 6, // 4 x 6 bits: lanes whose partial damping wrench belongs to this body (63 = none)
+  IF_LIMIT_ORDER = 7,  // joint whose limit constraint is solved at position `lane` of the limit block
   IF_COUNT = 8
 };
 
@@ -72,23 +76,40 @@ struct Uniform {
   float r0[NB][3];  // static-index copy of F_R0 (body index, not lane)
   int iters, n_sub, max_episode_steps, head_lane, n_cand, n_rounds, contacts_on, reset_mode;
   unsigned seed;
+  unsigned char order[2 * NJ];  // non-contact constraint order (Bullet's sorted constraint array)
+  unsigned char depth[NB];      // tree depth per body
+  unsigned char head_chain[MAX_DEPTH];  // lanes of the bodies from the base's child down to the head body
+  int head_depth;
 };
 
-// per-warp shared memory slab
+// per-warp shared memory slab.  The kinematics-phase arrays (k) and the contact-row arrays (c) are
+// never live at the same time and share storage; ~15.7 KB per warp at KMAX = 20 -> 14 warps per SM.
 struct WarpShared {
-  float E[9][32];     // parent -> body rotation, per body lane
-  float U[6][32];     // IA * S
-  float invD[32];
-  float Rw[9][32];    // world -> body rotation
-  float xw[3][32];    // body origin, world
-  float part[6][32];  // link-damping partial wrenches / scratch
+  float col[31][32];  // M^-1: col[g][lane] = entry g of the column owned by `lane`
+  float tmp[1][32];   // staging: motor impulses / per-joint power
   float lam_cache[TREX_NCAND_MAX];
   float cpos[TREX_KMAX][4];  // active contact point (world) + pad
   int ccand[TREX_KMAX];      // candidate index of the active contact
   int clane[TREX_KMAX];      // body lane of the active contact
-  float J[3 * TREX_KMAX][32];   // rows: 3*c + {0 normal, 1 t1, 2 t2}, indexed by LANE
-  float dV[3 * TREX_KMAX][32];
+  union {
+    struct {
+      float E[9][32];     // parent -> body rotation, per body lane
+      float U[6][32];     // IA * S
+      float invD[32];
+      float Rw[9][32];    // world -> body rotation
+      float xw[3][32];    // body origin, world
+    } k;
+    struct {
+      float dV[3 * TREX_KMAX][32];   // rows 3*c + {0 normal, 1 t1, 2 t2}: M^-1 J^T, indexed by lane
+      float Jc[3 * TREX_KMAX][12];   // compact Jacobian rows: [0:6] base coordinates, [6:11] chain joints by depth, [11] = 0
+      unsigned char slot[TREX_KMAX][32];  // which Jc entry each lane multiplies its velocity coordinate with
+    } c;
+  };
 };
+// link-damping partial wrenches live in dV rows beyond the kinematics-phase arrays
+#define TREX_PART_ROW 28
+static_assert(sizeof(((WarpShared*)0)->k) <= TREX_PART_ROW * 128, "partials must not overlap the kinematics arrays");
+static_assert(3 * TREX_KMAX >= TREX_PART_ROW + 6, "KMAX too small for the damping scratch");
 
 TREX_FN constexpr int SI(int i, int j) {  // upper-triangular index of a symmetric 6x6
   return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
@@ -148,7 +169,7 @@ TREX_FN void forward_pass(const float* mdl, const int* mdli, vi lane, const EnvR
       v[3 + i] = vbroadcast(Rb[3 * i] * R.vl[0] + Rb[3 * i + 1] * R.vl[1] + Rb[3 * i + 2] * R.vl[2]);
     }
   }
-  for (int d = 1; d <= MAX_DEPTH; d++) {
+  TREX_ROLLED for (int d = 1; d <= MAX_DEPTH; d++) {
     const vb at = depth == d;
     vf pR[9], px[3];
     TREX_UNROLL for (int k = 0; k < 9; k++) pR[k] = shflv(Rw[k], plane);
@@ -295,8 +316,8 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   TREX_UNROLL for (int k = 0; k < 9; k++) E[k] = sel(is_base, vbroadcast(Rb[k]), E[k]);
   vf Rw[9], xw[3], v[6];
   forward_pass<true>(mdl, mdli, lane, R, Rb, E, Rw, xw, v);
-  TREX_UNROLL for (int k = 0; k < 9; k++) { st(S.E[k], lane, E[k]); st(S.Rw[k], lane, Rw[k]); }
-  TREX_UNROLL for (int k = 0; k < 3; k++) st(S.xw[k], lane, xw[k]);
+  TREX_UNROLL for (int k = 0; k < 9; k++) { st(S.k.E[k], lane, E[k]); st(S.k.Rw[k], lane, Rw[k]); }
+  TREX_UNROLL for (int k = 0; k < 3; k++) st(S.k.xw[k], lane, xw[k]);
 
   // ---- 3. bias forces: p = v x* (I v) - gravity wrench + angular damping ------------------
   const vf mass = MDL(F_MASS);
@@ -341,7 +362,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
     TREX_UNROLL for (int k = 0; k < 6; k++) bv[k] = shflv(v[k], dl);
     vf acc[6];
     TREX_UNROLL for (int k = 0; k < 6; k++) acc[k] = 0.0f;
-    for (int rd = 0; rd < P.n_rounds; rd++) {
+    TREX_ROLLED for (int rd = 0; rd < P.n_rounds; rd++) {
       const float* t = tasks + rd * 4 * 32;
       const vf rx = ldg_ro(t, lane), ry = ldg_ro(t, lane + 32), rz = ldg_ro(t, lane + 64), m = ldg_ro(t, lane + 96);
       const vf cx = bv[3] + (bv[1] * rz - bv[2] * ry);
@@ -355,14 +376,14 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       acc[3] += fx; acc[4] += fy; acc[5] += fz;
     }
     warp_sync();
-    TREX_UNROLL for (int k = 0; k < 6; k++) st(S.part[k], lane, acc[k]);
+    TREX_UNROLL for (int k = 0; k < 6; k++) st(S.c.dV[TREX_PART_ROW + k], lane, acc[k]);
     warp_sync();
     const vi contrib = MDLI(IF_DAMP_CONTRIB);
     TREX_UNROLL for (int s = 0; s < 4; s++) {
       const vi cl = (contrib >> (6 * s)) & 63;
       const vb ok = cl != 63;
       const vi cls = seli(ok, cl, lane);
-      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, ld(S.part[k], cls), 0.0f);
+      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, ld(S.c.dV[TREX_PART_ROW + k], cls), 0.0f);
     }
     warp_sync();
   }
@@ -386,14 +407,15 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   const vi children = MDLI(IF_CHILDREN);
   vf U[6], invD = 0.0f, uu = 0.0f;
   TREX_UNROLL for (int k = 0; k < 6; k++) U[k] = 0.0f;
-  for (int d = MAX_DEPTH; d >= 1; d--) {
+  TREX_ROLLED for (int d = MAX_DEPTH; d >= 1; d--) {
     const vb at = depth == d;
     // U = IA S, D = S^T U, u = tau - S^T pA      (S = unit z rotation)
     vf Ut[6];
     Ut[0] = IA[SI(0, 2)]; Ut[1] = IA[SI(1, 2)]; Ut[2] = IA[SI(2, 2)];
     Ut[3] = IA[SI(2, 3)]; Ut[4] = IA[SI(2, 4)]; Ut[5] = IA[SI(2, 5)];
     const vf Dt = Ut[2];
-    const vf iD = sel(Dt >= 1.1920929e-7f, vdiv(1.0f, Dt), 0.0f);
+    const vb okD = Dt >= 1.1920929e-7f;
+    const vf iD = sel(okD, vdiv(1.0f, sel(okD, Dt, 1.0f)), 0.0f);
     const vf ut = tau_j - pA[2];
     TREX_UNROLL for (int k = 0; k < 6; k++) U[k] = sel(at, Ut[k], U[k]);
     invD = sel(at, iD, invD);
@@ -419,8 +441,8 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, shflv(pp[k], cls), 0.0f);
     }
   }
-  TREX_UNROLL for (int k = 0; k < 6; k++) st(S.U[k], lane, U[k]);
-  st(S.invD, lane, invD);
+  TREX_UNROLL for (int k = 0; k < 6; k++) st(S.k.U[k], lane, U[k]);
+  st(S.k.invD, lane, invD);
 
   // ---- 6. base acceleration --------------------------------------------------------------------
   float ia0[21], ia0inv[21], pA0[6], a0[6];
@@ -437,7 +459,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   vf a[6];
   TREX_UNROLL for (int k = 0; k < 6; k++) a[k] = vbroadcast(a0[k]);
   vf qdd = 0.0f;
-  for (int d = 1; d <= MAX_DEPTH; d++) {
+  TREX_ROLLED for (int d = 1; d <= MAX_DEPTH; d++) {
     const vb at = depth == d;
     vf ap[6];
     TREX_UNROLL for (int k = 0; k < 6; k++) ap[k] = shflv(a[k], plane);
@@ -475,7 +497,6 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   warp_sync();
 
   // ---- 9. M^-1, one column per lane (btMultiBody::calcAccelerationDeltasMultiDof for unit impulses) ----
-  vf col[trex_topo::NDOF];
   {
     // (a) inward along this lane's own ancestor path
     vf z[6];
@@ -483,11 +504,11 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
     vf Ydep[MAX_DEPTH + 1];
     TREX_UNROLL for (int dd = 0; dd <= MAX_DEPTH; dd++) Ydep[dd] = sel(is_joint && (depth == dd), 1.0f, 0.0f);
     vi cur = lane;
-    for (int s = 0; s < MAX_DEPTH; s++) {
+    TREX_ROLLED for (int s = 0; s < MAX_DEPTH; s++) {
       const vb active = is_joint && ((depth - s) >= 1);
       const vi cs = seli(active, cur, lane);
       vf Ec[9], rc[3];
-      TREX_UNROLL for (int k = 0; k < 9; k++) Ec[k] = ld(S.E[k], cs);
+      TREX_UNROLL for (int k = 0; k < 9; k++) Ec[k] = ld(S.k.E[k], cs);
       TREX_UNROLL for (int k = 0; k < 3; k++) rc[k] = ldg_ro(mdl, cs + (F_R0 + k) * 32);
       vf fn[3], ff[3];
       TREX_UNROLL for (int i = 0; i < 3; i++) {
@@ -504,9 +525,9 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const vi ps = seli(par_joint, par, lane);
       // at a joint parent: Y = -S^T z ; z += U * Y / D
       const vf Yp = -zn[2];
-      const vf sc = Yp * ld(S.invD, ps);
+      const vf sc = Yp * ld(S.k.invD, ps);
       TREX_UNROLL for (int k = 0; k < 6; k++) {
-        const vf up = ld(S.U[k], ps);
+        const vf up = ld(S.k.U[k], ps);
         z[k] = sel(active, sel(par_joint, zn[k] + up * sc, zn[k]), z[k]);
       }
       const vi pd = depth - s - 1;
@@ -526,38 +547,59 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       }
     }
     // (b) base: a0 = -IA0^-1 z
-    vf ab[NB][6];
+    vf astk[MAX_DEPTH + 1][6];  // accelerations along the current root-to-body path, by depth
     TREX_UNROLL for (int i = 0; i < 6; i++) {
       vf t = 0.0f;
       TREX_UNROLL for (int j = 0; j < 6; j++) t += ia0inv[SI(i, j)] * z[j];
-      ab[0][i] = -t;
+      astk[0][i] = -t;
     }
-    // (c) outward over the whole tree (static topology -> static registers)
-    TREX_UNROLL for (int b = 1; b < NB; b++) {
-      const int p = trex_topo::parent_of(b);
+    TREX_UNROLL for (int dd = 1; dd <= MAX_DEPTH; dd++)
+      TREX_UNROLL for (int k = 0; k < 6; k++) astk[dd][k] = 0.0f;
+    // (c) outward over the whole tree in body order (parents first).  The loop is rolled to keep the
+    // code in the instruction cache; the depth switch keeps every register index static.
+    TREX_ROLLED for (int b = 1; b < NB; b++) {
       const int bl = b - 1;
+      const int dep = P.depth[b];
       float Eb[9], Ub[6];
-      TREX_UNROLL for (int k = 0; k < 9; k++) Eb[k] = ldu(S.E[k], bl);
-      TREX_UNROLL for (int k = 0; k < 6; k++) Ub[k] = ldu(S.U[k], bl);
-      const float iDb = ldu(S.invD, bl);
+      TREX_UNROLL for (int k = 0; k < 9; k++) Eb[k] = ldu(S.k.E[k], bl);
+      TREX_UNROLL for (int k = 0; k < 6; k++) Ub[k] = ldu(S.k.U[k], bl);
+      const float iDb = ldu(S.k.invD, bl);
       const float rx = P.r0[b][0], ry = P.r0[b][1], rz = P.r0[b][2];
-      const vf lx = ab[p][3] + (ab[p][1] * rz - ab[p][2] * ry);
-      const vf ly = ab[p][4] + (ab[p][2] * rx - ab[p][0] * rz);
-      const vf lz = ab[p][5] + (ab[p][0] * ry - ab[p][1] * rx);
-      TREX_UNROLL for (int i = 0; i < 3; i++) {
-        ab[b][i] = Eb[3 * i] * ab[p][0] + Eb[3 * i + 1] * ab[p][1] + Eb[3 * i + 2] * ab[p][2];
-        ab[b][3 + i] = Eb[3 * i] * lx + Eb[3 * i + 1] * ly + Eb[3 * i + 2] * lz;
+      const vb onpath = ((anc >> bl) & 1) != 0;
+      vf ddq = 0.0f;
+#define TREX_COL_BODY(D)                                                                              \
+      {                                                                                               \
+        const vf* ap = astk[(D) - 1];                                                                 \
+        vf* an = astk[(D)];                                                                           \
+        const vf lx = ap[3] + (ap[1] * rz - ap[2] * ry);                                              \
+        const vf ly = ap[4] + (ap[2] * rx - ap[0] * rz);                                              \
+        const vf lz = ap[5] + (ap[0] * ry - ap[1] * rx);                                              \
+        vf t[6];                                                                                      \
+        TREX_UNROLL for (int i = 0; i < 3; i++) {                                                     \
+          t[i] = Eb[3 * i] * ap[0] + Eb[3 * i + 1] * ap[1] + Eb[3 * i + 2] * ap[2];                   \
+          t[3 + i] = Eb[3 * i] * lx + Eb[3 * i + 1] * ly + Eb[3 * i + 2] * lz;                        \
+        }                                                                                             \
+        const vf Yb = sel(onpath, Ydep[(D)], 0.0f);                                                   \
+        ddq = (Yb - (Ub[0] * t[0] + Ub[1] * t[1] + Ub[2] * t[2] + Ub[3] * t[3] + Ub[4] * t[4] + Ub[5] * t[5])) * iDb; \
+        t[2] += ddq;                                                                                  \
+        TREX_UNROLL for (int k = 0; k < 6; k++) an[k] = t[k];                                         \
       }
-      const vf Yb = sel(((anc >> bl) & 1) != 0, Ydep[trex_topo::depth_of(b)], 0.0f);
-      const vf dd = (Yb - (Ub[0] * ab[b][0] + Ub[1] * ab[b][1] + Ub[2] * ab[b][2] + Ub[3] * ab[b][3] + Ub[4] * ab[b][4] + Ub[5] * ab[b][5])) * iDb;
-      ab[b][2] += dd;
-      col[6 + bl] = dd;
+      switch (dep) {
+        case 1: TREX_COL_BODY(1) break;
+        case 2: TREX_COL_BODY(2) break;
+        case 3: TREX_COL_BODY(3) break;
+        case 4: TREX_COL_BODY(4) break;
+        default: TREX_COL_BODY(5) break;
+      }
+#undef TREX_COL_BODY
+      st(S.col[6 + bl], lane, ddq);
     }
     TREX_UNROLL for (int j = 0; j < 3; j++) {
-      col[j] = Rb[j] * ab[0][0] + Rb[3 + j] * ab[0][1] + Rb[6 + j] * ab[0][2];
-      col[3 + j] = Rb[j] * ab[0][3] + Rb[3 + j] * ab[0][4] + Rb[6 + j] * ab[0][5];
+      st(S.col[j], lane, Rb[j] * astk[0][0] + Rb[3 + j] * astk[0][1] + Rb[6 + j] * astk[0][2]);
+      st(S.col[3 + j], lane, Rb[j] * astk[0][3] + Rb[3 + j] * astk[0][4] + Rb[6 + j] * astk[0][5]);
     }
   }
+  warp_sync();
 
   // ---- 10. constraint rows -------------------------------------------------------------------------
   // this lane's own velocity coordinate and diagonal of M^-1
@@ -568,16 +610,20 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
     uown = sel(lane == 28 + k, vbroadcast(R.vl[k]), uown);
   }
   uown = sel(lane == 31, 0.0f, uown);
-  TREX_UNROLL for (int g = 0; g < trex_topo::NDOF; g++) {
-    const int ln = g < 6 ? 25 + g : g - 6;
-    dself = sel(lane == ln, col[g], dself);
+  {
+    // generalised index owned by this lane: joints 6+lane, base coordinates lane-25
+    const vi gown = seli(is_joint, lane + 6, seli(lane < 31, lane - 25, 0));
+    dself = sel(lane < 31, ld(&S.col[0][0], gown * 32 + lane), 0.0f);
   }
   // joint rows: J = +-e_j so the response is +-column j and J M^-1 J^T = M^-1[j][j]
-  const vf jdi = sel(is_joint && (dself > 1.1920929e-7f), vdiv(1.0f, dself), 0.0f);
+  const vb okJ = is_joint && (dself > 1.1920929e-7f);
+  const vf jdi = sel(okJ, vdiv(1.0f, sel(okJ, dself, 1.0f)), 0.0f);
   // motor (btMultiBodyJointMotor): target velocity kp*(target-q)/dt + qd + kd*(0-qd), impulse in [-max,max]
   const vf vt = kp * (R.tgt - R.q) / dt + R.qd + kd * (0.0f - R.qd);
   const vf rhs_m = (vt - R.qd) * jdi;
   vf lam_m = 0.0f;
+  vf lamr[NJ];  // motor impulses, replicated on every lane (uniform values)
+  TREX_UNROLL for (int j = 0; j < NJ; j++) lamr[j] = 0.0f;
   // joint limits (btMultiBodyJointLimitConstraint): a row only while the limit is violated
   const vf lower = MDL(F_LOWER), upper = MDL(F_UPPER);
   const vf pen_lo = R.q - lower, pen_hi = upper - R.q;
@@ -588,11 +634,17 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   const vf rhs_hi = sel(pen_hi > P.split_thresh, (R.qd) * jdi, (-pen_hi * P.erp / dt + (R.qd)) * jdi);
   vf lam_lo = 0.0f, lam_hi = 0.0f;
   const uint32_t mask_lo = vballot(act_lo), mask_hi = vballot(act_hi);
+  // violated joints in the order Bullet solves their limit constraints: bit p <=> order[NJ + p] is violated
+  uint32_t lim_perm;
+  {
+    const vi pj = ldi(mdli, lane + IF_LIMIT_ORDER * 32);
+    lim_perm = vballot((lane < NJ) && ((((vi((int)(mask_lo | mask_hi))) >> pj) & 1) != 0));
+  }
 
   // contacts: candidate points against the floor plane
   int n_act = 0;
-  vf c_lam[3], c_rhs[3], c_jdi[3];  // lane s holds the scalars of active contact s (normal, t1, t2)
-  TREX_UNROLL for (int k = 0; k < 3; k++) { c_lam[k] = 0.0f; c_rhs[k] = 0.0f; c_jdi[k] = 0.0f; }
+  vf c_lam[3], c_rhs[3], c_jdi[3], c_dd[3];  // lane s holds the scalars of active contact s (normal, t1, t2)
+  TREX_UNROLL for (int k = 0; k < 3; k++) { c_lam[k] = 0.0f; c_rhs[k] = 0.0f; c_jdi[k] = 0.0f; c_dd[k] = 0.0f; }
   vf dv = 0.0f;  // this lane's coordinate of the accumulated delta velocity
   if (P.contacts_on) {
     TREX_UNROLL for (int half = 0; half < 2; half++) {
@@ -602,9 +654,9 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const vi bl = ldi(cand_lane, cis);
       const vf px = ldg_ro(cand_p, cis), py = ldg_ro(cand_p, cis + TREX_NCAND_MAX), pz = ldg_ro(cand_p, cis + 2 * TREX_NCAND_MAX);
       // world point = xw + Rw^T p
-      const vf wx = ld(S.xw[0], bl) + ld(S.Rw[0], bl) * px + ld(S.Rw[3], bl) * py + ld(S.Rw[6], bl) * pz;
-      const vf wy = ld(S.xw[1], bl) + ld(S.Rw[1], bl) * px + ld(S.Rw[4], bl) * py + ld(S.Rw[7], bl) * pz;
-      const vf wz = ld(S.xw[2], bl) + ld(S.Rw[2], bl) * px + ld(S.Rw[5], bl) * py + ld(S.Rw[8], bl) * pz;
+      const vf wx = ld(S.k.xw[0], bl) + ld(S.k.Rw[0], bl) * px + ld(S.k.Rw[3], bl) * py + ld(S.k.Rw[6], bl) * pz;
+      const vf wy = ld(S.k.xw[1], bl) + ld(S.k.Rw[1], bl) * px + ld(S.k.Rw[4], bl) * py + ld(S.k.Rw[7], bl) * pz;
+      const vf wz = ld(S.k.xw[2], bl) + ld(S.k.Rw[2], bl) * px + ld(S.k.Rw[5], bl) * py + ld(S.k.Rw[8], bl) * pz;
       const vb active = valid && ((wz - P.floor_z) < P.breaking);
       const uint32_t am = vballot(active);
       // slot = n_act + rank among active lanes
@@ -624,9 +676,11 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       n_act = (n_act + cnt > TREX_KMAX) ? TREX_KMAX : n_act + cnt;
     }
     warp_sync();
-    // axis of this lane's joint in world coordinates and its origin
+    // From here on the kinematics-phase arrays are dead: their storage becomes the contact rows.
+    // axis of this lane's joint in world coordinates and its origin (registers)
     const vf ax = Rw[6], ay = Rw[7], az = Rw[8];
-    for (int c = 0; c < n_act; c++) {
+    const vi mydepth = seli(is_joint, depth, 0);
+    TREX_ROLLED for (int c = 0; c < n_act; c++) {
       const float Px = ldu(&S.cpos[0][0], 4 * c), Py = ldu(&S.cpos[0][0], 4 * c + 1), Pz = ldu(&S.cpos[0][0], 4 * c + 2);
       const int cl = ldui(S.clane, c);
       const int cc = ldui(S.ccand, c);
@@ -635,9 +689,9 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const vb moves = is_joint && (((vi(ancb) >> lane) & 1) != 0);
       // d(point velocity)/d(qd_lane) = axis x (P - origin)
       const vf ex = Px - xw[0], ey = Py - xw[1], ez = Pz - xw[2];
-      vf jx = sel(moves, ay * ez - az * ey, 0.0f);
-      vf jy = sel(moves, az * ex - ax * ez, 0.0f);
-      vf jz = sel(moves, ax * ey - ay * ex, 0.0f);
+      const vf jx = sel(moves, ay * ez - az * ey, 0.0f);
+      const vf jy = sel(moves, az * ex - ax * ez, 0.0f);
+      const vf jz = sel(moves, ax * ey - ay * ex, 0.0f);
       // base coordinates: angular (P - x_base) x dir, linear dir
       const float bx = Px - R.pos[0], by = Py - R.pos[1], bz = Pz - R.pos[2];
       // rows: 0 normal (0,0,1) ; 1 t1 (0,-1,0) ; 2 t2 (1,0,0)      [btPlaneSpace1 of (0,0,1)]
@@ -647,20 +701,33 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       J1 = sel(lane == 25, bz, sel(lane == 27, -bx, sel(lane == 29, -1.0f, J1)));
       J2 = sel(lane == 26, bz, sel(lane == 27, -by, sel(lane == 28, 1.0f, J2)));
       const vf Jr[3] = {Jn, J1, J2};
-      // response dV = M^-1 J^T : this lane's coordinate = <own column, J>
+      // compact storage: base lanes -> entries 0..5, chain joints -> entry 5 + depth, everyone else -> the zero entry
+      const vb isb = (lane >= 25) && (lane < 31);
+      const vi myslot = seli(isb, lane - 25, seli(moves, mydepth + 5, 11));
       warp_sync();
-      TREX_UNROLL for (int k = 0; k < 3; k++) st(S.part[k], lane, Jr[k]);
+      TREX_UNROLL for (int k = 0; k < 3; k++) st_if(S.c.Jc[3 * c + k], myslot, sel(lane == 31, 0.0f, Jr[k]), isb || moves || (lane == 31));
+      stb(S.c.slot[c], lane, myslot);
       warp_sync();
+      // response dV = M^-1 J^T: this lane's coordinate = <own column, J>, over the <= 11 non-zeros of J
       vf dVr[3];
       TREX_UNROLL for (int k = 0; k < 3; k++) dVr[k] = 0.0f;
-      TREX_UNROLL for (int g = 0; g < trex_topo::NDOF; g++) {
-        const int ln = g < 6 ? 25 + g : g - 6;
-        TREX_UNROLL for (int k = 0; k < 3; k++) dVr[k] = vfma(col[g], vbroadcast(ldu(S.part[k], ln)), dVr[k]);
+      TREX_UNROLL for (int g = 0; g < 6; g++) {
+        const vf cg = ld(S.col[g], lane);
+        TREX_UNROLL for (int k = 0; k < 3; k++) dVr[k] = vfma(cg, vbroadcast(ldu(S.c.Jc[3 * c + k], g)), dVr[k]);
+      }
+      {
+        uint32_t m = (uint32_t)ancb;
+        while (m) {
+          const int L = ctz_u(m);
+          m &= m - 1;
+          const int e = 5 + P.depth[L + 1];
+          const vf cg = ld(S.col[6 + L], lane);
+          TREX_UNROLL for (int k = 0; k < 3; k++) dVr[k] = vfma(cg, vbroadcast(ldu(S.c.Jc[3 * c + k], e)), dVr[k]);
+        }
       }
       TREX_UNROLL for (int k = 0; k < 3; k++) {
         dVr[k] = sel(lane == 31, 0.0f, dVr[k]);
-        st(S.J[3 * c + k], lane, Jr[k]);
-        st(S.dV[3 * c + k], lane, dVr[k]);
+        st(S.c.dV[3 * c + k], lane, dVr[k]);
       }
       // J M^-1 J^T and J u
       float dd[3], rel[3];
@@ -683,6 +750,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       TREX_UNROLL for (int k = 0; k < 3; k++) {
         c_rhs[k] = sel(lane == c, vbroadcast(rh[k]), c_rhs[k]);
         c_jdi[k] = sel(lane == c, vbroadcast(jd[k]), c_jdi[k]);
+        c_dd[k] = sel(lane == c, vbroadcast(jd[k] != 0.0f ? dd[k] : 0.0f), c_dd[k]);
       }
       c_lam[0] = sel(lane == c, vbroadcast(warm), c_lam[0]);
       dv = vfma(dVr[0], vbroadcast(warm), dv);
@@ -693,62 +761,79 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   // ---- 11. projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration) --------------------
   int it_done = 0;
   const float lim_hi = P.limit_max_impulse;
-  for (int it = 0; it < P.iters; it++) {
+  TREX_ROLLED for (int it = 0; it < P.iters; it++) {
     vf resid = 0.0f;  // per lane: max over the rows this lane owns of (delta impulse / jacDiagABInv)^2
-#define TREX_JOINT_ROW(ID)                                                                          \
+    const vf lam_lo0 = lam_lo, lam_hi0 = lam_hi;
+    // Non-contact rows in Bullet's constraint order, direction alternating with the iteration parity.
+    // Bullet's sorted constraint array for this model is [25 motors | 25 joint-limit constraints]
+    // (checked in trex_model.h): the motor block is unrolled with compile-time joints (M^-1 coefficient
+    // from shared memory at a static address, one shuffle + one FMA per lane and row); the limit block
+    // visits only the violated joints, in order.
+#define TREX_MOTOR_ROW(K)                                                                              \
     {                                                                                                  \
-      constexpr int id = (ID);                                                                         \
-      constexpr int j = id < NJ ? id : id - NJ;                                                        \
-      if (id < NJ) { /* limit constraint of joint id: lower row then upper row */                      \
-        if ((mask_lo >> j) & 1u) {                                                                     \
-          vf dl = rhs_lo - dv * jdi;                                                                   \
-          const vf sum = lam_lo + dl;                                                                  \
-          const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                                 \
-          dl = nl - lam_lo;                                                                            \
-          const float dlu = lane_value(dl, j);                                                         \
-          const vb own = lane == j;                                                                    \
-          lam_lo = sel(own, nl, lam_lo);                                                               \
-          resid = sel(own, vmax(resid, (dl * dself) * (dl * dself)), resid);                           \
-          dv = vfma(col[6 + j], vbroadcast(dlu), dv);                                                  \
+      constexpr int j = trex_topo::noncontact_order(K) - NJ;                                           \
+      const vf cj = ld(S.col[6 + j], lane);                                                            \
+      const vf sum = lamr[j] + (rhs_m - dv * jdi);   /* meaningful on lane j only */                   \
+      const vf nl = vmin(vmax(sum, -max_imp), max_imp);                                                \
+      const vf nlu = vbroadcast(lane_value(nl, j));  /* new impulse of motor j, known to every lane */ \
+      const vf d = nlu - lamr[j];                                                                      \
+      lamr[j] = nlu;                                                                                   \
+      dv = vfma(cj, d, dv);                                                                            \
+    }
+#define TREX_LIMIT_BLOCK(FORWARD)                                                                      \
+    {                                                                                                  \
+      uint32_t m = lim_perm;                                                                           \
+      while (m) {                                                                                      \
+        const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                          \
+        m &= ~(1u << pos);                                                                             \
+        const int j = P.order[NJ + pos];                                                               \
+        const vf cj = ld(S.col[6 + j], lane);                                                          \
+        TREX_UNROLL for (int pass = 0; pass < 2; pass++) {                                             \
+          const bool do_lo = (pass == 0) == (FORWARD);                                                 \
+          if (do_lo && ((mask_lo >> j) & 1u)) {                                                        \
+            const vf sum = lam_lo + (rhs_lo - dv * jdi);                                               \
+            const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
+            const float dlu = lane_value(nl - lam_lo, j);                                              \
+            lam_lo = sel(lane == j, nl, lam_lo);                                                       \
+            dv = vfma(cj, vbroadcast(dlu), dv);                                                        \
+          }                                                                                            \
+          if (!do_lo && ((mask_hi >> j) & 1u)) {                                                       \
+            const vf sum = lam_hi + (rhs_hi + dv * jdi);                                               \
+            const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
+            const float dlu = lane_value(nl - lam_hi, j);                                              \
+            lam_hi = sel(lane == j, nl, lam_hi);                                                       \
+            dv = vfma(cj, vbroadcast(-dlu), dv);                                                       \
+          }                                                                                            \
         }                                                                                              \
-        if ((mask_hi >> j) & 1u) {                                                                     \
-          vf dl = rhs_hi + dv * jdi;                                                                   \
-          const vf sum = lam_hi + dl;                                                                  \
-          const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                                 \
-          dl = nl - lam_hi;                                                                            \
-          const float dlu = lane_value(dl, j);                                                         \
-          const vb own = lane == j;                                                                    \
-          lam_hi = sel(own, nl, lam_hi);                                                               \
-          resid = sel(own, vmax(resid, (dl * dself) * (dl * dself)), resid);                           \
-          dv = vfma(col[6 + j], vbroadcast(-dlu), dv);                                                 \
-        }                                                                                              \
-      } else { /* motor of joint id-NJ */                                                              \
-        vf dl = rhs_m - dv * jdi;                                                                      \
-        const vf sum = lam_m + dl;                                                                     \
-        const vf nl = vmin(vmax(sum, -max_imp), max_imp);                                              \
-        dl = nl - lam_m;                                                                               \
-        const float dlu = lane_value(dl, j);                                                           \
-        const vb own = lane == j;                                                                      \
-        lam_m = sel(own, nl, lam_m);                                                                   \
-        resid = sel(own, vmax(resid, (dl * dself) * (dl * dself)), resid);                             \
-        dv = vfma(col[6 + j], vbroadcast(dlu), dv);                                                    \
       }                                                                                                \
     }
-#define R_(k) TREX_JOINT_ROW(trex_topo::noncontact_order(k))
+#define M_(k) TREX_MOTOR_ROW(k)
     if (it & 1) {
-      R_(0) R_(1) R_(2) R_(3) R_(4) R_(5) R_(6) R_(7) R_(8) R_(9) R_(10) R_(11) R_(12) R_(13) R_(14) R_(15) R_(16)
-      R_(17) R_(18) R_(19) R_(20) R_(21) R_(22) R_(23) R_(24) R_(25) R_(26) R_(27) R_(28) R_(29) R_(30) R_(31) R_(32)
-      R_(33) R_(34) R_(35) R_(36) R_(37) R_(38) R_(39) R_(40) R_(41) R_(42) R_(43) R_(44) R_(45) R_(46) R_(47) R_(48) R_(49)
+      M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7) M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16)
+      M_(17) M_(18) M_(19) M_(20) M_(21) M_(22) M_(23) M_(24)
+      TREX_LIMIT_BLOCK(true)
     } else {
-      R_(49) R_(48) R_(47) R_(46) R_(45) R_(44) R_(43) R_(42) R_(41) R_(40) R_(39) R_(38) R_(37) R_(36) R_(35) R_(34) R_(33)
-      R_(32) R_(31) R_(30) R_(29) R_(28) R_(27) R_(26) R_(25) R_(24) R_(23) R_(22) R_(21) R_(20) R_(19) R_(18) R_(17) R_(16)
-      R_(15) R_(14) R_(13) R_(12) R_(11) R_(10) R_(9) R_(8) R_(7) R_(6) R_(5) R_(4) R_(3) R_(2) R_(1) R_(0)
+      TREX_LIMIT_BLOCK(false)
+      M_(24) M_(23) M_(22) M_(21) M_(20) M_(19) M_(18) M_(17) M_(16) M_(15) M_(14) M_(13) M_(12) M_(11) M_(10) M_(9) M_(8)
+      M_(7) M_(6) M_(5) M_(4) M_(3) M_(2) M_(1) M_(0)
     }
-#undef R_
-#undef TREX_JOINT_ROW
+#undef M_
+#undef TREX_MOTOR_ROW
+#undef TREX_LIMIT_BLOCK
+    {  // every lane owns at most one motor / lower / upper row: residual from the impulse change of this sweep.
+       // The motor impulses are replicated on all lanes (no per-row select); each lane fetches its own via smem.
+      warp_sync();
+      TREX_UNROLL for (int j = 0; j < NJ; j++) st(S.tmp[0], vi(j), lamr[j]);
+      warp_sync();
+      const vf lam_new = sel(is_joint, ld(S.tmp[0], seli(is_joint, lane, 0)), 0.0f);
+      const vf dm = (lam_new - lam_m) * dself, dlo = (lam_lo - lam_lo0) * dself, dhi = (lam_hi - lam_hi0) * dself;
+      lam_m = lam_new;
+      resid = sel(is_joint, vmax(dm * dm, vmax(dlo * dlo, dhi * dhi)), 0.0f);
+    }
     // normal contact rows
-    for (int c = 0; c < n_act; c++) {
-      const vf jdv = warp_sum(ld(S.J[3 * c], lane) * dv);
+    TREX_ROLLED for (int c = 0; c < n_act; c++) {
+      const vi sl = ldb(S.c.slot[c], lane);
+      const vf jdv = warp_sum(ld(S.c.Jc[3 * c], sl) * dv);
       vf dl = c_rhs[0] - jdv * c_jdi[0];
       const vf sum = c_lam[0] + dl;
       const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
@@ -756,24 +841,26 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const vb own = lane == c;
       const float dlu = lane_value(dl, c);
       c_lam[0] = sel(own, nl, c_lam[0]);
-      const vf dvel = sel(c_jdi[0] != 0.0f, vdiv(dl, c_jdi[0]), 0.0f);
+      const vf dvel = dl * c_dd[0];  // delta impulse / jacDiagABInv
       resid = sel(own, vmax(resid, dvel * dvel), resid);
-      dv = vfma(ld(S.dV[3 * c], lane), vbroadcast(dlu), dv);
+      dv = vfma(ld(S.c.dV[3 * c], lane), vbroadcast(dlu), dv);
     }
     // friction rows, implicit cone (resolveConeFrictionConstraintRows); both rows read dv before either writes
-    for (int c = 0; c < n_act; c++) {
-      const vf jA = warp_sum(ld(S.J[3 * c + 1], lane) * dv);
-      const vf jB = warp_sum(ld(S.J[3 * c + 2], lane) * dv);
+    TREX_ROLLED for (int c = 0; c < n_act; c++) {
+      const vi sl = ldb(S.c.slot[c], lane);
+      const vf jA = warp_sum(ld(S.c.Jc[3 * c + 1], sl) * dv);
+      const vf jB = warp_sum(ld(S.c.Jc[3 * c + 2], sl) * dv);
       const vf lim = P.mu * c_lam[0];
       vf dB = c_rhs[2] - jB * c_jdi[2];
       const vf sumB = c_lam[2] + dB;
       vf dA = c_rhs[1] - jA * c_jdi[1];
       const vf sumA = c_lam[1] + dA;
       // |lim*sin(atan2(sumA,sumB))| , |lim*cos(atan2(sumA,sumB))| without the trigonometry
-      const vf nn = vsqrt(sumA * sumA + sumB * sumB);
-      const vb nz = nn > 0.0f;
-      const vf clipA = sel(nz, vabs(lim * vdiv(sumA, sel(nz, nn, 1.0f))), 0.0f);
-      const vf clipB = sel(nz, vabs(lim * vdiv(sumB, sel(nz, nn, 1.0f))), vabs(lim));
+      const vf n2 = sumA * sumA + sumB * sumB;
+      const vb nz = n2 > 0.0f;
+      const vf rn = vrsqrt(sel(nz, n2, 1.0f));
+      const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
+      const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
       const vf nA = vmin(vmax(sumA, -clipA), clipA);
       const vf nB = vmin(vmax(sumB, -clipB), clipB);
       dA = nA - c_lam[1];
@@ -782,10 +869,10 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const float dAu = lane_value(dA, c), dBu = lane_value(dB, c);
       c_lam[1] = sel(own, nA, c_lam[1]);
       c_lam[2] = sel(own, nB, c_lam[2]);
-      const vf dvel = sel(c_jdi[1] != 0.0f, vdiv(dA, c_jdi[1]), 0.0f) + sel(c_jdi[2] != 0.0f, vdiv(dB, c_jdi[2]), 0.0f);
+      const vf dvel = dA * c_dd[1] + dB * c_dd[2];
       resid = sel(own, vmax(resid, dvel * dvel), resid);
-      dv = vfma(ld(S.dV[3 * c + 1], lane), vbroadcast(dAu), dv);
-      dv = vfma(ld(S.dV[3 * c + 2], lane), vbroadcast(dBu), dv);
+      dv = vfma(ld(S.c.dV[3 * c + 1], lane), vbroadcast(dAu), dv);
+      dv = vfma(ld(S.c.dV[3 * c + 2], lane), vbroadcast(dBu), dv);
     }
     it_done = it + 1;
     const float rmax = lane_value(warp_max(resid), 0);
@@ -901,48 +988,70 @@ TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const
   bool is_done = false;
   float rew = 0.0f, head[3] = {0.0f, 0.0f, 0.0f}, terms[3] = {0.0f, 0.0f, 0.0f};
 
+  // np.clip(action, low, high)  (trex_env.py:147); targets held for all substeps (:148-150)
   if (!force_reset) {
-    // np.clip(action, low, high)  (trex_env.py:147); targets held for all substeps (:148-150)
     const vf a = ld_if(action, slot, is_joint, 0.0f);
     R.tgt = vmin(vmax(a, MDL(F_LOWER)), MDL(F_UPPER));
-    for (int s = 0; s < P.n_sub; s++) substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, stats);
-    step_count += 1.0f;
-
-    // reward (trex_env.py:186-196): head-link COM in world, total |qd * tau| in sorted-joint order
-    float Rb[9];
-    quat_to_Rb(R.quat, Rb);
-    vf E[9], Rw[9], xw[3], vdummy[6];
-    local_rotation(mdl, lane, R.q, E);
-    forward_pass<false>(mdl, mdli, lane, R, Rb, E, Rw, xw, vdummy);
-    TREX_UNROLL for (int j = 0; j < 3; j++)
-      head[j] = lane_value(xw[j] + Rw[j] * P.head_p[0] + Rw[3 + j] * P.head_p[1] + Rw[6 + j] * P.head_p[2], P.head_lane);
-    warp_sync();
-    st_if(S.part[0], slot, vabs(vmul_rn(R.qd, R.tau)), is_joint);
-    warp_sync();
-    float power = 0.0f;
-    for (int k = 0; k < NJ; k++) power = fadd_rn(power, ldu(S.part[0], k));
-    const float dz = fadd_rn(P.target_h, -head[2]);
-    terms[0] = fmul_rn(P.w_dist, fmul_rn(dz, dz));                                           // lifting
-    terms[1] = fmul_rn(P.w_drift, fadd_rn(fmul_rn(head[0], head[0]), fmul_rn(head[1], head[1])));  // station keeping
-    terms[2] = fmul_rn(P.w_energy, power);                                                   // energy
-    rew = fadd_rn(fadd_rn(-terms[0], -terms[1]), -terms[2]);
-    warp_sync();
-
-    // termination: the reference never terminates (trex_env.py:183-184); optional horizon + NaN guard
-    const bool bad = vany(visnan(R.q) || visnan(R.qd)) || !(fabsf(R.pos[0]) + fabsf(R.pos[1]) + fabsf(R.pos[2]) <= 3.0e38f) ||
-                     !(fabsf(R.quat[0]) + fabsf(R.quat[3]) <= 3.0e38f) || !(fabsf(R.om[0]) + fabsf(R.om[1]) + fabsf(R.om[2]) <= 3.0e38f);
-    if (bad) nan_resets += 1.0f;
-    is_done = bad || (P.max_episode_steps > 0 && step_count >= (float)P.max_episode_steps);
   }
-
-  if (force_reset || is_done) {
-    // TrexBulletEnv.reset: reset pose, zero-gain zero-force motors, ONE physics step (trex_env.py:120)
-    reset_pose(P, mdl, lane, S, R);
-    StepStats rs;
-    rs.iters = 0; rs.contacts = 0; rs.overflow = 0;
-    substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, 0.0f, 0.0f, 0.0f, rs);
-    step_count = 0.0f;
-    episode += 1.0f;
+  // One call site for the physics step (keeps the kernel small enough for the instruction cache):
+  //   phase 0: the n_sub substeps of an env step   phase 1: reset requested   phase 3: the ONE physics
+  //   step TrexBulletEnv.reset performs (trex_env.py:120)   phase 2: finished
+  int phase = force_reset ? 1 : 0, sdone = 0;
+  float kp = P.kp, kd = P.kd, mi = P.max_impulse;
+  StepStats rs;
+  rs.iters = 0; rs.contacts = 0; rs.overflow = 0;
+  TREX_ROLLED for (;;) {
+    if (phase == 0 && sdone == P.n_sub) {
+      step_count += 1.0f;
+      // reward (trex_env.py:186-196): head-link COM in world, total |qd * tau| in sorted-joint order.
+      // Forward kinematics along the base -> head chain only (uniform arithmetic).
+      float Rh[9], xh[3] = {R.pos[0], R.pos[1], R.pos[2]};
+      quat_to_Rb(R.quat, Rh);
+      TREX_ROLLED for (int d = 0; d < P.head_depth; d++) {
+        const int L = P.head_chain[d];
+        const float qj = lane_value(R.q, L);
+        const float c = cosf(qj), sn = sinf(qj);
+        float e0[9], r0h[3], El[9], Rn[9];
+        TREX_UNROLL for (int k = 0; k < 9; k++) e0[k] = ldu(mdl, (F_E0 + k) * 32 + L);
+        TREX_UNROLL for (int k = 0; k < 3; k++) r0h[k] = ldu(mdl, (F_R0 + k) * 32 + L);
+        TREX_UNROLL for (int j = 0; j < 3; j++) xh[j] += Rh[j] * r0h[0] + Rh[3 + j] * r0h[1] + Rh[6 + j] * r0h[2];
+        El[0] = c * e0[0] + sn * e0[1]; El[1] = c * e0[3] + sn * e0[4]; El[2] = c * e0[6] + sn * e0[7];
+        El[3] = c * e0[1] - sn * e0[0]; El[4] = c * e0[4] - sn * e0[3]; El[5] = c * e0[7] - sn * e0[6];
+        El[6] = e0[2]; El[7] = e0[5]; El[8] = e0[8];
+        TREX_UNROLL for (int i = 0; i < 3; i++)
+          TREX_UNROLL for (int j = 0; j < 3; j++) Rn[3 * i + j] = El[3 * i] * Rh[j] + El[3 * i + 1] * Rh[3 + j] + El[3 * i + 2] * Rh[6 + j];
+        TREX_UNROLL for (int k = 0; k < 9; k++) Rh[k] = Rn[k];
+      }
+      TREX_UNROLL for (int j = 0; j < 3; j++) head[j] = xh[j] + Rh[j] * P.head_p[0] + Rh[3 + j] * P.head_p[1] + Rh[6 + j] * P.head_p[2];
+      warp_sync();
+      st_if(S.tmp[0], slot, vabs(vmul_rn(R.qd, R.tau)), is_joint);
+      warp_sync();
+      float power = 0.0f;
+      TREX_ROLLED for (int k = 0; k < NJ; k++) power = fadd_rn(power, ldu(S.tmp[0], k));
+      const float dz = fadd_rn(P.target_h, -head[2]);
+      terms[0] = fmul_rn(P.w_dist, fmul_rn(dz, dz));                                           // lifting
+      terms[1] = fmul_rn(P.w_drift, fadd_rn(fmul_rn(head[0], head[0]), fmul_rn(head[1], head[1])));  // station keeping
+      terms[2] = fmul_rn(P.w_energy, power);                                                   // energy
+      rew = fadd_rn(fadd_rn(-terms[0], -terms[1]), -terms[2]);
+      warp_sync();
+      // termination: the reference never terminates (trex_env.py:183-184); optional horizon + NaN guard
+      const bool bad = vany(visnan(R.q) || visnan(R.qd)) || !(fabsf(R.pos[0]) + fabsf(R.pos[1]) + fabsf(R.pos[2]) <= 3.0e38f) ||
+                       !(fabsf(R.quat[0]) + fabsf(R.quat[3]) <= 3.0e38f) || !(fabsf(R.om[0]) + fabsf(R.om[1]) + fabsf(R.om[2]) <= 3.0e38f);
+      if (bad) nan_resets += 1.0f;
+      is_done = bad || (P.max_episode_steps > 0 && step_count >= (float)P.max_episode_steps);
+      phase = is_done ? 1 : 2;
+    }
+    if (phase == 2) break;
+    if (phase == 1) {
+      // TrexBulletEnv.reset: reset pose, zero-gain zero-force motors, then ONE physics step
+      reset_pose(P, mdl, lane, S, R);
+      kp = 0.0f; kd = 0.0f; mi = 0.0f;
+      step_count = 0.0f;
+      episode += 1.0f;
+      phase = 3;
+    }
+    substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, kp, kd, mi, phase == 3 ? rs : stats);
+    if (phase == 3) phase = 2; else sdone++;
   }
 
   // observations q | qd | tau in name-sorted joint order

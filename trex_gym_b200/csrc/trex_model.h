@@ -167,6 +167,11 @@ static inline bool build_tables(const void* blob, size_t bytes, ModelTables& T, 
     T.lower_sorted[k] = (float)lower[obs_dof[k] + 1];
     T.upper_sorted[k] = (float)upper[obs_dof[k] + 1];
   }
+  // constraint order: the kernel relies on [NJ motors | NJ limit constraints]
+  for (int k = 0; k < NJ; k++) {
+    if (order[k] < NJ || order[NJ + k] >= NJ) { T.err = "constraint order is not [motors | limits]"; return false; }
+    IF(7, k) = order[NJ + k];
+  }
   // link-damping tasks: every lane evaluates the links of exactly one body; R rounds
   const int nt = (int)task_body.size();
   int per_body[NB] = {0};
@@ -259,6 +264,14 @@ static inline void fill_uniform(const ModelTables& T, const EnvConfig& C, U& P) 
   P.contacts_on = C.enable_contacts;
   P.reset_mode = C.reset_mode;
   P.seed = C.seed;
+  for (int k = 0; k < 2 * trex_topo::NJ; k++) P.order[k] = (unsigned char)trex_topo::noncontact_order(k);
+  for (int b = 0; b < trex_topo::NB; b++) P.depth[b] = (unsigned char)trex_topo::depth_of(b);
+  {  // bodies from the base's child down to the head body
+    int chain[8], n = 0;
+    for (int b = T.head_lane == 25 ? 0 : T.head_lane + 1; b > 0; b = trex_topo::parent_of(b)) chain[n++] = b;
+    P.head_depth = n;
+    for (int d = 0; d < n; d++) P.head_chain[d] = (unsigned char)body_lane(chain[n - 1 - d]);
+  }
 }
 
 }  // namespace trex_host
