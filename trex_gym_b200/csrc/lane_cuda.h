@@ -80,3 +80,4 @@ TREX_FN int clz_u(uint32_t m) { return __clz((int)m); }
 TREX_FN vf vrsqrt(vf x) { return rsqrtf(x); }
 TREX_FN void stb(unsigned char* p, vi idx, vi v) { p[idx] = (unsigned char)v; }
 TREX_FN vi ldb(const unsigned char* p, vi idx) { return (int)p[idx]; }
+TREX_FN long long cycle_count() { return clock64(); }

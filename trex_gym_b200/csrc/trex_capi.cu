@@ -21,7 +21,9 @@
 #define TREX_STR(x) TREX_STR2(x)
 
 static_assert(TREX_STATE_DIM == TREX_STATE_STRIDE, "state record size");
+#ifndef TREX_PHASES
 static_assert(TREX_AUX_DIM == TREX_AUX_STRIDE, "aux record size");
+#endif
 static_assert(trex::F_COUNT == 32, "float field table");
 
 namespace {

@@ -33,7 +33,13 @@
 #define TREX_NCAND_MAX 64
 #define TREX_MAX_ROUNDS 12
 #define TREX_STATE_STRIDE 160  // floats per environment record (see include/trex_b200.h)
+#ifdef TREX_PHASES
+#define TREX_AUX_STRIDE 16
+#define TREX_TICK(i) { const long long _t = cycle_count(); stats.phase[i] += (float)(_t - _t0); _t0 = _t; }
+#else
 #define TREX_AUX_STRIDE 8
+#define TREX_TICK(i)
+#endif
 
 namespace trex {
 
@@ -125,6 +131,9 @@ struct StepStats {
   int iters;     // PGS iterations executed (summed over substeps)
   int contacts;  // active contact points (last substep)
   int overflow;  // contact points dropped because more than TREX_KMAX were active
+#ifdef TREX_PHASES
+  float phase[8];
+#endif
 };
 
 #define MDL(f) ldg_ro(mdl, lane + (f) * 32)
@@ -307,6 +316,9 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   const vi anc = MDLI(IF_ANC_MASK);
   const float dt = P.dt;
 
+#ifdef TREX_PHASES
+  long long _t0 = cycle_count();
+#endif
   float Rb[9];
   quat_to_Rb(R.quat, Rb);
 
@@ -319,6 +331,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   TREX_UNROLL for (int k = 0; k < 9; k++) { st(S.k.E[k], lane, E[k]); st(S.k.Rw[k], lane, Rw[k]); }
   TREX_UNROLL for (int k = 0; k < 3; k++) st(S.k.xw[k], lane, xw[k]);
 
+  TREX_TICK(0)
   // ---- 3. bias forces: p = v x* (I v) - gravity wrench + angular damping ------------------
   const vf mass = MDL(F_MASS);
   vf mc[3], I3[6];
@@ -393,6 +406,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   // explicit joint damping torque (pybullet adds -damping*qd before each step)
   const vf tau_j = -(MDL(F_JDAMP) * R.qd);
 
+  TREX_TICK(1)
   // ---- 5. inward pass: articulated inertias ---------------------------------------------------
   vf IA[21];
   TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] = 0.0f;
@@ -444,6 +458,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   TREX_UNROLL for (int k = 0; k < 6; k++) st(S.k.U[k], lane, U[k]);
   st(S.k.invD, lane, invD);
 
+  TREX_TICK(2)
   // ---- 6. base acceleration --------------------------------------------------------------------
   float ia0[21], ia0inv[21], pA0[6], a0[6];
   TREX_UNROLL for (int k = 0; k < 21; k++) ia0[k] = lane_value(IA[k], 25);
@@ -496,6 +511,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   }
   warp_sync();
 
+  TREX_TICK(3)
   // ---- 9. M^-1, one column per lane (btMultiBody::calcAccelerationDeltasMultiDof for unit impulses) ----
   {
     // (a) inward along this lane's own ancestor path
@@ -601,6 +617,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   }
   warp_sync();
 
+  TREX_TICK(4)
   // ---- 10. constraint rows -------------------------------------------------------------------------
   // this lane's own velocity coordinate and diagonal of M^-1
   vf uown = R.qd;
@@ -758,27 +775,65 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   }
   warp_sync();
 
+  TREX_TICK(5)
   // ---- 11. projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration) --------------------
+  // Velocity change dv = dvm + dvo: dvm = sum_j M^-1[:,6+j] * lambda_motor_j is rebuilt from the motor
+  // impulses after every motor block (25 independent FMAs, off the critical path); dvo accumulates the
+  // limit and contact rows.  Inside the motor block each lane carries only
+  //     w = lambda_own + rhs_own - jdi_own * dv_own      (its own row's unclamped new impulse)
+  // and updates it with the precomputed g[j] = -jdi_own * M^-1[own][6+j]  (0 for the own row, where the
+  // two contributions cancel): per row FMNMX, FMNMX, SHFL, FADD, FFMA -- one shuffle is the only shared-memory
+  // pipe operation.  After the block dvm is rebuilt from registers: S = sum_j g[j] lambda_j,
+  // dvm_own = D_own (lambda_own - S).
   int it_done = 0;
   const float lim_hi = P.limit_max_impulse;
+  const vf njdi = -jdi;
+  vf g[NJ];
+  TREX_UNROLL for (int j = 0; j < NJ; j++) {
+    const vf cj = ld(S.col[6 + j], lane);
+    g[j] = sel(is_joint, sel(lane == j, 0.0f, njdi * cj), cj);  // base-coordinate lanes keep the raw coefficient
+  }
+  vf dvo = dv;   // warm-started contact impulses
+  vf dvm = 0.0f;
+  vf w = 0.0f;
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
     vf resid = 0.0f;  // per lane: max over the rows this lane owns of (delta impulse / jacDiagABInv)^2
     const vf lam_lo0 = lam_lo, lam_hi0 = lam_hi;
     // Non-contact rows in Bullet's constraint order, direction alternating with the iteration parity.
     // Bullet's sorted constraint array for this model is [25 motors | 25 joint-limit constraints]
-    // (checked in trex_model.h): the motor block is unrolled with compile-time joints (M^-1 coefficient
-    // from shared memory at a static address, one shuffle + one FMA per lane and row); the limit block
+    // (checked in trex_model.h): the motor block is unrolled with compile-time joints; the limit block
     // visits only the violated joints, in order.
 #define TREX_MOTOR_ROW(K)                                                                              \
     {                                                                                                  \
       constexpr int j = trex_topo::noncontact_order(K) - NJ;                                           \
-      const vf cj = ld(S.col[6 + j], lane);                                                            \
-      const vf sum = lamr[j] + (rhs_m - dv * jdi);   /* meaningful on lane j only */                   \
-      const vf nl = vmin(vmax(sum, -max_imp), max_imp);                                                \
-      const vf nlu = vbroadcast(lane_value(nl, j));  /* new impulse of motor j, known to every lane */ \
-      const vf d = nlu - lamr[j];                                                                      \
+      const vf nl = vmin(vmax(w, -max_imp), max_imp);   /* meaningful on lane j only */                \
+      const vf t = vfma(-g[j], lamr[j], w);             /* off the critical path */                    \
+      const vf nlu = vbroadcast(lane_value(nl, j));     /* new impulse of motor j, on every lane */    \
       lamr[j] = nlu;                                                                                   \
-      dv = vfma(cj, d, dv);                                                                            \
+      w = vfma(g[j], nlu, t);                           /* w += g * (new - old impulse) */             \
+    }
+#define TREX_REBUILD_DVM()                                                                             \
+    {                                                                                                  \
+      /* S = sum_j g[j] * lambda_j from registers; dvm_own = D_own * (lambda_own - S) */               \
+      vf a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;                                                   \
+      TREX_UNROLL for (int j = 0; j + 3 < NJ; j += 4) {                                                \
+        a0 = vfma(g[j], lamr[j], a0);                                                                  \
+        a1 = vfma(g[j + 1], lamr[j + 1], a1);                                                          \
+        a2 = vfma(g[j + 2], lamr[j + 2], a2);                                                          \
+        a3 = vfma(g[j + 3], lamr[j + 3], a3);                                                          \
+      }                                                                                                \
+      TREX_UNROLL for (int j = NJ - (NJ % 4); j < NJ; j++) a0 = vfma(g[j], lamr[j], a0);               \
+      const vf Ssum = (a0 + a1) + (a2 + a3);                                                           \
+      /* this lane's own motor impulse out of the replicated registers, through shared memory */       \
+      warp_sync();                                                                                     \
+      TREX_UNROLL for (int j = 0; j < NJ; j++) st(S.tmp[0], vi(j), lamr[j]);                           \
+      warp_sync();                                                                                     \
+      const vf lam_new = sel(is_joint, ld(S.tmp[0], seli(is_joint, lane, 0)), 0.0f);                   \
+      const vf dm = (lam_new - lam_m) * dself;      /* delta impulse / jacDiagABInv of the own row */  \
+      lam_m = lam_new;                                                                                 \
+      resid = sel(is_joint, dm * dm, 0.0f);                                                            \
+      dvm = sel(is_joint, dself * (lam_m - Ssum), Ssum);  /* base lanes: g holds raw coefficients */   \
+      dv = dvm + dvo;                                                                                  \
     }
 #define TREX_LIMIT_BLOCK(FORWARD)                                                                      \
     {                                                                                                  \
@@ -793,42 +848,46 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
           if (do_lo && ((mask_lo >> j) & 1u)) {                                                        \
             const vf sum = lam_lo + (rhs_lo - dv * jdi);                                               \
             const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
-            const float dlu = lane_value(nl - lam_lo, j);                                              \
+            const vf dl = vbroadcast(lane_value(nl - lam_lo, j));                                      \
             lam_lo = sel(lane == j, nl, lam_lo);                                                       \
-            dv = vfma(cj, vbroadcast(dlu), dv);                                                        \
+            const vf t = cj * dl;                                                                      \
+            dv += t; dvo += t;                                                                         \
           }                                                                                            \
           if (!do_lo && ((mask_hi >> j) & 1u)) {                                                       \
             const vf sum = lam_hi + (rhs_hi + dv * jdi);                                               \
             const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
-            const float dlu = lane_value(nl - lam_hi, j);                                              \
+            const vf dl = vbroadcast(lane_value(nl - lam_hi, j));                                      \
             lam_hi = sel(lane == j, nl, lam_hi);                                                       \
-            dv = vfma(cj, vbroadcast(-dlu), dv);                                                       \
+            const vf t = -(cj * dl);                                                                   \
+            dv += t; dvo += t;                                                                         \
           }                                                                                            \
         }                                                                                              \
       }                                                                                                \
     }
 #define M_(k) TREX_MOTOR_ROW(k)
+#define TREX_MOTOR_BLOCK_BEGIN() w = lam_m + (rhs_m + njdi * dv);  /* exact at the start of every block */
+#define TREX_MOTOR_BLOCK_END() TREX_REBUILD_DVM()
     if (it & 1) {
+      TREX_MOTOR_BLOCK_BEGIN()
       M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7) M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16)
       M_(17) M_(18) M_(19) M_(20) M_(21) M_(22) M_(23) M_(24)
+      TREX_MOTOR_BLOCK_END()
       TREX_LIMIT_BLOCK(true)
     } else {
       TREX_LIMIT_BLOCK(false)
+      TREX_MOTOR_BLOCK_BEGIN()
       M_(24) M_(23) M_(22) M_(21) M_(20) M_(19) M_(18) M_(17) M_(16) M_(15) M_(14) M_(13) M_(12) M_(11) M_(10) M_(9) M_(8)
       M_(7) M_(6) M_(5) M_(4) M_(3) M_(2) M_(1) M_(0)
+      TREX_MOTOR_BLOCK_END()
     }
+#undef TREX_MOTOR_BLOCK_BEGIN
+#undef TREX_MOTOR_BLOCK_END
 #undef M_
 #undef TREX_MOTOR_ROW
 #undef TREX_LIMIT_BLOCK
-    {  // every lane owns at most one motor / lower / upper row: residual from the impulse change of this sweep.
-       // The motor impulses are replicated on all lanes (no per-row select); each lane fetches its own via smem.
-      warp_sync();
-      TREX_UNROLL for (int j = 0; j < NJ; j++) st(S.tmp[0], vi(j), lamr[j]);
-      warp_sync();
-      const vf lam_new = sel(is_joint, ld(S.tmp[0], seli(is_joint, lane, 0)), 0.0f);
-      const vf dm = (lam_new - lam_m) * dself, dlo = (lam_lo - lam_lo0) * dself, dhi = (lam_hi - lam_hi0) * dself;
-      lam_m = lam_new;
-      resid = sel(is_joint, vmax(dm * dm, vmax(dlo * dlo, dhi * dhi)), 0.0f);
+    {  // residual of the limit rows (each lane owns at most one lower / upper row)
+      const vf dlo = (lam_lo - lam_lo0) * dself, dhi = (lam_hi - lam_hi0) * dself;
+      resid = sel(is_joint, vmax(resid, vmax(dlo * dlo, dhi * dhi)), 0.0f);
     }
     // normal contact rows
     TREX_ROLLED for (int c = 0; c < n_act; c++) {
@@ -839,11 +898,12 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
       dl = nl - c_lam[0];
       const vb own = lane == c;
-      const float dlu = lane_value(dl, c);
+      const vf dlu = vbroadcast(lane_value(dl, c));
       c_lam[0] = sel(own, nl, c_lam[0]);
       const vf dvel = dl * c_dd[0];  // delta impulse / jacDiagABInv
       resid = sel(own, vmax(resid, dvel * dvel), resid);
-      dv = vfma(ld(S.c.dV[3 * c], lane), vbroadcast(dlu), dv);
+      const vf t = ld(S.c.dV[3 * c], lane) * dlu;
+      dv += t; dvo += t;
     }
     // friction rows, implicit cone (resolveConeFrictionConstraintRows); both rows read dv before either writes
     TREX_ROLLED for (int c = 0; c < n_act; c++) {
@@ -866,18 +926,20 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       dA = nA - c_lam[1];
       dB = nB - c_lam[2];
       const vb own = lane == c;
-      const float dAu = lane_value(dA, c), dBu = lane_value(dB, c);
+      const vf dAu = vbroadcast(lane_value(dA, c)), dBu = vbroadcast(lane_value(dB, c));
       c_lam[1] = sel(own, nA, c_lam[1]);
       c_lam[2] = sel(own, nB, c_lam[2]);
       const vf dvel = dA * c_dd[1] + dB * c_dd[2];
       resid = sel(own, vmax(resid, dvel * dvel), resid);
-      dv = vfma(ld(S.c.dV[3 * c + 1], lane), vbroadcast(dAu), dv);
-      dv = vfma(ld(S.c.dV[3 * c + 2], lane), vbroadcast(dBu), dv);
+      const vf t = ld(S.c.dV[3 * c + 1], lane) * dAu + ld(S.c.dV[3 * c + 2], lane) * dBu;
+      dv += t; dvo += t;
     }
     it_done = it + 1;
     const float rmax = lane_value(warp_max(resid), 0);
     if (rmax <= P.resid_thresh || it >= P.iters - 1) break;
   }
+#undef TREX_REBUILD_DVM
+  TREX_TICK(6)
   stats.iters += it_done;
   stats.contacts = n_act;
 
@@ -916,6 +978,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
     R.quat[0] = nx * inv; R.quat[1] = ny * inv; R.quat[2] = nz * inv; R.quat[3] = nw * inv;
   }
   R.q = sel(is_joint, R.q + dt * R.qd, 0.0f);
+  TREX_TICK(7)
 }
 
 
@@ -985,6 +1048,9 @@ TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const
   float step_count = ldu(rec, ST_STEP), episode = ldu(rec, ST_EPISODE), nan_resets = ldu(rec, ST_NANRESETS);
   StepStats stats;
   stats.iters = 0; stats.contacts = 0; stats.overflow = 0;
+#ifdef TREX_PHASES
+  for (int i = 0; i < 8; i++) stats.phase[i] = 0.0f;
+#endif
   bool is_done = false;
   float rew = 0.0f, head[3] = {0.0f, 0.0f, 0.0f}, terms[3] = {0.0f, 0.0f, 0.0f};
 
@@ -1000,6 +1066,9 @@ TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const
   float kp = P.kp, kd = P.kd, mi = P.max_impulse;
   StepStats rs;
   rs.iters = 0; rs.contacts = 0; rs.overflow = 0;
+#ifdef TREX_PHASES
+  for (int i = 0; i < 8; i++) rs.phase[i] = 0.0f;
+#endif
   TREX_ROLLED for (;;) {
     if (phase == 0 && sdone == P.n_sub) {
       step_count += 1.0f;
@@ -1076,6 +1145,9 @@ TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const
     }
     ax = sel(lane == 6, vbroadcast((float)stats.iters), ax);
     ax = sel(lane == 7, vbroadcast((float)(stats.contacts + 1000 * stats.overflow)), ax);
+#ifdef TREX_PHASES
+    TREX_UNROLL for (int k = 0; k < 8; k++) ax = sel(lane == 8 + k, vbroadcast(stats.phase[k]), ax);
+#endif
     st_if(aux, lane, ax, lane < TREX_AUX_STRIDE);
   }
 }
