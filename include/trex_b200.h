@@ -59,9 +59,12 @@ typedef struct trex_config {
   int32_t max_episode_steps; /* 0 = never terminate, the reference behaviour (trex_env.py:183-184) */
   int32_t enable_contacts;   /* 1 = floor contact on the derived candidate points; 0 = the literal
                                 collision-less URDF of the reference (free fall) */
-  int32_t reset_mode;        /* 0 = reference reset pose (trex_env.py:81-87,105-109) */
+  int32_t reset_mode;        /* 0 = reference reset pose (trex_env.py:81-87,105-109); 1 = fallen-start sampler
+                                (BASELINE configs[4]: base z U(0.3,3), uniform SO(3), joints U(limits); no
+                                reference counterpart), Philox keyed by (seed, global env id, episode) */
   uint32_t seed;
-  int32_t reserved[8];
+  int32_t reserved[8];       /* [0] warps per CTA (1..4, 0 = default); [1],[2] low/high word of the global id of
+                                environment 0 of this shard (multi-GPU: rank * n_envs) */
 } trex_config;
 
 typedef struct trex_stats {

@@ -38,13 +38,13 @@ def lib():
         L = ctypes.CDLL(_LIB)
         L.emu_create.restype = ctypes.c_void_p
         L.emu_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.c_float,
-                                 ctypes.c_float, ctypes.c_int, ctypes.c_int]
+                                 ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
         L.emu_destroy.argtypes = [ctypes.c_void_p]
         L.emu_last_error.restype = ctypes.c_char_p
         L.emu_state_stride.restype = ctypes.c_int
         L.emu_shared_bytes.restype = ctypes.c_int
         fp = ctypes.POINTER(ctypes.c_float)
-        L.emu_step.argtypes = [ctypes.c_void_p, fp, fp, fp, fp, ctypes.POINTER(ctypes.c_uint8), fp, ctypes.c_int]
+        L.emu_step.argtypes = [ctypes.c_void_p, fp, fp, fp, fp, ctypes.POINTER(ctypes.c_uint8), fp, ctypes.c_int, ctypes.c_longlong]
         _lib = L
     return _lib
 
@@ -57,10 +57,11 @@ class EmuEnv:
     """One environment stepped by the emulated warp.  State record = float32[stride]."""
 
     def __init__(self, blob: bytes, num_substeps=5, reward_weights=(1.0, 0.005, 0.002), max_episode_steps=0,
-                 contacts=True):
+                 contacts=True, reset_mode=0, seed=0, env_id=0):
         self._L = lib()
         d, e, k = reward_weights
-        self._h = self._L.emu_create(blob, len(blob), num_substeps, d, e, k, max_episode_steps, int(contacts))
+        self._h = self._L.emu_create(blob, len(blob), num_substeps, d, e, k, max_episode_steps, int(contacts), int(reset_mode), int(seed))
+        self.env_id = int(env_id)
         if not self._h:
             raise RuntimeError(self._L.emu_last_error().decode())
         self.stride = self._L.emu_state_stride()
@@ -78,7 +79,7 @@ class EmuEnv:
         r = np.zeros(1, np.float32)
         d = np.zeros(1, np.uint8)
         self._L.emu_step(self._h, _fp(self.rec), None, _fp(obs), _fp(r), d.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
-                         _fp(self.aux), 1)
+                         _fp(self.aux), 1, self.env_id)
         return obs
 
     def step(self, action):
@@ -87,7 +88,7 @@ class EmuEnv:
         r = np.zeros(1, np.float32)
         d = np.zeros(1, np.uint8)
         self._L.emu_step(self._h, _fp(self.rec), _fp(a), _fp(obs), _fp(r), d.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
-                         _fp(self.aux), 0)
+                         _fp(self.aux), 0, self.env_id)
         return obs, float(r[0]), bool(d[0])
 
     # state in the oracle's layout (63 core + 25 tau + n_cand lambda)

@@ -18,7 +18,8 @@ extern "C" {
 static char g_err[256];
 const char* emu_last_error() { return g_err; }
 
-void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, float wk, int max_episode_steps, int contacts) {
+void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, float wk, int max_episode_steps, int contacts,
+                 int reset_mode, unsigned seed) {
   Emu* e = new Emu();
   if (!trex_host::build_tables(blob, bytes, e->T, trex::F_COUNT, trex::IF_COUNT)) {
     snprintf(g_err, sizeof g_err, "%s", e->T.err.c_str());
@@ -28,6 +29,7 @@ void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, 
   trex_host::EnvConfig C;
   C.num_substeps = n_sub; C.distance_weight = wd; C.energy_weight = we; C.drift_weight = wk;
   C.max_episode_steps = max_episode_steps; C.enable_contacts = contacts;
+  C.reset_mode = reset_mode; C.seed = seed;
   trex_host::fill_uniform(e->T, C, e->P);
   memset(&e->S, 0, sizeof(e->S));
   return e;
@@ -37,9 +39,10 @@ int emu_state_stride() { return TREX_STATE_STRIDE; }
 int emu_shared_bytes() { return (int)sizeof(trex::WarpShared); }
 
 // one env step (or reset when force_reset) on a single environment record
-void emu_step(void* h, float* rec, const float* action, float* obs, float* reward, uint8_t* done, float* aux, int force_reset) {
+void emu_step(void* h, float* rec, const float* action, float* obs, float* reward, uint8_t* done, float* aux, int force_reset,
+              long long env_id) {
   Emu* e = (Emu*)h;
   trex::env_step(e->P, e->T.mdl.data(), e->T.mdli.data(), e->T.tasks.data(), e->T.cand_p.data(), e->T.cand_lane.data(), e->S, rec,
-                 action, obs, reward, done, aux, force_reset != 0);
+                 action, obs, reward, done, aux, force_reset != 0, env_id);
 }
 }

