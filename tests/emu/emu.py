@@ -45,6 +45,9 @@ def lib():
         L.emu_shared_bytes.restype = ctypes.c_int
         fp = ctypes.POINTER(ctypes.c_float)
         L.emu_step.argtypes = [ctypes.c_void_p, fp, fp, fp, fp, ctypes.POINTER(ctypes.c_uint8), fp, ctypes.c_int, ctypes.c_longlong]
+        L.emu_step4.argtypes = [ctypes.c_void_p, ctypes.c_int, fp, fp, fp, fp, ctypes.POINTER(ctypes.c_uint8), fp, ctypes.c_int,
+                                ctypes.c_longlong]
+        L.emu_set_deferred.argtypes = [ctypes.c_void_p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -57,11 +60,12 @@ class EmuEnv:
     """One environment stepped by the emulated warp.  State record = float32[stride]."""
 
     def __init__(self, blob: bytes, num_substeps=5, reward_weights=(1.0, 0.005, 0.002), max_episode_steps=0,
-                 contacts=True, reset_mode=0, seed=0, env_id=0):
+                 contacts=True, reset_mode=0, seed=0, env_id=0, deferred=True):
         self._L = lib()
         d, e, k = reward_weights
         self._h = self._L.emu_create(blob, len(blob), num_substeps, d, e, k, max_episode_steps, int(contacts), int(reset_mode), int(seed))
         self.env_id = int(env_id)
+        self._L.emu_set_deferred(self._h, int(bool(deferred)))
         if not self._h:
             raise RuntimeError(self._L.emu_last_error().decode())
         self.stride = self._L.emu_state_stride()
@@ -99,3 +103,39 @@ class EmuEnv:
         s = np.asarray(s, np.float64)
         self.rec[:88] = s[:88]
         self.rec[88 : 88 + (len(s) - 88)] = s[88:]
+
+
+class EmuWarp4:
+    """Up to four consecutive environments stepped by ONE emulated warp (the kernel's work unit)."""
+
+    def __init__(self, blob: bytes, n=4, deferred=True, **kw):
+        self.env = EmuEnv(blob, deferred=deferred, **kw)
+        self.n = n
+        self.stride = self.env.stride
+        self.rec = np.zeros((n, self.stride), np.float32)
+        self.rec[:, 6] = 1.0
+        self.aux = np.zeros((n, 8), np.float32)
+
+    def _call(self, action, force_reset):
+        L = self.env._L
+        obs = np.zeros((self.n, 75), np.float32)
+        r = np.zeros(self.n, np.float32)
+        d = np.zeros(self.n, np.uint8)
+        a = None if action is None else _fp(np.ascontiguousarray(action, np.float32))
+        L.emu_step4(self.env._h, self.n, _fp(self.rec), a, _fp(obs), _fp(r), d.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                    _fp(self.aux), int(force_reset), self.env.env_id)
+        return obs, r, d
+
+    def reset(self):
+        return self._call(None, True)[0]
+
+    def step(self, actions):
+        return self._call(actions, False)
+
+    def get_state(self, e, n_cand):
+        return np.concatenate([self.rec[e, :88], self.rec[e, 88:88 + n_cand]]).astype(np.float64)
+
+    def set_state(self, e, s):
+        s = np.asarray(s, np.float64)
+        self.rec[e, :88] = s[:88]
+        self.rec[e, 88:88 + (len(s) - 88)] = s[88:]

@@ -10,6 +10,8 @@ struct Emu {
   trex_host::ModelTables T;
   trex::Uniform P;
   trex::WarpShared S;
+  float work[4 * TREX_WORK_STRIDE];
+  int deferred = 1;
 };
 
 static_assert(trex::F_COUNT == 32, "field table");
@@ -38,11 +40,35 @@ void emu_destroy(void* h) { delete (Emu*)h; }
 int emu_state_stride() { return TREX_STATE_STRIDE; }
 int emu_shared_bytes() { return (int)sizeof(trex::WarpShared); }
 
-// one env step (or reset when force_reset) on a single environment record
+// one env step (or reset when force_reset) on n (1..4) consecutive environment records: the same phase sequence
+// the library launches as kernels (front per environment, solve4 per four environments, tail per environment)
+void emu_step4(void* h, int n, float* rec, const float* action, float* obs, float* reward, uint8_t* done, float* aux, int force_reset,
+               long long env_id0) {
+  Emu* e = (Emu*)h;
+  const float* mdl = e->T.mdl.data();
+  const int* mdli = e->T.mdli.data();
+  const float* tasks = e->T.tasks.data();
+  const float* cp = e->T.cand_p.data();
+  const int* cl = e->T.cand_lane.data();
+  if (!force_reset) {
+    for (int r = 0; r < e->P.n_sub; r++) {
+      uint8_t flags[4] = {0, 0, 0, 0};
+      for (int i = 0; i < n; i++)
+        trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
+                          e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, &flags[i], r == 0);
+      int pending = 0;
+      for (int i = 0; i < n; i++) pending |= (flags[i] ? 1 : 0) << i;
+      if (pending) trex::solve_phase(e->P, e->S, e->work, rec, pending);
+    }
+  }
+  for (int i = 0; i < n; i++)
+    trex::tail_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE, obs ? obs + i * 75 : nullptr,
+                     reward ? reward + i : nullptr, done ? done + i : nullptr, aux ? aux + i * TREX_AUX_STRIDE : nullptr,
+                     force_reset != 0, env_id0 + i);
+}
 void emu_step(void* h, float* rec, const float* action, float* obs, float* reward, uint8_t* done, float* aux, int force_reset,
               long long env_id) {
-  Emu* e = (Emu*)h;
-  trex::env_step(e->P, e->T.mdl.data(), e->T.mdli.data(), e->T.tasks.data(), e->T.cand_p.data(), e->T.cand_lane.data(), e->S, rec,
-                 action, obs, reward, done, aux, force_reset != 0, env_id);
+  emu_step4(h, 1, rec, action, obs, reward, done, aux, force_reset, env_id);
 }
+void emu_set_deferred(void* h, int on) { ((Emu*)h)->deferred = on; }
 }

@@ -161,3 +161,7 @@ TREX_FN void philox4_uniform(const vi& c0, const vi& c1, const vi& c2, const vi&
     for (int k = 0; k < 4; k++) out[k].v[l] = (float)(c[k] >> 8) * (1.0f / 16777216.0f);
   }
 }
+
+TREX_FN vf shfl_group8(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~7) | (src & 7)]; return r; }
+TREX_FN vf group8_sum(vf x) { for (int m = 4; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
+TREX_FN vf group8_max(vf x) { for (int m = 4; m > 0; m >>= 1) x = vmax(x, shfl_xor(x, m)); return x; }

@@ -209,3 +209,52 @@ def test_fallen_start_sampler(model, emu_cls):
     e2 = emu_cls(model.blob(), reset_mode=1, seed=seed, env_id=env_id, contacts=False)
     e2.reset()
     assert np.array_equal(e2.get_state(nc), states[0])  # deterministic
+
+
+def test_four_environments_per_warp(model, action_limits):
+    """The kernel's work unit: one warp steps four consecutive environments; contact-free substeps defer their
+    solve to solve4 (8 lanes per environment), substeps with contacts solve in the one-environment path.
+    Every environment is checked against the oracle, and against the same run with the deferral disabled."""
+    from emu import EmuWarp4
+
+    lo, hi = action_limits
+    qlo, qhi = model["mb_lower"][1:], model["mb_upper"][1:]
+    w4 = EmuWarp4(model.blob(), n=4)
+    w1 = EmuWarp4(model.blob(), n=4, deferred=False)
+    o = _oracle(model)
+    nc = o.num_candidates
+    w4.reset()
+    w1.reset()
+    rng = np.random.default_rng(11)
+    for e in range(4):
+        s = w4.get_state(e, nc)
+        s[13:38] = np.clip(s[13:38] + rng.uniform(-0.3, 0.3, 25), qlo - 0.02, qhi + 0.02)  # some limits violated
+        s[2] -= 0.12 * e  # environments 2 and 3 start close to / on the floor
+        w4.set_state(e, s)
+        w1.set_state(e, s)
+    saw_contact = saw_free = saw_limit = False
+    for t in range(30):
+        acts = rng.uniform(lo, hi, size=(4, 25))
+        pre = [w4.get_state(e, nc) for e in range(4)]
+        obs, rew, done = w4.step(acts)
+        for e in range(4):
+            o.set_state(pre[e])
+            oobs, orew = o.step(acts[e])
+            so, se = o.get_state(), w4.get_state(e, nc)
+            err = max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values())
+            contact = o.last_num_contacts > 0
+            saw_contact |= contact
+            saw_free |= not contact
+            saw_limit |= o.last_num_limit_rows > 0
+            assert err < (5e-3 if contact else 1e-4), (t, e, err, contact)  # wild perturbed states: up to 4e-5 contact-free
+            assert abs(orew - rew[e]) < (5e-3 if contact else 1e-4) * max(1.0, abs(orew))
+            assert int(w4.aux[e, 7]) == o.last_num_contacts
+            assert w4.aux[e, 6] == 300
+        # same inputs through the non-deferred path: agreement to rounding (different summation order)
+        for e in range(4):
+            w1.set_state(e, pre[e])
+        w1.step(acts)
+        for e in range(4):
+            a, b = w4.get_state(e, nc), w1.get_state(e, nc)
+            assert max(rel_err(a[sl], b[sl]) for sl in STATE_BLOCKS.values()) < 5e-3
+    assert saw_contact and saw_free and saw_limit

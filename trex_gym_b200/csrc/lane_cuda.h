@@ -96,3 +96,8 @@ TREX_FN void philox4_uniform(vi c0, vi c1, vi c2, vi c3, uint32_t k0, uint32_t k
 #pragma unroll
   for (int k = 0; k < 4; k++) out[k] = (float)(c[k] >> 8) * (1.0f / 16777216.0f);
 }
+
+// width-8 lane groups (four environments per warp in solve4)
+TREX_FN vf shfl_group8(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 8); }
+TREX_FN vf group8_sum(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
+TREX_FN vf group8_max(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(TREX_FULL, x, m)); return x; }

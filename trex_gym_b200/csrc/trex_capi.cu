@@ -15,7 +15,10 @@
 #include <new>
 
 #ifndef TREX_MIN_BLOCKS
-#define TREX_MIN_BLOCKS 14
+#define TREX_MIN_BLOCKS 14        // resident warps per SM targeted by the front / tail kernels (128 registers)
+#endif
+#ifndef TREX_SOLVE_MIN_BLOCKS
+#define TREX_SOLVE_MIN_BLOCKS 12  // ... by the 4-environments-per-warp solve kernel (168 registers)
 #endif
 #define TREX_STR2(x) #x
 #define TREX_STR(x) TREX_STR2(x)
@@ -41,31 +44,60 @@ int fail(int code, const char* fmt, const char* detail = "") {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// step / reset kernel: WARPS environments per CTA, one warp each, warp-private shared slab.
-//   mode 0: TrexBulletEnv.step for every environment
-//   mode 1: TrexBulletEnv.reset for environments with mask[env] != 0 (or all when mask == nullptr)
+// One env step = n_sub x [trex_front_kernel ; trex_solve_kernel] ; trex_tail_kernel   (trex_core.h).
+// Warp-private shared slabs, no block-level synchronisation anywhere.
 // ------------------------------------------------------------------------------------------------
+// one warp per environment: dynamics front end of one physics substep (+ the whole substep when in contact)
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
-trex_step_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
+trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
+                  const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
+                  float* __restrict__ state, float* __restrict__ work, const float* __restrict__ action,
+                  uint8_t* __restrict__ flags, int n_envs, int first_round) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * WARPS + warp;
+  if (env >= n_envs) return;
+  trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
+                    work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
+                    flags ? flags + env : nullptr, first_round != 0);
+}
+
+// one warp per FOUR consecutive environments: the deferred (contact-free) solves, eight lanes per environment
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, TREX_SOLVE_MIN_BLOCKS / WARPS)
+trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
+                  const uint8_t* __restrict__ flags, int n_envs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int env0 = (blockIdx.x * WARPS + warp) * 4;
+  if (env0 >= n_envs) return;
+  const int n_valid = min(4, n_envs - env0);
+  int pending = 0;
+  for (int e = 0; e < n_valid; e++) pending |= (flags[env0 + e] != 0) << e;
+  if (pending == 0) return;
+  trex::solve_phase(P, slabs[warp], work + (size_t)env0 * TREX_WORK_STRIDE, state + (size_t)env0 * TREX_STATE_STRIDE, pending);
+}
+
+// one warp per environment: reward / done / auto-reset / observations (mode 0), or reset only (mode 1, optional mask)
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
+trex_tail_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
                  const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
-                 float* __restrict__ state, const float* __restrict__ action, float* __restrict__ obs,
-                 float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ aux,
-                 const uint8_t* __restrict__ mask, int n_envs, int mode) {
+                 float* __restrict__ state, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
+                 float* __restrict__ aux, const uint8_t* __restrict__ mask, int n_envs, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS + warp;
   if (env >= n_envs) return;
   if (mode == 1 && mask != nullptr && mask[env] == 0) return;
-  trex::WarpShared& S = slabs[warp];
-  float* rec = state + (size_t)env * TREX_STATE_STRIDE;
-  trex::env_step(P, mdl, mdli, tasks, cand_p, cand_lane, S, rec,
-                 mode == 0 ? action + (size_t)env * trex::NJ : nullptr,
-                 obs ? obs + (size_t)env * (3 * trex::NJ) : nullptr,
-                 (mode == 0 && reward) ? reward + env : nullptr,
-                 (mode == 0 && done) ? done + env : nullptr,
-                 aux ? aux + (size_t)env * TREX_AUX_STRIDE : nullptr, mode == 1, (long long)env);
+  trex::tail_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
+                   obs ? obs + (size_t)env * (3 * trex::NJ) : nullptr, (mode == 0 && reward) ? reward + env : nullptr,
+                   (mode == 0 && done) ? done + env : nullptr, (mode == 0 && aux) ? aux + (size_t)env * TREX_AUX_STRIDE : nullptr,
+                   mode == 1, (long long)env);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -153,15 +185,17 @@ struct trex_handle {
   int device = 0;
   int n_envs = 0;
   int warps_per_block = 2;
+  bool deferred_solve = true;  // contact-free substeps solved four environments per warp (solve4)
   trex_host::ModelTables T;
   trex_host::EnvConfig C;
   trex::Uniform P;
-  float *d_mdl = nullptr, *d_tasks = nullptr, *d_cand_p = nullptr, *d_state = nullptr, *d_aux = nullptr;
+  float *d_mdl = nullptr, *d_tasks = nullptr, *d_cand_p = nullptr, *d_state = nullptr, *d_aux = nullptr, *d_work = nullptr;
   float *d_lower = nullptr, *d_upper = nullptr;
   int *d_mdli = nullptr, *d_cand_lane = nullptr;
   // staging for the host-buffer entry points
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   uint8_t* d_done = nullptr;
+  uint8_t* d_flags = nullptr;  // per environment: this substep's solve was deferred to trex_solve_kernel
   DevStats* d_stats = nullptr;
   int64_t launches = 0;
   int64_t env_steps = 0;
@@ -169,20 +203,43 @@ struct trex_handle {
 
 namespace {
 
+template <class K>
+int configure_kernel(K kernel, size_t smem) {
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return TREX_OK;
+}
+
+// mode 0: one env step (n_sub front/solve rounds + tail); mode 1: reset (tail only)
 template <int WARPS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
   const size_t smem = sizeof(trex::WarpShared) * WARPS;
   static bool configured[16] = {false};
   if (!configured[h->device & 15]) {
-    CUDA_TRY(cudaFuncSetAttribute(trex_step_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(trex_step_kernel<WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared));
+    int rc;
+    if ((rc = configure_kernel(trex_front_kernel<WARPS>, smem)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_solve_kernel<WARPS>, smem)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_tail_kernel<WARPS>, smem)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
   }
-  const int grid = (h->n_envs + WARPS - 1) / WARPS;
-  trex_step_kernel<WARPS><<<grid, 32 * WARPS, smem, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
-                                                          h->d_state, action, obs, reward, done, h->d_aux, mask, h->n_envs, mode);
+  const int grid1 = (h->n_envs + WARPS - 1) / WARPS;            // one warp per environment
+  const int grid4 = (h->n_envs + 4 * WARPS - 1) / (4 * WARPS);  // one warp per four environments
+  if (mode == 0) {
+    for (int r = 0; r < h->P.n_sub; r++) {
+      trex_front_kernel<WARPS><<<grid1, 32 * WARPS, smem, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+                                                               h->d_state, h->d_work, action, h->d_flags, h->n_envs, r == 0);
+      CUDA_TRY(cudaGetLastError());
+      h->launches++;
+      if (h->d_work) {
+        trex_solve_kernel<WARPS><<<grid4, 32 * WARPS, smem, st>>>(h->P, h->d_state, h->d_work, h->d_flags, h->n_envs);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+      }
+    }
+  }
+  trex_tail_kernel<WARPS><<<grid1, 32 * WARPS, smem, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane, h->d_state,
+                                                          obs, reward, done, h->d_aux, mask, h->n_envs, mode);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return TREX_OK;
@@ -193,9 +250,8 @@ int dispatch_step(trex_handle* h, const float* action, float* obs, float* reward
   switch (h->warps_per_block) {
     case 1: return launch_step<1>(h, action, obs, reward, done, mask, mode, st);
     case 2: return launch_step<2>(h, action, obs, reward, done, mask, mode, st);
-    case 3: return launch_step<3>(h, action, obs, reward, done, mask, mode, st);
     case 4: return launch_step<4>(h, action, obs, reward, done, mask, mode, st);
-    default: return fail(TREX_ERR_INVALID, "warps_per_block must be 1..4%s");
+    default: return fail(TREX_ERR_INVALID, "warps_per_block must be 1, 2 or 4%s");
   }
 }
 
@@ -239,7 +295,8 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     h->C.max_episode_steps = cfg->max_episode_steps; h->C.enable_contacts = cfg->enable_contacts;
     h->C.reset_mode = cfg->reset_mode; h->C.seed = cfg->seed;
     h->C.env_offset = ((long long)cfg->reserved[2] << 32) | (unsigned)cfg->reserved[1];
-    if (cfg->reserved[0] >= 1 && cfg->reserved[0] <= 4) h->warps_per_block = cfg->reserved[0];
+    if (cfg->reserved[0] == 1 || cfg->reserved[0] == 2 || cfg->reserved[0] == 4) h->warps_per_block = cfg->reserved[0];
+    h->deferred_solve = cfg->reserved[3] == 0;
   }
   trex_host::fill_uniform(h->T, h->C, h->P);
   int rc;
@@ -255,12 +312,15 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   const size_t N = (size_t)n_envs;
   CTRY(cudaMalloc((void**)&h->d_state, N * TREX_STATE_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_state, 0, N * TREX_STATE_STRIDE * sizeof(float)));
+  if (h->deferred_solve) CTRY(cudaMalloc((void**)&h->d_work, N * TREX_WORK_STRIDE * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_action, N * trex::NJ * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_obs, N * 3 * trex::NJ * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_reward, N * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_done, N));
+  CTRY(cudaMalloc((void**)&h->d_flags, N));
+  CTRY(cudaMemset(h->d_flags, 0, N));
   CTRY(cudaMalloc((void**)&h->d_stats, sizeof(DevStats)));
 #undef CTRY
   // all environments start from the reference reset (TrexBulletEnv.__init__ calls reset(), trex_env.py:92)
@@ -278,6 +338,7 @@ void trex_destroy(trex_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_mdl); cudaFree(h->d_mdli); cudaFree(h->d_tasks); cudaFree(h->d_cand_p); cudaFree(h->d_cand_lane);
+  cudaFree(h->d_work); cudaFree(h->d_flags);
   cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_action);
   cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_stats);
   delete h;

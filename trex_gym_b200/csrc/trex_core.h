@@ -33,6 +33,14 @@
 #define TREX_NCAND_MAX 64
 #define TREX_MAX_ROUNDS 12
 #define TREX_STATE_STRIDE 160  // floats per environment record (see include/trex_b200.h)
+// deferred-solve work record (floats): M^-1 columns [31][32], then per-lane rows
+#define W_COL 0
+#define W_RHSM 992
+#define W_JDI 1024
+#define W_DSELF 1056
+#define W_RHSL 1088
+#define W_SIGMA 1120
+#define TREX_WORK_STRIDE 1152
 #ifdef TREX_PHASES
 #define TREX_AUX_STRIDE 16
 #define TREX_TICK(i) { const long long _t = cycle_count(); stats.phase[i] += (float)(_t - _t0); _t0 = _t; }
@@ -141,7 +149,8 @@ struct StepStats {
 #define MDL(f) ldg_ro(mdl, lane + (f) * 32)
 #define MDLI(f) ldi(mdli, lane + (f) * 32)
 
-TREX_FN vf clampv(vf x, float lo, float hi) { return vmin(vmax(x, lo), hi); }
+// btClamp semantics: comparison based, so a NaN stays a NaN (fmin/fmax would launder it into a bound)
+TREX_FN vf clampv(vf x, float lo, float hi) { return sel(x < lo, lo, sel(x > hi, hi, x)); }
 TREX_FN float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // world -> base rotation from the base -> world quaternion (x,y,z,w)
@@ -307,9 +316,11 @@ TREX_FN void to_parent(const vf E[9], const vf r[3], const vf Ia[21], const vf p
 // One pybullet stepSimulation for the environment owned by this warp.
 // kp/kd/max_imp: motor settings of this substep (zero during the reset step).
 // ------------------------------------------------------------------------------------------
-TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+// Returns true when the solve was deferred: the solver inputs were written to `work` (contact-free
+// environment, `work` != nullptr) and the caller finishes the step with solve4(); otherwise the step is complete.
+TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                      const int* cand_lane, WarpShared& S, EnvRegs& R, float kp, float kd, float max_imp,
-                     StepStats& stats) {
+                     StepStats& stats, float* work) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vb is_base = lane == 25;
@@ -695,6 +706,21 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
       n_act = (n_act + cnt > TREX_KMAX) ? TREX_KMAX : n_act + cnt;
     }
     warp_sync();
+  }
+  if (work != nullptr && n_act == 0) {
+    // Deferred solve: no contact rows -> the rows are the 25 motors and the violated joint limits, all with unit
+    // Jacobians.  Write M^-1 and the per-joint row scalars; solve4() handles four such environments per warp.
+    TREX_ROLLED for (int gq = 0; gq < trex_topo::NDOF; gq++) st(work, lane + (W_COL + gq * 32), ld(S.col[gq], lane));
+    st(work, lane + W_RHSM, rhs_m);
+    st(work, lane + W_JDI, jdi);
+    st(work, lane + W_DSELF, sel(is_joint, dself, 0.0f));
+    st(work, lane + W_RHSL, sel(act_lo, rhs_lo, sel(act_hi, rhs_hi, 0.0f)));
+    st(work, lane + W_SIGMA, sel(act_lo, 1.0f, sel(act_hi, -1.0f, 0.0f)));
+    stats.contacts = 0;
+    warp_sync();
+    return true;
+  }
+  if (P.contacts_on) {
     // From here on the kinematics-phase arrays are dead: their storage becomes the contact rows.
     // axis of this lane's joint in world coordinates and its origin (registers)
     const vf ax = Rw[6], ay = Rw[7], az = Rw[8];
@@ -981,6 +1007,7 @@ TREX_FN void substep(const Uniform& P, const float* mdl, const int* mdli, const 
   }
   R.q = sel(is_joint, R.q + dt * R.qd, 0.0f);
   TREX_TICK(7)
+  return false;
 }
 
 
@@ -1057,122 +1084,365 @@ TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared&
   warp_sync();
 }
 
-// One TrexBulletEnv.step (trex_env.py:128-154) or reset (trex_env.py:98-122) for this warp's environment.
-//   action : 25 floats, name-sorted joint order (trex_robot.py:311-314), or nullptr when force_reset
-//   obs    : 75 floats  q | qd | applied motor torque  (trex_robot.py:359-365)
-//   aux    : TREX_AUX_STRIDE floats: head xyz, lifting/station/energy penalties, PGS iterations, contacts
-TREX_FN void env_step(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
-                      const int* cand_lane, WarpShared& S, float* rec, const float* action, float* obs, float* reward,
-                      uint8_t* done, float* aux, bool force_reset, long long env_id) {
+// ------------------------------------------------------------------------------------------
+// solve4: projected Gauss-Seidel for up to FOUR contact-free environments in one warp.
+//
+// Without contacts every row has a unit Jacobian (25 motors + the violated joint limits), so the solver
+// only needs the joint block of M^-1.  Eight lanes serve one environment (group = lane >> 3); lane l of a
+// group owns joints {l, l+8, l+16, l+24}.  Each lane carries, per owned joint k,
+//     w_k = lambda_m,k + rhs_m,k - jdi_k * dv_k      (the motor row's unclamped new impulse)
+// and the row of coefficients g[k][j] = -jdi_k * M^-1[6+k][6+j] in registers (0 on the diagonal, where the
+// impulse and velocity terms cancel).  A row update is then: clamp on the owner, one width-8 shuffle, four
+// FMAs per lane -- the same dependent chain as the one-environment sweep, shared by four environments.
+// Rows are visited in Bullet's order (motors in sorted-constraint order, then the violated limits; direction
+// alternates with the iteration); w is rebuilt exactly from the impulses after every sweep.
+// Ends with the velocity update, the write-back of the applied motor torque and the position integration.
+// Returns the number of solver iterations each group executed (per lane of the group).
+// ------------------------------------------------------------------------------------------
+#define TREX_GS_STRIDE 648  // floats per group in the shared stash of g (25*25 = 625, padded: bank offset 8 per group)
+TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* rec0, int pending, float max_imp) {
+  const vi lane = lane_id();
+  const vi grp = lane >> 3, gl = lane & 7;
+  const vb gact = ((vi(pending) >> grp) & 1) != 0;
+  const vi woff = grp * TREX_WORK_STRIDE, roff = grp * TREX_STATE_STRIDE;
+  const float dt = P.dt;
+  float* Gs = reinterpret_cast<float*>(&S.c);          // [4][TREX_GS_STRIDE]: g[k][j] at j*25 + k
+  float* Lam = Gs + 4 * TREX_GS_STRIDE;                // [4][32]: net joint impulses, exchanged once per sweep
+  static_assert(sizeof(S.c) >= (4 * TREX_GS_STRIDE + 128) * sizeof(float), "contact-row storage too small for the solve4 stash");
+
+  vi kk[4];
+  vb kv[4];
+  vf rhs_m[4], jdi[4], dself[4], rhs_l[4], sigma[4], g[4][NJ];
+  TREX_UNROLL for (int s = 0; s < 4; s++) {
+    kk[s] = gl + 8 * s;
+    kv[s] = gact && (kk[s] < NJ);
+    kk[s] = seli(kv[s], kk[s], 0);
+    rhs_m[s] = ld_if(work0, woff + kk[s] + W_RHSM, kv[s], 0.0f);
+    jdi[s] = ld_if(work0, woff + kk[s] + W_JDI, kv[s], 0.0f);
+    dself[s] = ld_if(work0, woff + kk[s] + W_DSELF, kv[s], 0.0f);
+    rhs_l[s] = ld_if(work0, woff + kk[s] + W_RHSL, kv[s], 0.0f);
+    sigma[s] = ld_if(work0, woff + kk[s] + W_SIGMA, kv[s], 0.0f);
+    TREX_UNROLL for (int j = 0; j < NJ; j++) {
+      const vf cj = ld_if(work0, woff + kk[s] + (W_COL + (6 + j) * 32), kv[s], 0.0f);
+      g[s][j] = sel(kk[s] == j, 0.0f, -(jdi[s] * cj));
+    }
+  }
+  // copy of g in shared memory for the limit rows (their joint index is only known at run time)
+  warp_sync();
+  TREX_UNROLL for (int s = 0; s < 4; s++)
+    TREX_UNROLL for (int j = 0; j < NJ; j++) st_if(Gs, grp * TREX_GS_STRIDE + kk[s] + j * 25, g[s][j], kv[s]);
+  // joints with a violated limit in ANY of the four environments, in Bullet's limit-constraint order
+  uint32_t uperm = 0;
+  {
+    uint32_t um = 0;
+    TREX_UNROLL for (int s = 0; s < 4; s++) {
+      const uint32_t b = vballot(kv[s] && (sigma[s] != 0.0f));
+      um |= (((b) | (b >> 8) | (b >> 16) | (b >> 24)) & 0xffu) << (8 * s);
+    }
+    for (int p = 0; p < NJ; p++) uperm |= ((um >> P.order[NJ + p]) & 1u) << p;
+  }
+  warp_sync();
+
+  vf w[4], lam_m[4], lam_l[4];
+  TREX_UNROLL for (int s = 0; s < 4; s++) { w[s] = rhs_m[s]; lam_m[s] = 0.0f; lam_l[s] = 0.0f; }
+  const float lim_hi = P.limit_max_impulse;
+  vb alive = gact;
+  vi itd = 0;
+
+#define TREX_S4_MOTOR(K)                                                                               \
+  {                                                                                                    \
+    constexpr int j = trex_topo::noncontact_order(K) - NJ;                                             \
+    constexpr int sj = j >> 3;                                                                         \
+    const vf nl = vmin(vmax(w[sj], -max_imp), max_imp);                                                \
+    const vb own = alive && (gl == (j & 7));                                                           \
+    const vf d = sel(own, nl - lam_m[sj], 0.0f);                                                       \
+    const vf db = shfl_group8(d, j & 7);                                                               \
+    lam_m[sj] = sel(own, nl, lam_m[sj]);                                                               \
+    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(g[s][j], db, w[s]);                            \
+  }
+  // one limit row of joint j (slot SJ static): sigma = +1 lower row, -1 upper row, impulse in [0, lim_hi]
+#define TREX_S4_LIMIT_SLOT(SJ)                                                                         \
+  {                                                                                                    \
+    const vf x = (lam_m[SJ] + rhs_m[SJ]) - w[SJ];              /* jdi * dv_j */                         \
+    const vf sum = lam_l[SJ] + (rhs_l[SJ] - sigma[SJ] * x);                                            \
+    const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                                       \
+    const vb own = alive && (gl == (j & 7)) && (sigma[SJ] != 0.0f);                                    \
+    const vf d = sel(own, (nl - lam_l[SJ]) * sigma[SJ], 0.0f);  /* change of the net joint impulse */   \
+    const vf db = shfl_group8(d, j & 7);                                                               \
+    lam_l[SJ] = sel(own, nl, lam_l[SJ]);                                                               \
+    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(ld(Gs, gbase + kk[s]), db, w[s]);              \
+    w[SJ] = w[SJ] - d;                                        /* self term: dv_j += D_j * d */         \
+  }
+#define TREX_S4_LIMITS(FORWARD)                                                                        \
+  {                                                                                                    \
+    uint32_t m = uperm;                                                                                \
+    while (m) {                                                                                        \
+      const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                            \
+      m &= ~(1u << pos);                                                                               \
+      const int j = P.order[NJ + pos];                                                                 \
+      const vi gbase = grp * TREX_GS_STRIDE + j * 25;                                                  \
+      switch (j >> 3) {                                                                                \
+        case 0: TREX_S4_LIMIT_SLOT(0) break;                                                           \
+        case 1: TREX_S4_LIMIT_SLOT(1) break;                                                           \
+        case 2: TREX_S4_LIMIT_SLOT(2) break;                                                           \
+        default: TREX_S4_LIMIT_SLOT(3) break;                                                          \
+      }                                                                                                \
+    }                                                                                                  \
+  }
+#define M_(k) TREX_S4_MOTOR(k)
+  TREX_ROLLED for (int it = 0; it < P.iters; it++) {
+    vf lam_m0[4], lam_l0[4];
+    TREX_UNROLL for (int s = 0; s < 4; s++) { lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s]; }
+    if (it & 1) {
+      M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7) M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16)
+      M_(17) M_(18) M_(19) M_(20) M_(21) M_(22) M_(23) M_(24)
+      TREX_S4_LIMITS(true)
+    } else {
+      TREX_S4_LIMITS(false)
+      M_(24) M_(23) M_(22) M_(21) M_(20) M_(19) M_(18) M_(17) M_(16) M_(15) M_(14) M_(13) M_(12) M_(11) M_(10) M_(9) M_(8)
+      M_(7) M_(6) M_(5) M_(4) M_(3) M_(2) M_(1) M_(0)
+    }
+    // residual per environment: max over its rows of (delta impulse / jacDiagABInv)^2
+    vf r = 0.0f;
+    TREX_UNROLL for (int s = 0; s < 4; s++) {
+      const vf dm = (lam_m[s] - lam_m0[s]) * dself[s], dl = (lam_l[s] - lam_l0[s]) * dself[s];
+      r = vmax(r, vmax(dm * dm, dl * dl));
+    }
+    r = group8_max(r);
+    itd = itd + seli(alive, vi(1), vi(0));
+    alive = alive && !(r <= P.resid_thresh) && (it < P.iters - 1);
+    if (!vany(alive)) break;
+    // rebuild w exactly from the impulses: w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j
+    warp_sync();
+    TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * 32 + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+    warp_sync();
+    vf acc[4];
+    TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = rhs_m[s] - sigma[s] * lam_l[s];
+    TREX_UNROLL for (int j = 0; j < NJ; j++) {
+      const vf Lj = ld(Lam, grp * 32 + j);
+      TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
+    }
+    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = sel(alive, acc[s], w[s]);
+  }
+#undef M_
+#undef TREX_S4_MOTOR
+#undef TREX_S4_LIMIT_SLOT
+#undef TREX_S4_LIMITS
+
+  // ---- velocity change of every coordinate from the final impulses ------------------------------------
+  warp_sync();
+  TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * 32 + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+  warp_sync();
+  vf Ssum[4];
+  TREX_UNROLL for (int s = 0; s < 4; s++) Ssum[s] = 0.0f;
+  TREX_UNROLL for (int j = 0; j < NJ; j++) {
+    const vf Lj = ld(Lam, grp * 32 + j);
+    TREX_UNROLL for (int s = 0; s < 4; s++) Ssum[s] = vfma(g[s][j], Lj, Ssum[s]);
+  }
+  vf dvb[6];
+  TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = 0.0f;
+  TREX_UNROLL for (int s = 0; s < 4; s++) {
+    const vf Lk = lam_m[s] + sigma[s] * lam_l[s];
+    TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = vfma(ld_if(work0, woff + kk[s] + (W_COL + b * 32), kv[s], 0.0f), Lk, dvb[b]);
+  }
+  TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = group8_sum(dvb[b]);
+
+  // ---- velocities += dv (clamped), applied motor torque, positions with the NEW velocities ----------------
+  TREX_UNROLL for (int s = 0; s < 4; s++) {
+    const vf Lk = lam_m[s] + sigma[s] * lam_l[s];
+    const vf dvk = dself[s] * (Lk - Ssum[s]);  // M^-1 row k times the impulses = D_k Lambda_k - S_k / jdi_k
+    const vf qd0 = ld_if(rec0, roff + kk[s] + ST_QD, kv[s], 0.0f);
+    const vf q0 = ld_if(rec0, roff + kk[s] + ST_Q, kv[s], 0.0f);
+    const vf qd1 = clampv(qd0 + dvk, -P.maxvel, P.maxvel);
+    st_if(rec0, roff + kk[s] + ST_QD, qd1, kv[s]);
+    st_if(rec0, roff + kk[s] + ST_Q, q0 + dt * qd1, kv[s]);
+    st_if(rec0, roff + kk[s] + ST_TAU, vdiv(lam_m[s], dt), kv[s]);
+  }
+  {
+    const vi rb = seli(gact, roff, 0);
+    vf om[3], vl[3], pos[3], qt[4];
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      om[k] = clampv(ld(rec0, rb + (ST_OM + k)) + dvb[k], -P.maxvel, P.maxvel);
+      vl[k] = clampv(ld(rec0, rb + (ST_VL + k)) + dvb[3 + k], -P.maxvel, P.maxvel);
+      pos[k] = ld(rec0, rb + (ST_POS + k)) + dt * vl[k];
+    }
+    TREX_UNROLL for (int k = 0; k < 4; k++) qt[k] = ld(rec0, rb + (ST_QUAT + k));
+    // btMultiBody::stepPositionsMultiDof: exponential map of the world angular velocity, q <- dq * q
+    vf fa = vsqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    fa = sel(fa * dt > 0.78539816339744831f, vbroadcast(0.78539816339744831f / dt), fa);
+    const vb small = fa < 0.001f;
+    const vf sc = sel(small, 0.5f * dt - (dt * dt * dt) * 0.020833333333f * fa * fa, vdiv(vsin(0.5f * fa * dt), sel(small, 1.0f, fa)));
+    const vf ax = om[0] * sc, ay = om[1] * sc, az = om[2] * sc, aw = vcos(fa * dt * 0.5f);
+    const vf nx = aw * qt[0] + ax * qt[3] + ay * qt[2] - az * qt[1];
+    const vf ny = aw * qt[1] - ax * qt[2] + ay * qt[3] + az * qt[0];
+    const vf nz = aw * qt[2] + ax * qt[1] - ay * qt[0] + az * qt[3];
+    const vf nw = aw * qt[3] - ax * qt[0] - ay * qt[1] - az * qt[2];
+    const vf inv = vdiv(1.0f, vsqrt(nx * nx + ny * ny + nz * nz + nw * nw));
+    warp_sync();
+    // lanes 0..12 of the group's first 13... one lane per field: lane gl + 8*t covers fields gl, gl+8
+    TREX_UNROLL for (int t = 0; t < 2; t++) {
+      const vi f = gl + 8 * t;  // field index 0..15 of the base block [pos3 quat4 om3 vl3]
+      vf val = 0.0f;
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        val = sel(f == ST_POS + k, pos[k], val);
+        val = sel(f == ST_OM + k, om[k], val);
+        val = sel(f == ST_VL + k, vl[k], val);
+      }
+      val = sel(f == ST_QUAT, nx * inv, sel(f == ST_QUAT + 1, ny * inv, sel(f == ST_QUAT + 2, nz * inv, sel(f == ST_QUAT + 3, nw * inv, val))));
+      st_if(rec0, rb + f, val, gact && (f < 13));
+    }
+  }
+  warp_sync();
+  return itd;
+}
+
+// reward (trex_env.py:186-196), termination (trex_env.py:183-184 + optional horizon / NaN guard) of one environment
+TREX_FN void reward_and_done(const Uniform& P, const float* mdl, vi lane, WarpShared& S, const EnvRegs& R, vi slot,
+                             float step_count, float head[3], float terms[3], float& rew, bool& bad, bool& is_done) {
+  const vb is_joint = lane < NJ;
+  // head-link COM in world: forward kinematics along the base -> head chain only (uniform arithmetic)
+  float Rh[9], xh[3] = {R.pos[0], R.pos[1], R.pos[2]};
+  quat_to_Rb(R.quat, Rh);
+  TREX_ROLLED for (int d = 0; d < P.head_depth; d++) {
+    const int L = P.head_chain[d];
+    const float qj = lane_value(R.q, L);
+    const float c = cosf(qj), sn = sinf(qj);
+    float e0[9], r0h[3], El[9], Rn[9];
+    TREX_UNROLL for (int k = 0; k < 9; k++) e0[k] = ldu(mdl, (F_E0 + k) * 32 + L);
+    TREX_UNROLL for (int k = 0; k < 3; k++) r0h[k] = ldu(mdl, (F_R0 + k) * 32 + L);
+    TREX_UNROLL for (int j = 0; j < 3; j++) xh[j] += Rh[j] * r0h[0] + Rh[3 + j] * r0h[1] + Rh[6 + j] * r0h[2];
+    El[0] = c * e0[0] + sn * e0[1]; El[1] = c * e0[3] + sn * e0[4]; El[2] = c * e0[6] + sn * e0[7];
+    El[3] = c * e0[1] - sn * e0[0]; El[4] = c * e0[4] - sn * e0[3]; El[5] = c * e0[7] - sn * e0[6];
+    El[6] = e0[2]; El[7] = e0[5]; El[8] = e0[8];
+    TREX_UNROLL for (int i = 0; i < 3; i++)
+      TREX_UNROLL for (int j = 0; j < 3; j++) Rn[3 * i + j] = El[3 * i] * Rh[j] + El[3 * i + 1] * Rh[3 + j] + El[3 * i + 2] * Rh[6 + j];
+    TREX_UNROLL for (int k = 0; k < 9; k++) Rh[k] = Rn[k];
+  }
+  TREX_UNROLL for (int j = 0; j < 3; j++) head[j] = xh[j] + Rh[j] * P.head_p[0] + Rh[3 + j] * P.head_p[1] + Rh[6 + j] * P.head_p[2];
+  // total |qd * tau| in sorted-joint order, sequential non-fused sum (reproducible from the outputs)
+  warp_sync();
+  st_if(S.tmp[0], slot, vabs(vmul_rn(R.qd, R.tau)), is_joint);
+  warp_sync();
+  float power = 0.0f;
+  TREX_ROLLED for (int k = 0; k < NJ; k++) power = fadd_rn(power, ldu(S.tmp[0], k));
+  const float dz = fadd_rn(P.target_h, -head[2]);
+  terms[0] = fmul_rn(P.w_dist, fmul_rn(dz, dz));                                                 // lifting
+  terms[1] = fmul_rn(P.w_drift, fadd_rn(fmul_rn(head[0], head[0]), fmul_rn(head[1], head[1])));  // station keeping
+  terms[2] = fmul_rn(P.w_energy, power);                                                         // energy
+  rew = fadd_rn(fadd_rn(-terms[0], -terms[1]), -terms[2]);
+  warp_sync();
+  bad = vany(visnan(R.q) || visnan(R.qd)) || !(fabsf(R.pos[0]) + fabsf(R.pos[1]) + fabsf(R.pos[2]) <= 3.0e38f) ||
+        !(fabsf(R.quat[0]) + fabsf(R.quat[3]) <= 3.0e38f) || !(fabsf(R.om[0]) + fabsf(R.om[1]) + fabsf(R.om[2]) <= 3.0e38f);
+  is_done = bad || (P.max_episode_steps > 0 && step_count >= (float)P.max_episode_steps);
+}
+
+// ------------------------------------------------------------------------------------------
+// One TrexBulletEnv.step (trex_env.py:128-154) = n_sub x [front_phase ; solve_phase] ; tail_phase, each phase
+// a kernel of its own (trex_capi.cu).  Splitting keeps every kernel's hot loop resident in the instruction
+// cache (a fused kernel mixing the two solvers measured 7.6 no-instruction stalls per issue) and lets the
+// 4-environments-per-warp solver run at its own occupancy.
+// ------------------------------------------------------------------------------------------
+enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // per-step accumulators in the record
+
+// front_phase: one physics substep of ONE environment by one warp up to the solve: kinematics, bias forces,
+// articulated inertias, accelerations, velocity update, M^-1, row setup, contact detection.  With contacts
+// the substep is finished here (one-environment solver + integration); without, the solver inputs go to
+// `work` and *flag = 1 (solve_phase finishes the substep).   action: [25] name-sorted (trex_robot.py:311-314)
+TREX_FN void front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+                         const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, uint8_t* flag,
+                         bool first_round) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vi slot = seli(is_joint, MDLI(IF_OBS_SLOT), 0);
   EnvRegs R;
   load_env(rec, lane, S, R);
-  float step_count = ldu(rec, ST_STEP), episode = ldu(rec, ST_EPISODE), nan_resets = ldu(rec, ST_NANRESETS);
-  StepStats stats;
-  stats.iters = 0; stats.contacts = 0; stats.overflow = 0;
+  // np.clip(action, low, high)  (trex_env.py:147); the targets are re-applied every substep (:148-150)
+  const vf a = ld_if(action, slot, is_joint, 0.0f);
+  R.tgt = vmin(vmax(a, MDL(F_LOWER)), MDL(F_UPPER));
+  StepStats st;
+  st.iters = 0; st.contacts = 0; st.overflow = 0;
 #ifdef TREX_PHASES
-  for (int i = 0; i < 8; i++) stats.phase[i] = 0.0f;
+  for (int i = 0; i < 8; i++) st.phase[i] = 0.0f;
 #endif
+  const bool deferred = substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, st, work);
+  store_env(rec, lane, S, R);  // deferred: positions unchanged, velocities after the unconstrained update
+  const float it0 = first_round ? 0.0f : ldu(rec, ST_ACC_ITERS), ov0 = first_round ? 0.0f : ldu(rec, ST_ACC_OVERFLOW);
+  vf acc = 0.0f;
+  acc = sel(lane == 0, vbroadcast(it0 + (float)st.iters), acc);
+  acc = sel(lane == 1, vbroadcast((float)st.contacts), acc);
+  acc = sel(lane == 2, vbroadcast(ov0 + (float)st.overflow), acc);
+  warp_sync();
+  st_if(rec, lane + ST_ACC_ITERS, acc, lane < 3);
+  if (flag) st_u8_if(flag, vi(0), vi(deferred ? 1 : 0), lane == 0);
+}
+
+// solve_phase: the deferred solves of four consecutive environments (pending bit e <=> environment e deferred)
+TREX_FN void solve_phase(const Uniform& P, WarpShared& S, const float* work0, float* rec0, int pending) {
+  const vi lane = lane_id();
+  const vi itd = solve4(P, S, work0, rec0, pending, P.max_impulse);
+  // iterations executed per environment -> its accumulator (lane 8e holds group e's count)
+  const vi grp = lane >> 3;
+  const vb wr = ((lane & 7) == 0) && ((((vi(pending)) >> grp) & 1) != 0);
+  const vi idx = seli(wr, grp * TREX_STATE_STRIDE + ST_ACC_ITERS, 0);
+  st_if(rec0, idx, ld(rec0, idx) + vi2f(itd), wr);
+}
+
+// tail_phase: end of the env step for ONE environment: reward (trex_env.py:186-196), done (trex_env.py:183-184 +
+// optional horizon / NaN guard), VecEnv auto-reset = TrexBulletEnv.reset (trex_env.py:98-122: reset pose, zero-gain
+// zero-force motors, ONE physics step), observations (trex_robot.py:359-365), diagnostics.
+// force_reset: only the reset (trex_reset).
+//   obs : [75] q | qd | motor torque   aux : [TREX_AUX_STRIDE] head xyz, lifting/station/energy, PGS iterations, contacts
+TREX_FN void tail_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+                        const int* cand_lane, WarpShared& S, float* rec, float* obs, float* reward, uint8_t* done,
+                        float* aux, bool force_reset, long long env_id) {
+  const vi lane = lane_id();
+  const vb is_joint = lane < NJ;
+  const vi slot = seli(is_joint, MDLI(IF_OBS_SLOT), 0);
+  EnvRegs R;
+  load_env(rec, lane, S, R);
   bool is_done = false;
-  float rew = 0.0f, head[3] = {0.0f, 0.0f, 0.0f}, terms[3] = {0.0f, 0.0f, 0.0f};
-
-  // np.clip(action, low, high)  (trex_env.py:147); targets held for all substeps (:148-150)
   if (!force_reset) {
-    const vf a = ld_if(action, slot, is_joint, 0.0f);
-    R.tgt = vmin(vmax(a, MDL(F_LOWER)), MDL(F_UPPER));
-  }
-  // One call site for the physics step (keeps the kernel small enough for the instruction cache):
-  //   phase 0: the n_sub substeps of an env step   phase 1: reset requested   phase 3: the ONE physics
-  //   step TrexBulletEnv.reset performs (trex_env.py:120)   phase 2: finished
-  int phase = force_reset ? 1 : 0, sdone = 0;
-  float kp = P.kp, kd = P.kd, mi = P.max_impulse;
-  StepStats rs;
-  rs.iters = 0; rs.contacts = 0; rs.overflow = 0;
-#ifdef TREX_PHASES
-  for (int i = 0; i < 8; i++) rs.phase[i] = 0.0f;
-#endif
-  TREX_ROLLED for (;;) {
-    if (phase == 0 && sdone == P.n_sub) {
-      step_count += 1.0f;
-      // reward (trex_env.py:186-196): head-link COM in world, total |qd * tau| in sorted-joint order.
-      // Forward kinematics along the base -> head chain only (uniform arithmetic).
-      float Rh[9], xh[3] = {R.pos[0], R.pos[1], R.pos[2]};
-      quat_to_Rb(R.quat, Rh);
-      TREX_ROLLED for (int d = 0; d < P.head_depth; d++) {
-        const int L = P.head_chain[d];
-        const float qj = lane_value(R.q, L);
-        const float c = cosf(qj), sn = sinf(qj);
-        float e0[9], r0h[3], El[9], Rn[9];
-        TREX_UNROLL for (int k = 0; k < 9; k++) e0[k] = ldu(mdl, (F_E0 + k) * 32 + L);
-        TREX_UNROLL for (int k = 0; k < 3; k++) r0h[k] = ldu(mdl, (F_R0 + k) * 32 + L);
-        TREX_UNROLL for (int j = 0; j < 3; j++) xh[j] += Rh[j] * r0h[0] + Rh[3 + j] * r0h[1] + Rh[6 + j] * r0h[2];
-        El[0] = c * e0[0] + sn * e0[1]; El[1] = c * e0[3] + sn * e0[4]; El[2] = c * e0[6] + sn * e0[7];
-        El[3] = c * e0[1] - sn * e0[0]; El[4] = c * e0[4] - sn * e0[3]; El[5] = c * e0[7] - sn * e0[6];
-        El[6] = e0[2]; El[7] = e0[5]; El[8] = e0[8];
-        TREX_UNROLL for (int i = 0; i < 3; i++)
-          TREX_UNROLL for (int j = 0; j < 3; j++) Rn[3 * i + j] = El[3 * i] * Rh[j] + El[3 * i + 1] * Rh[3 + j] + El[3 * i + 2] * Rh[6 + j];
-        TREX_UNROLL for (int k = 0; k < 9; k++) Rh[k] = Rn[k];
+    const float step_count = ldu(rec, ST_STEP) + 1.0f;
+    float head[3], terms[3], rew;
+    bool bad;
+    reward_and_done(P, mdl, lane, S, R, slot, step_count, head, terms, rew, bad, is_done);
+    vf meta = 0.0f;
+    meta = sel(lane == 0, vbroadcast(step_count), meta);
+    meta = sel(lane == 2, vbroadcast(ldu(rec, ST_NANRESETS) + (bad ? 1.0f : 0.0f)), meta);
+    st_if(rec, lane + ST_STEP, meta, (lane == 0) || (lane == 2));
+    if (reward) st_if(reward, vi(0), vbroadcast(rew), lane == 0);
+    if (done) st_u8_if(done, vi(0), vi(is_done ? 1 : 0), lane == 0);
+    if (aux) {
+      vf ax = 0.0f;
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        ax = sel(lane == k, vbroadcast(head[k]), ax);
+        ax = sel(lane == 3 + k, vbroadcast(terms[k]), ax);
       }
-      TREX_UNROLL for (int j = 0; j < 3; j++) head[j] = xh[j] + Rh[j] * P.head_p[0] + Rh[3 + j] * P.head_p[1] + Rh[6 + j] * P.head_p[2];
-      warp_sync();
-      st_if(S.tmp[0], slot, vabs(vmul_rn(R.qd, R.tau)), is_joint);
-      warp_sync();
-      float power = 0.0f;
-      TREX_ROLLED for (int k = 0; k < NJ; k++) power = fadd_rn(power, ldu(S.tmp[0], k));
-      const float dz = fadd_rn(P.target_h, -head[2]);
-      terms[0] = fmul_rn(P.w_dist, fmul_rn(dz, dz));                                           // lifting
-      terms[1] = fmul_rn(P.w_drift, fadd_rn(fmul_rn(head[0], head[0]), fmul_rn(head[1], head[1])));  // station keeping
-      terms[2] = fmul_rn(P.w_energy, power);                                                   // energy
-      rew = fadd_rn(fadd_rn(-terms[0], -terms[1]), -terms[2]);
-      warp_sync();
-      // termination: the reference never terminates (trex_env.py:183-184); optional horizon + NaN guard
-      const bool bad = vany(visnan(R.q) || visnan(R.qd)) || !(fabsf(R.pos[0]) + fabsf(R.pos[1]) + fabsf(R.pos[2]) <= 3.0e38f) ||
-                       !(fabsf(R.quat[0]) + fabsf(R.quat[3]) <= 3.0e38f) || !(fabsf(R.om[0]) + fabsf(R.om[1]) + fabsf(R.om[2]) <= 3.0e38f);
-      if (bad) nan_resets += 1.0f;
-      is_done = bad || (P.max_episode_steps > 0 && step_count >= (float)P.max_episode_steps);
-      phase = is_done ? 1 : 2;
+      ax = sel(lane == 6, vbroadcast(ldu(rec, ST_ACC_ITERS)), ax);
+      ax = sel(lane == 7, vbroadcast(ldu(rec, ST_ACC_CONTACTS) + 1000.0f * ldu(rec, ST_ACC_OVERFLOW)), ax);
+      st_if(aux, lane, ax, lane < 8);
     }
-    if (phase == 2) break;
-    if (phase == 1) {
-      // TrexBulletEnv.reset: reset pose, zero-gain zero-force motors, then ONE physics step
-      reset_pose(P, mdl, lane, S, R, env_id, episode);
-      kp = 0.0f; kd = 0.0f; mi = 0.0f;
-      step_count = 0.0f;
-      episode += 1.0f;
-      phase = 3;
-    }
-    substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, kp, kd, mi, phase == 3 ? rs : stats);
-    if (phase == 3) phase = 2; else sdone++;
+    warp_sync();
   }
-
-  // observations q | qd | tau in name-sorted joint order
+  if (force_reset || is_done) {
+    const float episode = ldu(rec, ST_EPISODE);
+    reset_pose(P, mdl, lane, S, R, env_id, episode);
+    StepStats rs;
+    rs.iters = 0; rs.contacts = 0; rs.overflow = 0;
+#ifdef TREX_PHASES
+    for (int i = 0; i < 8; i++) rs.phase[i] = 0.0f;
+#endif
+    substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, 0.0f, 0.0f, 0.0f, rs, nullptr);
+    store_env(rec, lane, S, R);
+    vf meta = 0.0f;
+    meta = sel(lane == 1, vbroadcast(episode + 1.0f), meta);
+    warp_sync();
+    st_if(rec, lane + ST_STEP, meta, lane < 2);  // step count 0, episode + 1
+  }
   if (obs) {
     st_if(obs, slot, R.q, is_joint);
     st_if(obs, slot + NJ, R.qd, is_joint);
     st_if(obs, slot + 2 * NJ, R.tau, is_joint);
-  }
-  store_env(rec, lane, S, R);
-  vf meta = 0.0f;
-  meta = sel(lane == 0, vbroadcast(step_count), meta);
-  meta = sel(lane == 1, vbroadcast(episode), meta);
-  meta = sel(lane == 2, vbroadcast(nan_resets), meta);
-  st_if(rec, lane + ST_STEP, meta, lane < 3);
-  if (reward) st_if(reward, lane, vbroadcast(rew), lane == 0);
-  if (done) st_u8_if(done, lane, vi(is_done ? 1 : 0), lane == 0);
-  if (aux) {
-    vf ax = 0.0f;
-    TREX_UNROLL for (int k = 0; k < 3; k++) {
-      ax = sel(lane == k, vbroadcast(head[k]), ax);
-      ax = sel(lane == 3 + k, vbroadcast(terms[k]), ax);
-    }
-    ax = sel(lane == 6, vbroadcast((float)stats.iters), ax);
-    ax = sel(lane == 7, vbroadcast((float)(stats.contacts + 1000 * stats.overflow)), ax);
-#ifdef TREX_PHASES
-    TREX_UNROLL for (int k = 0; k < 8; k++) ax = sel(lane == 8 + k, vbroadcast(stats.phase[k]), ax);
-#endif
-    st_if(aux, lane, ax, lane < TREX_AUX_STRIDE);
   }
 }
 
