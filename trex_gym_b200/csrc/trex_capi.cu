@@ -184,7 +184,7 @@ trex_stats_kernel(const float* __restrict__ state, const float* __restrict__ aux
 struct trex_handle {
   int device = 0;
   int n_envs = 0;
-  int warps_per_block = 2;
+  int warps_per_block = 1;  // front / tail kernels; the solve kernel uses 2 (4 when this is 4)
   bool deferred_solve = true;  // contact-free substeps solved four environments per warp (solve4)
   trex_host::ModelTables T;
   trex_host::EnvConfig C;
@@ -210,36 +210,38 @@ int configure_kernel(K kernel, size_t smem) {
   return TREX_OK;
 }
 
-// mode 0: one env step (n_sub front/solve rounds + tail); mode 1: reset (tail only)
-template <int WARPS>
+// mode 0: one env step (n_sub front/solve rounds + tail); mode 1: reset (tail only).
+// WF: warps per CTA of the front / tail kernels (one environment per warp; 1 schedules best when the work per
+// environment is skewed by contacts), WS: warps per CTA of the solve kernel (four environments per warp).
+template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
-  const size_t smem = sizeof(trex::WarpShared) * WARPS;
+  const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(trex::WarpShared) * WS;
   static bool configured[16] = {false};
   if (!configured[h->device & 15]) {
     int rc;
-    if ((rc = configure_kernel(trex_front_kernel<WARPS>, smem)) != TREX_OK) return rc;
-    if ((rc = configure_kernel(trex_solve_kernel<WARPS>, smem)) != TREX_OK) return rc;
-    if ((rc = configure_kernel(trex_tail_kernel<WARPS>, smem)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_front_kernel<WF>, smem_f)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_solve_kernel<WS>, smem_s)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
   }
-  const int grid1 = (h->n_envs + WARPS - 1) / WARPS;            // one warp per environment
-  const int grid4 = (h->n_envs + 4 * WARPS - 1) / (4 * WARPS);  // one warp per four environments
+  const int grid1 = (h->n_envs + WF - 1) / WF;            // one warp per environment
+  const int grid4 = (h->n_envs + 4 * WS - 1) / (4 * WS);  // one warp per four environments
   if (mode == 0) {
     for (int r = 0; r < h->P.n_sub; r++) {
-      trex_front_kernel<WARPS><<<grid1, 32 * WARPS, smem, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
-                                                               h->d_state, h->d_work, action, h->d_flags, h->n_envs, r == 0);
+      trex_front_kernel<WF><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+                                                           h->d_state, h->d_work, action, h->d_flags, h->n_envs, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
-        trex_solve_kernel<WARPS><<<grid4, 32 * WARPS, smem, st>>>(h->P, h->d_state, h->d_work, h->d_flags, h->n_envs);
+        trex_solve_kernel<WS><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_flags, h->n_envs);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
       }
     }
   }
-  trex_tail_kernel<WARPS><<<grid1, 32 * WARPS, smem, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane, h->d_state,
-                                                          obs, reward, done, h->d_aux, mask, h->n_envs, mode);
+  trex_tail_kernel<WF><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane, h->d_state,
+                                                      obs, reward, done, h->d_aux, mask, h->n_envs, mode);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return TREX_OK;
@@ -248,9 +250,9 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
 int dispatch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                   int mode, cudaStream_t st) {
   switch (h->warps_per_block) {
-    case 1: return launch_step<1>(h, action, obs, reward, done, mask, mode, st);
-    case 2: return launch_step<2>(h, action, obs, reward, done, mask, mode, st);
-    case 4: return launch_step<4>(h, action, obs, reward, done, mask, mode, st);
+    case 1: return launch_step<1, 2>(h, action, obs, reward, done, mask, mode, st);
+    case 2: return launch_step<2, 2>(h, action, obs, reward, done, mask, mode, st);
+    case 4: return launch_step<4, 4>(h, action, obs, reward, done, mask, mode, st);
     default: return fail(TREX_ERR_INVALID, "warps_per_block must be 1, 2 or 4%s");
   }
 }

@@ -94,6 +94,7 @@ struct Uniform {
   float reset_z_min, reset_z_max;  // reset_mode 1: base height range
   unsigned char order[2 * NJ];  // non-contact constraint order (Bullet's sorted constraint array)
   unsigned char depth[NB];      // tree depth per body
+  unsigned char max_children[MAX_DEPTH + 1];  // largest child count among the bodies of each depth
   unsigned char head_chain[MAX_DEPTH];  // lanes of the bodies from the base's child down to the head body
   int head_depth;
 };
@@ -458,14 +459,17 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
       pa[i] = pA[i] + (Ia[SI(i, 0)] * c0 + Ia[SI(i, 1)] * c1 + Ia[SI(i, 3)] * c3 + Ia[SI(i, 4)] * c4) + Ut[i] * s;
     vf Ip[21], pp[6];
     to_parent(E, r0, Ia, pa, Ip, pp);
-    // parents (depth d-1) gather from their children (all at depth d)
+    // parents (depth d-1) gather from their children (all at depth d); only as many child slots as any body
+    // of that depth has (tree constant), accumulated with a 0/1 mask through one FMA per element
     const vb parent_now = depth == (d - 1);
-    TREX_UNROLL for (int sidx = 0; sidx < 4; sidx++) {
+    const int nslots = P.max_children[d - 1];
+    TREX_ROLLED for (int sidx = 0; sidx < nslots; sidx++) {
       const vi cl = (children >> (6 * sidx)) & 63;
       const vb ok = parent_now && (cl != 63);
       const vi cls = seli(ok, cl, lane);
-      TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] += sel(ok, shflv(Ip[k], cls), 0.0f);
-      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, shflv(pp[k], cls), 0.0f);
+      const vf okf = sel(ok, 1.0f, 0.0f);
+      TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] = vfma(okf, shflv(Ip[k], cls), IA[k]);
+      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] = vfma(okf, shflv(pp[k], cls), pA[k]);
     }
   }
   TREX_UNROLL for (int k = 0; k < 6; k++) st(S.k.U[k], lane, U[k]);

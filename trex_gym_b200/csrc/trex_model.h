@@ -270,6 +270,13 @@ static inline void fill_uniform(const ModelTables& T, const EnvConfig& C, U& P) 
   P.reset_z_min = C.reset_z_min; P.reset_z_max = C.reset_z_max;
   for (int k = 0; k < 2 * trex_topo::NJ; k++) P.order[k] = (unsigned char)trex_topo::noncontact_order(k);
   for (int b = 0; b < trex_topo::NB; b++) P.depth[b] = (unsigned char)trex_topo::depth_of(b);
+  {
+    int nch[trex_topo::NB] = {0};
+    for (int b = 1; b < trex_topo::NB; b++) nch[trex_topo::parent_of(b)]++;
+    for (int d = 0; d <= trex_topo::MAX_DEPTH; d++) P.max_children[d] = 0;
+    for (int b = 0; b < trex_topo::NB; b++)
+      if (nch[b] > P.max_children[trex_topo::depth_of(b)]) P.max_children[trex_topo::depth_of(b)] = (unsigned char)nch[b];
+  }
   {  // bodies from the base's child down to the head body
     int chain[8], n = 0;
     for (int b = T.head_lane == 25 ? 0 : T.head_lane + 1; b > 0; b = trex_topo::parent_of(b)) chain[n++] = b;
