@@ -65,7 +65,7 @@ class EmuEnv:
         d, e, k = reward_weights
         self._h = self._L.emu_create(blob, len(blob), num_substeps, d, e, k, max_episode_steps, int(contacts), int(reset_mode), int(seed))
         self.env_id = int(env_id)
-        self._L.emu_set_deferred(self._h, int(bool(deferred)))
+        self._L.emu_set_deferred(self._h, int(deferred))  # bit 0: deferred solve, bit 1: pack lane groups in reverse
         if not self._h:
             raise RuntimeError(self._L.emu_last_error().decode())
         self.stride = self._L.emu_state_stride()

@@ -12,6 +12,7 @@ struct Emu {
   trex::WarpShared S;
   float work[4 * TREX_WORK_STRIDE];
   int deferred = 1;
+  int pack_reverse = 0;  // tests: fill the solver's lane groups from the top
 };
 
 static_assert(trex::F_COUNT == 32, "field table");
@@ -52,13 +53,14 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
   const int* cl = e->T.cand_lane.data();
   if (!force_reset) {
     for (int r = 0; r < e->P.n_sub; r++) {
-      uint8_t flags[4] = {0, 0, 0, 0};
+      // deferred environments are packed into the solver's lane groups in list order (any order is equivalent)
+      int envs[4] = {0, 0, 0, 0}, cnt = 0;
       for (int i = 0; i < n; i++)
-        trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
-                          e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, &flags[i], r == 0);
-      int pending = 0;
-      for (int i = 0; i < n; i++) pending |= (flags[i] ? 1 : 0) << i;
-      if (pending) trex::solve_phase(e->P, e->S, e->work, rec, pending);
+        if (trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
+                              e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0))
+          envs[e->pack_reverse ? 3 - cnt++ : cnt++] = i;
+      int pending = e->pack_reverse ? (((1 << cnt) - 1) << (4 - cnt)) : ((1 << cnt) - 1);
+      if (cnt) trex::solve_phase(e->P, e->S, e->work, rec, envs, pending);
     }
   }
   for (int i = 0; i < n; i++)
@@ -70,5 +72,5 @@ void emu_step(void* h, float* rec, const float* action, float* obs, float* rewar
               long long env_id) {
   emu_step4(h, 1, rec, action, obs, reward, done, aux, force_reset, env_id);
 }
-void emu_set_deferred(void* h, int on) { ((Emu*)h)->deferred = on; }
+void emu_set_deferred(void* h, int on) { ((Emu*)h)->deferred = on & 1; ((Emu*)h)->pack_reverse = (on >> 1) & 1; }
 }

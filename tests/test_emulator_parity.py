@@ -221,10 +221,12 @@ def test_four_environments_per_warp(model, action_limits):
     qlo, qhi = model["mb_lower"][1:], model["mb_upper"][1:]
     w4 = EmuWarp4(model.blob(), n=4)
     w1 = EmuWarp4(model.blob(), n=4, deferred=False)
+    wr = EmuWarp4(model.blob(), n=4, deferred=3)  # deferred environments packed into the lane groups in reverse
     o = _oracle(model)
     nc = o.num_candidates
     w4.reset()
     w1.reset()
+    wr.reset()
     rng = np.random.default_rng(11)
     for e in range(4):
         s = w4.get_state(e, nc)
@@ -253,7 +255,10 @@ def test_four_environments_per_warp(model, action_limits):
         # same inputs through the non-deferred path: agreement to rounding (different summation order)
         for e in range(4):
             w1.set_state(e, pre[e])
+            wr.set_state(e, pre[e])
         w1.step(acts)
+        wr.step(acts)
+        assert np.array_equal(wr.rec[:, :152], w4.rec[:, :152])  # lane-group assignment does not change a single bit
         for e in range(4):
             a, b = w4.get_state(e, nc), w1.get_state(e, nc)
             assert max(rel_err(a[sl], b[sl]) for sl in STATE_BLOCKS.values()) < 5e-3

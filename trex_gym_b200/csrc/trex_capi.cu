@@ -53,32 +53,33 @@ __global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
 trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
                   const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
                   float* __restrict__ state, float* __restrict__ work, const float* __restrict__ action,
-                  uint8_t* __restrict__ flags, int n_envs, int first_round) {
+                  int* __restrict__ list, int* __restrict__ list_count, int n_envs, int first_round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS + warp;
   if (env >= n_envs) return;
-  trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
-                    work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
-                    flags ? flags + env : nullptr, first_round != 0);
+  const bool deferred = trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
+                                          work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
+                                          first_round != 0);
+  // append to the list of deferred environments (any order: the solver's lane groups are independent)
+  if (deferred && (threadIdx.x & 31) == 0) list[atomicAdd(list_count, 1)] = env;
 }
 
-// one warp per FOUR consecutive environments: the deferred (contact-free) solves, eight lanes per environment
+// one warp per FOUR deferred (contact-free) environments taken from the list, eight lanes per environment
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, TREX_SOLVE_MIN_BLOCKS / WARPS)
 trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
-                  const uint8_t* __restrict__ flags, int n_envs) {
+                  const int* __restrict__ list, const int* __restrict__ list_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
   const int warp = threadIdx.x >> 5;
-  const int env0 = (blockIdx.x * WARPS + warp) * 4;
-  if (env0 >= n_envs) return;
-  const int n_valid = min(4, n_envs - env0);
-  int pending = 0;
-  for (int e = 0; e < n_valid; e++) pending |= (flags[env0 + e] != 0) << e;
-  if (pending == 0) return;
-  trex::solve_phase(P, slabs[warp], work + (size_t)env0 * TREX_WORK_STRIDE, state + (size_t)env0 * TREX_STATE_STRIDE, pending);
+  const int first = (blockIdx.x * WARPS + warp) * 4;
+  const int count = *list_count;
+  if (first >= count) return;
+  int envs[4] = {0, 0, 0, 0}, pending = 0;
+  for (int e = 0; e < 4 && first + e < count; e++) { envs[e] = list[first + e]; pending |= 1 << e; }
+  trex::solve_phase(P, slabs[warp], work, state, envs, pending);
 }
 
 // one warp per environment: reward / done / auto-reset / observations (mode 0), or reset only (mode 1, optional mask)
@@ -195,7 +196,8 @@ struct trex_handle {
   // staging for the host-buffer entry points
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   uint8_t* d_done = nullptr;
-  uint8_t* d_flags = nullptr;  // per environment: this substep's solve was deferred to trex_solve_kernel
+  int* d_list = nullptr;        // environments whose solve was deferred in the current substep round
+  int* d_list_count = nullptr;  // [64] one counter per substep round
   DevStats* d_stats = nullptr;
   int64_t launches = 0;
   int64_t env_steps = 0;
@@ -228,13 +230,14 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
   const int grid1 = (h->n_envs + WF - 1) / WF;            // one warp per environment
   const int grid4 = (h->n_envs + 4 * WS - 1) / (4 * WS);  // one warp per four environments
   if (mode == 0) {
+    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 64 * sizeof(int), st));  // one counter per substep round
     for (int r = 0; r < h->P.n_sub; r++) {
       trex_front_kernel<WF><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
-                                                           h->d_state, h->d_work, action, h->d_flags, h->n_envs, r == 0);
+                                                           h->d_state, h->d_work, action, h->d_list, h->d_list_count + r, h->n_envs, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
-        trex_solve_kernel<WS><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_flags, h->n_envs);
+        trex_solve_kernel<WS><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
       }
@@ -292,7 +295,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     return rc;
   }
   if (cfg) {
-    h->C.num_substeps = cfg->num_substeps > 0 ? cfg->num_substeps : 5;
+    h->C.num_substeps = cfg->num_substeps > 0 ? (cfg->num_substeps > 64 ? 64 : cfg->num_substeps) : 5;
     h->C.distance_weight = cfg->distance_weight; h->C.energy_weight = cfg->energy_weight; h->C.drift_weight = cfg->drift_weight;
     h->C.max_episode_steps = cfg->max_episode_steps; h->C.enable_contacts = cfg->enable_contacts;
     h->C.reset_mode = cfg->reset_mode; h->C.seed = cfg->seed;
@@ -321,8 +324,9 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   CTRY(cudaMalloc((void**)&h->d_obs, N * 3 * trex::NJ * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_reward, N * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_done, N));
-  CTRY(cudaMalloc((void**)&h->d_flags, N));
-  CTRY(cudaMemset(h->d_flags, 0, N));
+  CTRY(cudaMalloc((void**)&h->d_list, N * sizeof(int)));
+  CTRY(cudaMalloc((void**)&h->d_list_count, 64 * sizeof(int)));
+  CTRY(cudaMemset(h->d_list_count, 0, 64 * sizeof(int)));
   CTRY(cudaMalloc((void**)&h->d_stats, sizeof(DevStats)));
 #undef CTRY
   // all environments start from the reference reset (TrexBulletEnv.__init__ calls reset(), trex_env.py:92)
@@ -340,7 +344,7 @@ void trex_destroy(trex_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_mdl); cudaFree(h->d_mdli); cudaFree(h->d_tasks); cudaFree(h->d_cand_p); cudaFree(h->d_cand_lane);
-  cudaFree(h->d_work); cudaFree(h->d_flags);
+  cudaFree(h->d_work); cudaFree(h->d_list); cudaFree(h->d_list_count);
   cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_action);
   cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_stats);
   delete h;

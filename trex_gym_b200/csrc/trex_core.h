@@ -1104,11 +1104,13 @@ TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared&
 // Returns the number of solver iterations each group executed (per lane of the group).
 // ------------------------------------------------------------------------------------------
 #define TREX_GS_STRIDE 648  // floats per group in the shared stash of g (25*25 = 625, padded: bank offset 8 per group)
-TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* rec0, int pending, float max_imp) {
+// envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
+TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* rec0, const int envs[4], int pending, float max_imp) {
   const vi lane = lane_id();
   const vi grp = lane >> 3, gl = lane & 7;
   const vb gact = ((vi(pending) >> grp) & 1) != 0;
-  const vi woff = grp * TREX_WORK_STRIDE, roff = grp * TREX_STATE_STRIDE;
+  const vi genv = seli(grp == 0, vi(envs[0]), seli(grp == 1, vi(envs[1]), seli(grp == 2, vi(envs[2]), vi(envs[3]))));
+  const vi woff = seli(gact, genv, 0) * TREX_WORK_STRIDE, roff = seli(gact, genv, 0) * TREX_STATE_STRIDE;
   const float dt = P.dt;
   float* Gs = reinterpret_cast<float*>(&S.c);          // [4][TREX_GS_STRIDE]: g[k][j] at j*25 + k
   float* Lam = Gs + 4 * TREX_GS_STRIDE;                // [4][32]: net joint impulses, exchanged once per sweep
@@ -1263,7 +1265,7 @@ TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* re
     st_if(rec0, roff + kk[s] + ST_TAU, vdiv(lam_m[s], dt), kv[s]);
   }
   {
-    const vi rb = seli(gact, roff, 0);
+    const vi rb = roff;
     vf om[3], vl[3], pos[3], qt[4];
     TREX_UNROLL for (int k = 0; k < 3; k++) {
       om[k] = clampv(ld(rec0, rb + (ST_OM + k)) + dvb[k], -P.maxvel, P.maxvel);
@@ -1351,10 +1353,9 @@ enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // p
 // front_phase: one physics substep of ONE environment by one warp up to the solve: kinematics, bias forces,
 // articulated inertias, accelerations, velocity update, M^-1, row setup, contact detection.  With contacts
 // the substep is finished here (one-environment solver + integration); without, the solver inputs go to
-// `work` and *flag = 1 (solve_phase finishes the substep).   action: [25] name-sorted (trex_robot.py:311-314)
-TREX_FN void front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
-                         const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, uint8_t* flag,
-                         bool first_round) {
+// `work` and the function returns true (solve_phase finishes the substep).   action: [25] name-sorted (trex_robot.py:311-314)
+TREX_FN bool front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+                         const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, bool first_round) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vi slot = seli(is_joint, MDLI(IF_OBS_SLOT), 0);
@@ -1377,17 +1378,18 @@ TREX_FN void front_phase(const Uniform& P, const float* mdl, const int* mdli, co
   acc = sel(lane == 2, vbroadcast(ov0 + (float)st.overflow), acc);
   warp_sync();
   st_if(rec, lane + ST_ACC_ITERS, acc, lane < 3);
-  if (flag) st_u8_if(flag, vi(0), vi(deferred ? 1 : 0), lane == 0);
+  return deferred;
 }
 
-// solve_phase: the deferred solves of four consecutive environments (pending bit e <=> environment e deferred)
-TREX_FN void solve_phase(const Uniform& P, WarpShared& S, const float* work0, float* rec0, int pending) {
+// solve_phase: the deferred solves of up to four environments (any four: the groups are independent)
+TREX_FN void solve_phase(const Uniform& P, WarpShared& S, const float* work0, float* rec0, const int envs[4], int pending) {
   const vi lane = lane_id();
-  const vi itd = solve4(P, S, work0, rec0, pending, P.max_impulse);
+  const vi itd = solve4(P, S, work0, rec0, envs, pending, P.max_impulse);
   // iterations executed per environment -> its accumulator (lane 8e holds group e's count)
   const vi grp = lane >> 3;
   const vb wr = ((lane & 7) == 0) && ((((vi(pending)) >> grp) & 1) != 0);
-  const vi idx = seli(wr, grp * TREX_STATE_STRIDE + ST_ACC_ITERS, 0);
+  const vi genv = seli(grp == 0, vi(envs[0]), seli(grp == 1, vi(envs[1]), seli(grp == 2, vi(envs[2]), vi(envs[3]))));
+  const vi idx = seli(wr, genv * TREX_STATE_STRIDE + ST_ACC_ITERS, 0);
   st_if(rec0, idx, ld(rec0, idx) + vi2f(itd), wr);
 }
 
