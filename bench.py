@@ -242,7 +242,15 @@ def run_ours(args):
         tf = _native.ctypes.c_double(0.0)
         _native.check(_native.lib().trex_measure_fp32_peak(local, _native.ctypes.byref(tf)), "trex_measure_fp32_peak")
         fp32_peak = float(tf.value)
-        kernel_ms = dev_ms / args.steps  # one launch of trex_step_kernel per step (rank 0's own device time)
+        kernel_ms = dev_ms / args.steps  # all kernels of one env step (rank 0's own device time)
+        traffic = None
+        try:  # DRAM bytes per env step from the committed ncu capture (same batch size only)
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)
+            if tr["envs"] == n and sim.num_substeps == 5:
+                traffic = sum(tr["per_launch_bytes"][k] * tr["launches_per_step"][k] for k in tr["per_launch_bytes"])
+        except Exception:  # noqa: BLE001
+            pass
         flops = f_alg(sim.num_substeps, it_sum, ct_sum) * n
         achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
         hbm_gbs = B_ALG * n / (kernel_ms * 1e-3) / 1e9
@@ -260,7 +268,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak if fp32_peak else None,
-                         "traffic": None, "kernel": "trex_step_kernel", "kernel_ms": kernel_ms,
+                         "traffic": traffic,
+                         "kernel": "one env step = %d x (trex_front_kernel, trex_solve_kernel) + trex_tail_kernel; trex_front_kernel is ~80%% of the device time (profiles/r1_launches.txt)" % sim.num_substeps,
+                         "kernel_ms": kernel_ms,
                          "peak_source": "measured in this run: register-resident FFMA microbenchmark (trex_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                          "flops_per_env_step": f_alg(sim.num_substeps, it_sum, ct_sum),
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "bytes_per_env_step": B_ALG, "peak_source": hbm_src}},
