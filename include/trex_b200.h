@@ -121,6 +121,14 @@ int trex_get_stats(trex_handle* h, trex_stats* out); /* synchronises the device 
 /* Measurement aid (no reference counterpart): register-resident FFMA microbenchmark, best of 5, in
  * TFLOP/s -- the FP32 CUDA-core roofline denominator for this path.  Synchronises. */
 int trex_measure_fp32_peak(int32_t device, double* tflops_out);
+/* Rollout post-processing for the caller of the path (trex_train.py:49-61 -> baselines ppo2.Runner [RECALL]); buffers
+ * are time-major [T][N] on the device.  done_dev[t] = episode-start flag of the state step t acted in, last_done closes it.
+ *   A_t = delta_t + gamma*lam*(1-done_{t+1})*A_{t+1},  delta_t = r_t + gamma*V_{t+1}*(1-done_{t+1}) - V_t,  ret = A + V  */
+int trex_gae(int32_t device, const float* reward_dev, const float* value_dev, const uint8_t* done_dev, const float* last_value_dev,
+             const uint8_t* last_done_dev, float gamma, float lam, float* adv_dev, float* ret_dev, int32_t T, int32_t N, void* stream);
+/* baselines VecNormalize (trex_train.py:45): out = clip((x - mean) / sqrt(var + eps), -clip, clip), x [n_rows][dim] */
+int trex_normalize(int32_t device, const float* x_dev, const float* mean_dev, const float* var_dev, float eps, float clip,
+                   float* out_dev, int64_t n_rows, int32_t dim, void* stream);
 int64_t trex_kernel_launches(const trex_handle* h);  /* kernels launched by this handle so far */
 int32_t trex_num_envs(const trex_handle* h);
 const char* trex_last_error(void);

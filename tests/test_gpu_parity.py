@@ -305,3 +305,42 @@ def test_contact_stress_fallen_starts(model):
     # orientation is a unit quaternion, height within the sampler's range minus one free-fall step
     assert np.abs(np.linalg.norm(a[:, 3:7], axis=1) - 1).max() < 1e-5
     assert (a[:, 2] > 0.29).all() and (a[:, 2] < 3.01).all()
+
+
+def test_rollout_buffers_and_gae(model):
+    """BASELINE.json configs[3] plumbing: in-place rollout collection with auto-reset and the
+    GAE kernel, bit-exact against the baselines recursion evaluated in float32 numpy."""
+    import torch
+
+    from trex_gym_b200.rollout import RolloutBuffer, RunningMeanStd, normalize
+
+    T, N = 24, 256
+    sim = _sim(model, N, max_episode_steps=10, distance_weight=200.0, energy_weight=1e-6, drift_weight=1.0)
+    sim.reset()
+    buf = RolloutBuffer(sim, T)
+    buf.collect(policy=None, seed=4)
+    d = buf.dones.cpu().numpy()
+    assert d[10].all() and d[20].all() and not d[1:10].any() and not d[11:20].any()
+    assert torch.isfinite(buf.obs).all().item() and torch.isfinite(buf.rewards).all().item()
+    assert (buf.obs[10] == buf.obs[20]).all().item()  # both are the (deterministic) reset observation
+    g = torch.Generator(device="cpu").manual_seed(0)
+    buf.values.copy_(torch.randn(T, N, generator=g).cuda())
+    last_v = torch.randn(N, generator=g).cuda()
+    adv, ret = buf.compute_gae(last_v, gamma=0.99, lam=0.95)
+    f = np.float32
+    r, v, dn = buf.rewards.cpu().numpy(), buf.values.cpu().numpy(), d
+    exp = np.zeros((T, N), np.float32)
+    a = np.zeros(N, np.float32)
+    for t in reversed(range(T)):
+        nonterm = (f(1.0) - dn[t + 1].astype(np.float32)).astype(np.float32)
+        nv = last_v.cpu().numpy() if t == T - 1 else v[t + 1]
+        delta = ((r[t] + (f(0.99) * nv) * nonterm).astype(np.float32) - v[t]).astype(np.float32)
+        a = (delta + ((f(0.99) * f(0.95)) * nonterm).astype(np.float32) * a).astype(np.float32)
+        exp[t] = a
+    assert np.array_equal(adv.cpu().numpy(), exp)
+    assert np.array_equal(ret.cpu().numpy(), (exp + v).astype(np.float32))
+    rms = RunningMeanStd(75, sim.device)
+    rms.update(buf.obs[:T])
+    z = normalize(buf.obs[:T], rms)
+    ref = torch.clamp((buf.obs[:T] - rms.mean.float()) / torch.sqrt(rms.var.float() + 1e-8), -10, 10)
+    assert torch.allclose(z, ref, atol=1e-5) and z.abs().max().item() <= 10.0

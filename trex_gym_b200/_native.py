@@ -21,7 +21,7 @@ AUX_DIM = 8
 EXPORTED_SYMBOLS = (
     "trex_create", "trex_destroy", "trex_reset", "trex_step", "trex_step_host", "trex_reset_host",
     "trex_get_state", "trex_set_state", "trex_get_aux", "trex_get_joint_limits",
-    "trex_fill_random_actions", "trex_get_stats", "trex_measure_fp32_peak", "trex_kernel_launches", "trex_num_envs",
+    "trex_fill_random_actions", "trex_get_stats", "trex_measure_fp32_peak", "trex_gae", "trex_normalize", "trex_kernel_launches", "trex_num_envs",
     "trex_last_error", "trex_version",
 )
 
@@ -110,6 +110,10 @@ def lib():
     L.trex_get_stats.argtypes = [vp, ctypes.POINTER(TrexStats)]
     L.trex_measure_fp32_peak.restype = ctypes.c_int
     L.trex_measure_fp32_peak.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
+    L.trex_gae.restype = ctypes.c_int
+    L.trex_gae.argtypes = [ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
+    L.trex_normalize.restype = ctypes.c_int
+    L.trex_normalize.argtypes = [ctypes.c_int32, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, ctypes.c_int64, ctypes.c_int32, vp]
     L.trex_kernel_launches.restype = ctypes.c_int64
     L.trex_kernel_launches.argtypes = [vp]
     L.trex_num_envs.restype = ctypes.c_int32

@@ -151,6 +151,46 @@ trex_ffma_peak_kernel(float* out, int iters, float a, float b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rollout post-processing (caller of the path: trex_train.py:49-61, baselines ppo2 Runner):
+// generalised advantage estimation over a [T][N] rollout, one thread per environment, reverse scan over time
+// (loads/stores coalesced across environments).
+//   delta_t = r_t + gamma * V_{t+1} * (1 - done_{t+1}) - V_t ;  A_t = delta_t + gamma * lam * (1 - done_{t+1}) * A_{t+1}
+// done_in[t] is the flag of the state the action of step t was taken in (baselines convention: mb_dones[t] =
+// dones BEFORE step t; last_done closes the rollout), returns = A + V.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+trex_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done_in,
+                const float* __restrict__ last_val, const uint8_t* __restrict__ last_done, float gamma, float lam,
+                float* __restrict__ adv, float* __restrict__ ret, int T, int N) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  float next_val = last_val[e];
+  float next_nonterminal = 1.0f - (float)(last_done[e] != 0);
+  float a = 0.0f;
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t i = (size_t)t * N + e;
+    const float v = val[i];
+    const float delta = __fadd_rn(__fadd_rn(rew[i], __fmul_rn(__fmul_rn(gamma, next_val), next_nonterminal)), -v);
+    a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gamma, lam), next_nonterminal), a));
+    adv[i] = a;
+    ret[i] = __fadd_rn(a, v);
+    next_val = v;
+    next_nonterminal = 1.0f - (float)(done_in[i] != 0);
+  }
+}
+
+// VecNormalize-style observation normalisation (baselines VecNormalize: clip((obs - mean) / sqrt(var + eps), -clip, clip))
+__global__ void __launch_bounds__(256)
+trex_normalize_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                      float clip, float* __restrict__ out, int64_t n_rows, int dim) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  const int d = (int)(i % dim);
+  const float z = (x[i] - mean[d]) / sqrtf(var[d] + eps);
+  out[i] = fminf(fmaxf(z, -clip), clip);
+}
+
 struct DevStats {
   double steps, episodes, nan_resets, iters, contacts, overflow;
 };
@@ -448,6 +488,27 @@ int trex_get_stats(trex_handle* h, trex_stats* out) {
   out->mean_solver_iterations = s.iters / ((double)h->n_envs * h->P.n_sub);
   out->mean_contacts = s.contacts / (double)h->n_envs;
   out->contact_overflow = (int64_t)s.overflow;
+  return TREX_OK;
+}
+
+int trex_gae(int32_t device, const float* reward_dev, const float* value_dev, const uint8_t* done_dev, const float* last_value_dev,
+             const uint8_t* last_done_dev, float gamma, float lam, float* adv_dev, float* ret_dev, int32_t T, int32_t N, void* stream) {
+  if (!reward_dev || !value_dev || !done_dev || !last_value_dev || !last_done_dev || !adv_dev || !ret_dev || T <= 0 || N <= 0)
+    return fail(TREX_ERR_INVALID, "trex_gae: NULL buffer or empty rollout%s");
+  CUDA_TRY(cudaSetDevice(device));
+  trex_gae_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reward_dev, value_dev, done_dev, last_value_dev, last_done_dev, gamma,
+                                                                    lam, adv_dev, ret_dev, T, N);
+  CUDA_TRY(cudaGetLastError());
+  return TREX_OK;
+}
+
+int trex_normalize(int32_t device, const float* x_dev, const float* mean_dev, const float* var_dev, float eps, float clip,
+                   float* out_dev, int64_t n_rows, int32_t dim, void* stream) {
+  if (!x_dev || !mean_dev || !var_dev || !out_dev || n_rows <= 0 || dim <= 0) return fail(TREX_ERR_INVALID, "trex_normalize: bad argument%s");
+  CUDA_TRY(cudaSetDevice(device));
+  const int64_t n = n_rows * dim;
+  trex_normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, mean_dev, var_dev, eps, clip, out_dev, n_rows, dim);
+  CUDA_TRY(cudaGetLastError());
   return TREX_OK;
 }
 
