@@ -165,3 +165,6 @@ TREX_FN void philox4_uniform(const vi& c0, const vi& c1, const vi& c2, const vi&
 TREX_FN vf shfl_group8(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~7) | (src & 7)]; return r; }
 TREX_FN vf group8_sum(vf x) { for (int m = 4; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN vf group8_max(vf x) { for (int m = 4; m > 0; m >>= 1) x = vmax(x, shfl_xor(x, m)); return x; }
+
+TREX_FN void st16(float* p, const vi& idx, const vf v[16]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 16; k++) p[idx.v[l] + k] = v[k].v[l]; }
+TREX_FN void ldu16(const float* p, int idx, float out[16]) { for (int k = 0; k < 16; k++) out[k] = p[idx + k]; }

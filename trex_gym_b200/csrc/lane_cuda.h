@@ -101,3 +101,14 @@ TREX_FN void philox4_uniform(vi c0, vi c1, vi c2, vi c3, uint32_t k0, uint32_t k
 TREX_FN vf shfl_group8(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 8); }
 TREX_FN vf group8_sum(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
 TREX_FN vf group8_max(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(TREX_FULL, x, m)); return x; }
+
+// 16 consecutive floats (64-byte aligned offset): per-lane store / uniform load as four 128-bit accesses
+TREX_FN void st16(float* p, vi idx, const vf v[16]) {
+  float4* q = reinterpret_cast<float4*>(p + idx);
+  q[0] = make_float4(v[0], v[1], v[2], v[3]); q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  q[2] = make_float4(v[8], v[9], v[10], v[11]); q[3] = make_float4(v[12], v[13], v[14], v[15]);
+}
+TREX_FN void ldu16(const float* p, int idx, float out[16]) {
+  const float4* q = reinterpret_cast<const float4*>(p + idx);
+  TREX_UNROLL for (int i = 0; i < 4; i++) { const float4 t = q[i]; out[4 * i] = t.x; out[4 * i + 1] = t.y; out[4 * i + 2] = t.z; out[4 * i + 3] = t.w; }
+}

@@ -101,7 +101,7 @@ struct Uniform {
 
 // per-warp shared memory slab.  The kinematics-phase arrays (k) and the contact-row arrays (c) are
 // never live at the same time and share storage; ~15.7 KB per warp at KMAX = 20 -> 14 warps per SM.
-struct WarpShared {
+struct alignas(16) WarpShared {
   float col[31][32];  // M^-1: col[g][lane] = entry g of the column owned by `lane`
   float tmp[1][32];   // staging: motor impulses / per-joint power
   float lam_cache[TREX_NCAND_MAX];
@@ -115,6 +115,7 @@ struct WarpShared {
       float invD[32];
       float Rw[9][32];    // world -> body rotation
       float xw[3][32];    // body origin, world
+      float pack[32][16]; // per body lane: E (9), U (6), invD -- the same data body-major, for 128-bit broadcast loads
     } k;
     struct {
       float dV[3 * TREX_KMAX][32];   // rows 3*c + {0 normal, 1 t1, 2 t2}: M^-1 J^T, indexed by lane
@@ -124,7 +125,7 @@ struct WarpShared {
   };
 };
 // link-damping partial wrenches live in dV rows beyond the kinematics-phase arrays
-#define TREX_PART_ROW 28
+#define TREX_PART_ROW 44
 static_assert(sizeof(((WarpShared*)0)->k) <= TREX_PART_ROW * 128, "partials must not overlap the kinematics arrays");
 static_assert(3 * TREX_KMAX >= TREX_PART_ROW + 6, "KMAX too small for the damping scratch");
 
@@ -474,6 +475,13 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
   }
   TREX_UNROLL for (int k = 0; k < 6; k++) st(S.k.U[k], lane, U[k]);
   st(S.k.invD, lane, invD);
+  {
+    vf pk[16];
+    TREX_UNROLL for (int k = 0; k < 9; k++) pk[k] = E[k];
+    TREX_UNROLL for (int k = 0; k < 6; k++) pk[9 + k] = U[k];
+    pk[15] = invD;
+    st16(&S.k.pack[0][0], lane * 16, pk);
+  }
 
   TREX_TICK(2)
   // ---- 6. base acceleration --------------------------------------------------------------------
@@ -593,10 +601,11 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
     TREX_ROLLED for (int b = 1; b < NB; b++) {
       const int bl = b - 1;
       const int dep = P.depth[b];
-      float Eb[9], Ub[6];
-      TREX_UNROLL for (int k = 0; k < 9; k++) Eb[k] = ldu(S.k.E[k], bl);
-      TREX_UNROLL for (int k = 0; k < 6; k++) Ub[k] = ldu(S.k.U[k], bl);
-      const float iDb = ldu(S.k.invD, bl);
+      float pk[16];
+      ldu16(&S.k.pack[0][0], bl * 16, pk);  // four 128-bit broadcast loads
+      const float* Eb = pk;
+      const float* Ub = pk + 9;
+      const float iDb = pk[15];
       const float rx = P.r0[b][0], ry = P.r0[b][1], rz = P.r0[b][2];
       const vb onpath = ((anc >> bl) & 1) != 0;
       vf ddq = 0.0f;
@@ -1160,10 +1169,8 @@ TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* re
     constexpr int j = trex_topo::noncontact_order(K) - NJ;                                             \
     constexpr int sj = j >> 3;                                                                         \
     const vf nl = vmin(vmax(w[sj], -max_imp), max_imp);                                                \
-    const vb own = alive && (gl == (j & 7));                                                           \
-    const vf d = sel(own, nl - lam_m[sj], 0.0f);                                                       \
-    const vf db = shfl_group8(d, j & 7);                                                               \
-    lam_m[sj] = sel(own, nl, lam_m[sj]);                                                               \
+    const vf db = shfl_group8(nl - lam_m[sj], j & 7);   /* only the owner's value is read */           \
+    lam_m[sj] = sel(gl == (j & 7), nl, lam_m[sj]);                                                     \
     TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(g[s][j], db, w[s]);                            \
   }
   // one limit row of joint j (slot SJ static): sigma = +1 lower row, -1 upper row, impulse in [0, lim_hi]
@@ -1198,7 +1205,11 @@ TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* re
 #define M_(k) TREX_S4_MOTOR(k)
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
     vf lam_m0[4], lam_l0[4];
-    TREX_UNROLL for (int s = 0; s < 4; s++) { lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s]; }
+    TREX_UNROLL for (int s = 0; s < 4; s++) {
+      lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s];
+      // an environment that has finished (converged) is frozen: clamp(w) == its impulse, so every row yields 0
+      w[s] = sel(alive, w[s], lam_m[s]);
+    }
     if (it & 1) {
       M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7) M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16)
       M_(17) M_(18) M_(19) M_(20) M_(21) M_(22) M_(23) M_(24)
@@ -1218,17 +1229,20 @@ TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* re
     itd = itd + seli(alive, vi(1), vi(0));
     alive = alive && !(r <= P.resid_thresh) && (it < P.iters - 1);
     if (!vany(alive)) break;
-    // rebuild w exactly from the impulses: w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j
-    warp_sync();
-    TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * 32 + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
-    warp_sync();
-    vf acc[4];
-    TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = rhs_m[s] - sigma[s] * lam_l[s];
-    TREX_UNROLL for (int j = 0; j < NJ; j++) {
-      const vf Lj = ld(Lam, grp * 32 + j);
-      TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
+    // every 4th sweep rebuild w exactly from the impulses (bounds the FP32 drift of the incremental updates):
+    // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j
+    if ((it & 3) == 3) {
+      warp_sync();
+      TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * 32 + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+      warp_sync();
+      vf acc[4];
+      TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = rhs_m[s] - sigma[s] * lam_l[s];
+      TREX_UNROLL for (int j = 0; j < NJ; j++) {
+        const vf Lj = ld(Lam, grp * 32 + j);
+        TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
+      }
+      TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = sel(alive, acc[s], w[s]);
     }
-    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = sel(alive, acc[s], w[s]);
   }
 #undef M_
 #undef TREX_S4_MOTOR
