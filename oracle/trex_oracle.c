@@ -173,7 +173,7 @@ static void solve6(const double A[36], const sv b, sv x) {
 enum {
   P_TIME_STEP, P_SOLVER_ITERS, P_NUM_SUBSTEPS, P_GRAVITY, P_KP, P_KD, P_MAX_TORQUE, P_LIN_DAMP, P_ANG_DAMP,
   P_MAX_COORD_VEL, P_ERP, P_CONTACT_ERP, P_SPLIT_THRESH, P_LINEAR_SLOP, P_RESIDUAL, P_WARMSTART, P_FRICTION,
-  P_BREAKING, P_FLOOR, P_LIMIT_MAX_IMPULSE, P_RESET_HEIGHT, P_TARGET_HEIGHT, P_COUNT
+  P_BREAKING, P_FLOOR, P_LIMIT_MAX_IMPULSE, P_RESET_HEIGHT, P_TARGET_HEIGHT, P_MAX_CONTACTS, P_COUNT
 };
 
 typedef struct {
@@ -656,11 +656,33 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
   row_t* nrm = rows + n_nc;
   const v3 nz = {0, 0, 1}, t1 = {0, -1, 0}, t2 = {1, 0, 0};
   if (o->contacts_on) {
+    /* contact capacity (definition N2, shared with the kernels): at most max_contacts points have rows; when more
+     * candidates are inside the breaking distance the deepest ones are kept (ties by candidate index) */
+    int keep[MAXC];
+    double zc[MAXC];
+    int n_in = 0;
+    for (int c = 0; c < o->ncand; c++) {
+      v3 P;
+      candidate_world(o, c, P);
+      zc[c] = P[2];
+      keep[c] = (P[2] - o->P[P_FLOOR]) < o->P[P_BREAKING];
+      n_in += keep[c];
+    }
+    const int cap = (int)o->P[P_MAX_CONTACTS];
+    if (n_in > cap) {
+      for (int c = 0; c < o->ncand; c++) {
+        if (!keep[c]) continue;
+        int better = 0;
+        for (int c2 = 0; c2 < o->ncand; c2++)
+          if (c2 != c && (zc[c2] - o->P[P_FLOOR]) < o->P[P_BREAKING] && (zc[c2] < zc[c] || (zc[c2] == zc[c] && c2 < c))) better++;
+        if (better >= cap) keep[c] = 0;
+      }
+    }
     for (int c = 0; c < o->ncand; c++) {
       v3 P;
       candidate_world(o, c, P);
       double dist = P[2] - o->P[P_FLOOR];
-      if (!(dist < o->P[P_BREAKING])) { o->lam_cache[c] = 0; continue; }
+      if (!keep[c]) { o->lam_cache[c] = 0; continue; }
       row_t* r = &nrm[n_normal++];
       point_jacobian(o, o->cand_link[c], P, nz, r->J);
       r->cand = c; r->motor_dof = -1; r->fric_index = -1;

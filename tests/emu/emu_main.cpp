@@ -11,6 +11,7 @@ struct Emu {
   trex::Uniform P;
   trex::WarpShared S;
   float work[4 * TREX_WORK_STRIDE];
+  float scratch[TREX_SOLVE_SCRATCH];
   int deferred = 1;
   int pack_reverse = 0;  // tests: fill the solver's lane groups from the top
 };
@@ -26,6 +27,11 @@ void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, 
   Emu* e = new Emu();
   if (!trex_host::build_tables(blob, bytes, e->T, trex::F_COUNT, trex::IF_COUNT)) {
     snprintf(g_err, sizeof g_err, "%s", e->T.err.c_str());
+    delete e;
+    return nullptr;
+  }
+  if ((int)e->T.params[trex_host::P_MAX_CONTACTS] != TREX_KMAX) {
+    snprintf(g_err, sizeof g_err, "model max_contacts != TREX_KMAX");
     delete e;
     return nullptr;
   }
@@ -60,7 +66,7 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
                               e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0))
           envs[e->pack_reverse ? 3 - cnt++ : cnt++] = i;
       int pending = e->pack_reverse ? (((1 << cnt) - 1) << (4 - cnt)) : ((1 << cnt) - 1);
-      if (cnt) trex::solve_phase(e->P, e->S, e->work, rec, envs, pending);
+      if (cnt) trex::solve_phase(e->P, e->scratch, e->work, rec, envs, pending);
     }
   }
   for (int i = 0; i < n; i++)

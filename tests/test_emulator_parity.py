@@ -75,6 +75,52 @@ def test_per_substep_parity_with_contacts(model, emu_cls, action_limits):
     assert np.percentile(errs, 50) < 2e-5 and np.percentile(errs, 99) < 2e-3, (np.percentile(errs, 50), errs.max())
 
 
+def test_contact_capacity_keeps_the_deepest_points(model, emu_cls, action_limits):
+    """More candidates inside the breaking distance than contact slots (model parameter max_contacts): kernel and
+    oracle keep the same, deepest points (definition N2), so single substeps still agree."""
+    from trex_gym_b200.model_compiler import with_params
+
+    lo, hi = action_limits
+    params = dict(zip(model.meta["param_names"], model["param_values"]))
+    cap = int(params["max_contacts"])
+    sub = with_params(model, time_step=0.002, solver_iterations=60)
+    e, o = emu_cls(sub.blob(), num_substeps=1), _oracle(sub, num_substeps=1)
+    nc = o.num_candidates
+    e.reset()
+    rng = np.random.default_rng(23)
+    n_over, errs = 0, []
+    for trial in range(12):
+        e.reset()
+        s = e.get_state(nc)
+        # lay the robot on its side just above the floor: most candidate points come into range
+        ang = rng.uniform(-0.2, 0.2)
+        s[3:7] = [np.sin((np.pi / 2 + ang) / 2), 0.0, 0.0, np.cos((np.pi / 2 + ang) / 2)]
+        s[13:38] = np.clip(s[13:38] + rng.uniform(-0.2, 0.2, 25), model["mb_lower"][1:], model["mb_upper"][1:])
+        o.set_state(s)
+        z = np.array([o.candidate_position(k)[2] for k in range(nc)])
+        s[2] += params["floor_height"] + 0.005 - np.sort(z)[min(cap + 3, nc - 1)]  # cap+4 points at or below 5 mm
+        s[88:152] = 0.0
+        e.set_state(s)
+        for t in range(4):
+            a = rng.uniform(lo, hi)
+            pre = e.get_state(nc)
+            o.set_state(pre)
+            z = np.array([o.candidate_position(k)[2] for k in range(nc)])
+            in_range = int(((z - params["floor_height"]) < params["contact_breaking_threshold"]).sum())
+            o.step(a)
+            e.step(a)
+            over = int(e.aux[7]) // 1000
+            assert over == max(0, in_range - cap), (trial, t, over, in_range)
+            assert int(e.aux[7]) % 1000 == o.last_num_contacts == min(in_range, cap)
+            so, se = o.get_state(), e.get_state(nc)
+            if over:
+                n_over += 1
+                errs.append(max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()))
+    assert n_over >= 10
+    errs = np.asarray(errs)
+    assert np.percentile(errs, 50) < 5e-5 and errs.max() < 5e-3, (np.percentile(errs, 50), errs.max())
+
+
 def test_standing_drop_matches_oracle_qualitatively(model, emu_cls):
     """Free-running (no re-seeding) hold-pose drop: both land on the feet and stand at the same height."""
     e, o = emu_cls(model.blob()), _oracle(model)
@@ -250,7 +296,7 @@ def test_four_environments_per_warp(model, action_limits):
             saw_limit |= o.last_num_limit_rows > 0
             assert err < (5e-3 if contact else 1e-4), (t, e, err, contact)  # wild perturbed states: up to 4e-5 contact-free
             assert abs(orew - rew[e]) < (5e-3 if contact else 1e-4) * max(1.0, abs(orew))
-            assert int(w4.aux[e, 7]) == o.last_num_contacts
+            assert int(w4.aux[e, 7]) % 1000 == o.last_num_contacts  # + 1000 x points over capacity
             assert w4.aux[e, 6] == 300
         # same inputs through the non-deferred path: agreement to rounding (different summation order)
         for e in range(4):

@@ -72,14 +72,14 @@ __global__ void __launch_bounds__(32 * WARPS, TREX_SOLVE_MIN_BLOCKS / WARPS)
 trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
                   const int* __restrict__ list, const int* __restrict__ list_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
+  float* scratch = reinterpret_cast<float*>(smem_raw) + (threadIdx.x >> 5) * TREX_SOLVE_SCRATCH;
   const int warp = threadIdx.x >> 5;
   const int first = (blockIdx.x * WARPS + warp) * 4;
   const int count = *list_count;
   if (first >= count) return;
   int envs[4] = {0, 0, 0, 0}, pending = 0;
   for (int e = 0; e < 4 && first + e < count; e++) { envs[e] = list[first + e]; pending |= 1 << e; }
-  trex::solve_phase(P, slabs[warp], work, state, envs, pending);
+  trex::solve_phase(P, scratch, work, state, envs, pending);
 }
 
 // one warp per environment: reward / done / auto-reset / observations (mode 0), or reset only (mode 1, optional mask)
@@ -258,7 +258,7 @@ int configure_kernel(K kernel, size_t smem) {
 template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
-  const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(trex::WarpShared) * WS;
+  const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH * WS;
   static bool configured[16] = {false};
   if (!configured[h->device & 15]) {
     int rc;
@@ -342,6 +342,11 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     h->C.env_offset = ((long long)cfg->reserved[2] << 32) | (unsigned)cfg->reserved[1];
     if (cfg->reserved[0] == 1 || cfg->reserved[0] == 2 || cfg->reserved[0] == 4) h->warps_per_block = cfg->reserved[0];
     h->deferred_solve = cfg->reserved[3] == 0;
+  }
+  if ((int)h->T.params[trex_host::P_MAX_CONTACTS] != TREX_KMAX) {
+    int rc_ = fail(TREX_ERR_MODEL, "model blob max_contacts differs from the compiled contact capacity (TREX_KMAX)%s");
+    delete h;
+    return rc_;
   }
   trex_host::fill_uniform(h->T, h->C, h->P);
   int rc;

@@ -25,7 +25,7 @@
 #include "trex_topology.h"
 
 #ifndef TREX_KMAX
-#define TREX_KMAX 20  // max simultaneously active contact points per environment
+#define TREX_KMAX 16  // contact slots per environment (model parameter max_contacts; deepest points first)
 #endif
 #ifndef TREX_PGS_UNROLL
 #define TREX_PGS_UNROLL TREX_ROLLED
@@ -125,9 +125,9 @@ struct alignas(16) WarpShared {
   };
 };
 // link-damping partial wrenches live in dV rows beyond the kinematics-phase arrays
-#define TREX_PART_ROW 44
+#define TREX_PART_ROW 44  // row (of 32 floats) inside the union where the 6 damping partial rows live
 static_assert(sizeof(((WarpShared*)0)->k) <= TREX_PART_ROW * 128, "partials must not overlap the kinematics arrays");
-static_assert(3 * TREX_KMAX >= TREX_PART_ROW + 6, "KMAX too small for the damping scratch");
+static_assert(sizeof(((WarpShared*)0)->c) >= (TREX_PART_ROW + 6) * 128, "contact-row storage too small for the damping scratch");
 
 TREX_FN constexpr int SI(int i, int j) {  // upper-triangular index of a symmetric 6x6
   return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
@@ -404,14 +404,14 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
       acc[3] += fx; acc[4] += fy; acc[5] += fz;
     }
     warp_sync();
-    TREX_UNROLL for (int k = 0; k < 6; k++) st(S.c.dV[TREX_PART_ROW + k], lane, acc[k]);
+    TREX_UNROLL for (int k = 0; k < 6; k++) st(reinterpret_cast<float*>(&S.c) + (TREX_PART_ROW + k) * 32, lane, acc[k]);
     warp_sync();
     const vi contrib = MDLI(IF_DAMP_CONTRIB);
     TREX_UNROLL for (int s = 0; s < 4; s++) {
       const vi cl = (contrib >> (6 * s)) & 63;
       const vb ok = cl != 63;
       const vi cls = seli(ok, cl, lane);
-      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, ld(S.c.dV[TREX_PART_ROW + k], cls), 0.0f);
+      TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] += sel(ok, ld(reinterpret_cast<float*>(&S.c) + (TREX_PART_ROW + k) * 32, cls), 0.0f);
     }
     warp_sync();
   }
@@ -690,6 +690,10 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
   TREX_UNROLL for (int k = 0; k < 3; k++) { c_lam[k] = 0.0f; c_rhs[k] = 0.0f; c_jdi[k] = 0.0f; c_dd[k] = 0.0f; }
   vf dv = 0.0f;  // this lane's coordinate of the accumulated delta velocity
   if (P.contacts_on) {
+    vf wpos[2][3];
+    vi cbl[2];
+    vb cact[2];
+    uint32_t am[2];
     TREX_UNROLL for (int half = 0; half < 2; half++) {
       const vi ci = lane + 32 * half;
       const vb valid = ci < P.n_cand;
@@ -697,26 +701,49 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const vi bl = ldi(cand_lane, cis);
       const vf px = ldg_ro(cand_p, cis), py = ldg_ro(cand_p, cis + TREX_NCAND_MAX), pz = ldg_ro(cand_p, cis + 2 * TREX_NCAND_MAX);
       // world point = xw + Rw^T p
-      const vf wx = ld(S.k.xw[0], bl) + ld(S.k.Rw[0], bl) * px + ld(S.k.Rw[3], bl) * py + ld(S.k.Rw[6], bl) * pz;
-      const vf wy = ld(S.k.xw[1], bl) + ld(S.k.Rw[1], bl) * px + ld(S.k.Rw[4], bl) * py + ld(S.k.Rw[7], bl) * pz;
-      const vf wz = ld(S.k.xw[2], bl) + ld(S.k.Rw[2], bl) * px + ld(S.k.Rw[5], bl) * py + ld(S.k.Rw[8], bl) * pz;
-      const vb active = valid && ((wz - P.floor_z) < P.breaking);
-      const uint32_t am = vballot(active);
-      // slot = n_act + rank among active lanes
-      vi rank;
-      rank = rank_below(am) + n_act;
-      const vb keep = active && (rank < TREX_KMAX);
+      wpos[half][0] = ld(S.k.xw[0], bl) + ld(S.k.Rw[0], bl) * px + ld(S.k.Rw[3], bl) * py + ld(S.k.Rw[6], bl) * pz;
+      wpos[half][1] = ld(S.k.xw[1], bl) + ld(S.k.Rw[1], bl) * px + ld(S.k.Rw[4], bl) * py + ld(S.k.Rw[7], bl) * pz;
+      wpos[half][2] = ld(S.k.xw[2], bl) + ld(S.k.Rw[2], bl) * px + ld(S.k.Rw[5], bl) * py + ld(S.k.Rw[8], bl) * pz;
+      cbl[half] = bl;
+      cact[half] = valid && ((wpos[half][2] - P.floor_z) < P.breaking);
+      am[half] = vballot(cact[half]);
+    }
+    const int total = popc_u(am[0]) + popc_u(am[1]);
+    if (total > TREX_KMAX) {
+      // more candidates inside the breaking distance than contact slots: keep the TREX_KMAX deepest
+      // (ties by candidate index) -- the points left out are the ones hovering highest above the floor
+      stats.overflow += total - TREX_KMAX;
+      TREX_UNROLL for (int half = 0; half < 2; half++) {
+        vi better = 0;
+        TREX_UNROLL for (int h2 = 0; h2 < 2; h2++) {
+          TREX_ROLLED for (int l2 = 0; l2 < 32; l2++) {
+            if (!((am[h2] >> l2) & 1u)) continue;
+            const float z2 = lane_value(wpos[h2][2], l2);
+            const vi idx2 = vi(l2 + 32 * h2), idx = lane + 32 * half;
+            better = better + seli((z2 < wpos[half][2]) || ((z2 == wpos[half][2]) && (idx2 < idx)), vi(1), vi(0));
+          }
+        }
+        cact[half] = cact[half] && (better < TREX_KMAX);
+      }
+      am[0] = vballot(cact[0]);
+      am[1] = vballot(cact[1]);
+    }
+    TREX_UNROLL for (int half = 0; half < 2; half++) {
+      const vi ci = lane + 32 * half;
+      const vb valid = ci < P.n_cand;
+      const vi cis = seli(valid, ci, 0);
+      // slot = rank among the kept candidates, in candidate order
+      const vi rank = rank_below(am[half]) + n_act;
+      const vb keep = cact[half];
       const vi slot = seli(keep, rank, 0);
-      st_if(&S.cpos[0][0], slot * 4 + 0, wx, keep);
-      st_if(&S.cpos[0][0], slot * 4 + 1, wy, keep);
-      st_if(&S.cpos[0][0], slot * 4 + 2, wz, keep);
+      st_if(&S.cpos[0][0], slot * 4 + 0, wpos[half][0], keep);
+      st_if(&S.cpos[0][0], slot * 4 + 1, wpos[half][1], keep);
+      st_if(&S.cpos[0][0], slot * 4 + 2, wpos[half][2], keep);
       sti_if(S.ccand, slot, ci, keep);
-      sti_if(S.clane, slot, bl, keep);
+      sti_if(S.clane, slot, cbl[half], keep);
       // contact points that left the manifold lose their cached impulse
       st_if(S.lam_cache, cis, 0.0f, valid && !keep);
-      const int cnt = popc_u(am);
-      if (n_act + cnt > TREX_KMAX) stats.overflow += n_act + cnt - TREX_KMAX;
-      n_act = (n_act + cnt > TREX_KMAX) ? TREX_KMAX : n_act + cnt;
+      n_act += popc_u(am[half]);
     }
     warp_sync();
   }
@@ -1113,17 +1140,17 @@ TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared&
 // Returns the number of solver iterations each group executed (per lane of the group).
 // ------------------------------------------------------------------------------------------
 #define TREX_GS_STRIDE 648  // floats per group in the shared stash of g (25*25 = 625, padded: bank offset 8 per group)
+#define TREX_SOLVE_SCRATCH (4 * TREX_GS_STRIDE + 128)  // floats of warp-private shared memory solve4 needs
 // envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
-TREX_FN vi solve4(const Uniform& P, WarpShared& S, const float* work0, float* rec0, const int envs[4], int pending, float max_imp) {
+TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending, float max_imp) {
   const vi lane = lane_id();
   const vi grp = lane >> 3, gl = lane & 7;
   const vb gact = ((vi(pending) >> grp) & 1) != 0;
   const vi genv = seli(grp == 0, vi(envs[0]), seli(grp == 1, vi(envs[1]), seli(grp == 2, vi(envs[2]), vi(envs[3]))));
   const vi woff = seli(gact, genv, 0) * TREX_WORK_STRIDE, roff = seli(gact, genv, 0) * TREX_STATE_STRIDE;
   const float dt = P.dt;
-  float* Gs = reinterpret_cast<float*>(&S.c);          // [4][TREX_GS_STRIDE]: g[k][j] at j*25 + k
-  float* Lam = Gs + 4 * TREX_GS_STRIDE;                // [4][32]: net joint impulses, exchanged once per sweep
-  static_assert(sizeof(S.c) >= (4 * TREX_GS_STRIDE + 128) * sizeof(float), "contact-row storage too small for the solve4 stash");
+  float* Gs = scratch;                                 // [4][TREX_GS_STRIDE]: g[k][j] at j*25 + k
+  float* Lam = Gs + 4 * TREX_GS_STRIDE;                // [4][32]: net joint impulses, exchanged every few sweeps
 
   vi kk[4];
   vb kv[4];
@@ -1396,9 +1423,9 @@ TREX_FN bool front_phase(const Uniform& P, const float* mdl, const int* mdli, co
 }
 
 // solve_phase: the deferred solves of up to four environments (any four: the groups are independent)
-TREX_FN void solve_phase(const Uniform& P, WarpShared& S, const float* work0, float* rec0, const int envs[4], int pending) {
+TREX_FN void solve_phase(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending) {
   const vi lane = lane_id();
-  const vi itd = solve4(P, S, work0, rec0, envs, pending, P.max_impulse);
+  const vi itd = solve4(P, scratch, work0, rec0, envs, pending, P.max_impulse);
   // iterations executed per environment -> its accumulator (lane 8e holds group e's count)
   const vi grp = lane >> 3;
   const vb wr = ((lane & 7) == 0) && ((((vi(pending)) >> grp) & 1) != 0);

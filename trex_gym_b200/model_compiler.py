@@ -103,6 +103,7 @@ DEFAULT_PARAMS = OrderedDict(
         ("limit_max_impulse", 100.0),  # [RECALL] btMultiBodyConstraint::m_maxAppliedImpulse default
         ("reset_height", 3.0),  # trex_env.py:105
         ("reward_target_height", 2.5),  # trex_env.py:189
+        ("max_contacts", 16.0),  # contact definition N2: capacity per environment (deepest first), = kernel TREX_KMAX
     ]
 )
 
