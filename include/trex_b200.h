@@ -64,8 +64,9 @@ typedef struct trex_config {
                                 reference counterpart), Philox keyed by (seed, global env id, episode) */
   uint32_t seed;
   int32_t reserved[8];       /* [0] warps per CTA of the front/tail kernels (1, 2 or 4; 0 = default 1); [1],[2] low/high word of the global id of
-                                environment 0 of this shard (multi-GPU: rank * n_envs); [3] != 0 disables the
-                                four-environments-per-warp deferred solve (diagnostics) */
+                                environment 0 of this shard (multi-GPU: rank * n_envs); [3] solver placement (diagnostics):
+                                0 = contact-free substeps and substeps with <= 4 contacts are solved four environments
+                                per warp, 2 = contact-free substeps only, 1 = everything in the one-environment path */
 } trex_config;
 
 typedef struct trex_stats {

@@ -78,6 +78,12 @@ class EmuEnv:
         if h:
             self._L.emu_destroy(h)
 
+    def solve_counts(self):
+        """Substeps finished by (the one-environment path, solve4<0>, solve4<KC>)."""
+        out = (ctypes.c_longlong * 3)()
+        self._L.emu_solve_counts(self._h, out)
+        return tuple(int(x) for x in out)
+
     def reset(self):
         obs = np.zeros(75, np.float32)
         r = np.zeros(1, np.float32)

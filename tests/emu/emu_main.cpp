@@ -10,10 +10,11 @@ struct Emu {
   trex_host::ModelTables T;
   trex::Uniform P;
   trex::WarpShared S;
-  float work[4 * TREX_WORK_STRIDE];
-  float scratch[TREX_SOLVE_SCRATCH];
+  alignas(16) float work[4 * TREX_WORK_STRIDE];
+  alignas(16) float scratch[TREX_SOLVE_SCRATCH(TREX_KC)];
   int deferred = 1;
   int pack_reverse = 0;  // tests: fill the solver's lane groups from the top
+  long long solves[3] = {0, 0, 0};  // substeps finished in front_phase / by solve4<0> / by solve4<TREX_KC>
 };
 
 static_assert(trex::F_COUNT == 32, "field table");
@@ -60,13 +61,19 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
   if (!force_reset) {
     for (int r = 0; r < e->P.n_sub; r++) {
       // deferred environments are packed into the solver's lane groups in list order (any order is equivalent)
-      int envs[4] = {0, 0, 0, 0}, cnt = 0;
-      for (int i = 0; i < n; i++)
-        if (trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
-                              e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0))
-          envs[e->pack_reverse ? 3 - cnt++ : cnt++] = i;
-      int pending = e->pack_reverse ? (((1 << cnt) - 1) << (4 - cnt)) : ((1 << cnt) - 1);
-      if (cnt) trex::solve_phase(e->P, e->scratch, e->work, rec, envs, pending);
+      // (two lists, as in the library: contact-free environments and environments with 1..TREX_KC contacts)
+      int envs[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, cnt[2] = {0, 0};
+      for (int i = 0; i < n; i++) {
+        const int d = trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
+                                        e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0);
+        e->solves[d]++;
+        if (d) { int& c = cnt[d - 1]; envs[d - 1][e->pack_reverse ? 3 - c : c] = i; c++; }
+      }
+      for (int d = 0; d < 2; d++) {
+        const int pending = e->pack_reverse ? (((1 << cnt[d]) - 1) << (4 - cnt[d])) : ((1 << cnt[d]) - 1);
+        if (cnt[d] && d == 0) trex::solve_phase<0>(e->P, e->scratch, e->work, rec, envs[0], pending);
+        if (cnt[d] && d == 1) trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[1], pending);
+      }
     }
   }
   for (int i = 0; i < n; i++)
@@ -78,5 +85,9 @@ void emu_step(void* h, float* rec, const float* action, float* obs, float* rewar
               long long env_id) {
   emu_step4(h, 1, rec, action, obs, reward, done, aux, force_reset, env_id);
 }
-void emu_set_deferred(void* h, int on) { ((Emu*)h)->deferred = on & 1; ((Emu*)h)->pack_reverse = (on >> 1) & 1; }
+void emu_solve_counts(void* h, long long* out) { for (int i = 0; i < 3; i++) out[i] = ((Emu*)h)->solves[i]; }
+void emu_set_deferred(void* h, int on) {  // bit 0 deferral on, bit 1 reverse packing, bit 2 contact-free substeps only
+  Emu* e = (Emu*)h;
+  e->deferred = on & 1; e->pack_reverse = (on >> 1) & 1; e->P.defer_contacts = ((on >> 2) & 1) ? 0 : 1;
+}
 }

@@ -162,9 +162,19 @@ TREX_FN void philox4_uniform(const vi& c0, const vi& c1, const vi& c2, const vi&
   }
 }
 
+TREX_FN vi vmini(const vi& a, int b) { vi r; for (int l = 0; l < 32; l++) r.v[l] = a.v[l] < b ? a.v[l] : b; return r; }
+TREX_FN vi vf2i(const vf& x) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)x.v[l]; return r; }
+TREX_FN vi warp_maxi(const vi& x) { int m = x.v[0]; for (int l = 1; l < 32; l++) m = x.v[l] > m ? x.v[l] : m; return vi(m); }
 TREX_FN vf shfl_group8(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~7) | (src & 7)]; return r; }
 TREX_FN vf group8_sum(vf x) { for (int m = 4; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN vf group8_max(vf x) { for (int m = 4; m > 0; m >>= 1) x = vmax(x, shfl_xor(x, m)); return x; }
 
+TREX_FN void ld4(const float* p, const vi& idx, vf out[4]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 4; k++) out[k].v[l] = p[idx.v[l] + k]; }
+TREX_FN void ld4_if(const float* p, const vi& idx, const vb& pred, vf out[4]) {
+  for (int l = 0; l < 32; l++) for (int k = 0; k < 4; k++) out[k].v[l] = pred.v[l] ? p[idx.v[l] + k] : 0.0f;
+}
+TREX_FN void st4_if(float* p, const vi& idx, const vf v[4], const vb& pred) {
+  for (int l = 0; l < 32; l++) if (pred.v[l]) for (int k = 0; k < 4; k++) p[idx.v[l] + k] = v[k].v[l];
+}
 TREX_FN void st16(float* p, const vi& idx, const vf v[16]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 16; k++) p[idx.v[l] + k] = v[k].v[l]; }
 TREX_FN void ldu16(const float* p, int idx, float out[16]) { for (int k = 0; k < 16; k++) out[k] = p[idx + k]; }

@@ -50,12 +50,17 @@ def test_per_step_parity_contact_free(model, emu_cls, action_limits):
     assert worst < 2e-5, worst
 
 
-def test_per_substep_parity_with_contacts(model, emu_cls, action_limits):
+@pytest.mark.parametrize("mode", ["row_space", "one_env"])
+def test_per_substep_parity_with_contacts(model, emu_cls, action_limits, mode):
+    """Single substeps in contact against the oracle.  "row_space": substeps with 1..4 contacts go through solve4<4>
+    (four environments per warp, contact rows tracked in row space); "one_env": all of them through the
+    one-environment sweep.  Both are the same Gauss-Seidel iteration in the same row order."""
     from trex_gym_b200.model_compiler import with_params
 
     lo, hi = action_limits
     sub = with_params(model, time_step=0.002, solver_iterations=60)
-    e, o = emu_cls(sub.blob(), num_substeps=1), _oracle(sub, num_substeps=1)
+    e = emu_cls(sub.blob(), num_substeps=1, deferred=1 if mode == "row_space" else 5)
+    o = _oracle(sub, num_substeps=1)
     e.reset()
     rng = np.random.default_rng(5)
     errs, n_contact = [], 0
@@ -71,7 +76,9 @@ def test_per_substep_parity_with_contacts(model, emu_cls, action_limits):
         n_contact += o.last_num_contacts > 0
         assert int(e.aux[7]) == o.last_num_contacts
     errs = np.asarray(errs)
+    inline, free, rowspace = e.solve_counts()
     assert n_contact > 60
+    assert (rowspace > 50 and inline < rowspace) if mode == "row_space" else (rowspace == 0 and inline > 60)
     assert np.percentile(errs, 50) < 2e-5 and np.percentile(errs, 99) < 2e-3, (np.percentile(errs, 50), errs.max())
 
 

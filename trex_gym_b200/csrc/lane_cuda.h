@@ -97,10 +97,30 @@ TREX_FN void philox4_uniform(vi c0, vi c1, vi c2, vi c3, uint32_t k0, uint32_t k
   for (int k = 0; k < 4; k++) out[k] = (float)(c[k] >> 8) * (1.0f / 16777216.0f);
 }
 
+TREX_FN vi vmini(vi a, int b) { return a < b ? a : b; }
+TREX_FN vi vf2i(vf x) { return (int)x; }
+TREX_FN vi warp_maxi(vi x) {
+  TREX_UNROLL for (int m = 16; m > 0; m >>= 1) { const int y = __shfl_xor_sync(TREX_FULL, x, m); x = x > y ? x : y; }
+  return x;
+}
 // width-8 lane groups (four environments per warp in solve4)
 TREX_FN vf shfl_group8(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 8); }
 TREX_FN vf group8_sum(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
 TREX_FN vf group8_max(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(TREX_FULL, x, m)); return x; }
+
+// 4 consecutive floats per lane (16-byte aligned offset): one 128-bit access
+TREX_FN void ld4(const float* p, vi idx, vf out[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p + idx);
+  out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+}
+TREX_FN void ld4_if(const float* p, vi idx, vb pred, vf out[4]) {
+  float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (pred) t = *reinterpret_cast<const float4*>(p + idx);
+  out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+}
+TREX_FN void st4_if(float* p, vi idx, const vf v[4], vb pred) {
+  if (pred) *reinterpret_cast<float4*>(p + idx) = make_float4(v[0], v[1], v[2], v[3]);
+}
 
 // 16 consecutive floats (64-byte aligned offset): per-lane store / uniform load as four 128-bit accesses
 TREX_FN void st16(float* p, vi idx, const vf v[16]) {

@@ -20,11 +20,14 @@
 #ifndef TREX_SOLVE_MIN_BLOCKS
 #define TREX_SOLVE_MIN_BLOCKS 12  // ... by the 4-environments-per-warp solve kernel (168 registers)
 #endif
+#ifndef TREX_SOLVEC_MIN_BLOCKS
+#define TREX_SOLVEC_MIN_BLOCKS 8  // ... by its contact variant (<= 255 registers: 2 warps per scheduler; 3 would cap it at 168 and spill)
+#endif
 #define TREX_STR2(x) #x
 #define TREX_STR(x) TREX_STR2(x)
 
-static_assert(TREX_STATE_DIM == TREX_STATE_STRIDE, "state record size");
 #ifndef TREX_PHASES
+static_assert(TREX_STATE_DIM == TREX_STATE_STRIDE, "state record size");
 static_assert(TREX_AUX_DIM == TREX_AUX_STRIDE, "aux record size");
 #endif
 static_assert(trex::F_COUNT == 32, "float field table");
@@ -59,27 +62,32 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS + warp;
   if (env >= n_envs) return;
-  const bool deferred = trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
+  const int deferred = trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
                                           work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
                                           first_round != 0);
-  // append to the list of deferred environments (any order: the solver's lane groups are independent)
-  if (deferred && (threadIdx.x & 31) == 0) list[atomicAdd(list_count, 1)] = env;
+  // append to the list of deferred environments (any order: the solver's lane groups are independent):
+  // list 0 = contact-free substeps, list 1 (second half, counters + 64) = substeps with 1..TREX_KC contacts
+  if (deferred && (threadIdx.x & 31) == 0) {
+    const int which = deferred - 1;
+    list[(size_t)which * n_envs + atomicAdd(list_count + 64 * which, 1)] = env;
+  }
 }
 
-// one warp per FOUR deferred (contact-free) environments taken from the list, eight lanes per environment
-template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, TREX_SOLVE_MIN_BLOCKS / WARPS)
+// one warp per FOUR deferred environments taken from the list, eight lanes per environment; KC = 0: the contact-free
+// list, KC = TREX_KC: the list of environments with 1..TREX_KC contacts (rows in row space, see solve4)
+template <int WARPS, int KC>
+__global__ void __launch_bounds__(32 * WARPS, (KC ? TREX_SOLVEC_MIN_BLOCKS : TREX_SOLVE_MIN_BLOCKS) / WARPS)
 trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
                   const int* __restrict__ list, const int* __restrict__ list_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* scratch = reinterpret_cast<float*>(smem_raw) + (threadIdx.x >> 5) * TREX_SOLVE_SCRATCH;
+  float* scratch = reinterpret_cast<float*>(smem_raw) + (threadIdx.x >> 5) * TREX_SOLVE_SCRATCH(KC);
   const int warp = threadIdx.x >> 5;
   const int first = (blockIdx.x * WARPS + warp) * 4;
   const int count = *list_count;
   if (first >= count) return;
   int envs[4] = {0, 0, 0, 0}, pending = 0;
   for (int e = 0; e < 4 && first + e < count; e++) { envs[e] = list[first + e]; pending |= 1 << e; }
-  trex::solve_phase(P, scratch, work, state, envs, pending);
+  trex::solve_phase<KC>(P, scratch, work, state, envs, pending);
 }
 
 // one warp per environment: reward / done / auto-reset / observations (mode 0), or reset only (mode 1, optional mask)
@@ -258,28 +266,36 @@ int configure_kernel(K kernel, size_t smem) {
 template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
-  const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH * WS;
+  const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS,
+               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS;
   static bool configured[16] = {false};
   if (!configured[h->device & 15]) {
     int rc;
     if ((rc = configure_kernel(trex_front_kernel<WF>, smem_f)) != TREX_OK) return rc;
-    if ((rc = configure_kernel(trex_solve_kernel<WS>, smem_s)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_solve_kernel<WS, 0>, smem_s)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_solve_kernel<WS, TREX_KC>, smem_c)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
   }
   const int grid1 = (h->n_envs + WF - 1) / WF;            // one warp per environment
   const int grid4 = (h->n_envs + 4 * WS - 1) / (4 * WS);  // one warp per four environments
   if (mode == 0) {
-    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 64 * sizeof(int), st));  // one counter per substep round
+    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 128 * sizeof(int), st));  // one counter per list and substep round
     for (int r = 0; r < h->P.n_sub; r++) {
       trex_front_kernel<WF><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
                                                            h->d_state, h->d_work, action, h->d_list, h->d_list_count + r, h->n_envs, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
-        trex_solve_kernel<WS><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r);
+        trex_solve_kernel<WS, 0><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
+        if (h->P.defer_contacts && h->P.contacts_on) {
+          trex_solve_kernel<WS, TREX_KC><<<grid4, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
+                                                                        h->d_list_count + 64 + r);
+          CUDA_TRY(cudaGetLastError());
+          h->launches++;
+        }
       }
     }
   }
@@ -341,7 +357,8 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     h->C.reset_mode = cfg->reset_mode; h->C.seed = cfg->seed;
     h->C.env_offset = ((long long)cfg->reserved[2] << 32) | (unsigned)cfg->reserved[1];
     if (cfg->reserved[0] == 1 || cfg->reserved[0] == 2 || cfg->reserved[0] == 4) h->warps_per_block = cfg->reserved[0];
-    h->deferred_solve = cfg->reserved[3] == 0;
+    h->deferred_solve = cfg->reserved[3] != 1;
+    h->C.defer_contacts = cfg->reserved[3] == 0;
   }
   if ((int)h->T.params[trex_host::P_MAX_CONTACTS] != TREX_KMAX) {
     int rc_ = fail(TREX_ERR_MODEL, "model blob max_contacts differs from the compiled contact capacity (TREX_KMAX)%s");
@@ -369,9 +386,9 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   CTRY(cudaMalloc((void**)&h->d_obs, N * 3 * trex::NJ * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_reward, N * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_done, N));
-  CTRY(cudaMalloc((void**)&h->d_list, N * sizeof(int)));
-  CTRY(cudaMalloc((void**)&h->d_list_count, 64 * sizeof(int)));
-  CTRY(cudaMemset(h->d_list_count, 0, 64 * sizeof(int)));
+  CTRY(cudaMalloc((void**)&h->d_list, 2 * N * sizeof(int)));
+  CTRY(cudaMalloc((void**)&h->d_list_count, 128 * sizeof(int)));
+  CTRY(cudaMemset(h->d_list_count, 0, 128 * sizeof(int)));
   CTRY(cudaMalloc((void**)&h->d_stats, sizeof(DevStats)));
 #undef CTRY
   // all environments start from the reference reset (TrexBulletEnv.__init__ calls reset(), trex_env.py:92)

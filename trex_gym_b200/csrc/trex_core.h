@@ -32,7 +32,11 @@
 #endif
 #define TREX_NCAND_MAX 64
 #define TREX_MAX_ROUNDS 12
+#ifdef TREX_PHASES
+#define TREX_STATE_STRIDE 176  // diagnostics build: + 8 per-phase cycle counters at [160,168)
+#else
 #define TREX_STATE_STRIDE 160  // floats per environment record (see include/trex_b200.h)
+#endif
 // deferred-solve work record (floats): M^-1 columns [31][32], then per-lane rows
 #define W_COL 0
 #define W_RHSM 992
@@ -40,7 +44,15 @@
 #define W_DSELF 1056
 #define W_RHSL 1088
 #define W_SIGMA 1120
-#define TREX_WORK_STRIDE 1152
+// ... followed, for environments with 1..TREX_KC contacts, by the contact rows in "row space" (see solve4):
+#define TREX_KC 4                          // contacts per environment the four-environments-per-warp solver accepts
+#define W_NC 1152                          // number of contacts (as float)
+#define W_CS 1160                          // [KC][16]: rhs n,t1,t2 | jdi | J M^-1 J^T | warm-started normal impulse | candidate index
+#define W_CBASE (W_CS + 16 * TREX_KC)      // [3*KC][8]: base coordinates of the row responses M^-1 J^T
+#define W_B4 (W_CBASE + 24 * TREX_KC)      // [KC][25][4]: joint coordinates of the responses, B4[c][j][k] = (M^-1 J_{c,k}^T)[6+j]
+#define W_A4 (W_B4 + 100 * TREX_KC)        // [3*KC][KC][4]: A4[r][c'][k'] = J_{c',k'} M^-1 J_r^T
+#define TREX_WORK_STRIDE 1920
+static_assert(W_A4 + 48 * TREX_KC <= TREX_WORK_STRIDE && (W_B4 % 4) == 0 && (W_A4 % 4) == 0, "work record layout");
 #ifdef TREX_PHASES
 #define TREX_AUX_STRIDE 16
 #define TREX_TICK(i) { const long long _t = cycle_count(); stats.phase[i] += (float)(_t - _t0); _t0 = _t; }
@@ -89,6 +101,7 @@ struct Uniform {
   float head_p[3];
   float r0[NB][3];  // static-index copy of F_R0 (body index, not lane)
   int iters, n_sub, max_episode_steps, head_lane, n_cand, n_rounds, contacts_on, reset_mode;
+  int defer_contacts;     // != 0: substeps with 1..TREX_KC contacts are also solved four environments per warp
   unsigned seed;
   long long env_offset;   // global id of environment 0 of this shard (keys the reset sampler)
   float reset_z_min, reset_z_max;  // reset_mode 1: base height range
@@ -121,6 +134,7 @@ struct alignas(16) WarpShared {
       float dV[3 * TREX_KMAX][32];   // rows 3*c + {0 normal, 1 t1, 2 t2}: M^-1 J^T, indexed by lane
       float Jc[3 * TREX_KMAX][12];   // compact Jacobian rows: [0:6] base coordinates, [6:11] chain joints by depth, [11] = 0
       unsigned char slot[TREX_KMAX][32];  // which Jc entry each lane multiplies its velocity coordinate with
+      unsigned char inv[TREX_KC][16];     // inverse of slot for the first KC contacts: lane (coordinate) of each Jc entry
     } c;
   };
 };
@@ -320,7 +334,7 @@ TREX_FN void to_parent(const vf E[9], const vf r[3], const vf Ia[21], const vf p
 // ------------------------------------------------------------------------------------------
 // Returns true when the solve was deferred: the solver inputs were written to `work` (contact-free
 // environment, `work` != nullptr) and the caller finishes the step with solve4(); otherwise the step is complete.
-TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                      const int* cand_lane, WarpShared& S, EnvRegs& R, float kp, float kd, float max_imp,
                      StepStats& stats, float* work) {
   const vi lane = lane_id();
@@ -747,18 +761,23 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
     }
     warp_sync();
   }
-  if (work != nullptr && n_act == 0) {
-    // Deferred solve: no contact rows -> the rows are the 25 motors and the violated joint limits, all with unit
-    // Jacobians.  Write M^-1 and the per-joint row scalars; solve4() handles four such environments per warp.
+  // Deferred solve: solve4() finishes this substep, four environments per warp.  Always when there are no contact
+  // rows (the rows are then the 25 motors and the violated joint limits, all with unit Jacobians); with up to
+  // TREX_KC contacts when P.defer_contacts.  The solver inputs go to the work record: M^-1, the per-joint row
+  // scalars and -- below -- the contact rows.
+  const bool defer_c = work != nullptr && P.defer_contacts != 0 && n_act > 0 && n_act <= TREX_KC;
+  if (work != nullptr && (n_act == 0 || defer_c)) {
     TREX_ROLLED for (int gq = 0; gq < trex_topo::NDOF; gq++) st(work, lane + (W_COL + gq * 32), ld(S.col[gq], lane));
     st(work, lane + W_RHSM, rhs_m);
     st(work, lane + W_JDI, jdi);
     st(work, lane + W_DSELF, sel(is_joint, dself, 0.0f));
     st(work, lane + W_RHSL, sel(act_lo, rhs_lo, sel(act_hi, rhs_hi, 0.0f)));
     st(work, lane + W_SIGMA, sel(act_lo, 1.0f, sel(act_hi, -1.0f, 0.0f)));
-    stats.contacts = 0;
-    warp_sync();
-    return true;
+    stats.contacts = n_act;
+    if (n_act == 0) {
+      warp_sync();
+      return 1;
+    }
   }
   if (P.contacts_on) {
     // From here on the kinematics-phase arrays are dead: their storage becomes the contact rows.
@@ -790,8 +809,14 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
       const vb isb = (lane >= 25) && (lane < 31);
       const vi myslot = seli(isb, lane - 25, seli(moves, mydepth + 5, 11));
       warp_sync();
+      if (defer_c) {  // the Delassus pass below walks all 11 entries of the compact rows: unused ones must read 0 * finite
+        TREX_UNROLL for (int k = 0; k < 3; k++) st_if(S.c.Jc[3 * c + k], seli(lane < 12, lane, 0), 0.0f, lane < 12);
+        stb(S.c.inv[c], lane & 15, vi(31));
+        warp_sync();
+      }
       TREX_UNROLL for (int k = 0; k < 3; k++) st_if(S.c.Jc[3 * c + k], myslot, sel(lane == 31, 0.0f, Jr[k]), isb || moves || (lane == 31));
       stb(S.c.slot[c], lane, myslot);
+      if (defer_c) stb(S.c.inv[c], myslot, lane);  // entry 11 (the zero entry) ends up with an arbitrary lane
       warp_sync();
       // response dV = M^-1 J^T: this lane's coordinate = <own column, J>, over the <= 11 non-zeros of J
       vf dVr[3];
@@ -839,6 +864,51 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
       }
       c_lam[0] = sel(lane == c, vbroadcast(warm), c_lam[0]);
       dv = vfma(dVr[0], vbroadcast(warm), dv);
+    }
+    if (defer_c) {
+      // Contact rows for solve4, in row space: the solver tracks the velocity along every row instead of the
+      // 31 coordinates, so it needs the responses at the joints (B4), at the base (for the final update) and the
+      // Delassus blocks A[r'][r] = J_r' M^-1 J_r^T between contact rows.
+      warp_sync();
+      {
+        const vb own = lane < n_act;
+        const vi ls = seli(own, lane, 0);
+        const vi sb = ls * 16 + W_CS;
+        TREX_UNROLL for (int k = 0; k < 3; k++) {
+          st_if(work, sb + k, c_rhs[k], own);
+          st_if(work, sb + (3 + k), c_jdi[k], own);
+          st_if(work, sb + (6 + k), c_dd[k], own);
+        }
+        st_if(work, sb + 9, c_lam[0], own);
+        st_if(work, sb + 10, vi2f(ldi(S.ccand, ls)), own);
+        st_if(work, vi(W_NC), vbroadcast((float)n_act), lane == 0);
+      }
+      const vb isb = (lane >= 25) && (lane < 31);
+      TREX_ROLLED for (int c = 0; c < n_act; c++) {
+        vf d4[4];
+        TREX_UNROLL for (int k = 0; k < 3; k++) d4[k] = ld(S.c.dV[3 * c + k], lane);
+        d4[3] = 0.0f;
+        st4_if(work, (seli(is_joint, lane, 0) + c * 25) * 4 + W_B4, d4, is_joint);
+        TREX_UNROLL for (int k = 0; k < 3; k++) st_if(work, seli(isb, lane - 25, 0) + ((3 * c + k) * 8 + W_CBASE), d4[k], isb);
+      }
+      const int n3 = 3 * n_act, nn = n3 * n3, recip = 65536 / n3 + 1;
+      TREX_ROLLED for (int i0 = 0; i0 < nn; i0 += 32) {
+        const vi idx = lane + i0;
+        const vb valid = idx < nn;
+        const vi is = seli(valid, idx, 0);
+        const vi rp = (is * recip) >> 16;        // affected row (c', k')
+        const vi r = is - rp * n3;               // source row (c, k)
+        const vi cp = (rp * 11) >> 5, kp = rp - cp * 3;
+        vf acc = 0.0f;
+        TREX_UNROLL for (int e = 0; e < 11; e++) {
+          const vf jv = ld(&S.c.Jc[0][0], rp * 12 + e);
+          const vi dl = ldb(&S.c.inv[0][0], cp * 16 + e);
+          acc = vfma(jv, ld(&S.c.dV[0][0], r * 32 + dl), acc);
+        }
+        st_if(work, (r * TREX_KC + cp) * 4 + kp + W_A4, acc, valid);
+      }
+      warp_sync();
+      return 2;
     }
   }
   warp_sync();
@@ -1047,7 +1117,7 @@ TREX_FN bool substep(const Uniform& P, const float* mdl, const int* mdli, const 
   }
   R.q = sel(is_joint, R.q + dt * R.qd, 0.0f);
   TREX_TICK(7)
-  return false;
+  return 0;
 }
 
 
@@ -1129,36 +1199,95 @@ TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared&
 //
 // Without contacts every row has a unit Jacobian (25 motors + the violated joint limits), so the solver
 // only needs the joint block of M^-1.  Eight lanes serve one environment (group = lane >> 3); lane l of a
-// group owns joints {l, l+8, l+16, l+24}.  Each lane carries, per owned joint k,
+// group owns the joints at positions 4l..4l+3 of the solve order.  Each lane carries, per owned joint k,
 //     w_k = lambda_m,k + rhs_m,k - jdi_k * dv_k      (the motor row's unclamped new impulse)
 // and the row of coefficients g[k][j] = -jdi_k * M^-1[6+k][6+j] in registers (0 on the diagonal, where the
-// impulse and velocity terms cancel).  A row update is then: clamp on the owner, one width-8 shuffle, four
-// FMAs per lane -- the same dependent chain as the one-environment sweep, shared by four environments.
+// impulse and velocity terms cancel).  A motor sweep goes block by block: the owner runs its four consecutive
+// rows as a private register chain (clamp, difference, FMA into its later rows), then the four impulse changes
+// are published with width-8 shuffles and every lane applies them -- one shuffle latency per FOUR rows on the
+// dependent chain instead of one per row (measured: ~90 cycles per row with a shuffle in every row).
 // Rows are visited in Bullet's order (motors in sorted-constraint order, then the violated limits; direction
 // alternates with the iteration); w is rebuilt exactly from the impulses after every sweep.
 // Ends with the velocity update, the write-back of the applied motor torque and the position integration.
 // Returns the number of solver iterations each group executed (per lane of the group).
 // ------------------------------------------------------------------------------------------
+//
+// solve4<KC> with KC > 0 also takes environments with up to KC floor contacts.  The contact rows are dense in the
+// coordinates, so they are carried in ROW SPACE: lane c (< KC) of a group owns contact c and tracks the velocity
+// change u along its three rows (normal, t1, t2) next to their impulses.  A joint row (motor / limit) at joint j
+// adds B4[c][j][:] * d(impulse) to u, a contact row adds B4[c][j][k] * d(impulse) to the joint velocities (through w)
+// and the Delassus block A4 to every owner's u: one 128-bit shared load and 3 FMAs on top of a motor row, no
+// reduction over coordinates anywhere.  B4 and A4 come from front_phase through the work record.  Row order as
+// in the one-environment sweep: joint rows, then the normal rows, then the friction pairs (implicit cone).
+// One block of a motor sweep: rows at solve-order positions 4B..4B+3 (block 6: position 24 only), owned by lane B
+// of every group.  FWD: ascending positions.  Same operations on w, in the same order, as row-by-row updates.
+TREX_TOPO_FN bool limit_order_matches_motor_order() {
+  for (int p = 0; p < NJ; p++)
+    if (trex_topo::noncontact_order(NJ + p) != trex_topo::noncontact_order(p) - NJ) return false;
+  return true;
+}
+template <int B, bool FWD, int KC>
+TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf (&cu)[3], vi gl, vi stash_b4, const float* Gs,
+                            float max_imp) {
+  constexpr int n = (4 * B + 4 <= NJ) ? 4 : NJ - 4 * B;
+  vf t[4], d[4];
+  TREX_UNROLL for (int i = 0; i < 4; i++) { t[i] = w[i]; d[i] = 0.0f; }
+  const vb own = gl == B;
+  // the owner's private chain (the other lanes compute on their own registers and discard)
+  TREX_UNROLL for (int ii = 0; ii < n; ii++) {
+    const int i = FWD ? ii : n - 1 - ii;
+    const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
+    const vf nl = vmin(vmax(t[i], -max_imp), max_imp);
+    d[i] = nl - lam_m[i];
+    lam_m[i] = sel(own, nl, lam_m[i]);
+    TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
+      const int i3 = FWD ? i2 : n - 1 - i2;
+      t[i3] = vfma(g[i3][j], d[i], t[i3]);
+    }
+  }
+  // publish: every lane applies the four impulse changes of lane B
+  TREX_UNROLL for (int ii = 0; ii < n; ii++) {
+    const int i = FWD ? ii : n - 1 - ii;
+    const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
+    const vf db = shfl_group8(d[i], B);
+    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(g[s][j], db, w[s]);
+    if (KC > 0) {
+      vf b4[4];
+      ld4(Gs, stash_b4 + 4 * j, b4);
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(b4[k], db, cu[k]);
+    }
+  }
+}
+
 #define TREX_GS_STRIDE 648  // floats per group in the shared stash of g (25*25 = 625, padded: bank offset 8 per group)
-#define TREX_SOLVE_SCRATCH (4 * TREX_GS_STRIDE + 128)  // floats of warp-private shared memory solve4 needs
+#define TREX_GC_STRIDE(KC) (TREX_GS_STRIDE + 148 * (KC))  // + B4 [KC][25][4] + A4 [3*KC][KC][4]
+#define TREX_SOLVE_SCRATCH(KC) (4 * TREX_GC_STRIDE(KC) + 4 * (32 + 4 * (KC)))  // floats of warp-private shared memory
 // envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
+template <int KC>
 TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending, float max_imp) {
+  static_assert((KC == 0 || KC == 1 || KC == 2 || KC == 4 || KC == 8) && KC <= TREX_KC, "one contact per lane of a group");
+  constexpr int GC = TREX_GC_STRIDE(KC), LS = 32 + 4 * KC;
   const vi lane = lane_id();
   const vi grp = lane >> 3, gl = lane & 7;
   const vb gact = ((vi(pending) >> grp) & 1) != 0;
   const vi genv = seli(grp == 0, vi(envs[0]), seli(grp == 1, vi(envs[1]), seli(grp == 2, vi(envs[2]), vi(envs[3]))));
   const vi woff = seli(gact, genv, 0) * TREX_WORK_STRIDE, roff = seli(gact, genv, 0) * TREX_STATE_STRIDE;
   const float dt = P.dt;
-  float* Gs = scratch;                                 // [4][TREX_GS_STRIDE]: g[k][j] at j*25 + k
-  float* Lam = Gs + 4 * TREX_GS_STRIDE;                // [4][32]: net joint impulses, exchanged every few sweeps
+  float* Gs = scratch;                                 // [4][GC]: g[k][j] at j*25 + k, then B4, then A4
+  float* Lam = Gs + 4 * GC;                            // [4][LS]: net joint impulses + contact impulses, exchanged every few sweeps
+  const vi gb = grp * GC;                              // this group's stash
+  const vi glc = KC > 0 ? vmini(gl, KC - 1) : vi(0);  // contact slot of this lane (lanes >= KC shadow the last owner, unused)
+  const vi stash_b4 = gb + glc * 100 + TREX_GS_STRIDE; // B4 rows of the owned contact
 
   vi kk[4];
   vb kv[4];
   vf rhs_m[4], jdi[4], dself[4], rhs_l[4], sigma[4], g[4][NJ];
   TREX_UNROLL for (int s = 0; s < 4; s++) {
-    kk[s] = gl + 8 * s;
-    kv[s] = gact && (kk[s] < NJ);
-    kk[s] = seli(kv[s], kk[s], 0);
+    // lane l owns the joints at positions 4l .. 4l+3 of the solve order: four consecutive rows of a sweep
+    kk[s] = 0;
+    TREX_UNROLL for (int l = 0; l < 7; l++)
+      if (4 * l + s < NJ) kk[s] = seli(gl == l, vi(trex_topo::noncontact_order(4 * l + s) - NJ), kk[s]);
+    kv[s] = gact && (gl * 4 + s < NJ);
     rhs_m[s] = ld_if(work0, woff + kk[s] + W_RHSM, kv[s], 0.0f);
     jdi[s] = ld_if(work0, woff + kk[s] + W_JDI, kv[s], 0.0f);
     dself[s] = ld_if(work0, woff + kk[s] + W_DSELF, kv[s], 0.0f);
@@ -1172,16 +1301,52 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
   // copy of g in shared memory for the limit rows (their joint index is only known at run time)
   warp_sync();
   TREX_UNROLL for (int s = 0; s < 4; s++)
-    TREX_UNROLL for (int j = 0; j < NJ; j++) st_if(Gs, grp * TREX_GS_STRIDE + kk[s] + j * 25, g[s][j], kv[s]);
-  // joints with a violated limit in ANY of the four environments, in Bullet's limit-constraint order
-  uint32_t uperm = 0;
-  {
-    uint32_t um = 0;
-    TREX_UNROLL for (int s = 0; s < 4; s++) {
-      const uint32_t b = vballot(kv[s] && (sigma[s] != 0.0f));
-      um |= (((b) | (b >> 8) | (b >> 16) | (b >> 24)) & 0xffu) << (8 * s);
+    TREX_UNROLL for (int j = 0; j < NJ; j++) st_if(Gs, gb + kk[s] + j * 25, g[s][j], kv[s]);
+  // contact rows: scalars of the owned contact in registers, B4 / A4 of the group's environment into the stash
+  // (rows of absent contacts are zero: their updates then add exactly 0)
+  vf cu[3], cl[3], crhs[3], cjdi[3], cdd[3], njdi[4];
+  TREX_UNROLL for (int k = 0; k < 3; k++) { cu[k] = 0.0f; cl[k] = 0.0f; crhs[k] = 0.0f; cjdi[k] = 0.0f; cdd[k] = 0.0f; }
+  TREX_UNROLL for (int s = 0; s < 4; s++) njdi[s] = 0.0f;
+  vi ccand = 0;
+  vb cown = gact && !gact;
+  int kmax = 0;
+  if (KC > 0) {
+    const vi nc = seli(gact, vf2i(ld(work0, woff + W_NC)), 0);
+    kmax = lane_value_i(warp_maxi(nc), 0);
+    cown = gact && (gl < nc) && (gl < KC);
+    const vi sb = woff + glc * 16 + W_CS;
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      crhs[k] = ld_if(work0, sb + k, cown, 0.0f);
+      cjdi[k] = ld_if(work0, sb + (3 + k), cown, 0.0f);
+      cdd[k] = ld_if(work0, sb + (6 + k), cown, 0.0f);
     }
-    for (int p = 0; p < NJ; p++) uperm |= ((um >> P.order[NJ + p]) & 1u) << p;
+    cl[0] = ld_if(work0, sb + 9, cown, 0.0f);  // warm start
+    ccand = seli(cown, vf2i(ld_if(work0, sb + 10, cown, 0.0f)), 0);
+    TREX_UNROLL for (int s = 0; s < 4; s++) njdi[s] = -jdi[s];
+    TREX_ROLLED for (int i0 = 0; i0 < 37 * KC; i0 += 8) {
+      const vi i = gl + i0;
+      const vb in = i < 37 * KC;
+      const vi is = seli(in, i, 0);
+      // float4 index -> the contacts it couples: B4 part [c][25], A4 part [r = 3c+k][c']
+      const vi ia = is - 25 * KC;
+      const vb isA = ia >= 0;
+      const vi ias = seli(isA, ia, 0);
+      const vi rA = KC == 4 ? (ias >> 2) : (KC == 8 ? (ias >> 3) : (KC == 2 ? (ias >> 1) : ias));  // ias / KC
+      const vi c1 = seli(isA, (rA * 11) >> 5, (is * 41) >> 10);   // source contact: r / 3 resp. i / 25
+      const vi c2 = seli(isA, ias - rA * KC, 0);                  // affected contact
+      vf v4[4];
+      ld4_if(work0, woff + is * 4 + W_B4, in && gact && (c1 < nc) && (c2 < nc), v4);
+      st4_if(Gs, gb + is * 4 + TREX_GS_STRIDE, v4, in);
+    }
+  }
+  // joints with a violated limit in ANY of the four environments, in Bullet's limit-constraint order
+  // (bit p <=> the joint at position p; the limit block visits the joints in the same order as the motor block)
+  static_assert(limit_order_matches_motor_order(), "solve4 assumes order[NJ + p] == order[p] - NJ");
+  uint32_t uperm = 0;
+  TREX_UNROLL for (int s = 0; s < 4; s++) {
+    const uint32_t b = vballot(kv[s] && (sigma[s] != 0.0f));
+    const uint32_t any = (b | (b >> 8) | (b >> 16) | (b >> 24)) & 0xffu;  // bit l: lane l of some group
+    TREX_UNROLL for (int l = 0; l < 8; l++) uperm |= ((any >> l) & 1u) << (4 * l + s);
   }
   warp_sync();
 
@@ -1191,27 +1356,23 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
   vb alive = gact;
   vi itd = 0;
 
-#define TREX_S4_MOTOR(K)                                                                               \
-  {                                                                                                    \
-    constexpr int j = trex_topo::noncontact_order(K) - NJ;                                             \
-    constexpr int sj = j >> 3;                                                                         \
-    const vf nl = vmin(vmax(w[sj], -max_imp), max_imp);                                                \
-    const vf db = shfl_group8(nl - lam_m[sj], j & 7);   /* only the owner's value is read */           \
-    lam_m[sj] = sel(gl == (j & 7), nl, lam_m[sj]);                                                     \
-    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(g[s][j], db, w[s]);                            \
-  }
   // one limit row of joint j (slot SJ static): sigma = +1 lower row, -1 upper row, impulse in [0, lim_hi]
 #define TREX_S4_LIMIT_SLOT(SJ)                                                                         \
   {                                                                                                    \
     const vf x = (lam_m[SJ] + rhs_m[SJ]) - w[SJ];              /* jdi * dv_j */                         \
     const vf sum = lam_l[SJ] + (rhs_l[SJ] - sigma[SJ] * x);                                            \
     const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                                       \
-    const vb own = alive && (gl == (j & 7)) && (sigma[SJ] != 0.0f);                                    \
+    const vb own = alive && (gl == (pos >> 2)) && (sigma[SJ] != 0.0f);                                 \
     const vf d = sel(own, (nl - lam_l[SJ]) * sigma[SJ], 0.0f);  /* change of the net joint impulse */   \
-    const vf db = shfl_group8(d, j & 7);                                                               \
+    const vf db = shfl_group8(d, pos >> 2);                                                            \
     lam_l[SJ] = sel(own, nl, lam_l[SJ]);                                                               \
     TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(ld(Gs, gbase + kk[s]), db, w[s]);              \
     w[SJ] = w[SJ] - d;                                        /* self term: dv_j += D_j * d */         \
+    if (KC > 0) {                                                                                      \
+      vf b4[4];                                                                                        \
+      ld4(Gs, stash_b4 + 4 * j, b4);                                                                   \
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(b4[k], db, cu[k]);                          \
+    }                                                                                                  \
   }
 #define TREX_S4_LIMITS(FORWARD)                                                                        \
   {                                                                                                    \
@@ -1220,8 +1381,8 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                            \
       m &= ~(1u << pos);                                                                               \
       const int j = P.order[NJ + pos];                                                                 \
-      const vi gbase = grp * TREX_GS_STRIDE + j * 25;                                                  \
-      switch (j >> 3) {                                                                                \
+      const vi gbase = gb + j * 25;                                                                    \
+      switch (pos & 3) {  /* the limit block visits the joints in the motor block's order */            \
         case 0: TREX_S4_LIMIT_SLOT(0) break;                                                           \
         case 1: TREX_S4_LIMIT_SLOT(1) break;                                                           \
         case 2: TREX_S4_LIMIT_SLOT(2) break;                                                           \
@@ -1229,25 +1390,106 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       }                                                                                                \
     }                                                                                                  \
   }
-#define M_(k) TREX_S4_MOTOR(k)
+#define MB_(b, fwd) s4_motor_block<b, fwd, KC>(w, lam_m, g, cu, gl, stash_b4, Gs, max_imp);
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
+    // every 4th sweep rebuild w (and u) exactly from the impulses (bounds the FP32 drift of the incremental updates):
+    // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j - jdi_k sum_r B[r][k] lambda_r
+    // u_r = sum_j B[r][j] Lambda_j + sum_r' A[r][r'] lambda_r'         (also the warm-started initial state)
+    if ((it & 3) == 0 && (KC > 0 || it > 0)) {
+      warp_sync();
+      TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * LS + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+      if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) st_if(Lam, grp * LS + glc * 4 + (32 + k), cl[k], gl < KC);
+      warp_sync();
+      vf acc[4], ua[3];
+      TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = rhs_m[s] - sigma[s] * lam_l[s];
+      TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = 0.0f;
+      TREX_UNROLL for (int j = 0; j < NJ; j++) {
+        const vf Lj = ld(Lam, grp * LS + j);
+        TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
+        if (KC > 0) {
+          vf b4[4];
+          ld4(Gs, gb + glc * 100 + (4 * j + TREX_GS_STRIDE), b4);
+          TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(b4[k], Lj, ua[k]);
+        }
+      }
+      if (KC > 0) {
+        vf bs[4];
+        TREX_UNROLL for (int s = 0; s < 4; s++) bs[s] = 0.0f;
+        TREX_ROLLED for (int c = 0; c < kmax; c++) {
+          TREX_UNROLL for (int k = 0; k < 3; k++) {
+            const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
+            TREX_UNROLL for (int s = 0; s < 4; s++) bs[s] = vfma(ld(Gs, gb + kk[s] * 4 + (c * 100 + k + TREX_GS_STRIDE)), Lr, bs[s]);
+            vf a4[4];
+            ld4(Gs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), a4);
+            TREX_UNROLL for (int k2 = 0; k2 < 3; k2++) ua[k2] = vfma(a4[k2], Lr, ua[k2]);
+          }
+        }
+        TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(njdi[s], bs[s], acc[s]);
+        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = ua[k];
+      }
+      TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = sel(alive, acc[s], w[s]);
+    }
     vf lam_m0[4], lam_l0[4];
+    vf cres = 0.0f;
     TREX_UNROLL for (int s = 0; s < 4; s++) {
       lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s];
       // an environment that has finished (converged) is frozen: clamp(w) == its impulse, so every row yields 0
       w[s] = sel(alive, w[s], lam_m[s]);
     }
     if (it & 1) {
-      M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7) M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16)
-      M_(17) M_(18) M_(19) M_(20) M_(21) M_(22) M_(23) M_(24)
+      MB_(0, true) MB_(1, true) MB_(2, true) MB_(3, true) MB_(4, true) MB_(5, true) MB_(6, true)
       TREX_S4_LIMITS(true)
     } else {
       TREX_S4_LIMITS(false)
-      M_(24) M_(23) M_(22) M_(21) M_(20) M_(19) M_(18) M_(17) M_(16) M_(15) M_(14) M_(13) M_(12) M_(11) M_(10) M_(9) M_(8)
-      M_(7) M_(6) M_(5) M_(4) M_(3) M_(2) M_(1) M_(0)
+      MB_(6, false) MB_(5, false) MB_(4, false) MB_(3, false) MB_(2, false) MB_(1, false) MB_(0, false)
+    }
+    if (KC > 0) {
+      // normal rows: every lane evaluates its own contact, the owner of contact c publishes
+      TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
+        const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
+        const vb own = alive && (gl == c);
+        const vf dl = sel(own, nl - cl[0], 0.0f);
+        const vf d = shfl_group8(dl, c);
+        cl[0] = sel(own, nl, cl[0]);
+        const vf dvel = dl * cdd[0];
+        cres = vmax(cres, dvel * dvel);
+        vf a4[4];
+        ld4(Gs, gb + glc * 4 + ((3 * c) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), a4);
+        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
+        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(ld(Gs, gb + kk[s] * 4 + (c * 100 + TREX_GS_STRIDE)), njdi[s] * d, w[s]);
+      }
+      // friction pairs, implicit cone; both rows read the velocities before either writes
+      TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        const vf lim = P.mu * cl[0];
+        const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
+        const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
+        const vf n2 = sumA * sumA + sumB * sumB;
+        const vb nz = n2 > 0.0f;
+        const vf rn = vrsqrt(sel(nz, n2, 1.0f));
+        const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
+        const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
+        const vf nA = vmin(vmax(sumA, -clipA), clipA);
+        const vf nB = vmin(vmax(sumB, -clipB), clipB);
+        const vb own = alive && (gl == c);
+        const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
+        const vf dAu = shfl_group8(dA, c), dBu = shfl_group8(dB, c);
+        cl[1] = sel(own, nA, cl[1]);
+        cl[2] = sel(own, nB, cl[2]);
+        const vf dvel = dA * cdd[1] + dB * cdd[2];
+        cres = vmax(cres, dvel * dvel);
+        vf aA[4], aB[4];
+        ld4(Gs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), aA);
+        ld4(Gs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), aB);
+        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
+        TREX_UNROLL for (int s = 0; s < 4; s++) {
+          const vi bi = gb + kk[s] * 4 + (c * 100 + TREX_GS_STRIDE);
+          w[s] = vfma(njdi[s], vfma(ld(Gs, bi + 1), dAu, ld(Gs, bi + 2) * dBu), w[s]);
+        }
+      }
     }
     // residual per environment: max over its rows of (delta impulse / jacDiagABInv)^2
-    vf r = 0.0f;
+    vf r = cres;
     TREX_UNROLL for (int s = 0; s < 4; s++) {
       const vf dm = (lam_m[s] - lam_m0[s]) * dself[s], dl = (lam_l[s] - lam_l0[s]) * dself[s];
       r = vmax(r, vmax(dm * dm, dl * dl));
@@ -1256,34 +1498,20 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     itd = itd + seli(alive, vi(1), vi(0));
     alive = alive && !(r <= P.resid_thresh) && (it < P.iters - 1);
     if (!vany(alive)) break;
-    // every 4th sweep rebuild w exactly from the impulses (bounds the FP32 drift of the incremental updates):
-    // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j
-    if ((it & 3) == 3) {
-      warp_sync();
-      TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * 32 + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
-      warp_sync();
-      vf acc[4];
-      TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = rhs_m[s] - sigma[s] * lam_l[s];
-      TREX_UNROLL for (int j = 0; j < NJ; j++) {
-        const vf Lj = ld(Lam, grp * 32 + j);
-        TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
-      }
-      TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = sel(alive, acc[s], w[s]);
-    }
   }
-#undef M_
-#undef TREX_S4_MOTOR
+#undef MB_
 #undef TREX_S4_LIMIT_SLOT
 #undef TREX_S4_LIMITS
 
   // ---- velocity change of every coordinate from the final impulses ------------------------------------
   warp_sync();
-  TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * 32 + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+  TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * LS + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+  if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) st_if(Lam, grp * LS + glc * 4 + (32 + k), cl[k], gl < KC);
   warp_sync();
-  vf Ssum[4];
-  TREX_UNROLL for (int s = 0; s < 4; s++) Ssum[s] = 0.0f;
+  vf Ssum[4], bsum[4];
+  TREX_UNROLL for (int s = 0; s < 4; s++) { Ssum[s] = 0.0f; bsum[s] = 0.0f; }
   TREX_UNROLL for (int j = 0; j < NJ; j++) {
-    const vf Lj = ld(Lam, grp * 32 + j);
+    const vf Lj = ld(Lam, grp * LS + j);
     TREX_UNROLL for (int s = 0; s < 4; s++) Ssum[s] = vfma(g[s][j], Lj, Ssum[s]);
   }
   vf dvb[6];
@@ -1292,12 +1520,24 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     const vf Lk = lam_m[s] + sigma[s] * lam_l[s];
     TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = vfma(ld_if(work0, woff + kk[s] + (W_COL + b * 32), kv[s], 0.0f), Lk, dvb[b]);
   }
+  if (KC > 0) {
+    // contact impulses: joint coordinates through B4, base coordinates through the owner's rows of M^-1 J^T
+    TREX_ROLLED for (int c = 0; c < kmax; c++)
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
+        TREX_UNROLL for (int s = 0; s < 4; s++) bsum[s] = vfma(ld(Gs, gb + kk[s] * 4 + (c * 100 + k + TREX_GS_STRIDE)), Lr, bsum[s]);
+      }
+    TREX_UNROLL for (int k = 0; k < 3; k++)
+      TREX_UNROLL for (int b = 0; b < 6; b++)
+        dvb[b] = vfma(ld_if(work0, woff + glc * 24 + (W_CBASE + k * 8 + b), cown, 0.0f), cl[k], dvb[b]);
+    st_if(rec0, roff + ccand + ST_LAM, cl[0], cown);  // cached normal impulse of the candidate (next substep's warm start)
+  }
   TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = group8_sum(dvb[b]);
 
   // ---- velocities += dv (clamped), applied motor torque, positions with the NEW velocities ----------------
   TREX_UNROLL for (int s = 0; s < 4; s++) {
     const vf Lk = lam_m[s] + sigma[s] * lam_l[s];
-    const vf dvk = dself[s] * (Lk - Ssum[s]);  // M^-1 row k times the impulses = D_k Lambda_k - S_k / jdi_k
+    const vf dvk = dself[s] * (Lk - Ssum[s]) + bsum[s];  // M^-1 row k times the joint impulses = D_k Lambda_k - S_k / jdi_k, + contacts
     const vf qd0 = ld_if(rec0, roff + kk[s] + ST_QD, kv[s], 0.0f);
     const vf q0 = ld_if(rec0, roff + kk[s] + ST_Q, kv[s], 0.0f);
     const vf qd1 = clampv(qd0 + dvk, -P.maxvel, P.maxvel);
@@ -1395,7 +1635,7 @@ enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // p
 // articulated inertias, accelerations, velocity update, M^-1, row setup, contact detection.  With contacts
 // the substep is finished here (one-environment solver + integration); without, the solver inputs go to
 // `work` and the function returns true (solve_phase finishes the substep).   action: [25] name-sorted (trex_robot.py:311-314)
-TREX_FN bool front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
+TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                          const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, bool first_round) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
@@ -1410,7 +1650,7 @@ TREX_FN bool front_phase(const Uniform& P, const float* mdl, const int* mdli, co
 #ifdef TREX_PHASES
   for (int i = 0; i < 8; i++) st.phase[i] = 0.0f;
 #endif
-  const bool deferred = substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, st, work);
+  const int deferred = substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, st, work);
   store_env(rec, lane, S, R);  // deferred: positions unchanged, velocities after the unconstrained update
   const float it0 = first_round ? 0.0f : ldu(rec, ST_ACC_ITERS), ov0 = first_round ? 0.0f : ldu(rec, ST_ACC_OVERFLOW);
   vf acc = 0.0f;
@@ -1419,13 +1659,21 @@ TREX_FN bool front_phase(const Uniform& P, const float* mdl, const int* mdli, co
   acc = sel(lane == 2, vbroadcast(ov0 + (float)st.overflow), acc);
   warp_sync();
   st_if(rec, lane + ST_ACC_ITERS, acc, lane < 3);
+#ifdef TREX_PHASES
+  {  // cycles per phase of this environment's front kernel work, summed over the substeps of the env step
+    vf ph = 0.0f;
+    for (int i = 0; i < 8; i++) ph = sel(lane == i, vbroadcast(st.phase[i] + (first_round ? 0.0f : ldu(rec, 160 + i))), ph);
+    st_if(rec, lane + 160, ph, lane < 8);
+  }
+#endif
   return deferred;
 }
 
 // solve_phase: the deferred solves of up to four environments (any four: the groups are independent)
+template <int KC>
 TREX_FN void solve_phase(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending) {
   const vi lane = lane_id();
-  const vi itd = solve4(P, scratch, work0, rec0, envs, pending, P.max_impulse);
+  const vi itd = solve4<KC>(P, scratch, work0, rec0, envs, pending, P.max_impulse);
   // iterations executed per environment -> its accumulator (lane 8e holds group e's count)
   const vi grp = lane >> 3;
   const vb wr = ((lane & 7) == 0) && ((((vi(pending)) >> grp) & 1) != 0);
@@ -1468,6 +1716,9 @@ TREX_FN void tail_phase(const Uniform& P, const float* mdl, const int* mdli, con
       ax = sel(lane == 6, vbroadcast(ldu(rec, ST_ACC_ITERS)), ax);
       ax = sel(lane == 7, vbroadcast(ldu(rec, ST_ACC_CONTACTS) + 1000.0f * ldu(rec, ST_ACC_OVERFLOW)), ax);
       st_if(aux, lane, ax, lane < 8);
+#ifdef TREX_PHASES
+      st_if(aux, lane, ld(rec, seli(lane >= 8 && lane < 16, lane + 152, 0)), lane >= 8 && lane < 16);
+#endif
     }
     warp_sync();
   }

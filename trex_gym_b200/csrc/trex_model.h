@@ -234,6 +234,7 @@ struct EnvConfig {
   unsigned seed = 0;
   long long env_offset = 0;
   float reset_z_min = 0.3f, reset_z_max = 3.0f;
+  int defer_contacts = 1;  // substeps with a few contacts also go to the four-environments-per-warp solver
 };
 
 // Fill a trex::Uniform (templated so this header stays free of the lane vocabulary).
@@ -265,6 +266,7 @@ static inline void fill_uniform(const ModelTables& T, const EnvConfig& C, U& P) 
   P.n_rounds = T.n_rounds;
   P.contacts_on = C.enable_contacts;
   P.reset_mode = C.reset_mode;
+  P.defer_contacts = C.defer_contacts;
   P.seed = C.seed;
   P.env_offset = C.env_offset;
   P.reset_z_min = C.reset_z_min; P.reset_z_max = C.reset_z_max;
