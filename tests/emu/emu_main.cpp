@@ -61,18 +61,19 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
   if (!force_reset) {
     for (int r = 0; r < e->P.n_sub; r++) {
       // deferred environments are packed into the solver's lane groups in list order (any order is equivalent)
-      // (two lists, as in the library: contact-free environments and environments with 1..TREX_KC contacts)
-      int envs[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, cnt[2] = {0, 0};
+      // (one list per class, as in the library: contact-free, 1-2, 3-4 and 5-8 contacts)
+      int envs[TREX_NCLASS][4] = {}, cnt[TREX_NCLASS] = {};
       for (int i = 0; i < n; i++) {
         const int d = trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
                                         e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0);
-        e->solves[d]++;
+        e->solves[d == 0 ? 0 : (d == 1 ? 1 : 2)]++;
         if (d) { int& c = cnt[d - 1]; envs[d - 1][e->pack_reverse ? 3 - c : c] = i; c++; }
       }
-      for (int d = 0; d < 2; d++) {
+      for (int d = 0; d < TREX_NCLASS; d++) {
+        if (!cnt[d]) continue;
         const int pending = e->pack_reverse ? (((1 << cnt[d]) - 1) << (4 - cnt[d])) : ((1 << cnt[d]) - 1);
-        if (cnt[d] && d == 0) trex::solve_phase<0>(e->P, e->scratch, e->work, rec, envs[0], pending);
-        if (cnt[d] && d == 1) trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[1], pending);
+        if (d == 0) trex::solve_phase<0>(e->P, e->scratch, e->work, rec, envs[0], pending);
+        else trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[d], pending);
       }
     }
   }

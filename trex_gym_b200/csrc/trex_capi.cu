@@ -65,25 +65,34 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
   const int deferred = trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
                                           work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
                                           first_round != 0);
-  // append to the list of deferred environments (any order: the solver's lane groups are independent):
-  // list 0 = contact-free substeps, list 1 (second half, counters + 64) = substeps with 1..TREX_KC contacts
+  // append to the list of its class of deferred environments (any order: the solver's lane groups are independent):
+  // class 0 = contact-free substeps, classes 1..3 = 1-2 / 3-4 / 5-8 contacts; list c at list + c * n_envs, counters + 64 * c
   if (deferred && (threadIdx.x & 31) == 0) {
     const int which = deferred - 1;
     list[(size_t)which * n_envs + atomicAdd(list_count + 64 * which, 1)] = env;
   }
 }
 
-// one warp per FOUR deferred environments taken from the list, eight lanes per environment; KC = 0: the contact-free
-// list, KC = TREX_KC: the list of environments with 1..TREX_KC contacts (rows in row space, see solve4)
+// one warp per FOUR deferred environments of one class, eight lanes per environment; KC = 0: the contact-free list,
+// KC = TREX_KC: the three lists of environments in contact (rows in row space, see solve4), warps assigned class by class
 template <int WARPS, int KC>
 __global__ void __launch_bounds__(32 * WARPS, (KC ? TREX_SOLVEC_MIN_BLOCKS : TREX_SOLVE_MIN_BLOCKS) / WARPS)
 trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
-                  const int* __restrict__ list, const int* __restrict__ list_count) {
+                  const int* __restrict__ list, const int* __restrict__ list_count, int n_envs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* scratch = reinterpret_cast<float*>(smem_raw) + (threadIdx.x >> 5) * TREX_SOLVE_SCRATCH(KC);
   const int warp = threadIdx.x >> 5;
-  const int first = (blockIdx.x * WARPS + warp) * 4;
-  const int count = *list_count;
+  int first = (blockIdx.x * WARPS + warp) * 4;
+  int count = *list_count;
+  if (KC > 0) {
+    // list / list_count point at class 1; skip the classes whose warps come before this one
+    for (int c = 1; c < TREX_NCLASS - 1 && first >= ((count + 3) & ~3); c++) {
+      first -= (count + 3) & ~3;
+      list += n_envs;
+      list_count += 64;
+      count = *list_count;
+    }
+  }
   if (first >= count) return;
   int envs[4] = {0, 0, 0, 0}, pending = 0;
   for (int e = 0; e < 4 && first + e < count; e++) { envs[e] = list[first + e]; pending |= 1 << e; }
@@ -280,19 +289,19 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
   const int grid1 = (h->n_envs + WF - 1) / WF;            // one warp per environment
   const int grid4 = (h->n_envs + 4 * WS - 1) / (4 * WS);  // one warp per four environments
   if (mode == 0) {
-    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 128 * sizeof(int), st));  // one counter per list and substep round
+    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 64 * TREX_NCLASS * sizeof(int), st));  // one counter per list and substep round
     for (int r = 0; r < h->P.n_sub; r++) {
       trex_front_kernel<WF><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
                                                            h->d_state, h->d_work, action, h->d_list, h->d_list_count + r, h->n_envs, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
-        trex_solve_kernel<WS, 0><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r);
+        trex_solve_kernel<WS, 0><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r, h->n_envs);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
         if (h->P.defer_contacts && h->P.contacts_on) {
-          trex_solve_kernel<WS, TREX_KC><<<grid4, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
-                                                                        h->d_list_count + 64 + r);
+          trex_solve_kernel<WS, TREX_KC><<<grid4 + 2, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
+                                                                            h->d_list_count + 64 + r, h->n_envs);
           CUDA_TRY(cudaGetLastError());
           h->launches++;
         }
@@ -386,9 +395,9 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   CTRY(cudaMalloc((void**)&h->d_obs, N * 3 * trex::NJ * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_reward, N * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_done, N));
-  CTRY(cudaMalloc((void**)&h->d_list, 2 * N * sizeof(int)));
-  CTRY(cudaMalloc((void**)&h->d_list_count, 128 * sizeof(int)));
-  CTRY(cudaMemset(h->d_list_count, 0, 128 * sizeof(int)));
+  CTRY(cudaMalloc((void**)&h->d_list, TREX_NCLASS * N * sizeof(int)));
+  CTRY(cudaMalloc((void**)&h->d_list_count, 64 * TREX_NCLASS * sizeof(int)));
+  CTRY(cudaMemset(h->d_list_count, 0, 64 * TREX_NCLASS * sizeof(int)));
   CTRY(cudaMalloc((void**)&h->d_stats, sizeof(DevStats)));
 #undef CTRY
   // all environments start from the reference reset (TrexBulletEnv.__init__ calls reset(), trex_env.py:92)

@@ -45,14 +45,17 @@
 #define W_RHSL 1088
 #define W_SIGMA 1120
 // ... followed, for environments with 1..TREX_KC contacts, by the contact rows in "row space" (see solve4):
-#define TREX_KC 4                          // contacts per environment the four-environments-per-warp solver accepts
+#define TREX_KC 8                          // contacts per environment the four-environments-per-warp solver accepts
 #define W_NC 1152                          // number of contacts (as float)
 #define W_CS 1160                          // [KC][16]: rhs n,t1,t2 | jdi | J M^-1 J^T | warm-started normal impulse | candidate index
-#define W_CBASE (W_CS + 16 * TREX_KC)      // [3*KC][8]: base coordinates of the row responses M^-1 J^T
-#define W_B4 (W_CBASE + 24 * TREX_KC)      // [KC][25][4]: joint coordinates of the responses, B4[c][j][k] = (M^-1 J_{c,k}^T)[6+j]
-#define W_A4 (W_B4 + 100 * TREX_KC)        // [3*KC][KC][4]: A4[r][c'][k'] = J_{c',k'} M^-1 J_r^T
-#define TREX_WORK_STRIDE 1920
-static_assert(W_A4 + 48 * TREX_KC <= TREX_WORK_STRIDE && (W_B4 % 4) == 0 && (W_A4 % 4) == 0, "work record layout");
+#define W_BT (W_CS + 16 * TREX_KC)         // [3*KC][32]: the row responses M^-1 J^T by lane (joints 0..24, base coordinates 25..30)
+#define W_A4 (W_BT + 96 * TREX_KC)         // [3*KC][KC][4]: A4[r][c'][k'] = J_{c',k'} M^-1 J_r^T
+#define TREX_WORK_STRIDE 2848
+static_assert(W_A4 + 12 * TREX_KC * TREX_KC <= TREX_WORK_STRIDE && (W_BT % 4) == 0 && (W_A4 % 4) == 0 && (TREX_WORK_STRIDE % 32) == 0,
+              "work record layout");
+// deferred environments are listed by class so that the four environments of a solver warp have similar row counts
+#define TREX_NCLASS 4                      // 0: contact-free, 1: 1-2 contacts, 2: 3-4, 3: 5-8
+TREX_TOPO_FN int defer_class(int n_contacts) { return n_contacts == 0 ? 0 : (n_contacts <= 2 ? 1 : (n_contacts <= 4 ? 2 : 3)); }
 #ifdef TREX_PHASES
 #define TREX_AUX_STRIDE 16
 #define TREX_TICK(i) { const long long _t = cycle_count(); stats.phase[i] += (float)(_t - _t0); _t0 = _t; }
@@ -883,14 +886,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
         st_if(work, sb + 10, vi2f(ldi(S.ccand, ls)), own);
         st_if(work, vi(W_NC), vbroadcast((float)n_act), lane == 0);
       }
-      const vb isb = (lane >= 25) && (lane < 31);
-      TREX_ROLLED for (int c = 0; c < n_act; c++) {
-        vf d4[4];
-        TREX_UNROLL for (int k = 0; k < 3; k++) d4[k] = ld(S.c.dV[3 * c + k], lane);
-        d4[3] = 0.0f;
-        st4_if(work, (seli(is_joint, lane, 0) + c * 25) * 4 + W_B4, d4, is_joint);
-        TREX_UNROLL for (int k = 0; k < 3; k++) st_if(work, seli(isb, lane - 25, 0) + ((3 * c + k) * 8 + W_CBASE), d4[k], isb);
-      }
+      TREX_ROLLED for (int r = 0; r < 3 * n_act; r++) st(work, lane + (r * 32 + W_BT), ld(S.c.dV[r], lane));
       const int n3 = 3 * n_act, nn = n3 * n3, recip = 65536 / n3 + 1;
       TREX_ROLLED for (int i0 = 0; i0 < nn; i0 += 32) {
         const vi idx = lane + i0;
@@ -898,7 +894,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
         const vi is = seli(valid, idx, 0);
         const vi rp = (is * recip) >> 16;        // affected row (c', k')
         const vi r = is - rp * n3;               // source row (c, k)
-        const vi cp = (rp * 11) >> 5, kp = rp - cp * 3;
+        const vi cp = (rp * 11) >> 5, kp = rp - cp * 3;  // rp / 3, rp % 3 (rp < 24)
         vf acc = 0.0f;
         TREX_UNROLL for (int e = 0; e < 11; e++) {
           const vf jv = ld(&S.c.Jc[0][0], rp * 12 + e);
@@ -908,7 +904,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
         st_if(work, (r * TREX_KC + cp) * 4 + kp + W_A4, acc, valid);
       }
       warp_sync();
-      return 2;
+      return 1 + defer_class(n_act);
     }
   }
   warp_sync();
@@ -1227,7 +1223,7 @@ TREX_TOPO_FN bool limit_order_matches_motor_order() {
   return true;
 }
 template <int B, bool FWD, int KC>
-TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf (&cu)[3], vi gl, vi stash_b4, const float* Gs,
+TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf (&cu)[3], vi gl, vi bt_own, const float* Bs,
                             float max_imp) {
   constexpr int n = (4 * B + 4 <= NJ) ? 4 : NJ - 4 * B;
   vf t[4], d[4];
@@ -1251,17 +1247,18 @@ TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf
     const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
     const vf db = shfl_group8(d[i], B);
     TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(g[s][j], db, w[s]);
-    if (KC > 0) {
-      vf b4[4];
-      ld4(Gs, stash_b4 + 4 * j, b4);
-      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(b4[k], db, cu[k]);
-    }
+    if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bs, bt_own + (k * 33 + j)), db, cu[k]);
   }
 }
 
-#define TREX_GS_STRIDE 648  // floats per group in the shared stash of g (25*25 = 625, padded: bank offset 8 per group)
-#define TREX_GC_STRIDE(KC) (TREX_GS_STRIDE + 148 * (KC))  // + B4 [KC][25][4] + A4 [3*KC][KC][4]
-#define TREX_SOLVE_SCRATCH(KC) (4 * TREX_GC_STRIDE(KC) + 4 * (32 + 4 * (KC)))  // floats of warp-private shared memory
+// warp-private shared memory of solve4<KC>, per lane group: Bt [3*KC][33] (row responses at the joints, padded rows:
+// conflict-free for "one row per owner" and for "one column per joint owner"), A4 [3*KC][KC][4], then for all groups
+// Lam [4][32 + 4*KC] (net joint impulses + contact impulses, exchanged every few sweeps)
+#define TREX_BT_SIZE(KC) ((99 * (KC) + 3) & ~3)
+#define TREX_GC_STRIDE(KC) (TREX_BT_SIZE(KC) + 12 * (KC) * (KC))
+// and Lg [slots][4][32]: per lane and owned joint, the column of g of the first few joints with a violated limit
+#define TREX_LIMIT_SLOTS(KC) ((KC) > 4 ? 3 : 6)
+#define TREX_SOLVE_SCRATCH(KC) (4 * TREX_GC_STRIDE(KC) + 4 * (32 + 4 * (KC)) + 128 * TREX_LIMIT_SLOTS(KC))  // floats
 // envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
 template <int KC>
 TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending, float max_imp) {
@@ -1273,11 +1270,13 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
   const vi genv = seli(grp == 0, vi(envs[0]), seli(grp == 1, vi(envs[1]), seli(grp == 2, vi(envs[2]), vi(envs[3]))));
   const vi woff = seli(gact, genv, 0) * TREX_WORK_STRIDE, roff = seli(gact, genv, 0) * TREX_STATE_STRIDE;
   const float dt = P.dt;
-  float* Gs = scratch;                                 // [4][GC]: g[k][j] at j*25 + k, then B4, then A4
-  float* Lam = Gs + 4 * GC;                            // [4][LS]: net joint impulses + contact impulses, exchanged every few sweeps
+  constexpr int BT = TREX_BT_SIZE(KC);
+  float* Bs = scratch;                                 // [4][GC]: Bt, then A4
+  float* Lam = Bs + 4 * GC;                            // [4][LS]
+  float* Lg = Lam + 4 * LS;                            // [TREX_LIMIT_SLOTS][4][32]
   const vi gb = grp * GC;                              // this group's stash
   const vi glc = KC > 0 ? vmini(gl, KC - 1) : vi(0);  // contact slot of this lane (lanes >= KC shadow the last owner, unused)
-  const vi stash_b4 = gb + glc * 100 + TREX_GS_STRIDE; // B4 rows of the owned contact
+  const vi bt_own = gb + glc * 99;                     // Bt rows of the owned contact
 
   vi kk[4];
   vb kv[4];
@@ -1293,20 +1292,19 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     dself[s] = ld_if(work0, woff + kk[s] + W_DSELF, kv[s], 0.0f);
     rhs_l[s] = ld_if(work0, woff + kk[s] + W_RHSL, kv[s], 0.0f);
     sigma[s] = ld_if(work0, woff + kk[s] + W_SIGMA, kv[s], 0.0f);
-    TREX_UNROLL for (int j = 0; j < NJ; j++) {
-      const vf cj = ld_if(work0, woff + kk[s] + (W_COL + (6 + j) * 32), kv[s], 0.0f);
-      g[s][j] = sel(kk[s] == j, 0.0f, -(jdi[s] * cj));
+    // row 6+k of M^-1 (= column 6+k: the matrix is symmetric), lanes 0..24 of the record's row: seven 128-bit loads
+    TREX_UNROLL for (int j4 = 0; j4 < 7; j4++) {
+      vf c4[4];
+      ld4_if(work0, woff + kk[s] * 32 + (W_COL + 6 * 32 + 4 * j4), kv[s], c4);
+      TREX_UNROLL for (int e = 0; e < 4; e++)
+        if (4 * j4 + e < NJ) g[s][4 * j4 + e] = sel(kk[s] == 4 * j4 + e, 0.0f, -(jdi[s] * c4[e]));
     }
   }
-  // copy of g in shared memory for the limit rows (their joint index is only known at run time)
-  warp_sync();
-  TREX_UNROLL for (int s = 0; s < 4; s++)
-    TREX_UNROLL for (int j = 0; j < NJ; j++) st_if(Gs, gb + kk[s] + j * 25, g[s][j], kv[s]);
   // contact rows: scalars of the owned contact in registers, B4 / A4 of the group's environment into the stash
   // (rows of absent contacts are zero: their updates then add exactly 0)
   vf cu[3], cl[3], crhs[3], cjdi[3], cdd[3], njdi[4];
   TREX_UNROLL for (int k = 0; k < 3; k++) { cu[k] = 0.0f; cl[k] = 0.0f; crhs[k] = 0.0f; cjdi[k] = 0.0f; cdd[k] = 0.0f; }
-  TREX_UNROLL for (int s = 0; s < 4; s++) njdi[s] = 0.0f;
+  TREX_UNROLL for (int s = 0; s < 4; s++) njdi[s] = -jdi[s];
   vi ccand = 0;
   vb cown = gact && !gact;
   int kmax = 0;
@@ -1322,23 +1320,22 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     }
     cl[0] = ld_if(work0, sb + 9, cown, 0.0f);  // warm start
     ccand = seli(cown, vf2i(ld_if(work0, sb + 10, cown, 0.0f)), 0);
-    TREX_UNROLL for (int s = 0; s < 4; s++) njdi[s] = -jdi[s];
-    TREX_ROLLED for (int i0 = 0; i0 < 37 * KC; i0 += 8) {
-      const vi i = gl + i0;
-      const vb in = i < 37 * KC;
-      const vi is = seli(in, i, 0);
-      // float4 index -> the contacts it couples: B4 part [c][25], A4 part [r = 3c+k][c']
-      const vi ia = is - 25 * KC;
-      const vb isA = ia >= 0;
-      const vi ias = seli(isA, ia, 0);
-      const vi rA = KC == 4 ? (ias >> 2) : (KC == 8 ? (ias >> 3) : (KC == 2 ? (ias >> 1) : ias));  // ias / KC
-      const vi c1 = seli(isA, (rA * 11) >> 5, (is * 41) >> 10);   // source contact: r / 3 resp. i / 25
-      const vi c2 = seli(isA, ias - rA * KC, 0);                  // affected contact
-      vf v4[4];
-      ld4_if(work0, woff + is * 4 + W_B4, in && gact && (c1 < nc) && (c2 < nc), v4);
-      st4_if(Gs, gb + is * 4 + TREX_GS_STRIDE, v4, in);
+    // Bt: rows 3c+k of the record (32 floats each) -> rows of 33; one float4 per lane and step, 8 per row
+    // A4: record [r][TREX_KC][4] -> stash [r][KC][4]; lane gl takes the block of affected contact gl
+    // (the three rows of one contact per step: six independent loads in flight)
+    TREX_ROLLED for (int c = 0; c < kmax; c++) {
+      vf b4[3][4], a4[3][4];
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        ld4_if(work0, woff + gl * 4 + ((3 * c + k) * 32 + W_BT), gact && (vi(c) < nc), b4[k]);
+        ld4_if(work0, woff + glc * 4 + ((3 * c + k) * (4 * TREX_KC) + W_A4), cown && (vi(c) < nc), a4[k]);
+      }
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        TREX_UNROLL for (int e = 0; e < 4; e++) st(Bs, gb + gl * 4 + ((3 * c + k) * 33 + e), b4[k][e]);
+        st4_if(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4[k], gl < KC);
+      }
     }
   }
+  warp_sync();
   // joints with a violated limit in ANY of the four environments, in Bullet's limit-constraint order
   // (bit p <=> the joint at position p; the limit block visits the joints in the same order as the motor block)
   static_assert(limit_order_matches_motor_order(), "solve4 assumes order[NJ + p] == order[p] - NJ");
@@ -1347,6 +1344,20 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     const uint32_t b = vballot(kv[s] && (sigma[s] != 0.0f));
     const uint32_t any = (b | (b >> 8) | (b >> 16) | (b >> 24)) & 0xffu;  // bit l: lane l of some group
     TREX_UNROLL for (int l = 0; l < 8; l++) uperm |= ((any >> l) & 1u) << (4 * l + s);
+  }
+  // their columns of g (joint index known only at run time) into shared memory; beyond the slots: from the record
+  uint32_t cached = 0;
+  {
+    uint32_t m = uperm;
+    TREX_ROLLED for (int slot = 0; slot < TREX_LIMIT_SLOTS(KC) && m != 0; slot++) {
+      const int pos = ctz_u(m);
+      m &= m - 1;
+      cached |= 1u << pos;
+      const int j = P.order[NJ + pos];
+      TREX_UNROLL for (int s = 0; s < 4; s++)
+        st(Lg, lane + (slot * 4 + s) * 32,
+           sel(kk[s] == j, 0.0f, njdi[s] * ld_if(work0, woff + kk[s] * 32 + (W_COL + 6 * 32 + j), kv[s], 0.0f)));
+    }
   }
   warp_sync();
 
@@ -1366,13 +1377,9 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     const vf d = sel(own, (nl - lam_l[SJ]) * sigma[SJ], 0.0f);  /* change of the net joint impulse */   \
     const vf db = shfl_group8(d, pos >> 2);                                                            \
     lam_l[SJ] = sel(own, nl, lam_l[SJ]);                                                               \
-    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(ld(Gs, gbase + kk[s]), db, w[s]);              \
+    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(gj[s], db, w[s]);                              \
     w[SJ] = w[SJ] - d;                                        /* self term: dv_j += D_j * d */         \
-    if (KC > 0) {                                                                                      \
-      vf b4[4];                                                                                        \
-      ld4(Gs, stash_b4 + 4 * j, b4);                                                                   \
-      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(b4[k], db, cu[k]);                          \
-    }                                                                                                  \
+    if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bs, bt_own + (k * 33 + j)), db, cu[k]); \
   }
 #define TREX_S4_LIMITS(FORWARD)                                                                        \
   {                                                                                                    \
@@ -1381,7 +1388,15 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                            \
       m &= ~(1u << pos);                                                                               \
       const int j = P.order[NJ + pos];                                                                 \
-      const vi gbase = gb + j * 25;                                                                    \
+      /* column j of g from the record (limit rows are rare; their joint is only known at run time) */  \
+      vf gj[4];                                                                                        \
+      if ((cached >> pos) & 1u) {                                                                      \
+        const int slot = popc_u(cached & ((1u << pos) - 1u));                                          \
+        TREX_UNROLL for (int s = 0; s < 4; s++) gj[s] = ld(Lg, lane + (slot * 4 + s) * 32);            \
+      } else {                                                                                         \
+        TREX_UNROLL for (int s = 0; s < 4; s++)                                                        \
+          gj[s] = sel(kk[s] == j, 0.0f, njdi[s] * ld_if(work0, woff + kk[s] * 32 + (W_COL + 6 * 32 + j), kv[s], 0.0f)); \
+      }                                                                                                \
       switch (pos & 3) {  /* the limit block visits the joints in the motor block's order */            \
         case 0: TREX_S4_LIMIT_SLOT(0) break;                                                           \
         case 1: TREX_S4_LIMIT_SLOT(1) break;                                                           \
@@ -1390,7 +1405,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       }                                                                                                \
     }                                                                                                  \
   }
-#define MB_(b, fwd) s4_motor_block<b, fwd, KC>(w, lam_m, g, cu, gl, stash_b4, Gs, max_imp);
+#define MB_(b, fwd) s4_motor_block<b, fwd, KC>(w, lam_m, g, cu, gl, bt_own, Bs, max_imp);
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
     // every 4th sweep rebuild w (and u) exactly from the impulses (bounds the FP32 drift of the incremental updates):
     // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j - jdi_k sum_r B[r][k] lambda_r
@@ -1406,11 +1421,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       TREX_UNROLL for (int j = 0; j < NJ; j++) {
         const vf Lj = ld(Lam, grp * LS + j);
         TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
-        if (KC > 0) {
-          vf b4[4];
-          ld4(Gs, gb + glc * 100 + (4 * j + TREX_GS_STRIDE), b4);
-          TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(b4[k], Lj, ua[k]);
-        }
+        if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(ld(Bs, bt_own + (k * 33 + j)), Lj, ua[k]);
       }
       if (KC > 0) {
         vf bs[4];
@@ -1418,9 +1429,9 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         TREX_ROLLED for (int c = 0; c < kmax; c++) {
           TREX_UNROLL for (int k = 0; k < 3; k++) {
             const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
-            TREX_UNROLL for (int s = 0; s < 4; s++) bs[s] = vfma(ld(Gs, gb + kk[s] * 4 + (c * 100 + k + TREX_GS_STRIDE)), Lr, bs[s]);
+            TREX_UNROLL for (int s = 0; s < 4; s++) bs[s] = vfma(ld(Bs, gb + kk[s] + (3 * c + k) * 33), Lr, bs[s]);
             vf a4[4];
-            ld4(Gs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), a4);
+            ld4(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4);
             TREX_UNROLL for (int k2 = 0; k2 < 3; k2++) ua[k2] = vfma(a4[k2], Lr, ua[k2]);
           }
         }
@@ -1455,9 +1466,9 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         const vf dvel = dl * cdd[0];
         cres = vmax(cres, dvel * dvel);
         vf a4[4];
-        ld4(Gs, gb + glc * 4 + ((3 * c) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), a4);
+        ld4(Bs, gb + glc * 4 + ((3 * c) * (4 * KC) + BT), a4);
         TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
-        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(ld(Gs, gb + kk[s] * 4 + (c * 100 + TREX_GS_STRIDE)), njdi[s] * d, w[s]);
+        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(ld(Bs, gb + kk[s] + (3 * c) * 33), njdi[s] * d, w[s]);
       }
       // friction pairs, implicit cone; both rows read the velocities before either writes
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
@@ -1479,12 +1490,12 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         const vf dvel = dA * cdd[1] + dB * cdd[2];
         cres = vmax(cres, dvel * dvel);
         vf aA[4], aB[4];
-        ld4(Gs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), aA);
-        ld4(Gs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + TREX_GS_STRIDE + 100 * KC), aB);
+        ld4(Bs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + BT), aA);
+        ld4(Bs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + BT), aB);
         TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
         TREX_UNROLL for (int s = 0; s < 4; s++) {
-          const vi bi = gb + kk[s] * 4 + (c * 100 + TREX_GS_STRIDE);
-          w[s] = vfma(njdi[s], vfma(ld(Gs, bi + 1), dAu, ld(Gs, bi + 2) * dBu), w[s]);
+          const vi bi = gb + kk[s] + (3 * c + 1) * 33;
+          w[s] = vfma(njdi[s], vfma(ld(Bs, bi), dAu, ld(Bs, bi + 33) * dBu), w[s]);
         }
       }
     }
@@ -1494,10 +1505,13 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       const vf dm = (lam_m[s] - lam_m0[s]) * dself[s], dl = (lam_l[s] - lam_l0[s]) * dself[s];
       r = vmax(r, vmax(dm * dm, dl * dl));
     }
-    r = group8_max(r);
+    // (leastSquaresResidual <= threshold stops the environment: true iff no lane of the group exceeds it)
+    const uint32_t over = vballot(alive && !(r <= P.resid_thresh));
     itd = itd + seli(alive, vi(1), vi(0));
-    alive = alive && !(r <= P.resid_thresh) && (it < P.iters - 1);
-    if (!vany(alive)) break;
+    const vi ob = seli(grp == 0, vi((int)(over & 0xffu)), seli(grp == 1, vi((int)((over >> 8) & 0xffu)),
+                       seli(grp == 2, vi((int)((over >> 16) & 0xffu)), vi((int)(over >> 24)))));
+    alive = alive && (ob != 0) && (it < P.iters - 1);
+    if (over == 0u || it >= P.iters - 1) break;
   }
 #undef MB_
 #undef TREX_S4_LIMIT_SLOT
@@ -1525,11 +1539,11 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     TREX_ROLLED for (int c = 0; c < kmax; c++)
       TREX_UNROLL for (int k = 0; k < 3; k++) {
         const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
-        TREX_UNROLL for (int s = 0; s < 4; s++) bsum[s] = vfma(ld(Gs, gb + kk[s] * 4 + (c * 100 + k + TREX_GS_STRIDE)), Lr, bsum[s]);
+        TREX_UNROLL for (int s = 0; s < 4; s++) bsum[s] = vfma(ld(Bs, gb + kk[s] + (3 * c + k) * 33), Lr, bsum[s]);
       }
     TREX_UNROLL for (int k = 0; k < 3; k++)
       TREX_UNROLL for (int b = 0; b < 6; b++)
-        dvb[b] = vfma(ld_if(work0, woff + glc * 24 + (W_CBASE + k * 8 + b), cown, 0.0f), cl[k], dvb[b]);
+        dvb[b] = vfma(ld_if(work0, woff + glc * 96 + (W_BT + k * 32 + 25 + b), cown, 0.0f), cl[k], dvb[b]);
     st_if(rec0, roff + ccand + ST_LAM, cl[0], cown);  // cached normal impulse of the candidate (next substep's warm start)
   }
   TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = group8_sum(dvb[b]);
