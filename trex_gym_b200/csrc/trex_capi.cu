@@ -15,7 +15,7 @@
 #include <new>
 
 #ifndef TREX_MIN_BLOCKS
-#define TREX_MIN_BLOCKS 14        // resident warps per SM targeted by the front / tail kernels (128 registers)
+#define TREX_MIN_BLOCKS 16        // resident warps per SM targeted by the front / tail kernels (128 registers)
 #endif
 #ifndef TREX_SOLVE_MIN_BLOCKS
 #define TREX_SOLVE_MIN_BLOCKS 12  // ... by the 4-environments-per-warp solve kernel (168 registers)
@@ -62,6 +62,9 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS + warp;
   if (env >= n_envs) return;
+#ifdef TREX_PHASES
+  const long long t_entry = clock64();
+#endif
   const int deferred = trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
                                           work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
                                           first_round != 0);
@@ -71,6 +74,10 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
     const int which = deferred - 1;
     list[(size_t)which * n_envs + atomicAdd(list_count + 64 * which, 1)] = env;
   }
+#ifdef TREX_PHASES
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) state[(size_t)env * TREX_STATE_STRIDE + 167] += (float)(clock64() - t_entry);  // warp lifetime
+#endif
 }
 
 // one warp per FOUR deferred environments of one class, eight lanes per environment; KC = 0: the contact-free list,
@@ -242,7 +249,7 @@ trex_stats_kernel(const float* __restrict__ state, const float* __restrict__ aux
 struct trex_handle {
   int device = 0;
   int n_envs = 0;
-  int warps_per_block = 1;  // front / tail kernels; the solve kernel uses 2 (4 when this is 4)
+  int warps_per_block = 2;  // front / tail kernels; the solve kernel uses 2 (4 when this is 4)
   bool deferred_solve = true;  // contact-free substeps solved four environments per warp (solve4)
   trex_host::ModelTables T;
   trex_host::EnvConfig C;
