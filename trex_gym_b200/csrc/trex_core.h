@@ -770,7 +770,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
   // scalars and -- below -- the contact rows.
   const bool defer_c = work != nullptr && P.defer_contacts != 0 && n_act > 0 && n_act <= TREX_KC;
   if (work != nullptr && (n_act == 0 || defer_c)) {
-    TREX_ROLLED for (int gq = 0; gq < trex_topo::NDOF; gq++) st(work, lane + (W_COL + gq * 32), ld(S.col[gq], lane));
+    _Pragma("unroll 8") for (int gq = 0; gq < trex_topo::NDOF; gq++) st(work, lane + (W_COL + gq * 32), ld(S.col[gq], lane));
     st(work, lane + W_RHSM, rhs_m);
     st(work, lane + W_JDI, jdi);
     st(work, lane + W_DSELF, sel(is_joint, dself, 0.0f));
@@ -779,6 +779,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
     stats.contacts = n_act;
     if (n_act == 0) {
       warp_sync();
+      TREX_TICK(5)
       return 1;
     }
   }
@@ -904,6 +905,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
         st_if(work, (r * TREX_KC + cp) * 4 + kp + W_A4, acc, valid);
       }
       warp_sync();
+      TREX_TICK(5)
       return 1 + defer_class(n_act);
     }
   }
@@ -1257,6 +1259,9 @@ TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf
 #define TREX_BT_SIZE(KC) ((99 * (KC) + 3) & ~3)
 #define TREX_GC_STRIDE(KC) (TREX_BT_SIZE(KC) + 12 * (KC) * (KC))
 // and Lg [slots][4][32]: per lane and owned joint, the column of g of the first few joints with a violated limit
+#ifndef TREX_REBUILD_MASK
+#define TREX_REBUILD_MASK 3  // exact rebuild of w (and u) every 4th sweep (every 8th: the 2e-5 per-env-step parity bound is exceeded, 2.1e-5)
+#endif
 #define TREX_LIMIT_SLOTS(KC) ((KC) > 4 ? 3 : 6)
 #define TREX_SOLVE_SCRATCH(KC) (4 * TREX_GC_STRIDE(KC) + 4 * (32 + 4 * (KC)) + 128 * TREX_LIMIT_SLOTS(KC))  // floats
 // envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
@@ -1407,10 +1412,10 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
   }
 #define MB_(b, fwd) s4_motor_block<b, fwd, KC>(w, lam_m, g, cu, gl, bt_own, Bs, max_imp);
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
-    // every 4th sweep rebuild w (and u) exactly from the impulses (bounds the FP32 drift of the incremental updates):
+    // every 4th sweep (TREX_REBUILD_MASK) rebuild w (and u) exactly from the impulses (bounds the FP32 drift of the incremental updates):
     // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j - jdi_k sum_r B[r][k] lambda_r
     // u_r = sum_j B[r][j] Lambda_j + sum_r' A[r][r'] lambda_r'         (also the warm-started initial state)
-    if ((it & 3) == 0 && (KC > 0 || it > 0)) {
+    if ((it & TREX_REBUILD_MASK) == 0 && (KC > 0 || it > 0)) {
       warp_sync();
       TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * LS + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
       if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) st_if(Lam, grp * LS + glc * 4 + (32 + k), cl[k], gl < KC);
