@@ -269,7 +269,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak if fp32_peak else None,
                          "traffic": traffic,
-                         "kernel": "one env step = %d x (trex_front_kernel, trex_solve_kernel) + trex_tail_kernel; trex_front_kernel is ~80%% of the device time (profiles/r1_launches.txt)" % sim.num_substeps,
+                         "kernel": "one env step = %d x (trex_front_kernel, trex_solve_kernel<0>, trex_solve_kernel<8>) + trex_tail_kernel; shares of the device time in profiles/r1c_launches.txt" % sim.num_substeps,
                          "kernel_ms": kernel_ms,
                          "peak_source": "measured in this run: register-resident FFMA microbenchmark (trex_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                          "flops_per_env_step": f_alg(sim.num_substeps, it_sum, ct_sum),

@@ -2,7 +2,7 @@
 """Turn ncu output brought back in gpurun_out/ into the small text summaries committed under profiles/.
 
     python profiles/summarize.py launches gpurun_out/launches_r1.csv > profiles/r1_launches.txt
-    python profiles/summarize.py full gpurun_out/prof_r1_step.ncu-rep > profiles/r1_step_kernel_full.txt
+    python profiles/summarize.py full gpurun_out/prof_r1c_kernels.ncu-rep 0 > profiles/r1c_front_kernel_full.txt   # 0 = first launch in the report
 """
 import csv
 import subprocess
@@ -51,8 +51,10 @@ KEYS = [
 ]
 
 
-def full(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def full(path, index=0):
+    """index: which launch of a multi-launch report to summarise."""
+    pick = ["--launch-skip", str(int(index)), "--launch-count", "1"]
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"] + pick, capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = OrderedDict((h, (v, u)) for h, u, v in zip(hdr, units, vals))
@@ -65,10 +67,15 @@ def full(path):
     for h, v in sorted(st, key=lambda x: -x[1]):
         if v > 0.005:
             print("  %-40s %8.3f" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
-    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"] + pick, capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     h = rows[1]
-    data = rows[2:]
+    data = []
+    for r in rows[2:]:  # the page repeats per kernel section: keep the first section's instruction rows
+        if r and r[0] == "Kernel Name":
+            break
+        if r and r[0].startswith("0x"):
+            data.append(r)
     isrc, iex, ismp = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
     tot = sum(int(r[iex]) for r in data)
     totsmp = max(1, sum(int(r[ismp]) for r in data))
@@ -98,4 +105,4 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
