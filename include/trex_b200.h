@@ -130,6 +130,17 @@ int trex_gae(int32_t device, const float* reward_dev, const float* value_dev, co
 /* baselines VecNormalize (trex_train.py:45): out = clip((x - mean) / sqrt(var + eps), -clip, clip), x [n_rows][dim] */
 int trex_normalize(int32_t device, const float* x_dev, const float* mean_dev, const float* var_dev, float eps, float clip,
                    float* out_dev, int64_t n_rows, int32_t dim, void* stream);
+/* Fused policy / value forward of the rollout loop (what baselines ppo2 evaluates per env step around
+ * TrexBulletEnv.step, trex_train.py:48,107 [RECALL MlpPolicy]): observation filter (ob_mean/ob_var NULL = identity), two tanh
+ * trunks 75 -> 64 -> 64, Gaussian-mean head (25) with state-independent log-std, value head (1);
+ * action = mean + exp(logstd) * eps with eps ~ N(0,1) from Philox keyed by (seed, env_offset + row, step) (deterministic != 0:
+ * action = mean), neglogp = 0.5 sum eps^2 + sum logstd + 0.5 D log(2 pi).  params_dev: trex_policy_param_count() floats,
+ * row-major [in][out]:  pi W1[75][64] b1[64] W2[64][64] b2[64] Wo[64][25] bo[25] | vf W1 b1 W2 b2 Wo[64][1] bo[1] | logstd[25].
+ * obs_dev [n_rows][75] is read in place; neglogp_dev, value_dev, mean_dev (the Gaussian means [n_rows][25]) may be NULL. */
+int trex_policy_param_count(void);
+int trex_policy_forward(int32_t device, const float* obs_dev, const float* ob_mean_dev, const float* ob_var_dev, float eps, float clip,
+                        const float* params_dev, uint32_t seed, uint64_t step, int64_t env_offset, int32_t deterministic,
+                        float* action_dev, float* neglogp_dev, float* value_dev, float* mean_dev, int64_t n_rows, void* stream);
 int64_t trex_kernel_launches(const trex_handle* h);  /* kernels launched by this handle so far */
 int32_t trex_num_envs(const trex_handle* h);
 const char* trex_last_error(void);

@@ -344,3 +344,53 @@ def test_rollout_buffers_and_gae(model):
     z = normalize(buf.obs[:T], rms)
     ref = torch.clamp((buf.obs[:T] - rms.mean.float()) / torch.sqrt(rms.var.float() + 1e-8), -10, 10)
     assert torch.allclose(z, ref, atol=1e-5) and z.abs().max().item() <= 10.0
+
+
+def test_fused_policy_forward(model):
+    """the trainer's policy / value networks as one kernel, against the same networks in plain
+    PyTorch FP32 (tolerance 2e-5 on means and values), the diagonal-Gaussian neglogp recomputed from the outputs, the
+    Philox noise (keyed by global environment and step: independent of the sharding) and the in-place rollout path."""
+    import torch
+
+    from trex_gym_b200.rollout import MlpPolicy, RolloutBuffer, RunningMeanStd
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N = 1000  # not a multiple of the 128-row tile
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    obs = (torch.randn(N, 75, generator=g) * torch.logspace(-1, 1.5, 75)).to(dev)
+    rms = RunningMeanStd(75, dev)
+    rms.update(obs)
+    pol = MlpPolicy(dev, seed=1, rms=rms)
+    # non-trivial heads and log-std so every term of the outputs is exercised
+    pol.view("pi_wo").mul_(50.0)
+    pol.view("pi_bo").copy_(torch.linspace(-0.3, 0.3, 25))
+    pol.view("vf_bo").fill_(0.7)
+    pol.view("logstd").copy_(torch.linspace(-1.0, 0.2, 25))
+    mean = torch.empty(N, 25, device=dev)
+    a, v, nlp = pol(obs, step=5, seed=9)
+    pol.act_into(obs, torch.empty_like(a), None, None, mean=mean, step=5, seed=9)
+    ref_mean, ref_v = pol.reference_forward(obs)
+    assert (mean - ref_mean).abs().max().item() < 2e-5 * max(1.0, ref_mean.abs().max().item())
+    assert (v - ref_v).abs().max().item() < 2e-5 * max(1.0, ref_v.abs().max().item())
+    # sampling: eps = (a - mean) / std is N(0,1); neglogp is the DiagGaussianPd formula on those outputs
+    ls = pol.view("logstd")
+    eps = ((a - mean) / torch.exp(ls)).double()
+    assert abs(eps.mean().item()) < 0.02 and abs(eps.var().item() - 1.0) < 0.03 and eps.abs().max().item() < 6.5
+    ref_nlp = 0.5 * (eps * eps).sum(1) + ls.double().sum() + 0.5 * np.log(2.0 * np.pi) * 25
+    assert (nlp.double() - ref_nlp).abs().max().item() < 1e-3
+    # deterministic mode returns the mean; the same (seed, step, global env) gives the same noise on any shard
+    a_det, _, nlp_det = pol(obs, step=5, seed=9, deterministic=True)
+    assert torch.equal(a_det, mean)
+    a_shard = torch.empty(N - 300, 25, device=dev)
+    pol.act_into(obs[300:].contiguous(), a_shard, None, None, step=5, seed=9, env_offset=300)
+    assert torch.equal(a_shard, a[300:])
+    a_other, _, _ = pol(obs, step=6, seed=9)
+    assert not torch.equal(a_other, a)
+    # rollout: the kernel reads obs[t] in place and fills actions / values / neglogp of the buffers
+    sim = _sim(model, 256)
+    sim.reset()
+    buf = RolloutBuffer(sim, 6)
+    buf.collect(policy=MlpPolicy(dev, seed=2), seed=4)
+    assert torch.isfinite(buf.actions).all().item() and torch.isfinite(buf.neglogp).all().item()
+    assert buf.values.abs().max().item() > 0 and (buf.actions[0] != buf.actions[1]).any().item()

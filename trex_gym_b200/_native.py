@@ -21,7 +21,8 @@ AUX_DIM = 8
 EXPORTED_SYMBOLS = (
     "trex_create", "trex_destroy", "trex_reset", "trex_step", "trex_step_host", "trex_reset_host",
     "trex_get_state", "trex_set_state", "trex_get_aux", "trex_get_joint_limits",
-    "trex_fill_random_actions", "trex_get_stats", "trex_measure_fp32_peak", "trex_gae", "trex_normalize", "trex_kernel_launches", "trex_num_envs",
+    "trex_fill_random_actions", "trex_get_stats", "trex_measure_fp32_peak", "trex_gae", "trex_normalize",
+    "trex_policy_param_count", "trex_policy_forward", "trex_kernel_launches", "trex_num_envs",
     "trex_last_error", "trex_version",
 )
 
@@ -60,7 +61,7 @@ NVCC_FLAGS = [
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in
-            ("trex_capi.cu", "trex_core.h", "trex_model.h", "trex_topology.h", "lane_cuda.h")]
+            ("trex_capi.cu", "trex_core.h", "trex_model.h", "trex_topology.h", "lane_cuda.h", "trex_policy.h")]
     srcs.append(os.path.join(_HERE, "..", "include", "trex_b200.h"))
     stale = force or not os.path.isfile(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     if stale:
@@ -114,6 +115,11 @@ def lib():
     L.trex_gae.argtypes = [ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
     L.trex_normalize.restype = ctypes.c_int
     L.trex_normalize.argtypes = [ctypes.c_int32, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, ctypes.c_int64, ctypes.c_int32, vp]
+    L.trex_policy_param_count.restype = ctypes.c_int
+    L.trex_policy_param_count.argtypes = []
+    L.trex_policy_forward.restype = ctypes.c_int
+    L.trex_policy_forward.argtypes = [ctypes.c_int32, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, ctypes.c_uint32, ctypes.c_uint64,
+                                      ctypes.c_int64, ctypes.c_int32, vp, vp, vp, vp, ctypes.c_int64, vp]
     L.trex_kernel_launches.restype = ctypes.c_int64
     L.trex_kernel_launches.argtypes = [vp]
     L.trex_num_envs.restype = ctypes.c_int32

@@ -5,6 +5,7 @@
 #include "lane_cuda.h"
 #include "trex_core.h"
 #include "trex_model.h"
+#include "trex_policy.h"
 
 #include "../../include/trex_b200.h"
 
@@ -546,6 +547,27 @@ int trex_normalize(int32_t device, const float* x_dev, const float* mean_dev, co
   CUDA_TRY(cudaSetDevice(device));
   const int64_t n = n_rows * dim;
   trex_normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, mean_dev, var_dev, eps, clip, out_dev, n_rows, dim);
+  CUDA_TRY(cudaGetLastError());
+  return TREX_OK;
+}
+
+int trex_policy_param_count(void) { return trex_policy::PARAM_COUNT; }
+
+int trex_policy_forward(int32_t device, const float* obs_dev, const float* ob_mean_dev, const float* ob_var_dev, float eps, float clip,
+                        const float* params_dev, uint32_t seed, uint64_t step, int64_t env_offset, int32_t deterministic,
+                        float* action_dev, float* neglogp_dev, float* value_dev, float* mean_dev, int64_t n_rows, void* stream) {
+  if (!obs_dev || !params_dev || !action_dev || n_rows <= 0 || ((ob_mean_dev == nullptr) != (ob_var_dev == nullptr)))
+    return fail(TREX_ERR_INVALID, "trex_policy_forward: bad argument%s");
+  CUDA_TRY(cudaSetDevice(device));
+  static bool configured[16] = {false};
+  if (!configured[device & 15]) {
+    CUDA_TRY(cudaFuncSetAttribute(trex_policy::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trex_policy::SMEM_BYTES));
+    configured[device & 15] = true;
+  }
+  const unsigned grid = (unsigned)((n_rows + trex_policy::ROWS - 1) / trex_policy::ROWS);
+  trex_policy::forward_kernel<<<grid, trex_policy::ROWS, trex_policy::SMEM_BYTES, (cudaStream_t)stream>>>(
+      obs_dev, ob_mean_dev, ob_var_dev, eps, clip, params_dev, seed, step, env_offset, deterministic, action_dev, neglogp_dev, value_dev,
+      mean_dev, n_rows);
   CUDA_TRY(cudaGetLastError());
   return TREX_OK;
 }
