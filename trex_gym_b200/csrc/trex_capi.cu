@@ -93,11 +93,15 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   int first = (blockIdx.x * WARPS + warp) * 4;
   int count = *list_count;
   if (KC > 0) {
-    // list / list_count point at class 1; skip the classes whose warps come before this one
-    for (int c = 1; c < TREX_NCLASS - 1 && first >= ((count + 3) & ~3); c++) {
+    // list / list_count point at class 1.  Warps are handed out heaviest class first (5-8 contacts, then 3-4, then 1-2):
+    // the longest-running warps start first instead of forming the tail of the launch.
+    list += (size_t)(TREX_NCLASS - 2) * n_envs;
+    list_count += 64 * (TREX_NCLASS - 2);
+    count = *list_count;
+    for (int c = TREX_NCLASS - 1; c > 1 && first >= ((count + 3) & ~3); c--) {
       first -= (count + 3) & ~3;
-      list += n_envs;
-      list_count += 64;
+      list -= n_envs;
+      list_count -= 64;
       count = *list_count;
     }
   }
