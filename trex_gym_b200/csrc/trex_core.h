@@ -1219,6 +1219,11 @@ TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared&
 // in the one-environment sweep: joint rows, then the normal rows, then the friction pairs (implicit cone).
 // One block of a motor sweep: rows at solve-order positions 4B..4B+3 (block 6: position 24 only), owned by lane B
 // of every group.  FWD: ascending positions.  Same operations on w, in the same order, as row-by-row updates.
+TREX_TOPO_FN int motor_position(int joint) {  // position of a joint's motor row in the solve order
+  for (int p = 0; p < NJ; p++)
+    if (trex_topo::noncontact_order(p) - NJ == joint) return p;
+  return 0;
+}
 TREX_TOPO_FN bool limit_order_matches_motor_order() {
   for (int p = 0; p < NJ; p++)
     if (trex_topo::noncontact_order(NJ + p) != trex_topo::noncontact_order(p) - NJ) return false;
@@ -1228,6 +1233,8 @@ template <int B, bool FWD, int KC>
 TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf (&cu)[3], vi gl, vi bt_own, const float* Bs,
                             float max_imp) {
   constexpr int n = (4 * B + 4 <= NJ) ? 4 : NJ - 4 * B;
+  vf bk[3][4];  // responses of the owned contact's three rows at this block's four joints
+  if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) ld4(Bs, bt_own + (k * 36 + 4 * B), bk[k]);
   vf t[4], d[4];
   TREX_UNROLL for (int i = 0; i < 4; i++) { t[i] = w[i]; d[i] = 0.0f; }
   const vb own = gl == B;
@@ -1249,20 +1256,21 @@ TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf
     const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
     const vf db = shfl_group8(d[i], B);
     TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(g[s][j], db, w[s]);
-    if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bs, bt_own + (k * 33 + j)), db, cu[k]);
+    if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(bk[k][i], db, cu[k]);
   }
 }
 
-// warp-private shared memory of solve4<KC>, per lane group: Bt [3*KC][33] (row responses at the joints, padded rows:
-// conflict-free for "one row per owner" and for "one column per joint owner"), A4 [3*KC][KC][4], then for all groups
+// warp-private shared memory of solve4<KC>, per lane group: Bp [3*KC][36] (row responses at the joints, indexed by the
+// joint's POSITION in the solve order, so a motor block's four entries and a lane's four owned joints are each one
+// 128-bit load; stride 36: conflict-free across the owners), A4 [3*KC][KC][4], then for all groups
 // Lam [4][32 + 4*KC] (net joint impulses + contact impulses, exchanged every few sweeps)
-#define TREX_BT_SIZE(KC) ((99 * (KC) + 3) & ~3)
+#define TREX_BT_SIZE(KC) (108 * (KC))
 #define TREX_GC_STRIDE(KC) (TREX_BT_SIZE(KC) + 12 * (KC) * (KC))
 // and Lg [slots][4][32]: per lane and owned joint, the column of g of the first few joints with a violated limit
 #ifndef TREX_REBUILD_MASK
 #define TREX_REBUILD_MASK 3  // exact rebuild of w (and u) every 4th sweep (every 8th: the 2e-5 per-env-step parity bound is exceeded, 2.1e-5)
 #endif
-#define TREX_LIMIT_SLOTS(KC) ((KC) > 4 ? 3 : 6)
+#define TREX_LIMIT_SLOTS(KC) ((KC) > 4 ? 2 : 6)
 #define TREX_SOLVE_SCRATCH(KC) (4 * TREX_GC_STRIDE(KC) + 4 * (32 + 4 * (KC)) + 128 * TREX_LIMIT_SLOTS(KC))  // floats
 // envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
 template <int KC>
@@ -1281,7 +1289,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
   float* Lg = Lam + 4 * LS;                            // [TREX_LIMIT_SLOTS][4][32]
   const vi gb = grp * GC;                              // this group's stash
   const vi glc = KC > 0 ? vmini(gl, KC - 1) : vi(0);  // contact slot of this lane (lanes >= KC shadow the last owner, unused)
-  const vi bt_own = gb + glc * 99;                     // Bt rows of the owned contact
+  const vi bt_own = gb + glc * 108;                    // Bp rows of the owned contact
 
   vi kk[4];
   vb kv[4];
@@ -1331,11 +1339,12 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     TREX_ROLLED for (int c = 0; c < kmax; c++) {
       vf b4[3][4], a4[3][4];
       TREX_UNROLL for (int k = 0; k < 3; k++) {
-        ld4_if(work0, woff + gl * 4 + ((3 * c + k) * 32 + W_BT), gact && (vi(c) < nc), b4[k]);
+        TREX_UNROLL for (int s = 0; s < 4; s++)  // the lane's own four joints = positions 4 gl .. 4 gl + 3
+          b4[k][s] = ld_if(work0, woff + kk[s] + ((3 * c + k) * 32 + W_BT), kv[s] && (vi(c) < nc), 0.0f);
         ld4_if(work0, woff + glc * 4 + ((3 * c + k) * (4 * TREX_KC) + W_A4), cown && (vi(c) < nc), a4[k]);
       }
       TREX_UNROLL for (int k = 0; k < 3; k++) {
-        TREX_UNROLL for (int e = 0; e < 4; e++) st(Bs, gb + gl * 4 + ((3 * c + k) * 33 + e), b4[k][e]);
+        st4_if(Bs, gb + gl * 4 + (3 * c + k) * 36, b4[k], gl < 8);
         st4_if(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4[k], gl < KC);
       }
     }
@@ -1384,7 +1393,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     lam_l[SJ] = sel(own, nl, lam_l[SJ]);                                                               \
     TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(gj[s], db, w[s]);                              \
     w[SJ] = w[SJ] - d;                                        /* self term: dv_j += D_j * d */         \
-    if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bs, bt_own + (k * 33 + j)), db, cu[k]); \
+    if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bs, bt_own + (k * 36 + pos)), db, cu[k]); \
   }
 #define TREX_S4_LIMITS(FORWARD)                                                                        \
   {                                                                                                    \
@@ -1426,7 +1435,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       TREX_UNROLL for (int j = 0; j < NJ; j++) {
         const vf Lj = ld(Lam, grp * LS + j);
         TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
-        if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(ld(Bs, bt_own + (k * 33 + j)), Lj, ua[k]);
+        if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(ld(Bs, bt_own + (k * 36 + motor_position(j))), Lj, ua[k]);
       }
       if (KC > 0) {
         vf bs[4];
@@ -1434,7 +1443,9 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         TREX_ROLLED for (int c = 0; c < kmax; c++) {
           TREX_UNROLL for (int k = 0; k < 3; k++) {
             const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
-            TREX_UNROLL for (int s = 0; s < 4; s++) bs[s] = vfma(ld(Bs, gb + kk[s] + (3 * c + k) * 33), Lr, bs[s]);
+            vf b4[4];
+            ld4(Bs, gb + gl * 4 + (3 * c + k) * 36, b4);
+            TREX_UNROLL for (int s = 0; s < 4; s++) bs[s] = vfma(b4[s], Lr, bs[s]);
             vf a4[4];
             ld4(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4);
             TREX_UNROLL for (int k2 = 0; k2 < 3; k2++) ua[k2] = vfma(a4[k2], Lr, ua[k2]);
@@ -1473,7 +1484,9 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         vf a4[4];
         ld4(Bs, gb + glc * 4 + ((3 * c) * (4 * KC) + BT), a4);
         TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
-        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(ld(Bs, gb + kk[s] + (3 * c) * 33), njdi[s] * d, w[s]);
+        vf b4[4];
+        ld4(Bs, gb + gl * 4 + (3 * c) * 36, b4);
+        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(b4[s], njdi[s] * d, w[s]);
       }
       // friction pairs, implicit cone; both rows read the velocities before either writes
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
@@ -1498,10 +1511,10 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         ld4(Bs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + BT), aA);
         ld4(Bs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + BT), aB);
         TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
-        TREX_UNROLL for (int s = 0; s < 4; s++) {
-          const vi bi = gb + kk[s] + (3 * c + 1) * 33;
-          w[s] = vfma(njdi[s], vfma(ld(Bs, bi), dAu, ld(Bs, bi + 33) * dBu), w[s]);
-        }
+        vf bA[4], bB[4];
+        ld4(Bs, gb + gl * 4 + (3 * c + 1) * 36, bA);
+        ld4(Bs, gb + gl * 4 + (3 * c + 2) * 36, bB);
+        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
       }
     }
     // residual per environment: max over its rows of (delta impulse / jacDiagABInv)^2
@@ -1544,7 +1557,9 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     TREX_ROLLED for (int c = 0; c < kmax; c++)
       TREX_UNROLL for (int k = 0; k < 3; k++) {
         const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
-        TREX_UNROLL for (int s = 0; s < 4; s++) bsum[s] = vfma(ld(Bs, gb + kk[s] + (3 * c + k) * 33), Lr, bsum[s]);
+        vf b4[4];
+        ld4(Bs, gb + gl * 4 + (3 * c + k) * 36, b4);
+        TREX_UNROLL for (int s = 0; s < 4; s++) bsum[s] = vfma(b4[s], Lr, bsum[s]);
       }
     TREX_UNROLL for (int k = 0; k < 3; k++)
       TREX_UNROLL for (int b = 0; b < 6; b++)
