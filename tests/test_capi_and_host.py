@@ -146,3 +146,29 @@ def test_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_replay_export_layout():
+    """frames carry the base COM-frame pose and the joint angles by URDF joint name, in the
+    record's joint order (pybullet link order of the revolute joints), so the reference side can play them back."""
+    import numpy as np
+
+    from trex_gym_b200.model_compiler import load_builtin
+    from trex_gym_b200.replay import ReplayRecorder, joint_names_in_state_order
+
+    model = load_builtin()
+    names = joint_names_in_state_order(model)
+    assert len(names) == 25 and names[0] == "joint_femur_right" and len(set(names)) == 25
+    assert sorted(names) == list(model.meta["obs_joint_names"])  # the observation order is the name-sorted one
+    # the recorder's frame dictionary, without a simulator: fill frames by hand
+    rec = ReplayRecorder.__new__(ReplayRecorder)
+    rec.names, rec.dt, rec.frames = names, 0.01, []
+    f = np.zeros((1, 160), np.float32)
+    f[0, 0:3] = [0.0, 0.0, 3.0]
+    f[0, 3:7] = [0.0, 0.0, 0.0, 1.0]
+    f[0, 13:38] = np.arange(25) * 0.01
+    rec.frames = [f, f]
+    d = rec.as_dict()
+    assert d["joint_names"] == names and len(d["joint_positions"]) == 2 and len(d["joint_positions"][0]) == 25
+    assert d["base_position"][0] == [0.0, 0.0, 3.0] and d["base_orientation_xyzw"][1] == [0.0, 0.0, 0.0, 1.0]
+    assert abs(d["joint_positions"][0][3] - 0.03) < 1e-7
