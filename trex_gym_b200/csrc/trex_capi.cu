@@ -255,7 +255,7 @@ struct trex_handle {
   int device = 0;
   int n_envs = 0;
   int warps_per_block = 2;  // front / tail kernels; the solve kernel uses 2 (4 when this is 4)
-  bool deferred_solve = true;  // contact-free substeps solved four environments per warp (solve4)
+  bool deferred_solve = true;  // substeps with <= TREX_KC contacts solved four environments per warp (solve4)
   trex_host::ModelTables T;
   trex_host::EnvConfig C;
   trex::Uniform P;
@@ -265,8 +265,8 @@ struct trex_handle {
   // staging for the host-buffer entry points
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   uint8_t* d_done = nullptr;
-  int* d_list = nullptr;        // environments whose solve was deferred in the current substep round
-  int* d_list_count = nullptr;  // [64] one counter per substep round
+  int* d_list = nullptr;        // [TREX_NCLASS][n_envs] environments whose solve was deferred in the current substep round, by class
+  int* d_list_count = nullptr;  // [TREX_NCLASS][64] one counter per class and substep round
   DevStats* d_stats = nullptr;
   int64_t launches = 0;
   int64_t env_steps = 0;
@@ -282,8 +282,8 @@ int configure_kernel(K kernel, size_t smem) {
 }
 
 // mode 0: one env step (n_sub front/solve rounds + tail); mode 1: reset (tail only).
-// WF: warps per CTA of the front / tail kernels (one environment per warp; 1 schedules best when the work per
-// environment is skewed by contacts), WS: warps per CTA of the solve kernel (four environments per warp).
+// WF: warps per CTA of the front / tail kernels (one environment per warp; 2 gives 16 resident warps per SM),
+// WS: warps per CTA of the solve kernels (four environments per warp).
 template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {

@@ -6,7 +6,7 @@
 //   /root/reference/trex_gym/trex_robot.py:359-365 (observations), :377-422 (motor targets)
 //   pybullet.stepSimulation (external; semantics restated in SURVEY.md Appendix A)
 //
-// Mapping (B200: 32-wide warps, everything in registers + a ~23 KB per-warp shared slab):
+// Mapping (B200: 32-wide warps, everything in registers + a 13.7 KB per-warp shared slab):
 //   lane L in [0,25)   joint L  = rigid body L+1 = generalised velocity index 6+L
 //   lane 25            floating base body; lanes 25..30 own base velocity coordinates 0..5
 //   lane 31            spare
@@ -16,8 +16,9 @@
 //   concurrently, one per lane, reading the per-body data as shared-memory broadcasts).
 //   M^-1 is symmetric, so lane d ends up holding exactly the coefficients it needs to
 //   update "its" velocity coordinate in the projected Gauss-Seidel sweep;
-// * PGS rows are solved in Bullet's order; a row update is one shuffle + one FMA per lane
-//   for the 25 motor rows and a butterfly reduction + FMA for contact rows.
+// * the constraint solve (projected Gauss-Seidel in Bullet's row order) of every substep with at most 8 contacts is
+//   deferred to solve4(): four environments per warp, eight lanes each, contact rows carried in row space; only
+//   substeps with more contacts (and the reset step) use the one-environment sweep inside substep().
 //
 // Written against the lane vocabulary of lane_cuda.h (device) / tests/emu/lane_emu.h
 // (host emulation for the CPU test-suite).  All control flow is warp-uniform.
@@ -116,7 +117,7 @@ struct Uniform {
 };
 
 // per-warp shared memory slab.  The kinematics-phase arrays (k) and the contact-row arrays (c) are
-// never live at the same time and share storage; ~15.7 KB per warp at KMAX = 20 -> 14 warps per SM.
+// never live at the same time and share storage; 13.7 KB per warp at KMAX = 16 -> 16 warps per SM (two per CTA).
 struct alignas(16) WarpShared {
   float col[31][32];  // M^-1: col[g][lane] = entry g of the column owned by `lane`
   float tmp[1][32];   // staging: motor impulses / per-joint power
@@ -355,8 +356,9 @@ TREX_FN void to_parent(const vf E[9], const vf r[3], const vf Ia[21], const vf p
 // One pybullet stepSimulation for the environment owned by this warp.
 // kp/kd/max_imp: motor settings of this substep (zero during the reset step).
 // ------------------------------------------------------------------------------------------
-// Returns true when the solve was deferred: the solver inputs were written to `work` (contact-free
-// environment, `work` != nullptr) and the caller finishes the step with solve4(); otherwise the step is complete.
+// Returns 0 when the step is complete, or 1 + class when the solve was deferred (`work` != nullptr and at most TREX_KC
+// contacts): the solver inputs were written to `work` and the caller finishes the step with solve4() on the
+// environments of that class (0: contact-free, 1: 1-2 contacts, 2: 3-4, 3: 5-8).
 TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                      const int* cand_lane, WarpShared& S, EnvRegs& R, float kp, float kd, float max_imp,
                      StepStats& stats, float* work) {
@@ -1218,7 +1220,7 @@ TREX_FN void reset_pose(const Uniform& P, const float* mdl, vi lane, WarpShared&
 // are published with width-8 shuffles and every lane applies them -- one shuffle latency per FOUR rows on the
 // dependent chain instead of one per row (measured: ~90 cycles per row with a shuffle in every row).
 // Rows are visited in Bullet's order (motors in sorted-constraint order, then the violated limits; direction
-// alternates with the iteration); w is rebuilt exactly from the impulses after every sweep.
+// alternates with the iteration); w is rebuilt exactly from the impulses every 4th sweep.
 // Ends with the velocity update, the write-back of the applied motor torque and the position integration.
 // Returns the number of solver iterations each group executed (per lane of the group).
 // ------------------------------------------------------------------------------------------
@@ -1679,9 +1681,9 @@ TREX_FN void reward_and_done(const Uniform& P, const float* mdl, vi lane, WarpSh
 enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // per-step accumulators in the record
 
 // front_phase: one physics substep of ONE environment by one warp up to the solve: kinematics, bias forces,
-// articulated inertias, accelerations, velocity update, M^-1, row setup, contact detection.  With contacts
-// the substep is finished here (one-environment solver + integration); without, the solver inputs go to
-// `work` and the function returns true (solve_phase finishes the substep).   action: [25] name-sorted (trex_robot.py:311-314)
+// articulated inertias, accelerations, velocity update, M^-1, row setup, contact detection.  With more than TREX_KC
+// contacts the substep is finished here (one-environment solver + integration); otherwise the solver inputs go to
+// `work` and the function returns 1 + class (solve_phase finishes the substep).   action: [25] name-sorted (trex_robot.py:311-314)
 TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                          const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, bool first_round) {
   const vi lane = lane_id();
