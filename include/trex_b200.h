@@ -63,7 +63,8 @@ typedef struct trex_config {
                                 (BASELINE configs[4]: base z U(0.3,3), uniform SO(3), joints U(limits); no
                                 reference counterpart), Philox keyed by (seed, global env id, episode) */
   uint32_t seed;
-  int32_t reserved[8];       /* [0] warps per CTA of the front/tail kernels (1, 2 or 4; 0 = default 2); [1],[2] low/high word of the global id of
+  int32_t reserved[8];       /* [0] warps per CTA of the front/tail kernels (1, 2 or 4; 0 = default 2; with 4 the inward pass of the
+                                CTA's four environments runs on one warp, eight lanes per environment: bit-identical results); [1],[2] low/high word of the global id of
                                 environment 0 of this shard (multi-GPU: rank * n_envs); [3] solver placement (diagnostics):
                                 0 = contact-free substeps and substeps with <= 4 contacts are solved four environments
                                 per warp, 2 = contact-free substeps only, 1 = everything in the one-environment path */

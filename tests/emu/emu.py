@@ -25,7 +25,7 @@ def build(force=False):
     stale = force or not os.path.isfile(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs)
     if stale:
         subprocess.check_call(
-            ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + _CSRC, "-o", _LIB,
+            ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-I" + _CSRC, "-o", _LIB,
              os.path.join(_HERE, "emu_main.cpp")]
         )
     return _LIB
@@ -80,9 +80,15 @@ class EmuEnv:
 
     def solve_counts(self):
         """Substeps finished by (the one-environment path, solve4<0>, solve4<KC>)."""
-        out = (ctypes.c_longlong * 3)()
+        out = (ctypes.c_longlong * 4)()
         self._L.emu_solve_counts(self._h, out)
-        return tuple(int(x) for x in out)
+        return tuple(int(x) for x in out)[:3]
+
+    def packed_rounds(self):
+        """Substep rounds whose front phase ran as a 4-warp CTA (inward pass of four environments by one warp)."""
+        out = (ctypes.c_longlong * 4)()
+        self._L.emu_solve_counts(self._h, out)
+        return int(out[3])
 
     def reset(self):
         obs = np.zeros(75, np.float32)

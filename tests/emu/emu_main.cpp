@@ -5,16 +5,21 @@
 #include "../../trex_gym_b200/csrc/trex_model.h"
 
 #include <new>
+#include <thread>
+
+pthread_barrier_t* g_emu_cta_barrier = nullptr;
 
 struct Emu {
   trex_host::ModelTables T;
   trex::Uniform P;
-  trex::WarpShared S;
+  trex::WarpShared S;            // the slab of a lone warp
+  trex::WarpShared slabs[4];     // the slabs of a 4-warp CTA (packed inward pass)
+  int packed = 0;                // emu_step4 with n == 4: run the front phase as a 4-warp CTA (host threads)
   alignas(16) float work[4 * TREX_WORK_STRIDE];
   alignas(16) float scratch[TREX_SOLVE_SCRATCH(TREX_KC)];
   int deferred = 1;
   int pack_reverse = 0;  // tests: fill the solver's lane groups from the top
-  long long solves[3] = {0, 0, 0};  // substeps finished in front_phase / by solve4<0> / by solve4<TREX_KC>
+  long long solves[4] = {0, 0, 0, 0};  // substeps finished in front_phase / by solve4<0> / by solve4<TREX_KC>; [3] substep rounds run as a 4-warp CTA
 };
 
 static_assert(trex::F_COUNT == 32, "field table");
@@ -41,7 +46,12 @@ void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, 
   C.max_episode_steps = max_episode_steps; C.enable_contacts = contacts;
   C.reset_mode = reset_mode; C.seed = seed;
   trex_host::fill_uniform(e->T, C, e->P);
-  memset(&e->S, 0, sizeof(e->S));
+  // shared memory is NOT zero on the device: poison the emulated slabs (all-ones = NaN floats, -1 ints) so that any read
+  // of a never-written location shows up in the parity tests
+  memset(&e->S, 0xff, sizeof(e->S));
+  memset(e->slabs, 0xff, sizeof(e->slabs));
+  memset(e->scratch, 0xff, sizeof(e->scratch));
+  memset(e->work, 0xff, sizeof(e->work));
   return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
@@ -63,9 +73,30 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
       // deferred environments are packed into the solver's lane groups in list order (any order is equivalent)
       // (one list per class, as in the library: contact-free, 1-2, 3-4 and 5-8 contacts)
       int envs[TREX_NCLASS][4] = {}, cnt[TREX_NCLASS] = {};
+      int dres[4] = {0, 0, 0, 0};
+      if (e->packed && n == 4) {
+        // the library's 4-warp CTA: warps are host threads, cta_sync() a pthread barrier, warp 0 runs inward_packed
+        pthread_barrier_t bar;
+        pthread_barrier_init(&bar, nullptr, 4);
+        g_emu_cta_barrier = &bar;
+        e->solves[3]++;
+        std::thread th[4];
+        for (int i = 0; i < 4; i++)
+          th[i] = std::thread([=, &dres]() {
+            dres[i] = trex::front_phase<true>(e->P, mdl, mdli, tasks, cp, cl, e->slabs[i], rec + i * TREX_STATE_STRIDE,
+                                              e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0,
+                                              e->slabs, i, 0xf);
+          });
+        for (int i = 0; i < 4; i++) th[i].join();
+        g_emu_cta_barrier = nullptr;
+        pthread_barrier_destroy(&bar);
+      } else {
+        for (int i = 0; i < n; i++)
+          dres[i] = trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
+                                      e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0);
+      }
       for (int i = 0; i < n; i++) {
-        const int d = trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
-                                        e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0);
+        const int d = dres[i];
         e->solves[d == 0 ? 0 : (d == 1 ? 1 : 2)]++;
         if (d) { int& c = cnt[d - 1]; envs[d - 1][e->pack_reverse ? 3 - c : c] = i; c++; }
       }
@@ -86,9 +117,9 @@ void emu_step(void* h, float* rec, const float* action, float* obs, float* rewar
               long long env_id) {
   emu_step4(h, 1, rec, action, obs, reward, done, aux, force_reset, env_id);
 }
-void emu_solve_counts(void* h, long long* out) { for (int i = 0; i < 3; i++) out[i] = ((Emu*)h)->solves[i]; }
-void emu_set_deferred(void* h, int on) {  // bit 0 deferral on, bit 1 reverse packing, bit 2 contact-free substeps only
+void emu_solve_counts(void* h, long long* out) { for (int i = 0; i < 4; i++) out[i] = ((Emu*)h)->solves[i]; }
+void emu_set_deferred(void* h, int on) {  // bit 0 deferral on, bit 1 reverse packing, bit 2 contact-free substeps only, bit 3 front phase as a 4-warp CTA
   Emu* e = (Emu*)h;
-  e->deferred = on & 1; e->pack_reverse = (on >> 1) & 1; e->P.defer_contacts = ((on >> 2) & 1) ? 0 : 1;
+  e->deferred = on & 1; e->pack_reverse = (on >> 1) & 1; e->P.defer_contacts = ((on >> 2) & 1) ? 0 : 1; e->packed = (on >> 3) & 1;
 }
 }

@@ -147,6 +147,10 @@ TREX_FN vf vrsqrt(const vf& x) { vf r; for (int l = 0; l < 32; l++) r.v[l] = 1.0
 TREX_FN void stb(unsigned char* p, const vi& idx, const vi& v) { for (int l = 0; l < 32; l++) p[idx.v[l]] = (unsigned char)v.v[l]; }
 TREX_FN vi ldb(const unsigned char* p, const vi& idx) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)p[idx.v[l]]; return r; }
 TREX_FN long long cycle_count() { return 0; }
+// CTA barrier: the emulated warps of a CTA are host threads (emu_main.cpp) meeting at a pthread barrier
+#include <pthread.h>
+extern pthread_barrier_t* g_emu_cta_barrier;
+TREX_FN void cta_sync() { if (g_emu_cta_barrier) pthread_barrier_wait(g_emu_cta_barrier); }
 
 TREX_FN void philox4_uniform(const vi& c0, const vi& c1, const vi& c2, const vi& c3, uint32_t k0in, uint32_t k1in, vf out[4]) {
   for (int l = 0; l < 32; l++) {

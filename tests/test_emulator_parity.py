@@ -275,11 +275,13 @@ def test_four_environments_per_warp(model, action_limits):
     w4 = EmuWarp4(model.blob(), n=4)
     w1 = EmuWarp4(model.blob(), n=4, deferred=False)
     wr = EmuWarp4(model.blob(), n=4, deferred=3)  # deferred environments packed into the lane groups in reverse
-    o = _oracle(model)
+    wp = EmuWarp4(model.blob(), n=4, deferred=1 | 8)  # front phase as the library's 4-warp CTA: inward pass of the four
+    o = _oracle(model)                                # environments by one warp (inward_packed), warps = host threads
     nc = o.num_candidates
     w4.reset()
     w1.reset()
     wr.reset()
+    wp.reset()
     rng = np.random.default_rng(11)
     for e in range(4):
         s = w4.get_state(e, nc)
@@ -309,10 +311,14 @@ def test_four_environments_per_warp(model, action_limits):
         for e in range(4):
             w1.set_state(e, pre[e])
             wr.set_state(e, pre[e])
+            wp.set_state(e, pre[e])
         w1.step(acts)
         wr.step(acts)
+        wp.step(acts)
         assert np.array_equal(wr.rec[:, :152], w4.rec[:, :152])  # lane-group assignment does not change a single bit
+        assert np.array_equal(wp.rec[:, :152], w4.rec[:, :152])  # nor does the four-environments-per-warp inward pass
         for e in range(4):
             a, b = w4.get_state(e, nc), w1.get_state(e, nc)
             assert max(rel_err(a[sl], b[sl]) for sl in STATE_BLOCKS.values()) < 5e-3
     assert saw_contact and saw_free and saw_limit
+    assert wp.env.packed_rounds() == 30 * 5 and w4.env.packed_rounds() == 0

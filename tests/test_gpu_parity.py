@@ -394,3 +394,22 @@ def test_fused_policy_forward(model):
     buf.collect(policy=MlpPolicy(dev, seed=2), seed=4)
     assert torch.isfinite(buf.actions).all().item() and torch.isfinite(buf.neglogp).all().item()
     assert buf.values.abs().max().item() > 0 and (buf.actions[0] != buf.actions[1]).any().item()
+
+
+def test_packed_inward_pass_is_bit_identical(model, action_limits):
+    """4-warp CTAs run the inward pass of their four environments on one warp (inward_packed, eight lanes per
+    environment, through the shared slabs): same operations in the same order as the one-environment pass, so the
+    states agree bit for bit with the default 2-warp configuration -- also when the last CTA is only half full."""
+    import torch
+
+    n = 1026
+    sims = [_sim(model, n, warps_per_block=w) for w in (2, 4)]
+    for s in sims:
+        s.reset()
+    for t in range(40):
+        a = sims[0].random_actions(step=t, seed=3)
+        for s in sims:
+            s.step(a)
+    st = [s.get_state() for s in sims]
+    assert torch.equal(st[0][:, :152], st[1][:, :152])
+    assert sims[1].stats()["mean_contacts"] > 0.0

@@ -81,6 +81,7 @@ TREX_FN vf vrsqrt(vf x) { return rsqrtf(x); }
 TREX_FN void stb(unsigned char* p, vi idx, vi v) { p[idx] = (unsigned char)v; }
 TREX_FN vi ldb(const unsigned char* p, vi idx) { return (int)p[idx]; }
 TREX_FN long long cycle_count() { return clock64(); }
+TREX_FN void cta_sync() { __syncthreads(); }  // every warp of the CTA, the same number of times
 
 // Philox4x32-10 -> 4 uniforms in [0,1) per lane (counter-based: reset sampler)
 TREX_FN void philox4_uniform(vi c0, vi c1, vi c2, vi c3, uint32_t k0, uint32_t k1, vf out[4]) {

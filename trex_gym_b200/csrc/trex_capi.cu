@@ -49,10 +49,11 @@ int fail(int code, const char* fmt, const char* detail = "") {
 
 // ------------------------------------------------------------------------------------------------
 // One env step = n_sub x [trex_front_kernel ; trex_solve_kernel] ; trex_tail_kernel   (trex_core.h).
-// Warp-private shared slabs, no block-level synchronisation anywhere.
+// Warp-private shared slabs; the only block-level synchronisation is the pair of barriers around the packed inward pass.
 // ------------------------------------------------------------------------------------------------
-// one warp per environment: dynamics front end of one physics substep (+ the whole substep when in contact)
-template <int WARPS>
+// one warp per environment: dynamics front end of one physics substep (+ the whole substep with more than 8 contacts).
+// PACKED (4 warps per CTA): the inward pass of the CTA's four environments is done by warp 0, four environments at a time.
+template <int WARPS, bool PACKED>
 __global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
 trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
                   const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
@@ -61,14 +62,25 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
   extern __shared__ __align__(16) unsigned char smem_raw[];
   trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
   const int warp = threadIdx.x >> 5;
+  static_assert(!PACKED || WARPS == 4, "the packed inward pass serves four environments");
   const int env = blockIdx.x * WARPS + warp;
-  if (env >= n_envs) return;
+  int valid_mask = 0;
+  if (PACKED) {
+    for (int w = 0; w < WARPS; w++) valid_mask |= (blockIdx.x * WARPS + w < n_envs) ? (1 << w) : 0;
+    if (env >= n_envs) {  // keep the CTA's two barriers balanced; warp 0 always holds an environment
+      __syncthreads();
+      __syncthreads();
+      return;
+    }
+  } else if (env >= n_envs) {
+    return;
+  }
 #ifdef TREX_PHASES
   const long long t_entry = clock64();
 #endif
-  const int deferred = trex::front_phase(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
-                                          work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
-                                          first_round != 0);
+  const int deferred = trex::front_phase<PACKED>(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
+                                                  work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
+                                                  first_round != 0, slabs, warp, valid_mask);
   // append to the list of its class of deferred environments (any order: the solver's lane groups are independent):
   // class 0 = contact-free substeps, classes 1..3 = 1-2 / 3-4 / 5-8 contacts; list c at list + c * n_envs, counters + 64 * c
   if (deferred && (threadIdx.x & 31) == 0) {
@@ -292,7 +304,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
   static bool configured[16] = {false};
   if (!configured[h->device & 15]) {
     int rc;
-    if ((rc = configure_kernel(trex_front_kernel<WF>, smem_f)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_front_kernel<WF, WF == 4>, smem_f)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, 0>, smem_s)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, TREX_KC>, smem_c)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
@@ -303,7 +315,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
   if (mode == 0) {
     if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 64 * TREX_NCLASS * sizeof(int), st));  // one counter per list and substep round
     for (int r = 0; r < h->P.n_sub; r++) {
-      trex_front_kernel<WF><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+      trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
                                                            h->d_state, h->d_work, action, h->d_list, h->d_list_count + r, h->n_envs, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;

@@ -24,6 +24,7 @@
 // (host emulation for the CPU test-suite).  All control flow is warp-uniform.
 #pragma once
 #include "trex_topology.h"
+#include <stddef.h>
 
 #ifndef TREX_KMAX
 #define TREX_KMAX 16  // contact slots per environment (model parameter max_contacts; deepest points first)
@@ -95,7 +96,8 @@ enum {
   IF_DAMP_LANE = 5,    // lane of the body whose URDF links this lane evaluates for link damping
   IF_DAMP_CONTRIB = 6, // 4 x 6 bits: lanes whose partial damping wrench belongs to this body (63 = none)
   IF_LIMIT_ORDER = 7,  // joint whose limit constraint is solved at position `lane` of the limit block
-  IF_COUNT = 8
+  IF_LEVEL = 8,        // MAX_DEPTH fields: entry i (< 8) of field IF_LEVEL + d - 1 = lane of the i-th body of depth d, or -1
+  IF_COUNT = 8 + MAX_DEPTH
 };
 
 struct Uniform {
@@ -140,8 +142,19 @@ struct alignas(16) WarpShared {
       unsigned char slot[TREX_KMAX][32];  // which Jc entry each lane multiplies its velocity coordinate with
       unsigned char inv[TREX_KC][16];     // inverse of slot for the first KC contacts: lane (coordinate) of each Jc entry
     } c;
+    struct {                  // exchange with the four-environments-per-warp inward pass (front kernel, 4-warp CTAs):
+      float keep[28][32];     // k.E .. k.xw stay live (k.pack is written after the pass)
+      float pA[6][32];        // bias force per body lane (in), later unused
+      float cc[5][32];        // Coriolis terms c0 c1 c3 c4 and the joint damping torque (in)
+      float uu[32];           // tau - S^T pA per joint (out)
+      float Ip[21][32];       // articulated inertia of each body in its parent's frame (scratch between levels)
+      float pp[6][32];        // ... and its bias force
+      float base[32];         // [0:21] articulated inertia of the base, [21:27] its bias force (out)
+    } x;
   };
 };
+static_assert(sizeof(((WarpShared*)0)->x) <= sizeof(((WarpShared*)0)->c), "exchange area must fit the union");
+static_assert(sizeof(((WarpShared*)0)->x.keep) == 28 * 128, "exchange area must start behind k.E .. k.xw");
 // link-damping partial wrenches live in dV rows beyond the kinematics-phase arrays
 #define TREX_PART_ROW 44  // row (of 32 floats) inside the union where the 6 damping partial rows live
 static_assert(sizeof(((WarpShared*)0)->k) <= TREX_PART_ROW * 128, "partials must not overlap the kinematics arrays");
@@ -353,15 +366,106 @@ TREX_FN void to_parent(const vf E[9], const vf r[3], const vf Ia[21], const vf p
 }
 
 // ------------------------------------------------------------------------------------------
+// Inward pass (articulated inertias) of FOUR environments by one warp: the front kernel's 4-warp CTAs.
+//
+// In the one-environment pass a lane is a body and every tree level runs the whole 6x6 congruence on 32 lanes of
+// which 4-7 hold a body of that depth.  Here eight lanes serve one environment and lane i of a group takes the i-th
+// body of the current depth, so 16-28 of 32 lanes work on every level, for four environments at once.  Inputs (E, bias
+// force, Coriolis terms) and outputs (U, 1/D, u, the base's inertia and bias force) go through the environments'
+// shared slabs (WarpShared::x); children hand their transformed inertia to the parent through the slab as well.
+// Same operations in the same order as the one-environment pass: bit-identical results.
+// ------------------------------------------------------------------------------------------
+TREX_FN void inward_packed(const Uniform& P, const float* mdl, const int* mdli, WarpShared* slabs, int valid_mask) {
+  const vi lane = lane_id();
+  const vi e = lane >> 3, i = lane & 7;
+  const vb env_ok = ((vi(valid_mask) >> e) & 1) != 0;
+  float* sb = reinterpret_cast<float*>(slabs);
+  const vi eo = e * (int)(sizeof(WarpShared) / sizeof(float));
+  constexpr int O_E = offsetof(WarpShared, k.E) / 4, O_U = offsetof(WarpShared, k.U) / 4, O_ID = offsetof(WarpShared, k.invD) / 4;
+  constexpr int O_PA = offsetof(WarpShared, x.pA) / 4, O_CC = offsetof(WarpShared, x.cc) / 4, O_UU = offsetof(WarpShared, x.uu) / 4;
+  constexpr int O_IP = offsetof(WarpShared, x.Ip) / 4, O_PP = offsetof(WarpShared, x.pp) / 4, O_BASE = offsetof(WarpShared, x.base) / 4;
+  TREX_ROLLED for (int d = MAX_DEPTH; d >= 0; d--) {
+    // the body this lane handles: the i-th of depth d (depth 0: the base, lane 0 of the group)
+    const vi bl0 = d > 0 ? ldi(mdli, i + (IF_LEVEL + d - 1) * 32) : seli(i == 0, vi(25), vi(-1));
+    const vb has = env_ok && (bl0 >= 0);
+    const vi bl = seli(has, bl0, 0);
+    // own spatial inertia (model constants) and the bias force computed by the environment's own warp
+    vf mc[3], I3[6], pA[6];
+    const vf mass = ldg_ro(mdl, bl + F_MASS * 32);
+    TREX_UNROLL for (int k = 0; k < 3; k++) mc[k] = ldg_ro(mdl, bl + (F_MC + k) * 32);
+    TREX_UNROLL for (int k = 0; k < 6; k++) I3[k] = ldg_ro(mdl, bl + (F_I + k) * 32);
+    TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] = ld(sb, eo + bl + (O_PA + k * 32));
+    vf IA[21];
+    TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] = 0.0f;
+    IA[SI(0, 0)] = I3[0]; IA[SI(0, 1)] = I3[1]; IA[SI(0, 2)] = I3[2];
+    IA[SI(1, 1)] = I3[3]; IA[SI(1, 2)] = I3[4]; IA[SI(2, 2)] = I3[5];
+    IA[SI(0, 4)] = -mc[2]; IA[SI(0, 5)] = mc[1];
+    IA[SI(1, 3)] = mc[2];  IA[SI(1, 5)] = -mc[0];
+    IA[SI(2, 3)] = -mc[1]; IA[SI(2, 4)] = mc[0];
+    IA[SI(3, 3)] = mass; IA[SI(4, 4)] = mass; IA[SI(5, 5)] = mass;
+    // children (all one level deeper, finished in the previous round), in child-slot order
+    if (d < MAX_DEPTH) {
+      const vi children = ldi(mdli, bl + IF_CHILDREN * 32);
+      const int nslots = P.max_children[d];
+      TREX_ROLLED for (int sidx = 0; sidx < nslots; sidx++) {
+        const vi cl = (children >> (6 * sidx)) & 63;
+        const vb ok = has && (cl != 63);
+        const vi cls = seli(ok, cl, bl);
+        // (select, not a 0/1 factor: a row that was never written may hold anything, 0 * NaN included)
+        TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] = IA[k] + sel(ok, ld(sb, eo + cls + (O_IP + k * 32)), 0.0f);
+        TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] = pA[k] + sel(ok, ld(sb, eo + cls + (O_PP + k * 32)), 0.0f);
+      }
+    }
+    if (d == 0) {  // the base: hand its articulated inertia and bias force to the environment's warp
+      TREX_UNROLL for (int k = 0; k < 21; k++) st_if(sb, eo + (O_BASE + k), IA[k], has);
+      TREX_UNROLL for (int k = 0; k < 6; k++) st_if(sb, eo + (O_BASE + 21 + k), pA[k], has);
+      break;
+    }
+    vf E[9], r0[3];
+    TREX_UNROLL for (int k = 0; k < 9; k++) E[k] = ld(sb, eo + bl + (O_E + k * 32));
+    TREX_UNROLL for (int k = 0; k < 3; k++) r0[k] = ldg_ro(mdl, bl + (F_R0 + k) * 32);
+    const vf c0 = ld(sb, eo + bl + O_CC), c1 = ld(sb, eo + bl + (O_CC + 32)), c3 = ld(sb, eo + bl + (O_CC + 64)),
+             c4 = ld(sb, eo + bl + (O_CC + 96)), tau_j = ld(sb, eo + bl + (O_CC + 128));
+    // U = IA S, D = S^T U, u = tau - S^T pA      (S = unit z rotation)
+    vf Ut[6];
+    Ut[0] = IA[SI(0, 2)]; Ut[1] = IA[SI(1, 2)]; Ut[2] = IA[SI(2, 2)];
+    Ut[3] = IA[SI(2, 3)]; Ut[4] = IA[SI(2, 4)]; Ut[5] = IA[SI(2, 5)];
+    const vf Dt = Ut[2];
+    const vb okD = Dt >= 1.1920929e-7f;
+    const vf iD = sel(okD, vdiv(1.0f, sel(okD, Dt, 1.0f)), 0.0f);
+    const vf ut = tau_j - pA[2];
+    TREX_UNROLL for (int k = 0; k < 6; k++) st_if(sb, eo + bl + (O_U + k * 32), Ut[k], has);
+    st_if(sb, eo + bl + O_ID, iD, has);
+    st_if(sb, eo + bl + O_UU, ut, has);
+    vf Ia[21];
+    TREX_UNROLL for (int a = 0; a < 6; a++)
+      TREX_UNROLL for (int b = a; b < 6; b++) Ia[SI(a, b)] = IA[SI(a, b)] - (Ut[a] * iD) * Ut[b];
+    vf pa[6];
+    const vf s = ut * iD;
+    TREX_UNROLL for (int a = 0; a < 6; a++)  // (row 2 of Ia is zero)
+      pa[a] = a == 2 ? pA[a] + Ut[a] * s : pA[a] + (Ia[SI(a, 0)] * c0 + Ia[SI(a, 1)] * c1 + Ia[SI(a, 3)] * c3 + Ia[SI(a, 4)] * c4) + Ut[a] * s;
+    vf Ip[21], pp[6];
+    to_parent(E, r0, Ia, pa, Ip, pp);
+    TREX_UNROLL for (int k = 0; k < 21; k++) st_if(sb, eo + bl + (O_IP + k * 32), Ip[k], has);
+    TREX_UNROLL for (int k = 0; k < 6; k++) st_if(sb, eo + bl + (O_PP + k * 32), pp[k], has);
+    warp_sync();
+  }
+  warp_sync();
+}
+
+// ------------------------------------------------------------------------------------------
 // One pybullet stepSimulation for the environment owned by this warp.
 // kp/kd/max_imp: motor settings of this substep (zero during the reset step).
 // ------------------------------------------------------------------------------------------
 // Returns 0 when the step is complete, or 1 + class when the solve was deferred (`work` != nullptr and at most TREX_KC
 // contacts): the solver inputs were written to `work` and the caller finishes the step with solve4() on the
 // environments of that class (0: contact-free, 1: 1-2 contacts, 2: 3-4, 3: 5-8).
+// PACKED (front kernel with 4-warp CTAs): the inward pass of the CTA's four environments is done by warp 0
+// (inward_packed) between two CTA barriers; cta_slabs = slab of warp 0, valid_mask = which warps hold an environment.
+template <bool PACKED = false>
 TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                      const int* cand_lane, WarpShared& S, EnvRegs& R, float kp, float kd, float max_imp,
-                     StepStats& stats, float* work) {
+                     StepStats& stats, float* work, WarpShared* cta_slabs = nullptr, int warp_in_cta = 0, int valid_mask = 0) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vb is_base = lane == 25;
@@ -475,7 +579,18 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
   const vi children = MDLI(IF_CHILDREN);
   vf U[6], invD = 0.0f, uu = 0.0f;
   TREX_UNROLL for (int k = 0; k < 6; k++) U[k] = 0.0f;
-  TREX_ROLLED for (int d = MAX_DEPTH; d >= 1; d--) {
+  if (PACKED) {
+    // publish this environment's inputs, let warp 0 run the pass for the CTA's four environments, fetch the results
+    TREX_UNROLL for (int k = 0; k < 6; k++) st(S.x.pA[k], lane, pA[k]);
+    st(S.x.cc[0], lane, c0); st(S.x.cc[1], lane, c1); st(S.x.cc[2], lane, c3); st(S.x.cc[3], lane, c4); st(S.x.cc[4], lane, tau_j);
+    cta_sync();
+    if (warp_in_cta == 0) inward_packed(P, mdl, mdli, cta_slabs, valid_mask);
+    cta_sync();
+    TREX_UNROLL for (int k = 0; k < 6; k++) U[k] = sel(is_joint, ld(S.k.U[k], lane), 0.0f);
+    invD = sel(is_joint, ld(S.k.invD, lane), 0.0f);
+    uu = sel(is_joint, ld(S.x.uu, lane), 0.0f);
+  }
+  TREX_ROLLED for (int d = PACKED ? 0 : MAX_DEPTH; d >= 1; d--) {
     const vb at = depth == d;
     // U = IA S, D = S^T U, u = tau - S^T pA      (S = unit z rotation)
     vf Ut[6];
@@ -512,8 +627,17 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
       TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] = vfma(okf, shflv(pp[k], cls), pA[k]);
     }
   }
-  TREX_UNROLL for (int k = 0; k < 6; k++) st(S.k.U[k], lane, U[k]);
-  st(S.k.invD, lane, invD);
+  float ia0[21], pA0[6], a0[6];
+  if (PACKED) {
+    TREX_UNROLL for (int k = 0; k < 21; k++) ia0[k] = ldu(S.x.base, k);
+    TREX_UNROLL for (int k = 0; k < 6; k++) pA0[k] = ldu(S.x.base, 21 + k);
+    warp_sync();  // pack overwrites the exchange area
+  } else {
+    TREX_UNROLL for (int k = 0; k < 21; k++) ia0[k] = lane_value(IA[k], 25);
+    TREX_UNROLL for (int k = 0; k < 6; k++) pA0[k] = lane_value(pA[k], 25);
+    TREX_UNROLL for (int k = 0; k < 6; k++) st(S.k.U[k], lane, U[k]);
+    st(S.k.invD, lane, invD);
+  }
   {
     vf pk[16];
     TREX_UNROLL for (int k = 0; k < 9; k++) pk[k] = E[k];
@@ -524,10 +648,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
 
   TREX_TICK(2)
   // ---- 6. base acceleration --------------------------------------------------------------------
-  float ia0[21], pA0[6], a0[6];
   Chol6 chol0;
-  TREX_UNROLL for (int k = 0; k < 21; k++) ia0[k] = lane_value(IA[k], 25);
-  TREX_UNROLL for (int k = 0; k < 6; k++) pA0[k] = lane_value(pA[k], 25);
   spd6_factor(ia0, chol0);
   spd6_solve_neg<float>(chol0, pA0, a0);
 
@@ -1684,8 +1805,10 @@ enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // p
 // articulated inertias, accelerations, velocity update, M^-1, row setup, contact detection.  With more than TREX_KC
 // contacts the substep is finished here (one-environment solver + integration); otherwise the solver inputs go to
 // `work` and the function returns 1 + class (solve_phase finishes the substep).   action: [25] name-sorted (trex_robot.py:311-314)
+template <bool PACKED = false>
 TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
-                         const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, bool first_round) {
+                         const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, bool first_round,
+                         WarpShared* cta_slabs = nullptr, int warp_in_cta = 0, int valid_mask = 0) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vi slot = seli(is_joint, MDLI(IF_OBS_SLOT), 0);
@@ -1699,7 +1822,8 @@ TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, con
 #ifdef TREX_PHASES
   for (int i = 0; i < 8; i++) st.phase[i] = 0.0f;
 #endif
-  const int deferred = substep(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, st, work);
+  const int deferred = substep<PACKED>(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, st, work, cta_slabs,
+                                       warp_in_cta, valid_mask);
   store_env(rec, lane, S, R);  // deferred: positions unchanged, velocities after the unconstrained update
   const float it0 = first_round ? 0.0f : ldu(rec, ST_ACC_ITERS), ov0 = first_round ? 0.0f : ldu(rec, ST_ACC_OVERFLOW);
   vf acc = 0.0f;

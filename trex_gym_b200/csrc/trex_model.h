@@ -167,6 +167,19 @@ static inline bool build_tables(const void* blob, size_t bytes, ModelTables& T, 
     T.lower_sorted[k] = (float)lower[obs_dof[k] + 1];
     T.upper_sorted[k] = (float)upper[obs_dof[k] + 1];
   }
+  // bodies of each tree depth, for the four-environments-per-warp inward pass: field 8 + (d - 1), entry i = lane of the
+  // i-th body of depth d (or -1); at most 8 per depth (8 lanes serve one environment there)
+  if (n_int_fields >= 8 + trex_topo::MAX_DEPTH) {
+    for (int d = 1; d <= trex_topo::MAX_DEPTH; d++) {
+      int cnt = 0;
+      for (int i = 0; i < 32; i++) IF(8 + d - 1, i) = -1;
+      for (int b = 1; b < NB; b++)
+        if (depth[b] == d) {
+          if (cnt >= 8) { T.err = "more than 8 bodies at one tree depth"; return false; }
+          IF(8 + d - 1, cnt++) = body_lane(b);
+        }
+    }
+  }
   // constraint order: the kernel relies on [NJ motors | NJ limit constraints]
   for (int k = 0; k < NJ; k++) {
     if (order[k] < NJ || order[NJ + k] >= NJ) { T.err = "constraint order is not [motors | limits]"; return false; }
