@@ -384,16 +384,38 @@ TREX_FN void inward_packed(const Uniform& P, const float* mdl, const int* mdli, 
   constexpr int O_E = offsetof(WarpShared, k.E) / 4, O_U = offsetof(WarpShared, k.U) / 4, O_ID = offsetof(WarpShared, k.invD) / 4;
   constexpr int O_PA = offsetof(WarpShared, x.pA) / 4, O_CC = offsetof(WarpShared, x.cc) / 4, O_UU = offsetof(WarpShared, x.uu) / 4;
   constexpr int O_IP = offsetof(WarpShared, x.Ip) / 4, O_PP = offsetof(WarpShared, x.pp) / 4, O_BASE = offsetof(WarpShared, x.base) / 4;
+  // the body this lane handles at each level: the i-th of depth d (depth 0: the base, lane 0 of the group)
+  vi blv[MAX_DEPTH + 1];
+  blv[0] = seli(i == 0, vi(25), vi(-1));
+  TREX_UNROLL for (int d = 1; d <= MAX_DEPTH; d++) blv[d] = ldi(mdli, i + (IF_LEVEL + d - 1) * 32);
+  // model constants of the body, loaded one level ahead (global loads off the level-to-level dependence chain)
+  vf n_mass, n_mc[3], n_I3[6], n_r0[3];
+  vi n_children;
+#define TREX_LOAD_LEVEL_CONSTANTS(BL)                                                       \
+  {                                                                                         \
+    const vi b_ = (BL);                                                                     \
+    n_mass = ldg_ro(mdl, b_ + F_MASS * 32);                                                 \
+    TREX_UNROLL for (int k = 0; k < 3; k++) n_mc[k] = ldg_ro(mdl, b_ + (F_MC + k) * 32);    \
+    TREX_UNROLL for (int k = 0; k < 6; k++) n_I3[k] = ldg_ro(mdl, b_ + (F_I + k) * 32);     \
+    TREX_UNROLL for (int k = 0; k < 3; k++) n_r0[k] = ldg_ro(mdl, b_ + (F_R0 + k) * 32);    \
+    n_children = ldi(mdli, b_ + IF_CHILDREN * 32);                                          \
+  }
+  TREX_LOAD_LEVEL_CONSTANTS(seli(env_ok && (blv[MAX_DEPTH] >= 0), blv[MAX_DEPTH], 0))
   TREX_ROLLED for (int d = MAX_DEPTH; d >= 0; d--) {
-    // the body this lane handles: the i-th of depth d (depth 0: the base, lane 0 of the group)
-    const vi bl0 = d > 0 ? ldi(mdli, i + (IF_LEVEL + d - 1) * 32) : seli(i == 0, vi(25), vi(-1));
+    vi bl0 = blv[0], bln = blv[0];
+    TREX_UNROLL for (int dd = 1; dd <= MAX_DEPTH; dd++) {
+      bl0 = seli(vi(d) == dd, blv[dd], bl0);
+      bln = seli(vi(d) == dd + 1, blv[dd], bln);  // the next level's body (d - 1)
+    }
     const vb has = env_ok && (bl0 >= 0);
     const vi bl = seli(has, bl0, 0);
     // own spatial inertia (model constants) and the bias force computed by the environment's own warp
-    vf mc[3], I3[6], pA[6];
-    const vf mass = ldg_ro(mdl, bl + F_MASS * 32);
-    TREX_UNROLL for (int k = 0; k < 3; k++) mc[k] = ldg_ro(mdl, bl + (F_MC + k) * 32);
-    TREX_UNROLL for (int k = 0; k < 6; k++) I3[k] = ldg_ro(mdl, bl + (F_I + k) * 32);
+    vf mc[3], I3[6], r0[3], pA[6];
+    const vf mass = n_mass;
+    const vi children = n_children;
+    TREX_UNROLL for (int k = 0; k < 3; k++) { mc[k] = n_mc[k]; r0[k] = n_r0[k]; }
+    TREX_UNROLL for (int k = 0; k < 6; k++) I3[k] = n_I3[k];
+    if (d > 0) TREX_LOAD_LEVEL_CONSTANTS(seli(env_ok && (bln >= 0), bln, 0))
     TREX_UNROLL for (int k = 0; k < 6; k++) pA[k] = ld(sb, eo + bl + (O_PA + k * 32));
     vf IA[21];
     TREX_UNROLL for (int k = 0; k < 21; k++) IA[k] = 0.0f;
@@ -405,7 +427,6 @@ TREX_FN void inward_packed(const Uniform& P, const float* mdl, const int* mdli, 
     IA[SI(3, 3)] = mass; IA[SI(4, 4)] = mass; IA[SI(5, 5)] = mass;
     // children (all one level deeper, finished in the previous round), in child-slot order
     if (d < MAX_DEPTH) {
-      const vi children = ldi(mdli, bl + IF_CHILDREN * 32);
       const int nslots = P.max_children[d];
       TREX_ROLLED for (int sidx = 0; sidx < nslots; sidx++) {
         const vi cl = (children >> (6 * sidx)) & 63;
@@ -421,9 +442,8 @@ TREX_FN void inward_packed(const Uniform& P, const float* mdl, const int* mdli, 
       TREX_UNROLL for (int k = 0; k < 6; k++) st_if(sb, eo + (O_BASE + 21 + k), pA[k], has);
       break;
     }
-    vf E[9], r0[3];
+    vf E[9];
     TREX_UNROLL for (int k = 0; k < 9; k++) E[k] = ld(sb, eo + bl + (O_E + k * 32));
-    TREX_UNROLL for (int k = 0; k < 3; k++) r0[k] = ldg_ro(mdl, bl + (F_R0 + k) * 32);
     const vf c0 = ld(sb, eo + bl + O_CC), c1 = ld(sb, eo + bl + (O_CC + 32)), c3 = ld(sb, eo + bl + (O_CC + 64)),
              c4 = ld(sb, eo + bl + (O_CC + 96)), tau_j = ld(sb, eo + bl + (O_CC + 128));
     // U = IA S, D = S^T U, u = tau - S^T pA      (S = unit z rotation)
@@ -450,6 +470,7 @@ TREX_FN void inward_packed(const Uniform& P, const float* mdl, const int* mdli, 
     TREX_UNROLL for (int k = 0; k < 6; k++) st_if(sb, eo + bl + (O_PP + k * 32), pp[k], has);
     warp_sync();
   }
+#undef TREX_LOAD_LEVEL_CONSTANTS
   warp_sync();
 }
 
