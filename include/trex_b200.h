@@ -67,7 +67,9 @@ typedef struct trex_config {
                                 CTA's four environments runs on one warp, eight lanes per environment: bit-identical results); [1],[2] low/high word of the global id of
                                 environment 0 of this shard (multi-GPU: rank * n_envs); [3] solver placement (diagnostics):
                                 0 = contact-free substeps and substeps with <= 4 contacts are solved four environments
-                                per warp, 2 = contact-free substeps only, 1 = everything in the one-environment path */
+                                per warp and substeps with more by the one-environment row-space solver (trex_heavy_kernel),
+                                3 = the same but more than 8 contacts stay in the front kernel, 2 = contact-free substeps only,
+                                1 = everything in the front kernel */
 } trex_config;
 
 typedef struct trex_stats {

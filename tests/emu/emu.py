@@ -80,13 +80,19 @@ class EmuEnv:
 
     def solve_counts(self):
         """Substeps finished by (the one-environment path, solve4<0>, solve4<KC>)."""
-        out = (ctypes.c_longlong * 4)()
+        out = (ctypes.c_longlong * 5)()
         self._L.emu_solve_counts(self._h, out)
         return tuple(int(x) for x in out)[:3]
 
+    def heavy_solves(self):
+        """Substeps finished by solve_heavy (more than 8 contacts, one environment per warp, row space)."""
+        out = (ctypes.c_longlong * 5)()
+        self._L.emu_solve_counts(self._h, out)
+        return int(out[4])
+
     def packed_rounds(self):
         """Substep rounds whose front phase ran as a 4-warp CTA (inward pass of four environments by one warp)."""
-        out = (ctypes.c_longlong * 4)()
+        out = (ctypes.c_longlong * 5)()
         self._L.emu_solve_counts(self._h, out)
         return int(out[3])
 

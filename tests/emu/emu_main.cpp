@@ -14,12 +14,14 @@ struct Emu {
   trex::Uniform P;
   trex::WarpShared S;            // the slab of a lone warp
   trex::WarpShared slabs[4];     // the slabs of a 4-warp CTA (packed inward pass)
+  trex::HeavyShared heavy;       // shared memory of a solve_heavy warp
   int packed = 0;                // emu_step4 with n == 4: run the front phase as a 4-warp CTA (host threads)
   alignas(16) float work[4 * TREX_WORK_STRIDE];
+  alignas(16) float workh[4 * TREX_HEAVY_STRIDE];
   alignas(16) float scratch[TREX_SOLVE_SCRATCH(TREX_KC)];
   int deferred = 1;
   int pack_reverse = 0;  // tests: fill the solver's lane groups from the top
-  long long solves[4] = {0, 0, 0, 0};  // substeps finished in front_phase / by solve4<0> / by solve4<TREX_KC>; [3] substep rounds run as a 4-warp CTA
+  long long solves[5] = {0, 0, 0, 0, 0};  // substeps finished in front_phase / by solve4<0> / by solve4<TREX_KC>; [3] substep rounds run as a 4-warp CTA; [4] substeps finished by solve_heavy
 };
 
 static_assert(trex::F_COUNT == 32, "field table");
@@ -52,6 +54,8 @@ void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, 
   memset(e->slabs, 0xff, sizeof(e->slabs));
   memset(e->scratch, 0xff, sizeof(e->scratch));
   memset(e->work, 0xff, sizeof(e->work));
+  memset(e->workh, 0xff, sizeof(e->workh));
+  memset(&e->heavy, 0xff, sizeof(e->heavy));
   return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
@@ -83,28 +87,34 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
         std::thread th[4];
         for (int i = 0; i < 4; i++)
           th[i] = std::thread([=, &dres]() {
-            dres[i] = trex::front_phase<true>(e->P, mdl, mdli, tasks, cp, cl, e->slabs[i], rec + i * TREX_STATE_STRIDE,
+            dres[i] = 255 & trex::front_phase<true>(e->P, mdl, mdli, tasks, cp, cl, e->slabs[i], rec + i * TREX_STATE_STRIDE,
                                               e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0,
-                                              e->slabs, i, 0xf);
+                                              e->slabs, i, 0xf, e->deferred ? e->workh + i * TREX_HEAVY_STRIDE : nullptr);
           });
         for (int i = 0; i < 4; i++) th[i].join();
         g_emu_cta_barrier = nullptr;
         pthread_barrier_destroy(&bar);
       } else {
         for (int i = 0; i < n; i++)
-          dres[i] = trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
-                                      e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0);
+          dres[i] = 255 & trex::front_phase(e->P, mdl, mdli, tasks, cp, cl, e->S, rec + i * TREX_STATE_STRIDE,
+                                      e->deferred ? e->work + i * TREX_WORK_STRIDE : nullptr, action + i * trex::NJ, r == 0, nullptr, 0, 0,
+                                      e->deferred ? e->workh + i * TREX_HEAVY_STRIDE : nullptr);
       }
       for (int i = 0; i < n; i++) {
         const int d = dres[i];
-        e->solves[d == 0 ? 0 : (d == 1 ? 1 : 2)]++;
+        e->solves[d == 0 ? 0 : (d == 1 ? 1 : (d < 5 ? 2 : 4))]++;
         if (d) { int& c = cnt[d - 1]; envs[d - 1][e->pack_reverse ? 3 - c : c] = i; c++; }
       }
       for (int d = 0; d < TREX_NCLASS; d++) {
         if (!cnt[d]) continue;
         const int pending = e->pack_reverse ? (((1 << cnt[d]) - 1) << (4 - cnt[d])) : ((1 << cnt[d]) - 1);
         if (d == 0) trex::solve_phase<0>(e->P, e->scratch, e->work, rec, envs[0], pending);
-        else trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[d], pending);
+        else if (d < 4) trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[d], pending);
+        else  // class 4: one environment per warp
+          for (int g = 0; g < 4; g++)
+            if (pending & (1 << g))
+              trex::solve_heavy(e->P, mdli, e->heavy, e->work + envs[d][g] * TREX_WORK_STRIDE, e->workh + envs[d][g] * TREX_HEAVY_STRIDE,
+                                rec + envs[d][g] * TREX_STATE_STRIDE);
       }
     }
   }
@@ -117,9 +127,9 @@ void emu_step(void* h, float* rec, const float* action, float* obs, float* rewar
               long long env_id) {
   emu_step4(h, 1, rec, action, obs, reward, done, aux, force_reset, env_id);
 }
-void emu_solve_counts(void* h, long long* out) { for (int i = 0; i < 4; i++) out[i] = ((Emu*)h)->solves[i]; }
-void emu_set_deferred(void* h, int on) {  // bit 0 deferral on, bit 1 reverse packing, bit 2 contact-free substeps only, bit 3 front phase as a 4-warp CTA
+void emu_solve_counts(void* h, long long* out) { for (int i = 0; i < 5; i++) out[i] = ((Emu*)h)->solves[i]; }
+void emu_set_deferred(void* h, int on) {  // bit 0 deferral on, bit 1 reverse packing, bit 2 contact-free substeps only, bit 3 front phase as a 4-warp CTA, bit 4 more than TREX_KC contacts stay in the front phase
   Emu* e = (Emu*)h;
-  e->deferred = on & 1; e->pack_reverse = (on >> 1) & 1; e->P.defer_contacts = ((on >> 2) & 1) ? 0 : 1; e->packed = (on >> 3) & 1;
+  e->deferred = on & 1; e->pack_reverse = (on >> 1) & 1; e->P.defer_contacts = ((on >> 2) & 1) ? 0 : (((on >> 4) & 1) ? 1 : 2); e->packed = (on >> 3) & 1;
 }
 }

@@ -124,6 +124,7 @@ def test_contact_capacity_keeps_the_deepest_points(model, emu_cls, action_limits
                 n_over += 1
                 errs.append(max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()))
     assert n_over >= 10
+    assert e.heavy_solves() >= n_over  # 16 contacts: the row-space one-environment solver (solve_heavy)
     errs = np.asarray(errs)
     assert np.percentile(errs, 50) < 5e-5 and errs.max() < 5e-3, (np.percentile(errs, 50), errs.max())
 
@@ -139,6 +140,44 @@ def test_standing_drop_matches_oracle_qualitatively(model, emu_cls):
     so, se = o.get_state(), e.get_state(o.num_candidates)
     assert abs(so[2] - se[2]) < 0.02 and abs(se[2] - 2.19) < 0.1
     assert int(e.aux[7]) >= 6
+
+
+def test_standing_on_both_feet_per_substep(model, emu_cls):
+    """A T-rex standing on both feet has 12-16 active contact points: those substeps are finished by solve_heavy (one
+    environment per warp, contact rows in row space).  Per-substep parity against the oracle, and agreement with the
+    one-environment sweep inside the front phase, which runs the same Gauss-Seidel iteration in coordinate space."""
+    from trex_gym_b200.model_compiler import with_params
+
+    sub = with_params(model, time_step=0.002, solver_iterations=60)
+    e = emu_cls(sub.blob(), num_substeps=1)                 # row-space solvers
+    f = emu_cls(sub.blob(), num_substeps=1, deferred=1 | 16)  # more than 8 contacts: front phase
+    o = _oracle(sub, num_substeps=1)
+    nc = o.num_candidates
+    hold = o.reset()[:25].copy()
+    e.reset()
+    f.reset()
+    errs, errs_f, errs_fo, ks = [], [], [], []
+    for t in range(230):
+        pre = e.get_state(nc)
+        o.set_state(pre)
+        f.set_state(pre)
+        o.step(hold)
+        e.step(hold)
+        f.step(hold)
+        so, se, sf = o.get_state(), e.get_state(nc), f.get_state(nc)
+        if o.last_num_contacts > 8:
+            errs.append(max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()))
+            errs_fo.append(max(rel_err(so[sl], sf[sl]) for sl in STATE_BLOCKS.values()))
+            errs_f.append(max(rel_err(sf[sl], se[sl]) for sl in STATE_BLOCKS.values()))
+            ks.append(o.last_num_contacts)
+            assert int(e.aux[7]) % 1000 == o.last_num_contacts
+    errs, errs_f, errs_fo = np.asarray(errs), np.asarray(errs_f), np.asarray(errs_fo)
+    assert len(errs) > 60 and max(ks) >= 14
+    assert e.heavy_solves() == len(errs) and f.heavy_solves() == 0
+    # 14-16 stacked contact points make an ill-conditioned FP32 problem: 1.5e-4 median per substep for either solver
+    assert np.percentile(errs, 50) < 5e-4 and np.percentile(errs, 99) < 1e-2, (np.percentile(errs, 50), errs.max())
+    assert np.percentile(errs, 50) < 1.5 * np.percentile(errs_fo, 50) and errs.max() < 1.5 * errs_fo.max()
+    assert np.percentile(errs_f, 50) < 1e-4 and errs_f.max() < 1e-3, (np.percentile(errs_f, 50), errs_f.max())
 
 
 def test_reward_bit_exact_from_outputs(model, emu_cls, action_limits):

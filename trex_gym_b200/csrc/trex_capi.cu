@@ -57,8 +57,8 @@ template <int WARPS, bool PACKED>
 __global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
 trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
                   const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
-                  float* __restrict__ state, float* __restrict__ work, const float* __restrict__ action,
-                  int* __restrict__ list, int* __restrict__ list_count, int n_envs, int first_round) {
+                  float* __restrict__ state, float* __restrict__ work, float* __restrict__ workh, const float* __restrict__ action,
+                  int* __restrict__ list, int* __restrict__ list_count, const int* __restrict__ heavy_hint, int n_envs, int first_round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -78,15 +78,20 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
 #ifdef TREX_PHASES
   const long long t_entry = clock64();
 #endif
-  const int deferred = trex::front_phase<PACKED>(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
+  const int front_result = trex::front_phase<PACKED>(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
                                                   work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
-                                                  first_round != 0, slabs, warp, valid_mask);
+                                                  first_round != 0, slabs, warp, valid_mask,
+                                                  // class 4 is deferred only while few environments are in it (count of the previous round)
+                                                  (workh != nullptr && (long long)(*heavy_hint) * 16 <= (long long)n_envs) ? workh + (size_t)env * TREX_HEAVY_STRIDE : nullptr);
+  const int deferred = front_result & 255, n_contacts = front_result >> 8;
   // append to the list of its class of deferred environments (any order: the solver's lane groups are independent):
   // class 0 = contact-free substeps, classes 1..3 = 1-2 / 3-4 / 5-8 contacts; list c at list + c * n_envs, counters + 64 * c
   if (deferred && (threadIdx.x & 31) == 0) {
     const int which = deferred - 1;
     list[(size_t)which * n_envs + atomicAdd(list_count + 64 * which, 1)] = env;
   }
+  // environments with more than TREX_KC contacts in this round, whichever solver takes them (steers the next round)
+  if ((threadIdx.x & 31) == 0 && n_contacts > TREX_KC) atomicAdd(list_count + 64 * TREX_NCLASS, 1);
 #ifdef TREX_PHASES
   __syncwarp();
   if ((threadIdx.x & 31) == 0) state[(size_t)env * TREX_STATE_STRIDE + 167] += (float)(clock64() - t_entry);  // warp lifetime
@@ -107,10 +112,10 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   if (KC > 0) {
     // list / list_count point at class 1.  Warps are handed out heaviest class first (5-8 contacts, then 3-4, then 1-2):
     // the longest-running warps start first instead of forming the tail of the launch.
-    list += (size_t)(TREX_NCLASS - 2) * n_envs;
-    list_count += 64 * (TREX_NCLASS - 2);
+    list += (size_t)2 * n_envs;   // class 3
+    list_count += 64 * 2;
     count = *list_count;
-    for (int c = TREX_NCLASS - 1; c > 1 && first >= ((count + 3) & ~3); c--) {
+    for (int c = 3; c > 1 && first >= ((count + 3) & ~3); c--) {
       first -= (count + 3) & ~3;
       list -= n_envs;
       list_count -= 64;
@@ -121,6 +126,25 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   int envs[4] = {0, 0, 0, 0}, pending = 0;
   for (int e = 0; e < 4 && first + e < count; e++) { envs[e] = list[first + e]; pending |= 1 << e; }
   trex::solve_phase<KC>(P, scratch, work, state, envs, pending);
+}
+
+// one warp per environment of class 4 (more than TREX_KC contacts), a fixed grid striding over the list
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+trex_heavy_kernel(const trex::Uniform P, const int* __restrict__ mdli, float* __restrict__ state, const float* __restrict__ work,
+                  const float* __restrict__ workh,
+                  const int* __restrict__ list, const int* __restrict__ list_count, const int* __restrict__ seen, int* __restrict__ hint) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  trex::HeavyShared* H = reinterpret_cast<trex::HeavyShared*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int count = *list_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *hint = *seen;  // environments with > TREX_KC contacts in this round
+  for (int i = blockIdx.x * WARPS + warp; i < count; i += gridDim.x * WARPS) {
+    const int env = list[i];
+    trex::solve_heavy(P, mdli, H[warp], work + (size_t)env * TREX_WORK_STRIDE, workh + (size_t)env * TREX_HEAVY_STRIDE,
+                      state + (size_t)env * TREX_STATE_STRIDE);
+    __syncwarp();
+  }
 }
 
 // one warp per environment: reward / done / auto-reset / observations (mode 0), or reset only (mode 1, optional mask)
@@ -272,6 +296,7 @@ struct trex_handle {
   trex_host::EnvConfig C;
   trex::Uniform P;
   float *d_mdl = nullptr, *d_tasks = nullptr, *d_cand_p = nullptr, *d_state = nullptr, *d_aux = nullptr, *d_work = nullptr;
+  float* d_workh = nullptr;     // contact rows of the environments with more than TREX_KC contacts (class 4)
   float *d_lower = nullptr, *d_upper = nullptr;
   int *d_mdli = nullptr, *d_cand_lane = nullptr;
   // staging for the host-buffer entry points
@@ -280,6 +305,7 @@ struct trex_handle {
   int* d_list = nullptr;        // [TREX_NCLASS][n_envs] environments whose solve was deferred in the current substep round, by class
   int* d_list_count = nullptr;  // [TREX_NCLASS][64] one counter per class and substep round
   DevStats* d_stats = nullptr;
+  int heavy_grid = 148 * 9;     // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
   int64_t launches = 0;
   int64_t env_steps = 0;
 };
@@ -300,23 +326,25 @@ template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
   const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS,
-               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS;
+               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS, smem_h = sizeof(trex::HeavyShared);
   static bool configured[16] = {false};
   if (!configured[h->device & 15]) {
     int rc;
     if ((rc = configure_kernel(trex_front_kernel<WF, WF == 4>, smem_f)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, 0>, smem_s)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, TREX_KC>, smem_c)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_heavy_kernel<1>, smem_h)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
   }
   const int grid1 = (h->n_envs + WF - 1) / WF;            // one warp per environment
   const int grid4 = (h->n_envs + 4 * WS - 1) / (4 * WS);  // one warp per four environments
   if (mode == 0) {
-    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 64 * TREX_NCLASS * sizeof(int), st));  // one counter per list and substep round
+    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 64 * (TREX_NCLASS + 1) * sizeof(int), st));  // (not the hint behind them)  // one counter per list and substep round
     for (int r = 0; r < h->P.n_sub; r++) {
       trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
-                                                           h->d_state, h->d_work, action, h->d_list, h->d_list_count + r, h->n_envs, r == 0);
+                                                           h->d_state, h->d_work, h->d_workh, action, h->d_list, h->d_list_count + r,
+                                                           h->d_list_count + 64 * (TREX_NCLASS + 1), h->n_envs, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
@@ -328,6 +356,13 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
                                                                             h->d_list_count + 64 + r, h->n_envs);
           CUDA_TRY(cudaGetLastError());
           h->launches++;
+          if (h->P.defer_contacts > 1 && h->d_workh) {  // class 4: more than TREX_KC contacts, one environment per warp
+            trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, st>>>(h->P, h->d_mdli, h->d_state, h->d_work, h->d_workh,
+                                                                   h->d_list + (size_t)4 * h->n_envs, h->d_list_count + 64 * 4 + r,
+                                                                   h->d_list_count + 64 * TREX_NCLASS + r, h->d_list_count + 64 * (TREX_NCLASS + 1));
+            CUDA_TRY(cudaGetLastError());
+            h->launches++;
+          }
         }
       }
     }
@@ -391,7 +426,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     h->C.env_offset = ((long long)cfg->reserved[2] << 32) | (unsigned)cfg->reserved[1];
     if (cfg->reserved[0] == 1 || cfg->reserved[0] == 2 || cfg->reserved[0] == 4) h->warps_per_block = cfg->reserved[0];
     h->deferred_solve = cfg->reserved[3] != 1;
-    h->C.defer_contacts = cfg->reserved[3] == 0;
+    h->C.defer_contacts = cfg->reserved[3] == 0 ? 2 : (cfg->reserved[3] == 3 ? 1 : 0);
   }
   if ((int)h->T.params[trex_host::P_MAX_CONTACTS] != TREX_KMAX) {
     int rc_ = fail(TREX_ERR_MODEL, "model blob max_contacts differs from the compiled contact capacity (TREX_KMAX)%s");
@@ -413,6 +448,8 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   CTRY(cudaMalloc((void**)&h->d_state, N * TREX_STATE_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_state, 0, N * TREX_STATE_STRIDE * sizeof(float)));
   if (h->deferred_solve) CTRY(cudaMalloc((void**)&h->d_work, N * TREX_WORK_STRIDE * sizeof(float)));
+  if (h->deferred_solve && h->C.defer_contacts > 1 && h->C.enable_contacts)
+    CTRY(cudaMalloc((void**)&h->d_workh, N * TREX_HEAVY_STRIDE * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_action, N * trex::NJ * sizeof(float)));
@@ -420,8 +457,8 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   CTRY(cudaMalloc((void**)&h->d_reward, N * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_done, N));
   CTRY(cudaMalloc((void**)&h->d_list, TREX_NCLASS * N * sizeof(int)));
-  CTRY(cudaMalloc((void**)&h->d_list_count, 64 * TREX_NCLASS * sizeof(int)));
-  CTRY(cudaMemset(h->d_list_count, 0, 64 * TREX_NCLASS * sizeof(int)));
+  CTRY(cudaMalloc((void**)&h->d_list_count, 64 * (TREX_NCLASS + 2) * sizeof(int)));
+  CTRY(cudaMemset(h->d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int)));
   CTRY(cudaMalloc((void**)&h->d_stats, sizeof(DevStats)));
 #undef CTRY
   // all environments start from the reference reset (TrexBulletEnv.__init__ calls reset(), trex_env.py:92)
@@ -439,7 +476,7 @@ void trex_destroy(trex_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_mdl); cudaFree(h->d_mdli); cudaFree(h->d_tasks); cudaFree(h->d_cand_p); cudaFree(h->d_cand_lane);
-  cudaFree(h->d_work); cudaFree(h->d_list); cudaFree(h->d_list_count);
+  cudaFree(h->d_work); cudaFree(h->d_workh); cudaFree(h->d_list); cudaFree(h->d_list_count);
   cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_action);
   cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_stats);
   delete h;

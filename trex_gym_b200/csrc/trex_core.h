@@ -55,9 +55,20 @@
 #define TREX_WORK_STRIDE 2848
 static_assert(W_A4 + 12 * TREX_KC * TREX_KC <= TREX_WORK_STRIDE && (W_BT % 4) == 0 && (W_A4 % 4) == 0 && (TREX_WORK_STRIDE % 32) == 0,
               "work record layout");
+// environments with more contacts (class 4, solve_heavy) keep their contact rows in a record of their own, so the
+// main records stay dense: same fields for up to TREX_KW contacts
+#define TREX_KW TREX_KMAX
+#define H_NC 0
+#define H_CS 8
+#define H_BT (H_CS + 16 * TREX_KW)
+#define H_A4 (H_BT + 96 * TREX_KW)
+#define TREX_HEAVY_STRIDE (((H_A4 + 12 * TREX_KW * TREX_KW) + 31) / 32 * 32)
+static_assert((H_BT % 4) == 0 && (H_A4 % 4) == 0 && TREX_KC <= TREX_KW, "heavy record layout");
 // deferred environments are listed by class so that the four environments of a solver warp have similar row counts
-#define TREX_NCLASS 4                      // 0: contact-free, 1: 1-2 contacts, 2: 3-4, 3: 5-8
-TREX_TOPO_FN int defer_class(int n_contacts) { return n_contacts == 0 ? 0 : (n_contacts <= 2 ? 1 : (n_contacts <= 4 ? 2 : 3)); }
+#define TREX_NCLASS 5                      // 0: contact-free, 1: 1-2 contacts, 2: 3-4, 3: 5-8 (solve4); 4: 9..KW (solve_heavy)
+TREX_TOPO_FN int defer_class(int n_contacts) {
+  return n_contacts == 0 ? 0 : (n_contacts <= 2 ? 1 : (n_contacts <= 4 ? 2 : (n_contacts <= TREX_KC ? 3 : 4)));
+}
 #ifdef TREX_PHASES
 #define TREX_AUX_STRIDE 16
 #define TREX_TICK(i) { const long long _t = cycle_count(); stats.phase[i] += (float)(_t - _t0); _t0 = _t; }
@@ -107,7 +118,8 @@ struct Uniform {
   float head_p[3];
   float r0[NB][3];  // static-index copy of F_R0 (body index, not lane)
   int iters, n_sub, max_episode_steps, head_lane, n_cand, n_rounds, contacts_on, reset_mode;
-  int defer_contacts;     // != 0: substeps with 1..TREX_KC contacts are also solved four environments per warp
+  int defer_contacts;     // 1: substeps with 1..TREX_KC contacts are also solved four environments per warp; 2: and those with
+                          // more contacts by solve_heavy (one environment per warp, contact rows in row space)
   unsigned seed;
   long long env_offset;   // global id of environment 0 of this shard (keys the reset sampler)
   float reset_z_min, reset_z_max;  // reset_mode 1: base height range
@@ -140,7 +152,7 @@ struct alignas(16) WarpShared {
       float dV[3 * TREX_KMAX][32];   // rows 3*c + {0 normal, 1 t1, 2 t2}: M^-1 J^T, indexed by lane
       float Jc[3 * TREX_KMAX][12];   // compact Jacobian rows: [0:6] base coordinates, [6:11] chain joints by depth, [11] = 0
       unsigned char slot[TREX_KMAX][32];  // which Jc entry each lane multiplies its velocity coordinate with
-      unsigned char inv[TREX_KC][16];     // inverse of slot for the first KC contacts: lane (coordinate) of each Jc entry
+      unsigned char inv[TREX_KW][16];     // inverse of slot: lane (coordinate) of each Jc entry
     } c;
     struct {                  // exchange with the four-environments-per-warp inward pass (front kernel, 4-warp CTAs):
       float keep[28][32];     // k.E .. k.xw stay live (k.pack is written after the pass)
@@ -365,6 +377,37 @@ TREX_FN void to_parent(const vf E[9], const vf r[3], const vf Ia[21], const vf p
   pp[3] = ff[0]; pp[4] = ff[1]; pp[5] = ff[2];
 }
 
+// End of a physics substep: velocities += dv (each coordinate clamped, btMultiBody::applyDeltaVeeMultiDof), applied motor
+// torque read-back, then positions with the NEW velocities (btMultiBody::stepPositionsMultiDof).
+// dv: this lane's coordinate of the velocity change (joints on lanes 0..24, base coordinates on lanes 25..30).
+TREX_FN void finish_substep(const Uniform& P, vi lane, EnvRegs& R, vf dv, vf lam_m) {
+  const vb is_joint = lane < NJ;
+  const float dt = P.dt;
+  R.qd = sel(is_joint, clampv(R.qd + dv, -P.maxvel, P.maxvel), 0.0f);
+  TREX_UNROLL for (int k = 0; k < 3; k++) {
+    R.om[k] = clampf(R.om[k] + lane_value(dv, 25 + k), -P.maxvel, P.maxvel);
+    R.vl[k] = clampf(R.vl[k] + lane_value(dv, 28 + k), -P.maxvel, P.maxvel);
+  }
+  R.tau = sel(is_joint, vdiv(lam_m, dt), 0.0f);  // appliedJointMotorTorque = impulse / dt
+  TREX_UNROLL for (int k = 0; k < 3; k++) R.pos[k] += dt * R.vl[k];
+  {
+    float fAngle = sqrtf(R.om[0] * R.om[0] + R.om[1] * R.om[1] + R.om[2] * R.om[2]);
+    if (fAngle * dt > 0.78539816339744831f) fAngle = 0.78539816339744831f / dt;
+    float sc;
+    if (fAngle < 0.001f) sc = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * fAngle * fAngle;
+    else sc = sinf(0.5f * fAngle * dt) / fAngle;
+    const float ax = R.om[0] * sc, ay = R.om[1] * sc, az = R.om[2] * sc, aw = cosf(fAngle * dt * 0.5f);
+    const float x = R.quat[0], y = R.quat[1], z = R.quat[2], w = R.quat[3];
+    const float nx = aw * x + ax * w + ay * z - az * y;
+    const float ny = aw * y - ax * z + ay * w + az * x;
+    const float nz = aw * z + ax * y - ay * x + az * w;
+    const float nw = aw * w - ax * x - ay * y - az * z;
+    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    R.quat[0] = nx * inv; R.quat[1] = ny * inv; R.quat[2] = nz * inv; R.quat[3] = nw * inv;
+  }
+  R.q = sel(is_joint, R.q + dt * R.qd, 0.0f);
+}
+
 // ------------------------------------------------------------------------------------------
 // Inward pass (articulated inertias) of FOUR environments by one warp: the front kernel's 4-warp CTAs.
 //
@@ -486,7 +529,8 @@ TREX_FN void inward_packed(const Uniform& P, const float* mdl, const int* mdli, 
 template <bool PACKED = false>
 TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                      const int* cand_lane, WarpShared& S, EnvRegs& R, float kp, float kd, float max_imp,
-                     StepStats& stats, float* work, WarpShared* cta_slabs = nullptr, int warp_in_cta = 0, int valid_mask = 0) {
+                     StepStats& stats, float* work, WarpShared* cta_slabs = nullptr, int warp_in_cta = 0, int valid_mask = 0,
+                     float* workh = nullptr) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vb is_base = lane == 25;
@@ -925,7 +969,9 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
   // rows (the rows are then the 25 motors and the violated joint limits, all with unit Jacobians); with up to
   // TREX_KC contacts when P.defer_contacts.  The solver inputs go to the work record: M^-1, the per-joint row
   // scalars and -- below -- the contact rows.
-  const bool defer_c = work != nullptr && P.defer_contacts != 0 && n_act > 0 && n_act <= TREX_KC;
+  // (workh: more than TREX_KC contacts go to solve_heavy; the caller passes it only while few environments are in that
+  // class -- solve_heavy wins by taking the long-running warps out of the front kernel, not by being faster per environment)
+  const bool defer_c = work != nullptr && P.defer_contacts != 0 && n_act > 0 && n_act <= ((P.defer_contacts > 1 && workh != nullptr) ? TREX_KW : TREX_KC);
   if (work != nullptr && (n_act == 0 || defer_c)) {
     _Pragma("unroll 8") for (int gq = 0; gq < trex_topo::NDOF; gq++) st(work, lane + (W_COL + gq * 32), ld(S.col[gq], lane));
     st(work, lane + W_RHSM, rhs_m);
@@ -1031,35 +1077,39 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
       // 31 coordinates, so it needs the responses at the joints (B4), at the base (for the final update) and the
       // Delassus blocks A[r'][r] = J_r' M^-1 J_r^T between contact rows.
       warp_sync();
+      const bool heavy = n_act > TREX_KC;      // class 4: its own record, laid out for TREX_KW contacts
+      float* cw = heavy ? workh : work;
+      const int o_nc = heavy ? H_NC : W_NC, o_cs = heavy ? H_CS : W_CS, o_bt = heavy ? H_BT : W_BT, o_a4 = heavy ? H_A4 : W_A4;
+      const int kw = heavy ? TREX_KW : TREX_KC;
       {
         const vb own = lane < n_act;
         const vi ls = seli(own, lane, 0);
-        const vi sb = ls * 16 + W_CS;
+        const vi sb = ls * 16 + o_cs;
         TREX_UNROLL for (int k = 0; k < 3; k++) {
-          st_if(work, sb + k, c_rhs[k], own);
-          st_if(work, sb + (3 + k), c_jdi[k], own);
-          st_if(work, sb + (6 + k), c_dd[k], own);
+          st_if(cw, sb + k, c_rhs[k], own);
+          st_if(cw, sb + (3 + k), c_jdi[k], own);
+          st_if(cw, sb + (6 + k), c_dd[k], own);
         }
-        st_if(work, sb + 9, c_lam[0], own);
-        st_if(work, sb + 10, vi2f(ldi(S.ccand, ls)), own);
-        st_if(work, vi(W_NC), vbroadcast((float)n_act), lane == 0);
+        st_if(cw, sb + 9, c_lam[0], own);
+        st_if(cw, sb + 10, vi2f(ldi(S.ccand, ls)), own);
+        st_if(cw, vi(o_nc), vbroadcast((float)n_act), lane == 0);
       }
-      TREX_ROLLED for (int r = 0; r < 3 * n_act; r++) st(work, lane + (r * 32 + W_BT), ld(S.c.dV[r], lane));
-      const int n3 = 3 * n_act, nn = n3 * n3, recip = 65536 / n3 + 1;
+      TREX_ROLLED for (int r = 0; r < 3 * n_act; r++) st(cw, lane + (r * 32 + o_bt), ld(S.c.dV[r], lane));
+      const int n3 = 3 * n_act, nn = n3 * n3, recip = 1048576 / n3 + 1;  // idx / n3 == (idx * recip) >> 20 for idx < 2304
       TREX_ROLLED for (int i0 = 0; i0 < nn; i0 += 32) {
         const vi idx = lane + i0;
         const vb valid = idx < nn;
         const vi is = seli(valid, idx, 0);
-        const vi rp = (is * recip) >> 16;        // affected row (c', k')
+        const vi rp = (is * recip) >> 20;        // affected row (c', k')
         const vi r = is - rp * n3;               // source row (c, k)
-        const vi cp = (rp * 11) >> 5, kp = rp - cp * 3;  // rp / 3, rp % 3 (rp < 24)
+        const vi cp = (rp * 43) >> 7, kp = rp - cp * 3;  // rp / 3, rp % 3 (rp < 48)
         vf acc = 0.0f;
         TREX_UNROLL for (int e = 0; e < 11; e++) {
           const vf jv = ld(&S.c.Jc[0][0], rp * 12 + e);
           const vi dl = ldb(&S.c.inv[0][0], cp * 16 + e);
           acc = vfma(jv, ld(&S.c.dV[0][0], r * 32 + dl), acc);
         }
-        st_if(work, (r * TREX_KC + cp) * 4 + kp + W_A4, acc, valid);
+        st_if(cw, (r * kw + cp) * 4 + kp + o_a4, acc, valid);
       }
       warp_sync();
       TREX_TICK(5)
@@ -1236,41 +1286,14 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
   stats.iters += it_done;
   stats.contacts = n_act;
 
-  // ---- 12. velocities += dv (clamped); impulses written back ------------------------------------------------
-  R.qd = sel(is_joint, clampv(R.qd + dv, -P.maxvel, P.maxvel), 0.0f);
-  TREX_UNROLL for (int k = 0; k < 3; k++) {
-    R.om[k] = clampf(R.om[k] + lane_value(dv, 25 + k), -P.maxvel, P.maxvel);
-    R.vl[k] = clampf(R.vl[k] + lane_value(dv, 28 + k), -P.maxvel, P.maxvel);
-  }
-  R.tau = sel(is_joint, vdiv(lam_m, dt), 0.0f);  // appliedJointMotorTorque = impulse / dt
+  // ---- 12-13. velocities += dv (clamped), motor torque, cached contact impulses, positions with the NEW velocities ----
   if (P.contacts_on) {
-    vi cc = 0;
-    {
-      const vb has = lane < n_act;
-      cc = ldi(S.ccand, seli(has, lane, 0));
-      st_if(S.lam_cache, cc, c_lam[0], has);
-    }
+    const vb has = lane < n_act;
+    const vi cc = ldi(S.ccand, seli(has, lane, 0));
+    st_if(S.lam_cache, cc, c_lam[0], has);
   }
   warp_sync();
-
-  // ---- 13. positions with the NEW velocities (btMultiBody::stepPositionsMultiDof) ------------------------------
-  TREX_UNROLL for (int k = 0; k < 3; k++) R.pos[k] += dt * R.vl[k];
-  {
-    float fAngle = sqrtf(R.om[0] * R.om[0] + R.om[1] * R.om[1] + R.om[2] * R.om[2]);
-    if (fAngle * dt > 0.78539816339744831f) fAngle = 0.78539816339744831f / dt;
-    float sc;
-    if (fAngle < 0.001f) sc = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * fAngle * fAngle;
-    else sc = sinf(0.5f * fAngle * dt) / fAngle;
-    const float ax = R.om[0] * sc, ay = R.om[1] * sc, az = R.om[2] * sc, aw = cosf(fAngle * dt * 0.5f);
-    const float x = R.quat[0], y = R.quat[1], z = R.quat[2], w = R.quat[3];
-    const float nx = aw * x + ax * w + ay * z - az * y;
-    const float ny = aw * y - ax * z + ay * w + az * x;
-    const float nz = aw * z + ax * y - ay * x + az * w;
-    const float nw = aw * w - ax * x - ay * y - az * z;
-    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
-    R.quat[0] = nx * inv; R.quat[1] = ny * inv; R.quat[2] = nz * inv; R.quat[3] = nw * inv;
-  }
-  R.q = sel(is_joint, R.q + dt * R.qd, 0.0f);
+  finish_substep(P, lane, R, dv, lam_m);
   TREX_TICK(7)
   return 0;
 }
@@ -1280,7 +1303,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
 enum { ST_POS = 0, ST_QUAT = 3, ST_OM = 7, ST_VL = 10, ST_Q = 13, ST_QD = 38, ST_TAU = 63, ST_LAM = 88,
        ST_STEP = 152, ST_EPISODE = 153, ST_NANRESETS = 154 };
 
-TREX_FN void load_env(const float* rec, vi lane, WarpShared& S, EnvRegs& R) {
+TREX_FN void load_env_regs(const float* rec, vi lane, EnvRegs& R) {
   const vb is_joint = lane < NJ;
   const vi js = seli(is_joint, lane, 0);
   R.q = ld_if(rec, js + ST_Q, is_joint, 0.0f);
@@ -1289,12 +1312,15 @@ TREX_FN void load_env(const float* rec, vi lane, WarpShared& S, EnvRegs& R) {
   R.tgt = 0.0f;
   TREX_UNROLL for (int k = 0; k < 3; k++) { R.pos[k] = ldu(rec, ST_POS + k); R.om[k] = ldu(rec, ST_OM + k); R.vl[k] = ldu(rec, ST_VL + k); }
   TREX_UNROLL for (int k = 0; k < 4; k++) R.quat[k] = ldu(rec, ST_QUAT + k);
+}
+TREX_FN void load_env(const float* rec, vi lane, WarpShared& S, EnvRegs& R) {
+  load_env_regs(rec, lane, R);
   st(S.lam_cache, lane, ld(rec, lane + ST_LAM));
   st(S.lam_cache, lane + 32, ld(rec, lane + (ST_LAM + 32)));
   warp_sync();
 }
 
-TREX_FN void store_env(float* rec, vi lane, WarpShared& S, const EnvRegs& R) {
+TREX_FN void store_env_regs(float* rec, vi lane, const EnvRegs& R) {
   const vb is_joint = lane < NJ;
   const vi js = seli(is_joint, lane, 0);
   st_if(rec, js + ST_Q, R.q, is_joint);
@@ -1309,6 +1335,9 @@ TREX_FN void store_env(float* rec, vi lane, WarpShared& S, const EnvRegs& R) {
   }
   TREX_UNROLL for (int k = 0; k < 4; k++) bs = sel(lane == ST_QUAT + k, vbroadcast(R.quat[k]), bs);
   st_if(rec, lane, bs, lane < 13);
+}
+TREX_FN void store_env(float* rec, vi lane, WarpShared& S, const EnvRegs& R) {
+  store_env_regs(rec, lane, R);
   warp_sync();
   st(rec, lane + ST_LAM, ld(S.lam_cache, lane));
   st(rec, lane + (ST_LAM + 32), ld(S.lam_cache, lane + 32));
@@ -1774,6 +1803,231 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
   return itd;
 }
 
+// ------------------------------------------------------------------------------------------
+// solve_heavy: projected Gauss-Seidel for ONE environment with many contacts (class 4: more than TREX_KC, e.g. a T-rex
+// standing on both feet: 14-16 points), one warp per environment, in its own kernel with its own shared-memory budget.
+//
+// Same sweep as the one-environment solver inside substep() -- lane = coordinate, motors in w-form with replicated
+// impulses, violated limits in order, normal rows, friction pairs -- except that the contact rows are carried in ROW
+// SPACE like in solve4: lane c owns contact c and tracks the velocity change u along its three rows, so a contact row
+// needs no reduction over the 31 coordinates (the one-environment sweep spends a 5-level butterfly per row and
+// iteration on that): joint rows add B[r][j] * d(impulse) to u, contact rows add the Delassus block A4 to every
+// owner's u and B[r][lane] * d(impulse) to the coordinates.  Inputs come from the work record written by front_phase.
+// ------------------------------------------------------------------------------------------
+struct alignas(16) HeavyShared {
+  float col[31][32];                      // M^-1: col[g][lane] = entry g of the column owned by `lane`
+  float A4[3 * TREX_KW][TREX_KW][4];      // A4[r][c'][k'] = J_{c',k'} M^-1 J_r^T
+  float Bt[3 * TREX_KW][33];              // row responses M^-1 J^T by lane, rows padded (conflict-free for "one row per owner")
+  float tmp[32];
+};
+
+TREX_FN void solve_heavy(const Uniform& P, const int* mdli, HeavyShared& H, const float* work, const float* workh, float* rec) {
+  const vi lane = lane_id();
+  const vb is_joint = lane < NJ;
+  const float max_imp = P.max_impulse, lim_hi = P.limit_max_impulse;
+  const int n_act = (int)ldu(workh, H_NC);
+  // ---- inputs: M^-1, per-joint row scalars, contact rows ---------------------------------------------------
+  _Pragma("unroll 8") for (int gq = 0; gq < trex_topo::NDOF; gq++) st(H.col[gq], lane, ld(work, lane + (W_COL + gq * 32)));
+  const vf rhs_m = ld(work, lane + W_RHSM), jdi = ld(work, lane + W_JDI), dself = ld(work, lane + W_DSELF);
+  const vf rhs_l = ld(work, lane + W_RHSL), sigma = ld(work, lane + W_SIGMA);
+  const vb act_lo = is_joint && (sigma > 0.0f), act_hi = is_joint && (sigma < 0.0f);
+  const vf rhs_lo = rhs_l, rhs_hi = rhs_l;
+  const uint32_t mask_lo = vballot(act_lo), mask_hi = vballot(act_hi);
+  uint32_t lim_perm;
+  {
+    const vi pj = ldi(mdli, lane + IF_LIMIT_ORDER * 32);
+    lim_perm = vballot((lane < NJ) && ((((vi((int)(mask_lo | mask_hi))) >> pj) & 1) != 0));
+  }
+  const vb cown = lane < n_act;
+  const vi own = vmini(lane, TREX_KW - 1);  // lanes beyond the contacts shadow a row block; their u is never read
+  vf c_lam[3], c_rhs[3], c_jdi[3], c_dd[3], cu[3];
+  {
+    const vi sb = seli(cown, lane, 0) * 16 + H_CS;
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      c_rhs[k] = ld_if(workh, sb + k, cown, 0.0f);
+      c_jdi[k] = ld_if(workh, sb + (3 + k), cown, 0.0f);
+      c_dd[k] = ld_if(workh, sb + (6 + k), cown, 0.0f);
+      c_lam[k] = 0.0f; cu[k] = 0.0f;
+    }
+    c_lam[0] = ld_if(workh, sb + 9, cown, 0.0f);  // warm start
+  }
+  const vi ccand = seli(cown, vf2i(ld_if(workh, seli(cown, lane, 0) * 16 + (H_CS + 10), cown, 0.0f)), 0);
+  TREX_ROLLED for (int r = 0; r < 3 * n_act; r++) {
+    st(H.Bt[r], lane, ld(workh, lane + (r * 32 + H_BT)));
+    vf a4[4];
+    const vb lo16 = lane < TREX_KW;
+    ld4_if(workh, seli(lo16, lane, 0) * 4 + (r * (4 * TREX_KW) + H_A4), lo16 && cown, a4);
+    st4_if(&H.A4[0][0][0], seli(lo16, lane, 0) * 4 + r * (4 * TREX_KW), a4, lo16);
+  }
+  warp_sync();
+  const float* Bt = &H.Bt[0][0];
+  const float* A4 = &H.A4[0][0][0];
+  const vi bt_own = own * 99;   // rows 3*own .. 3*own+2 of Bt (33 floats per row)
+  // warm-started normal impulses: velocity change of the coordinates and along the rows
+  vf dv = 0.0f;
+  TREX_ROLLED for (int c = 0; c < n_act; c++) {
+    const vf wc = vbroadcast(lane_value(c_lam[0], c));
+    dv = vfma(ld(Bt, lane + (3 * c) * 33), wc, dv);
+    vf a4[4];
+    ld4(A4, own * 4 + (3 * c) * (4 * TREX_KW), a4);
+    TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], wc, cu[k]);
+  }
+  // ---- projected Gauss-Seidel, Bullet's row order --------------------------------------------------------------
+  int it_done = 0;
+  const vf njdi = -jdi;
+  vf g[NJ];
+  TREX_UNROLL for (int j = 0; j < NJ; j++) {
+    const vf cj = ld(H.col[6 + j], lane);
+    g[j] = sel(is_joint, sel(lane == j, 0.0f, njdi * cj), cj);  // base-coordinate lanes keep the raw coefficient
+  }
+  vf lamr[NJ];  // motor impulses, replicated on every lane (uniform values)
+  TREX_UNROLL for (int j = 0; j < NJ; j++) lamr[j] = 0.0f;
+  vf lam_m = 0.0f, lam_lo = 0.0f, lam_hi = 0.0f;
+  vf dvo = dv, dvm = 0.0f, w = 0.0f;
+  TREX_ROLLED for (int it = 0; it < P.iters; it++) {
+    vf resid = 0.0f;
+    const vf lam_lo0 = lam_lo, lam_hi0 = lam_hi;
+#define TREX_H_MOTOR_ROW(K)                                                                            \
+    {                                                                                                  \
+      constexpr int j = trex_topo::noncontact_order(K) - NJ;                                           \
+      const vf nl = vmin(vmax(w, -max_imp), max_imp);   /* meaningful on lane j only */                \
+      const vf t = vfma(-g[j], lamr[j], w);                                                            \
+      const vf nlu = vbroadcast(lane_value(nl, j));     /* new impulse of motor j, on every lane */    \
+      const vf dj = nlu - lamr[j];                                                                     \
+      lamr[j] = nlu;                                                                                   \
+      w = vfma(g[j], nlu, t);                                                                          \
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bt, bt_own + (k * 33 + j)), dj, cu[k]);  \
+    }
+#define TREX_H_REBUILD_DVM()                                                                           \
+    {                                                                                                  \
+      vf a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;                                                   \
+      TREX_UNROLL for (int j = 0; j + 3 < NJ; j += 4) {                                                \
+        a0 = vfma(g[j], lamr[j], a0);                                                                  \
+        a1 = vfma(g[j + 1], lamr[j + 1], a1);                                                          \
+        a2 = vfma(g[j + 2], lamr[j + 2], a2);                                                          \
+        a3 = vfma(g[j + 3], lamr[j + 3], a3);                                                          \
+      }                                                                                                \
+      TREX_UNROLL for (int j = NJ - (NJ % 4); j < NJ; j++) a0 = vfma(g[j], lamr[j], a0);               \
+      const vf Ssum = (a0 + a1) + (a2 + a3);                                                           \
+      warp_sync();                                                                                     \
+      TREX_UNROLL for (int j = 0; j < NJ; j++) st(H.tmp, vi(j), lamr[j]);                              \
+      warp_sync();                                                                                     \
+      const vf lam_new = sel(is_joint, ld(H.tmp, seli(is_joint, lane, 0)), 0.0f);                      \
+      const vf dm = (lam_new - lam_m) * dself;                                                         \
+      lam_m = lam_new;                                                                                 \
+      resid = sel(is_joint, dm * dm, 0.0f);                                                            \
+      dvm = sel(is_joint, dself * (lam_m - Ssum), Ssum);                                               \
+      dv = dvm + dvo;                                                                                  \
+    }
+#define TREX_H_LIMIT_BLOCK(FORWARD)                                                                    \
+    {                                                                                                  \
+      uint32_t m = lim_perm;                                                                           \
+      while (m) {                                                                                      \
+        const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                          \
+        m &= ~(1u << pos);                                                                             \
+        const int j = P.order[NJ + pos];                                                               \
+        const vf cj = ld(H.col[6 + j], lane);                                                          \
+        TREX_UNROLL for (int pass = 0; pass < 2; pass++) {                                             \
+          const bool do_lo = (pass == 0) == (FORWARD);                                                 \
+          if (do_lo && ((mask_lo >> j) & 1u)) {                                                        \
+            const vf sum = lam_lo + (rhs_lo - dv * jdi);                                               \
+            const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
+            const vf dl = vbroadcast(lane_value(nl - lam_lo, j));                                      \
+            lam_lo = sel(lane == j, nl, lam_lo);                                                       \
+            const vf t = cj * dl;                                                                      \
+            dv += t; dvo += t;                                                                         \
+            TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bt, bt_own + (k * 33 + j)), dl, cu[k]); \
+          }                                                                                            \
+          if (!do_lo && ((mask_hi >> j) & 1u)) {                                                       \
+            const vf sum = lam_hi + (rhs_hi + dv * jdi);                                               \
+            const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
+            const vf dl = vbroadcast(lane_value(nl - lam_hi, j));                                      \
+            lam_hi = sel(lane == j, nl, lam_hi);                                                       \
+            const vf t = -(cj * dl);                                                                   \
+            dv += t; dvo += t;                                                                         \
+            TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bt, bt_own + (k * 33 + j)), -dl, cu[k]); \
+          }                                                                                            \
+        }                                                                                              \
+      }                                                                                                \
+    }
+#define M_(k) TREX_H_MOTOR_ROW(k)
+    if (it & 1) {
+      w = lam_m + (rhs_m + njdi * dv);
+      M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7) M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16)
+      M_(17) M_(18) M_(19) M_(20) M_(21) M_(22) M_(23) M_(24)
+      TREX_H_REBUILD_DVM()
+      TREX_H_LIMIT_BLOCK(true)
+    } else {
+      TREX_H_LIMIT_BLOCK(false)
+      w = lam_m + (rhs_m + njdi * dv);
+      M_(24) M_(23) M_(22) M_(21) M_(20) M_(19) M_(18) M_(17) M_(16) M_(15) M_(14) M_(13) M_(12) M_(11) M_(10) M_(9) M_(8)
+      M_(7) M_(6) M_(5) M_(4) M_(3) M_(2) M_(1) M_(0)
+      TREX_H_REBUILD_DVM()
+    }
+#undef M_
+#undef TREX_H_MOTOR_ROW
+#undef TREX_H_REBUILD_DVM
+#undef TREX_H_LIMIT_BLOCK
+    {
+      const vf dlo = (lam_lo - lam_lo0) * dself, dhi = (lam_hi - lam_hi0) * dself;
+      resid = sel(is_joint, vmax(resid, vmax(dlo * dlo, dhi * dhi)), 0.0f);
+    }
+    // normal rows: every lane evaluates its own contact from its tracked u, the owner of contact c publishes
+    TREX_ROLLED for (int c = 0; c < n_act; c++) {
+      const vf sum = c_lam[0] + (c_rhs[0] - cu[0] * c_jdi[0]);
+      const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
+      const vf dl = nl - c_lam[0];
+      const vb ownr = lane == c;
+      const vf dlu = vbroadcast(lane_value(dl, c));
+      c_lam[0] = sel(ownr, nl, c_lam[0]);
+      const vf dvel = dl * c_dd[0];
+      resid = sel(ownr, vmax(resid, dvel * dvel), resid);
+      vf a4[4];
+      ld4(A4, own * 4 + (3 * c) * (4 * TREX_KW), a4);
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], dlu, cu[k]);
+      const vf t = ld(Bt, lane + (3 * c) * 33) * dlu;
+      dv += t; dvo += t;
+    }
+    // friction pairs, implicit cone; both rows read the velocities before either writes
+    TREX_ROLLED for (int c = 0; c < n_act; c++) {
+      const vf lim = P.mu * c_lam[0];
+      const vf sumB = c_lam[2] + (c_rhs[2] - cu[2] * c_jdi[2]);
+      const vf sumA = c_lam[1] + (c_rhs[1] - cu[1] * c_jdi[1]);
+      const vf n2 = sumA * sumA + sumB * sumB;
+      const vb nz = n2 > 0.0f;
+      const vf rn = vrsqrt(sel(nz, n2, 1.0f));
+      const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
+      const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
+      const vf nA = vmin(vmax(sumA, -clipA), clipA);
+      const vf nB = vmin(vmax(sumB, -clipB), clipB);
+      const vf dA = nA - c_lam[1], dB = nB - c_lam[2];
+      const vb ownr = lane == c;
+      const vf dAu = vbroadcast(lane_value(dA, c)), dBu = vbroadcast(lane_value(dB, c));
+      c_lam[1] = sel(ownr, nA, c_lam[1]);
+      c_lam[2] = sel(ownr, nB, c_lam[2]);
+      const vf dvel = dA * c_dd[1] + dB * c_dd[2];
+      resid = sel(ownr, vmax(resid, dvel * dvel), resid);
+      vf aA[4], aB[4];
+      ld4(A4, own * 4 + (3 * c + 1) * (4 * TREX_KW), aA);
+      ld4(A4, own * 4 + (3 * c + 2) * (4 * TREX_KW), aB);
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
+      const vf t = ld(Bt, lane + (3 * c + 1) * 33) * dAu + ld(Bt, lane + (3 * c + 2) * 33) * dBu;
+      dv += t; dvo += t;
+    }
+    it_done = it + 1;
+    const float rmax = lane_value(warp_max(resid), 0);
+    if (rmax <= P.resid_thresh || it >= P.iters - 1) break;
+  }
+  // ---- cached normal impulses, velocity update, integration -----------------------------------------------------
+  st_if(rec, ccand + ST_LAM, c_lam[0], cown);
+  EnvRegs R;
+  load_env_regs(rec, lane, R);
+  finish_substep(P, lane, R, sel(lane < 31, dv, 0.0f), lam_m);
+  store_env_regs(rec, lane, R);
+  warp_sync();
+  st_if(rec, vi(155), ld(rec, vi(155)) + (float)it_done, lane == 0);  // ST_ACC_ITERS (declared below)
+}
+
 // reward (trex_env.py:186-196), termination (trex_env.py:183-184 + optional horizon / NaN guard) of one environment
 TREX_FN void reward_and_done(const Uniform& P, const float* mdl, vi lane, WarpShared& S, const EnvRegs& R, vi slot,
                              float step_count, float head[3], float terms[3], float& rew, bool& bad, bool& is_done) {
@@ -1829,7 +2083,7 @@ enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // p
 template <bool PACKED = false>
 TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, const float* tasks, const float* cand_p,
                          const int* cand_lane, WarpShared& S, float* rec, float* work, const float* action, bool first_round,
-                         WarpShared* cta_slabs = nullptr, int warp_in_cta = 0, int valid_mask = 0) {
+                         WarpShared* cta_slabs = nullptr, int warp_in_cta = 0, int valid_mask = 0, float* workh = nullptr) {
   const vi lane = lane_id();
   const vb is_joint = lane < NJ;
   const vi slot = seli(is_joint, MDLI(IF_OBS_SLOT), 0);
@@ -1844,7 +2098,7 @@ TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, con
   for (int i = 0; i < 8; i++) st.phase[i] = 0.0f;
 #endif
   const int deferred = substep<PACKED>(P, mdl, mdli, tasks, cand_p, cand_lane, S, R, P.kp, P.kd, P.max_impulse, st, work, cta_slabs,
-                                       warp_in_cta, valid_mask);
+                                       warp_in_cta, valid_mask, workh);
   store_env(rec, lane, S, R);  // deferred: positions unchanged, velocities after the unconstrained update
   const float it0 = first_round ? 0.0f : ldu(rec, ST_ACC_ITERS), ov0 = first_round ? 0.0f : ldu(rec, ST_ACC_OVERFLOW);
   vf acc = 0.0f;
@@ -1860,7 +2114,7 @@ TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, con
     st_if(rec, lane + 160, ph, lane < 8);
   }
 #endif
-  return deferred;
+  return deferred + 256 * st.contacts;  // low byte: 0 = substep complete, 1 + class = solve deferred; above: active contacts
 }
 
 // solve_phase: the deferred solves of up to four environments (any four: the groups are independent)

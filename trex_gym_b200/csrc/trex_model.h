@@ -247,7 +247,7 @@ struct EnvConfig {
   unsigned seed = 0;
   long long env_offset = 0;
   float reset_z_min = 0.3f, reset_z_max = 3.0f;
-  int defer_contacts = 1;  // substeps with a few contacts also go to the four-environments-per-warp solver
+  int defer_contacts = 2;  // 1: substeps with <= 8 contacts also go to the four-environments-per-warp solver; 2: and those with more to solve_heavy
 };
 
 // Fill a trex::Uniform (templated so this header stays free of the lane vocabulary).

@@ -26,7 +26,7 @@ class TrexBatchSim:
                  num_substeps: int = 5, distance_weight: float = 1.0, energy_weight: float = 0.005,
                  drift_weight: float = 0.002, max_episode_steps: int = 0, contacts: bool = True,
                  seed: int = 0, warps_per_block: int | None = None, reset_mode: int = 0, env_offset: int = 0,
-                 deferred_solve: bool = True, defer_contacts: bool = True):
+                 deferred_solve: bool = True, defer_contacts: bool = True, heavy_solver: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("trex_gym_b200 needs a CUDA device (no CPU fallback)")
         dev = torch.device(device if not isinstance(device, int) else "cuda:%d" % device)
@@ -48,8 +48,9 @@ class TrexBatchSim:
         cfg.reserved[2] = ctypes.c_int32((int(env_offset) >> 32) & 0xFFFFFFFF).value
         cfg.seed = int(seed) & 0xFFFFFFFF
         # solver placement (diagnostics): 0 = contact-free substeps and substeps with <= 4 contacts go to the
-        # four-environments-per-warp solver, 2 = contact-free substeps only, 1 = everything in the one-environment path
-        cfg.reserved[3] = (0 if defer_contacts else 2) if deferred_solve else 1
+        # four-environments-per-warp solver and those with more to the row-space one-environment solver, 3 = the latter
+        # stay in the front kernel, 2 = contact-free substeps only, 1 = everything in the front kernel
+        cfg.reserved[3] = ((0 if heavy_solver else 3) if defer_contacts else 2) if deferred_solve else 1
         if warps_per_block:
             cfg.reserved[0] = int(warps_per_block)
         blob = self.model.blob()
