@@ -305,7 +305,11 @@ struct trex_handle {
   int* d_list = nullptr;        // [TREX_NCLASS][n_envs] environments whose solve was deferred in the current substep round, by class
   int* d_list_count = nullptr;  // [TREX_NCLASS][64] one counter per class and substep round
   DevStats* d_stats = nullptr;
-  int heavy_grid = 148 * 9;     // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
+  // trex_heavy_kernel touches a handful of environments but each takes ~200 us: it runs on a side stream, hidden under the
+  // two solve4 kernels of the same round (fork after the front kernel, join before the next one; no host synchronisation)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int heavy_grid = 148 * 12;    // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
   int64_t launches = 0;
   int64_t env_steps = 0;
 };
@@ -348,6 +352,18 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
+        const bool heavy = h->P.defer_contacts > 1 && h->P.contacts_on && h->d_workh != nullptr;
+        if (heavy) {  // class 4: more than TREX_KC contacts, one environment per warp, on the side stream
+          CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+          CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+          trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, h->side>>>(h->P, h->d_mdli, h->d_state, h->d_work, h->d_workh,
+                                                                      h->d_list + (size_t)4 * h->n_envs, h->d_list_count + 64 * 4 + r,
+                                                                      h->d_list_count + 64 * TREX_NCLASS + r,
+                                                                      h->d_list_count + 64 * (TREX_NCLASS + 1));
+          CUDA_TRY(cudaGetLastError());
+          h->launches++;
+          CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
+        }
         trex_solve_kernel<WS, 0><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r, h->n_envs);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
@@ -356,14 +372,8 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
                                                                             h->d_list_count + 64 + r, h->n_envs);
           CUDA_TRY(cudaGetLastError());
           h->launches++;
-          if (h->P.defer_contacts > 1 && h->d_workh) {  // class 4: more than TREX_KC contacts, one environment per warp
-            trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, st>>>(h->P, h->d_mdli, h->d_state, h->d_work, h->d_workh,
-                                                                   h->d_list + (size_t)4 * h->n_envs, h->d_list_count + 64 * 4 + r,
-                                                                   h->d_list_count + 64 * TREX_NCLASS + r, h->d_list_count + 64 * (TREX_NCLASS + 1));
-            CUDA_TRY(cudaGetLastError());
-            h->launches++;
-          }
         }
+        if (heavy) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
       }
     }
   }
@@ -434,6 +444,10 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     return rc_;
   }
   trex_host::fill_uniform(h->T, h->C, h->P);
+  {
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->heavy_grid = sms * 12;
+  }
   int rc;
 #define TRY(x) if ((rc = (x)) != TREX_OK) { trex_destroy(h); return rc; }
   TRY(upload(&h->d_mdl, h->T.mdl)); TRY(upload(&h->d_mdli, h->T.mdli)); TRY(upload(&h->d_tasks, h->T.tasks));
@@ -448,8 +462,12 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   CTRY(cudaMalloc((void**)&h->d_state, N * TREX_STATE_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_state, 0, N * TREX_STATE_STRIDE * sizeof(float)));
   if (h->deferred_solve) CTRY(cudaMalloc((void**)&h->d_work, N * TREX_WORK_STRIDE * sizeof(float)));
-  if (h->deferred_solve && h->C.defer_contacts > 1 && h->C.enable_contacts)
+  if (h->deferred_solve && h->C.defer_contacts > 1 && h->C.enable_contacts) {
     CTRY(cudaMalloc((void**)&h->d_workh, N * TREX_HEAVY_STRIDE * sizeof(float)));
+    CTRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CTRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CTRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMalloc((void**)&h->d_action, N * trex::NJ * sizeof(float)));
@@ -479,6 +497,9 @@ void trex_destroy(trex_handle* h) {
   cudaFree(h->d_work); cudaFree(h->d_workh); cudaFree(h->d_list); cudaFree(h->d_list_count);
   cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_action);
   cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_stats);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 

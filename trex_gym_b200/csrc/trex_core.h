@@ -1814,8 +1814,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
 // iteration on that): joint rows add B[r][j] * d(impulse) to u, contact rows add the Delassus block A4 to every
 // owner's u and B[r][lane] * d(impulse) to the coordinates.  Inputs come from the work record written by front_phase.
 // ------------------------------------------------------------------------------------------
-struct alignas(16) HeavyShared {
-  float col[31][32];                      // M^-1: col[g][lane] = entry g of the column owned by `lane`
+struct alignas(16) HeavyShared {             // 18.7 KB: 12 warps per SM (M^-1 stays in the work record: read once for g, and by limit rows)
   float A4[3 * TREX_KW][TREX_KW][4];      // A4[r][c'][k'] = J_{c',k'} M^-1 J_r^T
   float Bt[3 * TREX_KW][33];              // row responses M^-1 J^T by lane, rows padded (conflict-free for "one row per owner")
   float tmp[32];
@@ -1827,7 +1826,6 @@ TREX_FN void solve_heavy(const Uniform& P, const int* mdli, HeavyShared& H, cons
   const float max_imp = P.max_impulse, lim_hi = P.limit_max_impulse;
   const int n_act = (int)ldu(workh, H_NC);
   // ---- inputs: M^-1, per-joint row scalars, contact rows ---------------------------------------------------
-  _Pragma("unroll 8") for (int gq = 0; gq < trex_topo::NDOF; gq++) st(H.col[gq], lane, ld(work, lane + (W_COL + gq * 32)));
   const vf rhs_m = ld(work, lane + W_RHSM), jdi = ld(work, lane + W_JDI), dself = ld(work, lane + W_DSELF);
   const vf rhs_l = ld(work, lane + W_RHSL), sigma = ld(work, lane + W_SIGMA);
   const vb act_lo = is_joint && (sigma > 0.0f), act_hi = is_joint && (sigma < 0.0f);
@@ -1877,7 +1875,7 @@ TREX_FN void solve_heavy(const Uniform& P, const int* mdli, HeavyShared& H, cons
   const vf njdi = -jdi;
   vf g[NJ];
   TREX_UNROLL for (int j = 0; j < NJ; j++) {
-    const vf cj = ld(H.col[6 + j], lane);
+    const vf cj = ld(work, lane + (W_COL + (6 + j) * 32));
     g[j] = sel(is_joint, sel(lane == j, 0.0f, njdi * cj), cj);  // base-coordinate lanes keep the raw coefficient
   }
   vf lamr[NJ];  // motor impulses, replicated on every lane (uniform values)
@@ -1926,7 +1924,7 @@ TREX_FN void solve_heavy(const Uniform& P, const int* mdli, HeavyShared& H, cons
         const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                          \
         m &= ~(1u << pos);                                                                             \
         const int j = P.order[NJ + pos];                                                               \
-        const vf cj = ld(H.col[6 + j], lane);                                                          \
+        const vf cj = ld(work, lane + (W_COL + (6 + j) * 32));  /* limit rows are rare: from the record */ \
         TREX_UNROLL for (int pass = 0; pass < 2; pass++) {                                             \
           const bool do_lo = (pass == 0) == (FORWARD);                                                 \
           if (do_lo && ((mask_lo >> j) & 1u)) {                                                        \
