@@ -14,7 +14,9 @@
  * Ownership: the caller (PyTorch) owns action/obs/reward/done/state buffers and passes raw
  * device pointers; the library owns the uploaded model and its internal environment records
  * and never allocates, frees or retains caller memory.  All launches are asynchronous on the
- * caller's stream (a cudaStream_t passed as void*; NULL = default stream); only
+ * caller's stream (a cudaStream_t passed as void*; NULL = default stream) -- one kernel per substep runs
+ * on a library-owned side stream that is forked from and joined back into the caller's stream with events,
+ * so stream order (and CUDA-graph capture) of the caller is preserved; only
  * trex_get_stats, trex_step_host and trex_reset_host synchronise.
  *
  * Errors: 0 = success, negative = error; trex_last_error() returns the thread-local message.
