@@ -290,7 +290,7 @@ trex_stats_kernel(const float* __restrict__ state, const float* __restrict__ aux
 struct trex_handle {
   int device = 0;
   int n_envs = 0;
-  int warps_per_block = 2;  // front / tail kernels; the solve kernel uses 2 (4 when this is 4)
+  int warps_per_block = 2;  // front / tail kernels; the solve kernels then use 1 (see dispatch_step)
   bool deferred_solve = true;  // substeps with <= TREX_KC contacts solved four environments per warp (solve4)
   trex_host::ModelTables T;
   trex_host::EnvConfig C;
@@ -325,7 +325,7 @@ int configure_kernel(K kernel, size_t smem) {
 
 // mode 0: one env step (n_sub front/solve rounds + tail); mode 1: reset (tail only).
 // WF: warps per CTA of the front / tail kernels (one environment per warp; 2 gives 16 resident warps per SM),
-// WS: warps per CTA of the solve kernels (four environments per warp).
+// WS: warps per CTA of the solve kernels (four environments per warp; 1 with the default WF = 2: finest scheduling grain).
 template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
@@ -388,7 +388,7 @@ int dispatch_step(trex_handle* h, const float* action, float* obs, float* reward
                   int mode, cudaStream_t st) {
   switch (h->warps_per_block) {
     case 1: return launch_step<1, 2>(h, action, obs, reward, done, mask, mode, st);
-    case 2: return launch_step<2, 2>(h, action, obs, reward, done, mask, mode, st);
+    case 2: return launch_step<2, 1>(h, action, obs, reward, done, mask, mode, st);
     case 4: return launch_step<4, 4>(h, action, obs, reward, done, mask, mode, st);
     default: return fail(TREX_ERR_INVALID, "warps_per_block must be 1, 2 or 4%s");
   }
