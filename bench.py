@@ -46,9 +46,35 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
         self.samples = []
+        self.source = "nvidia-smi"
         self._halt = threading.Event()
 
+    def _nvml_loop(self):
+        """Fast path: NVML in-process (a sample every 20 ms); returns False if NVML is not usable."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        except Exception:  # noqa: BLE001
+            return False
+        self.source = "nvml (same fields as the nvidia-smi clocks query, sampled every 20 ms)"
+        while not self._halt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.samples.append([str(self.gpu_index), str(sm), str(mx), "", hex(r)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:  # noqa: BLE001
+                pass
+            self._halt.wait(0.02)
+        return True
+
     def run(self):
+        if self._nvml_loop():
+            return
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
@@ -78,7 +104,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def dist_setup(n_gpus):
