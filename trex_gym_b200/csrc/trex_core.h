@@ -1706,8 +1706,14 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     // residual per environment: max over its rows of (delta impulse / jacDiagABInv)^2
     vf r = cres;
     TREX_UNROLL for (int s = 0; s < 4; s++) {
-      const vf dm = (lam_m[s] - lam_m0[s]) * dself[s], dl = (lam_l[s] - lam_l0[s]) * dself[s];
-      r = vmax(r, vmax(dm * dm, dl * dl));
+      const vf dm = (lam_m[s] - lam_m0[s]) * dself[s];
+      r = vmax(r, dm * dm);
+    }
+    if (uperm != 0u) {  // limit rows exist in this warp (uniform; otherwise their impulses never leave 0)
+      TREX_UNROLL for (int s = 0; s < 4; s++) {
+        const vf dl = (lam_l[s] - lam_l0[s]) * dself[s];
+        r = vmax(r, dl * dl);
+      }
     }
     // (leastSquaresResidual <= threshold stops the environment: true iff no lane of the group exceeds it)
     const uint32_t over = vballot(alive && !(r <= P.resid_thresh));
