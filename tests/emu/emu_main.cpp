@@ -75,7 +75,7 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
   if (!force_reset) {
     for (int r = 0; r < e->P.n_sub; r++) {
       // deferred environments are packed into the solver's lane groups in list order (any order is equivalent)
-      // (one list per class, as in the library: contact-free, 1-2, 3-4 and 5-8 contacts)
+      // (one list per class, as in the library: contact-free, 1, 2, 3-4, 5-8 and more contacts)
       int envs[TREX_NCLASS][4] = {}, cnt[TREX_NCLASS] = {};
       int dres[4] = {0, 0, 0, 0};
       if (e->packed && n == 4) {
@@ -102,14 +102,14 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
       }
       for (int i = 0; i < n; i++) {
         const int d = dres[i];
-        e->solves[d == 0 ? 0 : (d == 1 ? 1 : (d < 5 ? 2 : 4))]++;
+        e->solves[d == 0 ? 0 : (d == 1 ? 1 : (d < 1 + TREX_CLASS_HEAVY ? 2 : 4))]++;
         if (d) { int& c = cnt[d - 1]; envs[d - 1][e->pack_reverse ? 3 - c : c] = i; c++; }
       }
       for (int d = 0; d < TREX_NCLASS; d++) {
         if (!cnt[d]) continue;
         const int pending = e->pack_reverse ? (((1 << cnt[d]) - 1) << (4 - cnt[d])) : ((1 << cnt[d]) - 1);
         if (d == 0) trex::solve_phase<0>(e->P, e->scratch, e->work, rec, envs[0], pending);
-        else if (d < 4) trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[d], pending);
+        else if (d < TREX_CLASS_HEAVY) trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[d], pending);
         else  // class 4: one environment per warp
           for (int g = 0; g < 4; g++)
             if (pending & (1 << g))

@@ -85,7 +85,7 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
                                                   (workh != nullptr && (long long)(*heavy_hint) * 16 <= (long long)n_envs) ? workh + (size_t)env * TREX_HEAVY_STRIDE : nullptr);
   const int deferred = front_result & 255, n_contacts = front_result >> 8;
   // append to the list of its class of deferred environments (any order: the solver's lane groups are independent):
-  // class 0 = contact-free substeps, classes 1..3 = 1-2 / 3-4 / 5-8 contacts; list c at list + c * n_envs, counters + 64 * c
+  // class 0 = contact-free substeps, classes 1..4 = 1 / 2 / 3-4 / 5-8 contacts, 5 = more; list c at list + c * n_envs, counters + 64 * c
   if (deferred && (threadIdx.x & 31) == 0) {
     const int which = deferred - 1;
     list[(size_t)which * n_envs + atomicAdd(list_count + 64 * which, 1)] = env;
@@ -112,10 +112,10 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   if (KC > 0) {
     // list / list_count point at class 1.  Warps are handed out heaviest class first (5-8 contacts, then 3-4, then 1-2):
     // the longest-running warps start first instead of forming the tail of the launch.
-    list += (size_t)2 * n_envs;   // class 3
-    list_count += 64 * 2;
+    list += (size_t)(TREX_CLASS_HEAVY - 2) * n_envs;   // the heaviest solve4 class
+    list_count += 64 * (TREX_CLASS_HEAVY - 2);
     count = *list_count;
-    for (int c = 3; c > 1 && first >= ((count + 3) & ~3); c--) {
+    for (int c = TREX_CLASS_HEAVY - 1; c > 1 && first >= ((count + 3) & ~3); c--) {
       first -= (count + 3) & ~3;
       list -= n_envs;
       list_count -= 64;
@@ -357,7 +357,8 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
           CUDA_TRY(cudaEventRecord(h->ev_fork, st));
           CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
           trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, h->side>>>(h->P, h->d_mdli, h->d_state, h->d_work, h->d_workh,
-                                                                      h->d_list + (size_t)4 * h->n_envs, h->d_list_count + 64 * 4 + r,
+                                                                      h->d_list + (size_t)TREX_CLASS_HEAVY * h->n_envs,
+                                                                      h->d_list_count + 64 * TREX_CLASS_HEAVY + r,
                                                                       h->d_list_count + 64 * TREX_NCLASS + r,
                                                                       h->d_list_count + 64 * (TREX_NCLASS + 1));
           CUDA_TRY(cudaGetLastError());
@@ -368,7 +369,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
         CUDA_TRY(cudaGetLastError());
         h->launches++;
         if (h->P.defer_contacts && h->P.contacts_on) {
-          trex_solve_kernel<WS, TREX_KC><<<grid4 + 2, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
+          trex_solve_kernel<WS, TREX_KC><<<grid4 + 3, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
                                                                             h->d_list_count + 64 + r, h->n_envs);
           CUDA_TRY(cudaGetLastError());
           h->launches++;

@@ -65,9 +65,10 @@ static_assert(W_A4 + 12 * TREX_KC * TREX_KC <= TREX_WORK_STRIDE && (W_BT % 4) ==
 #define TREX_HEAVY_STRIDE (((H_A4 + 12 * TREX_KW * TREX_KW) + 31) / 32 * 32)
 static_assert((H_BT % 4) == 0 && (H_A4 % 4) == 0 && TREX_KC <= TREX_KW, "heavy record layout");
 // deferred environments are listed by class so that the four environments of a solver warp have similar row counts
-#define TREX_NCLASS 5                      // 0: contact-free, 1: 1-2 contacts, 2: 3-4, 3: 5-8 (solve4); 4: 9..KW (solve_heavy)
+#define TREX_NCLASS 6                      // 0: contact-free; 1: 1 contact, 2: 2, 3: 3-4, 4: 5-8 (solve4); 5: 9..KW (solve_heavy)
+#define TREX_CLASS_HEAVY (TREX_NCLASS - 1)
 TREX_TOPO_FN int defer_class(int n_contacts) {
-  return n_contacts == 0 ? 0 : (n_contacts <= 2 ? 1 : (n_contacts <= 4 ? 2 : (n_contacts <= TREX_KC ? 3 : 4)));
+  return n_contacts <= 2 ? n_contacts : (n_contacts <= 4 ? 3 : (n_contacts <= TREX_KC ? 4 : TREX_CLASS_HEAVY));
 }
 #ifdef TREX_PHASES
 #define TREX_AUX_STRIDE 16
