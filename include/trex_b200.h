@@ -71,7 +71,9 @@ typedef struct trex_config {
                                 0 = contact-free substeps and substeps with <= 4 contacts are solved four environments
                                 per warp and substeps with more by the one-environment row-space solver (trex_heavy_kernel),
                                 3 = the same but more than 8 contacts stay in the front kernel, 2 = contact-free substeps only,
-                                1 = everything in the front kernel */
+                                1 = everything in the front kernel;
+                                [5] > 0: environments with 9-16 contacts go to trex_heavy_kernel while at most n_envs / [5] of
+                                the batch are in that class (default 16; 1 = always) */
 } trex_config;
 
 typedef struct trex_stats {

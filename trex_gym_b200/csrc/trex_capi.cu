@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
 trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const int* __restrict__ mdli,
                   const float* __restrict__ tasks, const float* __restrict__ cand_p, const int* __restrict__ cand_lane,
                   float* __restrict__ state, float* __restrict__ work, float* __restrict__ workh, const float* __restrict__ action,
-                  int* __restrict__ list, int* __restrict__ list_count, const int* __restrict__ heavy_hint, int n_envs, int first_round) {
+                  int* __restrict__ list, int* __restrict__ list_count, const int* __restrict__ heavy_hint, int heavy_div, int n_envs,
+                  int first_round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   trex::WarpShared* slabs = reinterpret_cast<trex::WarpShared*>(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -82,7 +83,7 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
                                                   work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
                                                   first_round != 0, slabs, warp, valid_mask,
                                                   // class 4 is deferred only while few environments are in it (count of the previous round)
-                                                  (workh != nullptr && (long long)(*heavy_hint) * 16 <= (long long)n_envs) ? workh + (size_t)env * TREX_HEAVY_STRIDE : nullptr);
+                                                  (workh != nullptr && (long long)(*heavy_hint) * heavy_div <= (long long)n_envs) ? workh + (size_t)env * TREX_HEAVY_STRIDE : nullptr);
   const int deferred = front_result & 255, n_contacts = front_result >> 8;
   // append to the list of its class of deferred environments (any order: the solver's lane groups are independent):
   // class 0 = contact-free substeps, classes 1..4 = 1 / 2 / 3-4 / 5-8 contacts, 5 = more; list c at list + c * n_envs, counters + 64 * c
@@ -309,7 +310,8 @@ struct trex_handle {
   // two solve4 kernels of the same round (fork after the front kernel, join before the next one; no host synchronisation)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int heavy_grid = 148 * 12;    // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
+  int heavy_div = 16;           // class 4 goes to trex_heavy_kernel while at most n_envs / heavy_div environments are in it
+  int heavy_grid = 148 * 11;    // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
   int64_t launches = 0;
   int64_t env_steps = 0;
 };
@@ -348,7 +350,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
     for (int r = 0; r < h->P.n_sub; r++) {
       trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
                                                            h->d_state, h->d_work, h->d_workh, action, h->d_list, h->d_list_count + r,
-                                                           h->d_list_count + 64 * (TREX_NCLASS + 1), h->n_envs, r == 0);
+                                                           h->d_list_count + 64 * (TREX_NCLASS + 1), h->heavy_div, h->n_envs, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
@@ -438,6 +440,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     if (cfg->reserved[0] == 1 || cfg->reserved[0] == 2 || cfg->reserved[0] == 4) h->warps_per_block = cfg->reserved[0];
     h->deferred_solve = cfg->reserved[3] != 1;
     h->C.defer_contacts = cfg->reserved[3] == 0 ? 2 : (cfg->reserved[3] == 3 ? 1 : 0);
+    if (cfg->reserved[5] > 0) h->heavy_div = cfg->reserved[5];
   }
   if ((int)h->T.params[trex_host::P_MAX_CONTACTS] != TREX_KMAX) {
     int rc_ = fail(TREX_ERR_MODEL, "model blob max_contacts differs from the compiled contact capacity (TREX_KMAX)%s");
@@ -446,8 +449,15 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   }
   trex_host::fill_uniform(h->T, h->C, h->P);
   {
-    int sms = 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->heavy_grid = sms * 12;
+    // trex_heavy_kernel strides over its list with a fixed grid: exactly the CTAs that are resident at once (a larger
+    // grid would run its surplus CTAs as a second wave after the first has walked the whole list)
+    int sms = 148, per_sm = 11;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaFuncSetAttribute(trex_heavy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trex::HeavyShared));
+    cudaFuncSetAttribute(trex_heavy_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trex_heavy_kernel<1>, 32, sizeof(trex::HeavyShared)) != cudaSuccess || per_sm < 1)
+      per_sm = 11;
+    if (sms > 0) h->heavy_grid = sms * per_sm;
   }
   int rc;
 #define TRY(x) if ((rc = (x)) != TREX_OK) { trex_destroy(h); return rc; }

@@ -26,7 +26,8 @@ class TrexBatchSim:
                  num_substeps: int = 5, distance_weight: float = 1.0, energy_weight: float = 0.005,
                  drift_weight: float = 0.002, max_episode_steps: int = 0, contacts: bool = True,
                  seed: int = 0, warps_per_block: int | None = None, reset_mode: int = 0, env_offset: int = 0,
-                 deferred_solve: bool = True, defer_contacts: bool = True, heavy_solver: bool = True):
+                 deferred_solve: bool = True, defer_contacts: bool = True, heavy_solver: bool = True,
+                 heavy_share_div: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("trex_gym_b200 needs a CUDA device (no CPU fallback)")
         dev = torch.device(device if not isinstance(device, int) else "cuda:%d" % device)
@@ -51,6 +52,7 @@ class TrexBatchSim:
         # four-environments-per-warp solver and those with more to the row-space one-environment solver, 3 = the latter
         # stay in the front kernel, 2 = contact-free substeps only, 1 = everything in the front kernel
         cfg.reserved[3] = ((0 if heavy_solver else 3) if defer_contacts else 2) if deferred_solve else 1
+        cfg.reserved[5] = int(heavy_share_div)  # 0 = default (1/16 of the batch), 1 = always use the heavy-contact kernel
         if warps_per_block:
             cfg.reserved[0] = int(warps_per_block)
         blob = self.model.blob()
