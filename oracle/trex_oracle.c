@@ -594,7 +594,7 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
   const double dt = o->P[P_TIME_STEP] / o->n_sub;
   const int iters = (int)(o->P[P_SOLVER_ITERS] / o->n_sub);
   const int nu = o->nu, nd = o->ndof;
-  double jt[MAXDOF], acc[MAXU], u[MAXU], dv[MAXU];
+  double jt[MAXDOF] = {0}, acc[MAXU], u[MAXU], dv[MAXU];
 
   /* 0: pybullet joint damping as explicit joint torque (PhysicsServerCommandProcessor) */
   for (int k = 0; k < nd; k++) jt[k] = -o->damping[o->dof_link[k]] * o->qd[k];
