@@ -16,11 +16,11 @@
  * and never allocates, frees or retains caller memory.  All launches are asynchronous on the
  * caller's stream (a cudaStream_t passed as void*; NULL = default stream) -- one kernel per substep runs
  * on a library-owned side stream that is forked from and joined back into the caller's stream with events,
- * so stream order (and CUDA-graph capture) of the caller is preserved; only
- * trex_get_stats, trex_step_host and trex_reset_host synchronise.
+ * so stream order (and CUDA-graph capture, tests/test_gpu_parity.py::test_cuda_graph_capture_of_a_step) of the caller
+ * is preserved; only trex_get_stats, trex_step_host, trex_host_wait and trex_reset_host synchronise.
  *
  * Errors: 0 = success, negative = error; trex_last_error() returns the thread-local message.
- * Calls on one handle are not re-entrant.
+ * Calls on one handle are not re-entrant; different handles may be created and used from different threads.
  */
 #ifndef TREX_B200_H
 #define TREX_B200_H
@@ -53,6 +53,11 @@ extern "C" {
 
 typedef struct trex_handle trex_handle;
 
+#define TREX_SOLVE_DEFAULT 0
+#define TREX_SOLVE_FRONT 1
+#define TREX_SOLVE_FREE_ONLY 2
+#define TREX_SOLVE_NO_HEAVY 3
+
 typedef struct trex_config {
   int32_t num_substeps;      /* trex_env.py:18 NUM_SUBSTEPS (5); dt = 0.01/n, iterations = int(300/n)  (:71-73) */
   float distance_weight;     /* trex_env.py:42 */
@@ -65,15 +70,20 @@ typedef struct trex_config {
                                 (BASELINE configs[4]: base z U(0.3,3), uniform SO(3), joints U(limits); no
                                 reference counterpart), Philox keyed by (seed, global env id, episode) */
   uint32_t seed;
-  int32_t reserved[8];       /* [0] warps per CTA of the front/tail kernels (1, 2 or 4; 0 = default 2; with 4 the inward pass of the
-                                CTA's four environments runs on one warp, eight lanes per environment: bit-identical results); [1],[2] low/high word of the global id of
-                                environment 0 of this shard (multi-GPU: rank * n_envs); [3] solver placement (diagnostics):
-                                0 = contact-free substeps and substeps with <= 4 contacts are solved four environments
-                                per warp and substeps with more by the one-environment row-space solver (trex_heavy_kernel),
-                                3 = the same but more than 8 contacts stay in the front kernel, 2 = contact-free substeps only,
-                                1 = everything in the front kernel;
-                                [5] > 0: environments with 9-16 contacts go to trex_heavy_kernel while at most n_envs / [5] of
-                                the batch are in that class (default 16; 1 = always) */
+  int64_t env_offset;        /* global id of environment 0 of this shard (multi-GPU: rank * n_envs); keys the reset sampler so
+                                results do not depend on the number of GPUs */
+  int32_t warps_per_block;   /* warps per CTA of the front / tail kernels: 1, 2 or 4; 0 = default (2).  With 4 the inward pass of
+                                the CTA's four environments runs on one warp, eight lanes per environment (bit-identical) */
+  int32_t solver_placement;  /* where a physics substep's constraint solve runs (results agree to FP32 round-off; diagnostics):
+                                TREX_SOLVE_DEFAULT   contact-free substeps and substeps with <= 8 contacts: four environments per
+                                                     warp (trex_solve_kernel); more contacts: trex_heavy_kernel
+                                TREX_SOLVE_FRONT     everything inside the front kernel (one environment per warp)
+                                TREX_SOLVE_FREE_ONLY only contact-free substeps are deferred
+                                TREX_SOLVE_NO_HEAVY  as DEFAULT, but more than 8 contacts stay in the front kernel */
+  int32_t heavy_share_div;   /* > 0: environments with 9-16 contacts go to trex_heavy_kernel only while at most
+                                n_envs / heavy_share_div of the batch were in that class in the previous substep (1 = always);
+                                0 = default: always (the routing then depends on the environment alone, never on its batch) */
+  int32_t reserved[11];      /* must be zero */
 } trex_config;
 
 typedef struct trex_stats {
@@ -104,10 +114,19 @@ int trex_reset(trex_handle* h, const uint8_t* mask_dev, float* obs_dev, void* st
 int trex_step(trex_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
               void* stream);
 
-/* Same step with HOST buffers (the reference-facing call: numpy in, numpy out): copies the
- * actions to the device, steps, copies obs/reward/done back and synchronises. */
+/* Same step with HOST buffers (the reference-facing call: numpy in, numpy out): copies the actions to the device, steps,
+ * copies obs/reward/done back and synchronises.  Runs on library-owned non-blocking streams (not the legacy default stream);
+ * a caller mixing it with device-pointer calls on its own stream must synchronise that stream first. */
 int trex_step_host(trex_handle* h, const float* action_host, float* obs_host, float* reward_host,
                    uint8_t* done_host);
+/* The same as a depth-1 pipeline, for callers that alternate between two sets of (pinned) host arrays: the host->device
+ * copy runs on a second stream under the previous step's kernels and the device->host copies on a third stream, behind
+ * events, under the next step's kernels (two internal sets of staging buffers).  Contract: when call k returns, the
+ * outputs of call k-1 are complete in host memory; the arrays passed to call k (action included) must stay untouched
+ * until call k+1 has returned or trex_host_wait() has.  trex_host_wait() drains everything outstanding. */
+int trex_step_host_async(trex_handle* h, const float* action_host, float* obs_host, float* reward_host,
+                         uint8_t* done_host);
+int trex_host_wait(trex_handle* h);
 int trex_reset_host(trex_handle* h, float* obs_host);
 
 /* Simulator-state checkpoint / parity hooks: copy the environment records out / in (device pointers). */

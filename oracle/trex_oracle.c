@@ -626,14 +626,16 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
         r->motor_dof = -1; r->cand = -1; r->fric_index = -1;
         double rel = finish_row(o, r, u);
         r->lo = 0; r->hi = o->P[P_LIMIT_MAX_IMPULSE];
-        /* split impulse is on but m_rhsPenetration is never consumed by the multibody solver:
-         * shallow violations (> threshold) get the velocity part only. */
+        /* btMultiBodyJointLimitConstraint::createConstraintRows [RECALL]: with split impulse on (the default),
+         * `penetration > m_splitImpulsePenetrationThreshold` (a SHALLOW violation, -0.04 < pen <= 0) combines the
+         * positional (erp = m_erp) and the velocity term into m_rhs; a DEEP violation splits them and the positional
+         * part goes to m_rhsPenetration, which the multibody solver never consumes: velocity part only. */
         double poserr = 0, velerr = -rel;
         if (pen > o->P[P_SPLIT_THRESH]) {
-          r->rhs = velerr * r->jdi;
-        } else {
           poserr = -pen * o->P[P_ERP] / dt;
           r->rhs = (poserr + velerr) * r->jdi;
+        } else {
+          r->rhs = velerr * r->jdi;
         }
         n_limits++;
       }

@@ -141,17 +141,45 @@ def test_motor_row_semantics(model):
 
 
 def test_joint_limit_row_only_when_violated(model):
+    """btMultiBodyJointLimitConstraint [RECALL]: a row exists only while the limit is violated; a SHALLOW violation
+    (-0.04 < pen <= 0, the split-impulse threshold) gets the Baumgarte push-back erp * |pen| / dt on top of the
+    velocity term, a DEEP one the velocity term only (its positional part lands in m_rhsPenetration, which the
+    multibody solver never reads)."""
     o = _oracle(model, contacts=False)
     o.reset()
     assert o.last_num_limit_rows == 0
-    s = o.get_state()
-    d = model.meta["body_joint_names"].index("joint_tibia_left") - 1
+    d = model.meta["body_joint_names"].index("joint_toe_04_d_left") - 1  # light distal joint: the 100 N m s cap stays inactive
     upper = model["mb_upper"][d + 1]
-    s[13 + d] = upper + 0.1  # 0.1 rad beyond the limit (deeper than the 0.04 split threshold)
+    lower = model["mb_lower"][d + 1]
+    # shallow: 0.01 rad beyond the upper limit -> target velocity 0.2 * 0.01 / 0.002 = 1 rad/s back towards the range
+    s = o.get_state()
+    s[7:13] = 0.0
+    s[38:63] = 0.0
+    s[13 + d] = upper + 0.01
     o.set_state(s)
     o.substep(s[13:38], 0.0)
     assert o.last_num_limit_rows == 1
-    assert o.get_state()[38 + d] < 0  # pushed back: erp * pen / dt = 0.2*0.1/0.002 = 10 rad/s target, impulse capped at 100
+    assert abs(o.get_state()[38 + d] - (-1.0)) < 1e-9
+    # ... and beyond the lower limit, the other way
+    s[13 + d] = lower - 0.01
+    o.set_state(s)
+    o.substep(s[13:38], 0.0)
+    assert o.last_num_limit_rows == 1
+    assert abs(o.get_state()[38 + d] - 1.0) < 1e-9
+    # deep: 0.1 rad beyond -> velocity-only row: the joint is stopped from moving further out, not pushed back
+    s[13 + d] = upper + 0.1
+    o.set_state(s)
+    o.substep(s[13:38], 0.0)
+    assert o.last_num_limit_rows == 1
+    assert abs(o.get_state()[38 + d]) < 1e-9
+    s[38 + d] = 0.5  # moving further out: stopped
+    o.set_state(s)
+    o.substep(s[13:38], 0.0)
+    assert abs(o.get_state()[38 + d]) < 1e-9
+    s[38 + d] = -0.5  # moving back in: left alone (joint damping only)
+    o.set_state(s)
+    o.substep(s[13:38], 0.0)
+    assert o.get_state()[38 + d] < -0.3
 
 
 def test_contact_holds_the_standing_trex(model):

@@ -19,7 +19,8 @@ STATE_DIM = 160
 AUX_DIM = 8
 
 EXPORTED_SYMBOLS = (
-    "trex_create", "trex_destroy", "trex_reset", "trex_step", "trex_step_host", "trex_reset_host",
+    "trex_create", "trex_destroy", "trex_reset", "trex_step", "trex_step_host", "trex_step_host_async", "trex_host_wait",
+    "trex_reset_host",
     "trex_get_state", "trex_set_state", "trex_get_aux", "trex_get_joint_limits",
     "trex_fill_random_actions", "trex_get_stats", "trex_measure_fp32_peak", "trex_gae", "trex_normalize",
     "trex_policy_param_count", "trex_policy_forward", "trex_kernel_launches", "trex_num_envs",
@@ -37,8 +38,15 @@ class TrexConfig(ctypes.Structure):
         ("enable_contacts", ctypes.c_int32),
         ("reset_mode", ctypes.c_int32),
         ("seed", ctypes.c_uint32),
-        ("reserved", ctypes.c_int32 * 8),
+        ("env_offset", ctypes.c_int64),
+        ("warps_per_block", ctypes.c_int32),
+        ("solver_placement", ctypes.c_int32),
+        ("heavy_share_div", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 11),
     ]
+
+
+SOLVE_DEFAULT, SOLVE_FRONT, SOLVE_FREE_ONLY, SOLVE_NO_HEAVY = 0, 1, 2, 3  # trex_config.solver_placement
 
 
 class TrexStats(ctypes.Structure):
@@ -97,6 +105,10 @@ def lib():
     L.trex_step.argtypes = [vp, fp, fp, fp, u8p, vp]
     L.trex_step_host.restype = ctypes.c_int
     L.trex_step_host.argtypes = [vp, fp, fp, fp, u8p]
+    L.trex_step_host_async.restype = ctypes.c_int
+    L.trex_step_host_async.argtypes = [vp, fp, fp, fp, u8p]
+    L.trex_host_wait.restype = ctypes.c_int
+    L.trex_host_wait.argtypes = [vp]
     L.trex_reset_host.restype = ctypes.c_int
     L.trex_reset_host.argtypes = [vp, fp]
     for name in ("trex_get_state", "trex_set_state", "trex_get_aux"):

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #ifndef TREX_MIN_BLOCKS
@@ -51,7 +52,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 // One env step = n_sub x [trex_front_kernel ; trex_solve_kernel] ; trex_tail_kernel   (trex_core.h).
 // Warp-private shared slabs; the only block-level synchronisation is the pair of barriers around the packed inward pass.
 // ------------------------------------------------------------------------------------------------
-// one warp per environment: dynamics front end of one physics substep (+ the whole substep with more than 8 contacts).
+// one warp per environment: dynamics front end of one physics substep (+ the whole substep when the solve is not deferred).
 // PACKED (4 warps per CTA): the inward pass of the CTA's four environments is done by warp 0, four environments at a time.
 template <int WARPS, bool PACKED>
 __global__ void __launch_bounds__(32 * WARPS, TREX_MIN_BLOCKS / WARPS)
@@ -82,8 +83,8 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
   const int front_result = trex::front_phase<PACKED>(P, mdl, mdli, tasks, cand_p, cand_lane, slabs[warp], state + (size_t)env * TREX_STATE_STRIDE,
                                                   work ? work + (size_t)env * TREX_WORK_STRIDE : nullptr, action + (size_t)env * trex::NJ,
                                                   first_round != 0, slabs, warp, valid_mask,
-                                                  // class 4 is deferred only while few environments are in it (count of the previous round)
-                                                  (workh != nullptr && (long long)(*heavy_hint) * heavy_div <= (long long)n_envs) ? workh + (size_t)env * TREX_HEAVY_STRIDE : nullptr);
+                                                  // class 5 (more than TREX_KC contacts) always goes to its own solver unless heavy_share_div asks for the batch-dependent rule
+                                                  (workh != nullptr && (heavy_div <= 0 || (long long)(*heavy_hint) * heavy_div <= (long long)n_envs)) ? workh + (size_t)env * TREX_HEAVY_STRIDE : nullptr);
   const int deferred = front_result & 255, n_contacts = front_result >> 8;
   // append to the list of its class of deferred environments (any order: the solver's lane groups are independent):
   // class 0 = contact-free substeps, classes 1..4 = 1 / 2 / 3-4 / 5-8 contacts, 5 = more; list c at list + c * n_envs, counters + 64 * c
@@ -129,7 +130,7 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   trex::solve_phase<KC>(P, scratch, work, state, envs, pending);
 }
 
-// one warp per environment of class 4 (more than TREX_KC contacts), a fixed grid striding over the list
+// one warp per environment of class 5 (more than TREX_KC contacts), a fixed grid striding over the list
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
 trex_heavy_kernel(const trex::Uniform P, const int* __restrict__ mdli, float* __restrict__ state, const float* __restrict__ work,
@@ -297,12 +298,16 @@ struct trex_handle {
   trex_host::EnvConfig C;
   trex::Uniform P;
   float *d_mdl = nullptr, *d_tasks = nullptr, *d_cand_p = nullptr, *d_state = nullptr, *d_aux = nullptr, *d_work = nullptr;
-  float* d_workh = nullptr;     // contact rows of the environments with more than TREX_KC contacts (class 4)
+  float* d_workh = nullptr;     // contact rows of the environments with more than TREX_KC contacts (class 5)
   float *d_lower = nullptr, *d_upper = nullptr;
   int *d_mdli = nullptr, *d_cand_lane = nullptr;
-  // staging for the host-buffer entry points
-  float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
-  uint8_t* d_done = nullptr;
+  // staging for the host-buffer entry points: two sets of output buffers, so the device->host copy of one step (on the
+  // copy stream, behind an event) can run under the next step's host->device copy and kernels (trex_step_host_async)
+  float *d_action[2] = {nullptr, nullptr}, *d_obs[2] = {nullptr, nullptr}, *d_reward[2] = {nullptr, nullptr};
+  uint8_t* d_done[2] = {nullptr, nullptr};
+  cudaStream_t host_main = nullptr, host_copy = nullptr, host_in = nullptr;
+  cudaEvent_t ev_step_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr}, ev_in_done[2] = {nullptr, nullptr};
+  int host_slot = 0;
   int* d_list = nullptr;        // [TREX_NCLASS][n_envs] environments whose solve was deferred in the current substep round, by class
   int* d_list_count = nullptr;  // [TREX_NCLASS][64] one counter per class and substep round
   DevStats* d_stats = nullptr;
@@ -310,7 +315,7 @@ struct trex_handle {
   // two solve4 kernels of the same round (fork after the front kernel, join before the next one; no host synchronisation)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int heavy_div = 16;           // class 4 goes to trex_heavy_kernel while at most n_envs / heavy_div environments are in it
+  int heavy_div = 0;            // > 0: class 5 goes to trex_heavy_kernel only while at most n_envs / heavy_div environments are in it (0: always)
   int heavy_grid = 148 * 11;    // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
   int64_t launches = 0;
   int64_t env_steps = 0;
@@ -333,7 +338,10 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
                 int mode, cudaStream_t st) {
   const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS,
                smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS, smem_h = sizeof(trex::HeavyShared);
+  // per template instance and device; handles may be created and stepped from different host threads
   static bool configured[16] = {false};
+  static std::mutex configure_lock;
+  std::lock_guard<std::mutex> guard(configure_lock);
   if (!configured[h->device & 15]) {
     int rc;
     if ((rc = configure_kernel(trex_front_kernel<WF, WF == 4>, smem_f)) != TREX_OK) return rc;
@@ -355,7 +363,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       h->launches++;
       if (h->d_work) {
         const bool heavy = h->P.defer_contacts > 1 && h->P.contacts_on && h->d_workh != nullptr;
-        if (heavy) {  // class 4: more than TREX_KC contacts, one environment per warp, on the side stream
+        if (heavy) {  // class 5: more than TREX_KC contacts, one environment per warp, on the side stream
           CUDA_TRY(cudaEventRecord(h->ev_fork, st));
           CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
           trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, h->side>>>(h->P, h->d_mdli, h->d_state, h->d_work, h->d_workh,
@@ -436,11 +444,28 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     h->C.distance_weight = cfg->distance_weight; h->C.energy_weight = cfg->energy_weight; h->C.drift_weight = cfg->drift_weight;
     h->C.max_episode_steps = cfg->max_episode_steps; h->C.enable_contacts = cfg->enable_contacts;
     h->C.reset_mode = cfg->reset_mode; h->C.seed = cfg->seed;
-    h->C.env_offset = ((long long)cfg->reserved[2] << 32) | (unsigned)cfg->reserved[1];
-    if (cfg->reserved[0] == 1 || cfg->reserved[0] == 2 || cfg->reserved[0] == 4) h->warps_per_block = cfg->reserved[0];
-    h->deferred_solve = cfg->reserved[3] != 1;
-    h->C.defer_contacts = cfg->reserved[3] == 0 ? 2 : (cfg->reserved[3] == 3 ? 1 : 0);
-    if (cfg->reserved[5] > 0) h->heavy_div = cfg->reserved[5];
+    h->C.env_offset = (long long)cfg->env_offset;
+    if (cfg->warps_per_block != 0 && cfg->warps_per_block != 1 && cfg->warps_per_block != 2 && cfg->warps_per_block != 4) {
+      delete h;
+      return fail(TREX_ERR_INVALID, "trex_config.warps_per_block must be 0 (default), 1, 2 or 4%s");
+    }
+    if (cfg->warps_per_block) h->warps_per_block = cfg->warps_per_block;
+    if (cfg->solver_placement < TREX_SOLVE_DEFAULT || cfg->solver_placement > TREX_SOLVE_NO_HEAVY) {
+      delete h;
+      return fail(TREX_ERR_INVALID, "trex_config.solver_placement must be one of TREX_SOLVE_*%s");
+    }
+    h->deferred_solve = cfg->solver_placement != TREX_SOLVE_FRONT;
+    h->C.defer_contacts = cfg->solver_placement == TREX_SOLVE_DEFAULT ? 2 : (cfg->solver_placement == TREX_SOLVE_NO_HEAVY ? 1 : 0);
+    if (cfg->heavy_share_div < 0) {
+      delete h;
+      return fail(TREX_ERR_INVALID, "trex_config.heavy_share_div must be >= 0%s");
+    }
+    h->heavy_div = cfg->heavy_share_div;
+    for (int i = 0; i < 11; i++)
+      if (cfg->reserved[i] != 0) {
+        delete h;
+        return fail(TREX_ERR_INVALID, "trex_config.reserved must be zero%s");
+      }
   }
   if ((int)h->T.params[trex_host::P_MAX_CONTACTS] != TREX_KMAX) {
     int rc_ = fail(TREX_ERR_MODEL, "model blob max_contacts differs from the compiled contact capacity (TREX_KMAX)%s");
@@ -481,10 +506,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   }
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
-  CTRY(cudaMalloc((void**)&h->d_action, N * trex::NJ * sizeof(float)));
-  CTRY(cudaMalloc((void**)&h->d_obs, N * 3 * trex::NJ * sizeof(float)));
-  CTRY(cudaMalloc((void**)&h->d_reward, N * sizeof(float)));
-  CTRY(cudaMalloc((void**)&h->d_done, N));
+  // (the staging buffers of the host-buffer entry points are allocated on first use: ensure_host_path)
   CTRY(cudaMalloc((void**)&h->d_list, TREX_NCLASS * N * sizeof(int)));
   CTRY(cudaMalloc((void**)&h->d_list_count, 64 * (TREX_NCLASS + 2) * sizeof(int)));
   CTRY(cudaMemset(h->d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int)));
@@ -506,8 +528,16 @@ void trex_destroy(trex_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_mdl); cudaFree(h->d_mdli); cudaFree(h->d_tasks); cudaFree(h->d_cand_p); cudaFree(h->d_cand_lane);
   cudaFree(h->d_work); cudaFree(h->d_workh); cudaFree(h->d_list); cudaFree(h->d_list_count);
-  cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_action);
-  cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_stats);
+  cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_stats);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(h->d_action[b]); cudaFree(h->d_obs[b]); cudaFree(h->d_reward[b]); cudaFree(h->d_done[b]);
+    if (h->ev_step_done[b]) cudaEventDestroy(h->ev_step_done[b]);
+    if (h->ev_copy_done[b]) cudaEventDestroy(h->ev_copy_done[b]);
+    if (h->ev_in_done[b]) cudaEventDestroy(h->ev_in_done[b]);
+  }
+  if (h->host_main) cudaStreamDestroy(h->host_main);
+  if (h->host_copy) cudaStreamDestroy(h->host_copy);
+  if (h->host_in) cudaStreamDestroy(h->host_in);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -529,29 +559,83 @@ int trex_step(trex_handle* h, const float* action_dev, float* obs_dev, float* re
   return rc;
 }
 
-int trex_step_host(trex_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host) {
+// staging buffers, streams and events of the host-buffer entry points (first use)
+static int ensure_host_path(trex_handle* h) {
+  if (h->host_main) return TREX_OK;
+  const size_t N = (size_t)h->n_envs;
+  for (int b = 0; b < 2; b++) {
+    CUDA_TRY(cudaMalloc((void**)&h->d_action[b], N * trex::NJ * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_obs[b], N * 3 * trex::NJ * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_reward[b], N * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_done[b], N));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_step_done[b], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy_done[b], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in_done[b], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->host_copy, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->host_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->host_main, cudaStreamNonBlocking));
+  return TREX_OK;
+}
+
+int trex_step_host_async(trex_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host) {
   if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
   if (!action_host) return fail(TREX_ERR_INVALID, "action is NULL%s");
   CUDA_TRY(cudaSetDevice(h->device));
+  int rc = ensure_host_path(h);
+  if (rc != TREX_OK) return rc;
   const size_t N = (size_t)h->n_envs;
-  CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, N * trex::NJ * sizeof(float), cudaMemcpyHostToDevice, 0));
-  int rc = dispatch_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, nullptr, 0, 0);
+  const int b = h->host_slot;
+  h->host_slot ^= 1;
+  // host->device copy on its own stream: it may run under the previous step's kernels (which read the other action buffer);
+  // the kernels that read THIS buffer two calls ago are complete once ev_step_done[b] has fired
+  CUDA_TRY(cudaStreamWaitEvent(h->host_in, h->ev_step_done[b], 0));
+  CUDA_TRY(cudaMemcpyAsync(h->d_action[b], action_host, N * trex::NJ * sizeof(float), cudaMemcpyHostToDevice, h->host_in));
+  CUDA_TRY(cudaEventRecord(h->ev_in_done[b], h->host_in));
+  CUDA_TRY(cudaStreamWaitEvent(h->host_main, h->ev_in_done[b], 0));
+  // the copy-out that last used this output buffer set (two calls ago) must have drained before the kernels overwrite it
+  CUDA_TRY(cudaStreamWaitEvent(h->host_main, h->ev_copy_done[b], 0));
+  rc = dispatch_step(h, h->d_action[b], h->d_obs[b], h->d_reward[b], h->d_done[b], nullptr, 0, h->host_main);
   if (rc != TREX_OK) return rc;
   h->env_steps += h->n_envs;
-  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs, N * 3 * trex::NJ * sizeof(float), cudaMemcpyDeviceToHost, 0));
-  if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, 0));
-  if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->d_done, N, cudaMemcpyDeviceToHost, 0));
-  CUDA_TRY(cudaStreamSynchronize(0));
+  CUDA_TRY(cudaEventRecord(h->ev_step_done[b], h->host_main));
+  CUDA_TRY(cudaStreamWaitEvent(h->host_copy, h->ev_step_done[b], 0));
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs[b], N * 3 * trex::NJ * sizeof(float), cudaMemcpyDeviceToHost, h->host_copy));
+  if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward[b], N * sizeof(float), cudaMemcpyDeviceToHost, h->host_copy));
+  if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->d_done[b], N, cudaMemcpyDeviceToHost, h->host_copy));
+  CUDA_TRY(cudaEventRecord(h->ev_copy_done[b], h->host_copy));
+  // contract: on return the PREVIOUS call's outputs are in host memory (this call's follow with the next call / trex_host_wait)
+  CUDA_TRY(cudaEventSynchronize(h->ev_copy_done[b ^ 1]));
   return TREX_OK;
+}
+
+int trex_host_wait(trex_handle* h) {
+  if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->host_main) {
+    CUDA_TRY(cudaStreamSynchronize(h->host_in));
+    CUDA_TRY(cudaStreamSynchronize(h->host_main));
+    CUDA_TRY(cudaStreamSynchronize(h->host_copy));
+  }
+  return TREX_OK;
+}
+
+int trex_step_host(trex_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host) {
+  const int rc = trex_step_host_async(h, action_host, obs_host, reward_host, done_host);
+  return rc != TREX_OK ? rc : trex_host_wait(h);
 }
 
 int trex_reset_host(trex_handle* h, float* obs_host) {
   if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
   CUDA_TRY(cudaSetDevice(h->device));
-  int rc = dispatch_step(h, nullptr, h->d_obs, nullptr, nullptr, nullptr, 1, 0);
+  int rc = ensure_host_path(h);
   if (rc != TREX_OK) return rc;
-  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs, (size_t)h->n_envs * 3 * trex::NJ * sizeof(float), cudaMemcpyDeviceToHost, 0));
-  CUDA_TRY(cudaStreamSynchronize(0));
+  rc = trex_host_wait(h);
+  if (rc != TREX_OK) return rc;
+  rc = dispatch_step(h, nullptr, h->d_obs[0], nullptr, nullptr, nullptr, 1, h->host_main);
+  if (rc != TREX_OK) return rc;
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs[0], (size_t)h->n_envs * 3 * trex::NJ * sizeof(float), cudaMemcpyDeviceToHost, h->host_main));
+  CUDA_TRY(cudaStreamSynchronize(h->host_main));
   return TREX_OK;
 }
 

@@ -891,9 +891,11 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
   const vf pen_lo = R.q - lower, pen_hi = upper - R.q;
   const vb act_lo = is_joint && !(pen_lo > 0.0f);
   const vb act_hi = is_joint && !(pen_hi > 0.0f);
-  // shallow violations (> split threshold) keep the velocity part only
-  const vf rhs_lo = sel(pen_lo > P.split_thresh, (-R.qd) * jdi, (-pen_lo * P.erp / dt + (-R.qd)) * jdi);
-  const vf rhs_hi = sel(pen_hi > P.split_thresh, (R.qd) * jdi, (-pen_hi * P.erp / dt + (R.qd)) * jdi);
+  // shallow violations (> split threshold, i.e. -0.04 < pen <= 0) combine the ERP push-back with the velocity term;
+  // deep ones keep the velocity part only (Bullet moves their positional part to m_rhsPenetration, which the
+  // multibody solver never consumes) [RECALL btMultiBodyJointLimitConstraint::createConstraintRows]
+  const vf rhs_lo = sel(pen_lo > P.split_thresh, (-pen_lo * P.erp / dt + (-R.qd)) * jdi, (-R.qd) * jdi);
+  const vf rhs_hi = sel(pen_hi > P.split_thresh, (-pen_hi * P.erp / dt + (R.qd)) * jdi, (R.qd) * jdi);
   vf lam_lo = 0.0f, lam_hi = 0.0f;
   const uint32_t mask_lo = vballot(act_lo), mask_hi = vballot(act_hi);
   // violated joints in the order Bullet solves their limit constraints: bit p <=> order[NJ + p] is violated

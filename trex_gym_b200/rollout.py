@@ -57,11 +57,11 @@ class RolloutBuffer:
         sim = self.sim
         for t in range(self.T):
             if policy is None:
-                sim.random_actions(step=step_offset + t, seed=seed, out=self.actions[t])
+                sim.random_actions(step=step_offset + t, seed=seed, env_offset=sim.env_offset, out=self.actions[t])
             elif isinstance(policy, MlpPolicy):
                 # fused kernel: reads obs[t] in place, writes the three rollout rows, no intermediate tensors
                 policy.act_into(self.obs[t], self.actions[t], self.values[t], self.neglogp[t], step=step_offset + t, seed=seed,
-                                env_offset=getattr(sim, "env_offset", 0))
+                                env_offset=sim.env_offset)
             else:
                 a, v, nlp = policy(self.obs[t])
                 self.actions[t].copy_(a)
@@ -155,12 +155,12 @@ class MlpPolicy:
                                                         p(value), p(mean), n, stream), "trex_policy_forward")
         return action, value, neglogp
 
-    def __call__(self, obs, step: int = 0, seed: int = 0, deterministic: bool = False):
+    def __call__(self, obs, step: int = 0, seed: int = 0, deterministic: bool = False, env_offset: int = 0):
         n = obs.shape[0]
         a = torch.empty(n, self.ACT, device=self.device, dtype=torch.float32)
         v = torch.empty(n, device=self.device, dtype=torch.float32)
         nlp = torch.empty(n, device=self.device, dtype=torch.float32)
-        return self.act_into(obs.contiguous(), a, v, nlp, step=step, seed=seed, deterministic=deterministic)
+        return self.act_into(obs.contiguous(), a, v, nlp, step=step, seed=seed, env_offset=env_offset, deterministic=deterministic)
 
     def reference_forward(self, obs: torch.Tensor):
         """The same networks in plain PyTorch FP32 (tests: numerics reference of the kernel)."""

@@ -35,6 +35,8 @@ class TrexBatchSim:
             raise ValueError("device must be a CUDA device")
         self.device = dev
         self.num_envs = int(num_envs)
+        self.env_offset = int(env_offset)  # global id of environment 0 of this shard
+        self.seed = int(seed)
         self.model = model if model is not None else load_builtin()
         self._L = _native.lib()
         cfg = _native.TrexConfig()
@@ -45,16 +47,13 @@ class TrexBatchSim:
         cfg.max_episode_steps = int(max_episode_steps)
         cfg.enable_contacts = int(bool(contacts))
         cfg.reset_mode = int(reset_mode)
-        cfg.reserved[1] = ctypes.c_int32(int(env_offset) & 0xFFFFFFFF).value
-        cfg.reserved[2] = ctypes.c_int32((int(env_offset) >> 32) & 0xFFFFFFFF).value
+        cfg.env_offset = int(env_offset)
         cfg.seed = int(seed) & 0xFFFFFFFF
-        # solver placement (diagnostics): 0 = contact-free substeps and substeps with <= 4 contacts go to the
-        # four-environments-per-warp solver and those with more to the row-space one-environment solver, 3 = the latter
-        # stay in the front kernel, 2 = contact-free substeps only, 1 = everything in the front kernel
-        cfg.reserved[3] = ((0 if heavy_solver else 3) if defer_contacts else 2) if deferred_solve else 1
-        cfg.reserved[5] = int(heavy_share_div)  # 0 = default (1/16 of the batch), 1 = always use the heavy-contact kernel
-        if warps_per_block:
-            cfg.reserved[0] = int(warps_per_block)
+        # solver placement (diagnostics; include/trex_b200.h TREX_SOLVE_*)
+        cfg.solver_placement = ((_native.SOLVE_DEFAULT if heavy_solver else _native.SOLVE_NO_HEAVY) if defer_contacts
+                                else _native.SOLVE_FREE_ONLY) if deferred_solve else _native.SOLVE_FRONT
+        cfg.heavy_share_div = int(heavy_share_div)
+        cfg.warps_per_block = int(warps_per_block or 0)
         blob = self.model.blob()
         h = ctypes.c_void_p()
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -66,6 +65,9 @@ class TrexBatchSim:
             self.obs = torch.zeros(self.num_envs, _native.OBS_DIM, device=dev, dtype=torch.float32)
             self.reward = torch.zeros(self.num_envs, device=dev, dtype=torch.float32)
             self.done = torch.zeros(self.num_envs, device=dev, dtype=torch.uint8)
+            # motor position targets last set through TrexRobot.set_actions (trex_robot.py:413-422): the counterpart of
+            # pybullet's motor state, which persists between setJointMotorControlArray calls; step(None) consumes it
+            self.targets = torch.zeros(self.num_envs, _native.NUM_JOINTS, device=dev, dtype=torch.float32)
         lo = np.zeros(_native.NUM_JOINTS, np.float32)
         hi = np.zeros(_native.NUM_JOINTS, np.float32)
         _native.check(self._L.trex_get_joint_limits(self._h, lo.ctypes.data, hi.ctypes.data), "trex_get_joint_limits")
@@ -103,9 +105,12 @@ class TrexBatchSim:
         _native.check(self._L.trex_reset(self._h, mp, ctypes.c_void_p(self.obs.data_ptr()), self._stream()), "trex_reset")
         return self.obs
 
-    def step(self, action: torch.Tensor):
+    def step(self, action: torch.Tensor | None = None):
         """``TrexBulletEnv.step`` (trex_env.py:128-154) for every environment; returns views of the
-        simulator-owned ``obs``, ``reward``, ``done`` tensors (overwritten by the next call)."""
+        simulator-owned ``obs``, ``reward``, ``done`` tensors (overwritten by the next call).
+        ``action=None`` steps with the targets last written through ``TrexRobot.set_actions`` (``self.targets``)."""
+        if action is None:
+            action = self.targets
         self._check_tensor(action, (self.num_envs, _native.NUM_JOINTS), torch.float32, "action")
         _native.check(
             self._L.trex_step(self._h, ctypes.c_void_p(action.data_ptr()), ctypes.c_void_p(self.obs.data_ptr()),
@@ -142,6 +147,22 @@ class TrexBatchSim:
         _native.check(self._L.trex_step_host(self._h, ctypes.c_void_p(ptr(action)), ctypes.c_void_p(ptr(obs)),
                                              ctypes.c_void_p(ptr(reward)), ctypes.c_void_p(ptr(done))), "trex_step_host")
         return obs, reward, done
+
+    def step_host_async(self, action, obs, reward, done):
+        """``step_host`` as a depth-1 pipeline (``trex_step_host_async``): when call k returns, the outputs of call k-1
+        are complete; the copies of call k overlap call k+1.  Alternate between two sets of caller-owned (ideally pinned)
+        arrays and finish with ``host_wait()``."""
+        def ptr(x):
+            return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        for x, shape in ((action, (self.num_envs, _native.NUM_JOINTS)), (obs, (self.num_envs, _native.OBS_DIM)),
+                         (reward, (self.num_envs,)), (done, (self.num_envs,))):
+            if tuple(x.shape) != shape:
+                raise ValueError("step_host_async: expected shape %s" % (shape,))
+        _native.check(self._L.trex_step_host_async(self._h, ctypes.c_void_p(ptr(action)), ctypes.c_void_p(ptr(obs)),
+                                                   ctypes.c_void_p(ptr(reward)), ctypes.c_void_p(ptr(done))), "trex_step_host_async")
+
+    def host_wait(self) -> None:
+        _native.check(self._L.trex_host_wait(self._h), "trex_host_wait")
 
     def reset_host(self) -> np.ndarray:
         obs = np.empty((self.num_envs, _native.OBS_DIM), np.float32)

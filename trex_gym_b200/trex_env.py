@@ -99,10 +99,12 @@ class TrexBulletEnv(spaces.Env):
         action = np.asarray(action, dtype=np.float32)
         if action.shape != (25,):
             raise ValueError("The action dimension is not the same as the number of motors.")
-        # the clip to the joint limits (trex_env.py:147) happens inside the kernel
-        a = torch.from_numpy(np.ascontiguousarray(action)).to(self._sim.device).view(1, 25)
+        clipped_action = np.clip(action, self.action_space.low, self.action_space.high)  # trex_env.py:147
+        # trex_env.py:148-150: `for _ in range(action_repeat): model.set_actions(clipped); stepSimulation()` -- the targets
+        # persist in the simulator (TrexRobot.set_actions) and one sim.step() runs NUM_SUBSTEPS physics steps on them
+        self.model.set_actions(clipped_action)
         for _ in range(self._repeat_env_steps):
-            self._sim.step(a)
+            self._sim.step()
         self._env_step_counter += 1
         self._observation = self.model.get_observations()
         return self._observation, self.compute_reward(), self.should_terminate(), {}
@@ -151,7 +153,7 @@ class TrexVecEnv(object):
         if tuple(actions.shape) != (self.num_envs, 25):
             raise ValueError("The action dimension is not the same as the number of motors.")
         obs, rew, done = self.sim.step(actions)
-        return obs, rew, done, [{}] * 0  # infos: empty, as the reference returns {} per env
+        return obs, rew, done, [{} for _ in range(self.num_envs)]  # one empty info dict per environment (trex_env.py:154)
 
     def step_async(self, actions):
         self._pending = actions

@@ -38,7 +38,6 @@ class TrexRobot(object):
                         "starting configuration %s=%r differs from the compiled model (%r); recompile the model"
                         % (k, v, known.get(name)))
                 self._starting_configuration[name] = float(v)
-        self._pending_action = None
 
     # --- reset --------------------------------------------------------------------------------
     def reset(self, reload_urdf=False):
@@ -89,11 +88,14 @@ class TrexRobot(object):
 
     # --- actions ----------------------------------------------------------------------------------
     def set_actions(self, actions):
-        """trex_robot.py:413-422: position targets for the 25 motors (kp = 5e-3, kd = 0.1, 3e5 N m).
-        The targets take effect in the env's next step (the kernel re-applies them every substep)."""
-        a = np.asarray(actions, dtype=np.float32)[: len(self._revolute_joint_indices)]
-        if a.shape != (len(self._revolute_joint_indices),):
-            raise ValueError("expected %d actions" % len(self._revolute_joint_indices))
-        self._pending_action = a
+        """trex_robot.py:413-422: position targets for the 25 motors (kp = 5e-3, kd = 0.1, 3e5 N m), name-sorted order.
+        Like ``setJointMotorControlArray`` the targets persist: they are written to this environment's row of the
+        simulator's target buffer and every following physics substep (``sim.step()`` without an argument, which is
+        what ``TrexBulletEnv.step`` calls, trex_env.py:148-150) servoes towards them until the next call."""
+        n = len(self._revolute_joint_indices)
+        a = np.asarray(actions, dtype=np.float32).reshape(-1)[:n]  # the reference slices actions[:num_joints]
+        if a.shape != (n,):
+            raise ValueError("expected %d actions" % n)
+        self.sim.targets[self.env_index].copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=False)
 
     apply_action = set_actions  # north-star alias
