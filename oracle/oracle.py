@@ -53,6 +53,7 @@ def lib():
         L.trex_oracle_set_substeps.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.trex_oracle_set_reward_weights.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 3
         L.trex_oracle_enable_contacts.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.trex_oracle_set_fixed_base.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.trex_oracle_reset.argtypes = [ctypes.c_void_p, dp]
         L.trex_oracle_step.argtypes = [ctypes.c_void_p, dp, dp, dp]
         L.trex_oracle_run.argtypes = [ctypes.c_void_p, dp, ctypes.c_int, dp, dp]
@@ -92,6 +93,9 @@ class Oracle:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._L.trex_oracle_destroy(h)
+
+    def set_fixed_base(self, on: bool) -> None:
+        self._L.trex_oracle_set_fixed_base(self._h, int(bool(on)))
 
     def get_state(self) -> np.ndarray:
         s = np.zeros(self.state_dim)

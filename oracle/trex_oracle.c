@@ -197,6 +197,7 @@ struct trex_oracle {
   int n_order, nc_order[2 * MAXDOF];
   double P[P_COUNT];
   int n_sub, contacts_on;
+  int fixed_base; /* btMultiBody m_fixedBase: base acceleration and acceleration deltas forced to zero (KATs only) */
   double w_dist, w_energy, w_drift;
   /* state */
   v3 pos, omega, vel;
@@ -307,6 +308,7 @@ void trex_oracle_set_state(trex_oracle* o, const double* s) {
 void trex_oracle_set_substeps(trex_oracle* o, int n) { o->n_sub = n < 1 ? 1 : n; }
 void trex_oracle_set_reward_weights(trex_oracle* o, double d, double e, double k) { o->w_dist = d; o->w_energy = e; o->w_drift = k; }
 void trex_oracle_enable_contacts(trex_oracle* o, int on) { o->contacts_on = on; }
+void trex_oracle_set_fixed_base(trex_oracle* o, int on) { o->fixed_base = on; }
 int trex_oracle_last_iterations(const trex_oracle* o) { return o->last_iters; }
 int trex_oracle_last_num_contacts(const trex_oracle* o) { return o->last_contacts; }
 int trex_oracle_last_num_limit_rows(const trex_oracle* o) { return o->last_limits; }
@@ -454,7 +456,7 @@ static void aba(trex_oracle* o, const double* joint_tau, double* acc) {
   /* base acceleration: a0 = -IA0^-1 pA0 */
   sv res;
   solve6(IA[0], pA[0], res);
-  for (int k = 0; k < 6; k++) a[0][k] = -res[k];
+  for (int k = 0; k < 6; k++) a[0][k] = o->fixed_base ? 0.0 : -res[k];
 
   /* outward */
   for (int i = 0; i < n; i++) {
@@ -472,6 +474,7 @@ static void aba(trex_oracle* o, const double* joint_tau, double* acc) {
   m3tmulv(acc, o->Rw[0], a[0]);
   v3set(t, a[0][3] + wv[0], a[0][4] + wv[1], a[0][5] + wv[2]);
   m3tmulv(acc + 3, o->Rw[0], t);
+  if (o->fixed_base) memset(acc, 0, 6 * sizeof(double));
 }
 
 /* btMultiBody::calcAccelerationDeltasMultiDof: out = M^-1 force, generalized coordinates
@@ -501,7 +504,7 @@ static void accel_deltas(const trex_oracle* o, const double* force, double* out)
   }
   sv res;
   solve6(o->IA0, z[0], res);
-  for (int k = 0; k < 6; k++) a[0][k] = -res[k];
+  for (int k = 0; k < 6; k++) a[0][k] = o->fixed_base ? 0.0 : -res[k];
   for (int i = 0; i < n; i++) {
     int b = i + 1, p = o->parent[i] + 1;
     xf_motion(a[b], o->Rp[b], o->rvec[i], a[p]);

@@ -45,6 +45,9 @@ void trex_oracle_set_state(trex_oracle* o, const double* in);
 void trex_oracle_set_substeps(trex_oracle* o, int n);
 void trex_oracle_set_reward_weights(trex_oracle* o, double distance, double energy, double drift);
 void trex_oracle_enable_contacts(trex_oracle* o, int on);
+/* btMultiBody's fixed-base mode (m_fixedBase): the base neither accelerates nor responds to impulses.  The reference loads
+ * the T-rex with a floating base (trex_robot.py:47-56); this switch exists for the fixed-base pendulum known-answer test. */
+void trex_oracle_set_fixed_base(trex_oracle* o, int on);
 
 /* TrexBulletEnv.reset (trex_env.py:98-122): reset pose, zero-force motors, ONE physics step. obs75 may be NULL */
 void trex_oracle_reset(trex_oracle* o, double* obs75);

@@ -201,3 +201,51 @@ def test_bullet_default_inertia_option():
     mass = m["full_mass"]
     I = m["full_inertia"].reshape(-1, 3)
     assert np.allclose(I[:, 0], mass / 12.0 * 2 * 0.002 ** 2)
+
+
+@needs_ref
+def test_derived_urdf_with_collision_elements(model, tmp_path):
+    """the 48 contact candidates written as <collision> meshes through the reference's own Urdf.to_string
+    (tools/urdf_parsing.py:217), for a pybullet run on the same contact geometry.  Re-parsed by the reference parser the
+    file has the collision shapes on the expected links at the expected places, and it compiles back to the same model
+    (masses, damping and limits survive the reference serialiser's defects)."""
+    from scipy.spatial.transform import Rotation
+
+    from trex_gym_b200.model_compiler import CONTACT_POINT_MESH, compile_model, emit_derived_urdf
+    from trex_gym_b200.reference_loader import find_tools_dir, load_urdf_parsing
+
+    out = emit_derived_urdf(URDF, str(tmp_path / "trex_contacts.urdf"), model=model)
+    assert os.path.isfile(str(tmp_path / CONTACT_POINT_MESH))
+    up = load_urdf_parsing(find_tools_dir(URDF))
+    with open(out) as f:
+        text = f.read()
+    parsed = up.Urdf.from_string(text)  # the reference's parser reads its own serialiser's output
+    assert len(parsed.joints) == 132 and len(parsed.links) == 133
+    shapes = {n: l.collision_shapes for n, l in parsed.links.items() if l.collision_shapes}
+    assert sum(len(v) for v in shapes.values()) == len(model["full_cand_link"]) == 48
+    names = model.meta["link_names"]
+    want_links = {names[int(li) + 1] for li in model["full_cand_link"]}
+    assert set(shapes) == want_links and "link_toe_04_d_left" in want_links and "link_cranium" in want_links
+    assert all(s.filename == CONTACT_POINT_MESH for v in shapes.values() for s in v)
+    # placement: link-frame origin -> inertial frame reproduces the candidate table
+    from xml.etree import ElementTree
+
+    et = ElementTree.fromstring(text)
+    local = model["full_cand_local"].reshape(-1, 3)
+    seen = {n: 0 for n in shapes}
+    for li, p in zip(model["full_cand_link"], local):
+        n = names[int(li) + 1]
+        org = et.find("link[@name='%s']/inertial/origin" % n)
+        cin = np.array([float(v) for v in org.get("xyz").split()])
+        rin = Rotation.from_euler("xyz", [float(v) for v in org.get("rpy").split()]).as_matrix()
+        got = rin.T @ (shapes[n][seen[n]].origin.translation - cin)
+        seen[n] += 1
+        assert np.abs(got - p).max() < 1e-9
+    # the reference serialiser's defects are patched: mass, damping, effort/velocity survive
+    assert et.find("link[@name='link_femur_right']/inertial/mass").get("value") == "390.7456359863281"
+    assert et.find("joint[@name='joint_femur_right']/dynamics").get("damping") == "1.0"
+    assert et.find("joint[@name='joint_femur_right']/limit").get("effort") == "100.0"
+    m2 = compile_model(out)
+    for k, a in model.sections.items():
+        b = m2.sections[k]
+        assert a.shape == b.shape and np.abs(a.astype(float) - b.astype(float)).max() < 1e-9, k

@@ -217,3 +217,188 @@ def test_substep_count_generalisation(model):
         assert abs(z - (3.0 - G * (0.01 / n) ** 2)) < 1e-14
         o.step(np.zeros(25))
         assert o.total_substeps == 1 + n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent KATs (SURVEY.md section 8c pins (1)): nothing below shares code or formulation with the oracle's ABA.
+# ---------------------------------------------------------------------------------------------------------------
+def _world_kinematics(model, quat_xyzw, pos, q_dof):
+    """World pose of every URDF link of the FULL model by plain numpy / scipy rotations (independent of the oracle):
+    returns COM (n+1,3), link->world rotation (n+1,3,3), and per revolute dof (world axis, a point on the axis, link)."""
+    from scipy.spatial.transform import Rotation
+
+    S = model.sections
+    n = int(S["full_n_links"][0])
+    parent, jtype, dof = S["full_parent"], S["full_jtype"], S["full_dof"]
+    rot0 = S["full_rot0"].reshape(n, 3, 3)   # parent coordinates -> link coordinates at q = 0
+    axis = S["full_axis"].reshape(n, 3)      # joint axis, link coordinates
+    dvec = S["full_d"].reshape(n, 3)         # joint -> link COM, link coordinates
+    evec = S["full_e"].reshape(n, 3)         # parent COM -> joint, parent coordinates
+    Rlw = [Rotation.from_quat(quat_xyzw).as_matrix()]  # link -> world
+    com = [np.asarray(pos, float)]
+    joints = {}
+    for i in range(n):
+        p = parent[i] + 1
+        R_pl = rot0[i]  # parent -> link
+        if jtype[i] == 1:
+            R_pl = Rotation.from_rotvec(-q_dof[dof[i]] * axis[i]).as_matrix() @ rot0[i]
+        R = Rlw[p] @ R_pl.T
+        joint_point = com[p] + Rlw[p] @ evec[i]
+        Rlw.append(R)
+        com.append(joint_point + R @ dvec[i])
+        if jtype[i] == 1:
+            joints[int(dof[i])] = (R @ axis[i], joint_point, i + 1)
+    return np.asarray(com), np.asarray(Rlw), joints, parent
+
+
+def _mass_matrix_by_jacobians(model, quat_xyzw, pos, q_dof):
+    """H = sum_links m Jv^T Jv + Jw^T I_world Jw in the coordinates (base omega world, base v world, joint rates):
+    the textbook kinetic-energy definition, no recursion, no spatial algebra."""
+    S = model.sections
+    com, Rlw, joints, parent = _world_kinematics(model, quat_xyzw, pos, q_dof)
+    n = len(com) - 1
+    mass, Idiag = S["full_mass"], S["full_inertia"].reshape(n + 1, 3)
+    nd = len(joints)
+    H = np.zeros((6 + nd, 6 + nd))
+    for b in range(n + 1):
+        Jw, Jv = np.zeros((3, 6 + nd)), np.zeros((3, 6 + nd))
+        Jw[:, 0:3] = np.eye(3)
+        Jv[:, 3:6] = np.eye(3)
+        r = com[b] - com[0]
+        Jv[:, 0:3] = -np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])  # omega x r
+        a = b
+        while a > 0:  # ancestors-or-self joints move link b
+            for k, (ax, pt, link) in joints.items():
+                if link == a:
+                    Jw[:, 6 + k] = ax
+                    Jv[:, 6 + k] = np.cross(ax, com[b] - pt)
+            a = parent[a - 1] + 1
+        Iw = Rlw[b] @ np.diag(Idiag[b]) @ Rlw[b].T
+        H += mass[b] * Jv.T @ Jv + Jw.T @ Iw @ Jw
+    return H
+
+
+# SURVEY.md Appendix B: diagonal of the joint-space mass matrix at the reset pose (inertia of the joint's subtree about its axis)
+_APPENDIX_B_MKK = {
+    "atlas_axis": 778.042530, "cranium": 307.322553, "femur_left": 1369.277762, "femur_right": 1367.687173,
+    "tibia_left": 339.905413, "tibia_right": 339.268167, "tarsometatarsus_left": 39.844658, "tarsometatarsus_right": 39.852452,
+    "toe_02_a_left": 0.678912, "toe_02_a_right": 0.674992, "toe_02_b_left": 0.169529, "toe_02_b_right": 0.167145,
+    "toe_03_a_left": 1.398201, "toe_03_a_right": 1.396973, "toe_03_c_left": 0.078078, "toe_03_c_right": 0.077754,
+    "toe_04_a_left": 0.969473, "toe_04_a_right": 0.966318, "toe_04_d_left": 0.040968, "toe_04_d_right": 0.040831,
+    "vertebra_caudal_02": 958.947119, "vertebra_caudal_10": 190.447149, "vertebra_caudal_24": 3.935202,
+    "vertebra_cervical_03": 973.609657, "vertebra_cervical_09": 1550.624604,
+}
+
+
+def test_unit_impulse_inverse_against_jacobian_mass_matrix(model):
+    """trex_oracle_minv_column (Bullet's calcAccelerationDeltasMultiDof restated) must be the inverse of the mass matrix
+    built independently from link Jacobians -- at the reset pose, where its joint diagonal is SURVEY Appendix B's M_kk
+    table, and at a random pose with a tilted base."""
+    o = _oracle(model, contacts=False)
+    o.reset()
+    s = o.get_state()
+    names = model.meta["body_joint_names"][1:]  # dof order
+    rng = np.random.default_rng(7)
+    qlo, qhi = model["mb_lower"][1:], model["mb_upper"][1:]
+    poses = [(s[3:7].copy(), s[0:3].copy(), s[13:38].copy())]
+    quat = rng.normal(size=4)
+    poses.append((quat / np.linalg.norm(quat), np.array([0.3, -0.2, 1.7]), rng.uniform(qlo, qhi)))
+    for idx, (quat, pos, q) in enumerate(poses):
+        s2 = s.copy()
+        s2[0:3], s2[3:7], s2[13:38] = pos, quat, q
+        s2[7:13] = 0.0
+        s2[38:63] = 0.0
+        o.set_state(s2)
+        H = _mass_matrix_by_jacobians(model, quat, pos, q)
+        assert np.allclose(H, H.T, rtol=0, atol=1e-9 * np.abs(H).max())
+        Minv = np.stack([o.minv_column(d) for d in range(31)], 1)
+        err = np.abs(H @ Minv - np.eye(31)).max()
+        assert err < 1e-8, (idx, err)
+        # column-wise relative agreement with the directly inverted matrix
+        Hinv = np.linalg.inv(H)
+        assert np.abs(Minv - Hinv).max() <= 1e-8 * np.abs(Hinv).max(), idx
+        if idx == 0:
+            # the reset pose is one physics step after the reference pose (q unchanged: free fall, zero joint rates)
+            for k, name in enumerate(names):
+                want = _APPENDIX_B_MKK[name.replace("joint_", "", 1)]
+                assert abs(H[6 + k, 6 + k] - want) < 5e-7 * max(1.0, want), (name, H[6 + k, 6 + k], want)
+            assert abs(H[3, 3] - MASS) < 1e-9 * MASS and abs(H[4, 4] - MASS) < 1e-9 * MASS
+
+
+def _pendulum_blob(model, m, l, I_axis_com, gravity=9.81, dt=0.002):
+    """A one-link model blob: fixed base, one revolute joint about x through the base COM, link COM at distance l below the
+    joint (link -z), principal inertia I_axis_com about the joint-parallel axis through the COM; all damping off."""
+    from collections import OrderedDict
+
+    from trex_gym_b200 import model_blob
+
+    names = model.meta["param_names"]
+    p = model.sections["param_values"].copy()
+    for k, v in (("time_step", dt), ("num_substeps", 1), ("gravity", gravity), ("linear_damping", 0.0), ("angular_damping", 0.0)):
+        p[names.index(k)] = v
+    S = OrderedDict()
+    S["param_values"] = p
+    S["full_n_links"] = np.asarray([1], np.int32)
+    S["full_parent"] = np.asarray([-1], np.int32)
+    S["full_jtype"] = np.asarray([1], np.int32)
+    S["full_dof"] = np.asarray([0], np.int32)
+    S["full_mass"] = np.asarray([1.0, m])
+    S["full_inertia"] = np.asarray([1.0, 1.0, 1.0, I_axis_com, 0.3 * I_axis_com + 0.01, 0.7 * I_axis_com + 0.02])
+    S["full_rot0"] = np.eye(3).reshape(-1)
+    S["full_axis"] = np.asarray([1.0, 0.0, 0.0])
+    S["full_d"] = np.asarray([0.0, 0.0, -l])
+    S["full_e"] = np.zeros(3)
+    S["full_lower"] = np.asarray([-10.0])
+    S["full_upper"] = np.asarray([10.0])
+    S["full_damping"] = np.zeros(1)
+    S["full_start_q"] = np.zeros(1)
+    S["full_head_link"] = np.asarray([0], np.int32)
+    S["obs_dof"] = np.zeros(25, np.int32)
+    S["full_cand_link"] = np.zeros(0, np.int32)
+    S["full_cand_local"] = np.zeros(0)
+    S["noncontact_order"] = np.asarray([1, 0], np.int32)  # the motor (id ndof + 0), then the limit constraint (id 0)
+    return model_blob.pack(S)
+
+
+def test_fixed_base_pendulum_closed_form(model):
+    """A compound pendulum on a fixed base: q_dd = -(m g l / (I_com + m l^2)) sin q.  (a) the first step from rest at a
+    large angle is exactly dt * q_dd (semi-implicit Euler); (b) small oscillations follow the exact solution of the
+    symplectic-Euler recurrence q_{n+1} - 2 cos(theta) q_n + q_{n-1} = 0, cos(theta) = 1 - (w dt)^2 / 2, to round-off,
+    and the continuous solution q0 cos(w t) to O(dt)."""
+    from oracle.oracle import Oracle
+
+    m, l, Ic, g, dt = 3.7, 0.45, 0.21, 9.81, 0.002
+    o = Oracle(_pendulum_blob(model, m, l, Ic, g, dt), num_substeps=1, contacts=False)
+    o.set_fixed_base(True)
+    w2 = m * g * l / (Ic + m * l * l)
+    tgt = np.zeros(25)
+
+    def state(q, qd=0.0):
+        s = np.zeros(o.state_dim)
+        s[6] = 1.0
+        s[13], s[38] = q, qd
+        return s
+
+    for q0 in (0.9, -2.2):  # (a) nonlinear, one step
+        o.set_state(state(q0))
+        o.substep(tgt, 0.0)
+        s = o.get_state()
+        assert abs(s[38] - (-dt * w2 * np.sin(q0))) < 1e-14
+        assert abs(s[13] - (q0 + dt * s[38])) < 1e-15
+        assert np.abs(s[7:13]).max() == 0.0 and np.abs(s[0:3]).max() == 0.0  # the base stays put
+    q0, nstep = 1e-6, 2000  # (b) linear regime: sin q = q to 1e-13 relative
+    o.set_state(state(q0))
+    traj = []
+    for _ in range(nstep):
+        o.substep(tgt, 0.0)
+        traj.append(o.get_state()[13])
+    traj = np.asarray(traj)
+    n = np.arange(1, nstep + 1)
+    th = np.arccos(1.0 - w2 * dt * dt / 2.0)
+    # q_0 = q0, q_1 = q0 (1 - (w dt)^2)  =>  q_n = A cos(n th) + B sin(n th)
+    A = q0
+    B = (q0 * (1.0 - w2 * dt * dt) - A * np.cos(th)) / np.sin(th)
+    exact_discrete = A * np.cos(n * th) + B * np.sin(n * th)
+    assert np.abs(traj - exact_discrete).max() < 1e-9 * q0
+    assert np.abs(traj - q0 * np.cos(np.sqrt(w2) * n * dt)).max() < 2.0 * np.sqrt(w2) * dt * q0
+    assert traj.min() < -0.99 * q0  # several full swings were covered

@@ -631,6 +631,100 @@ def compile_model(
 
 
 # ---------------------------------------------------------------------------
+# Derived URDF with <collision> elements: the contact geometry this repository
+# defines, in a form pybullet can load, so that a pybullet run uses the same contact points.
+# ---------------------------------------------------------------------------
+CONTACT_POINT_MESH = "contact_point.obj"
+
+
+def _write_contact_point_mesh(path: str, radius: float) -> None:
+    """A tiny octahedron centred on the origin: the only collision geometry the reference serialiser can express is a
+    mesh (tools/urdf_parsing.py:359-369), so every contact point becomes one instance of this mesh."""
+    r = float(radius)
+    v = [(r, 0, 0), (-r, 0, 0), (0, r, 0), (0, -r, 0), (0, 0, r), (0, 0, -r)]
+    f = [(1, 3, 5), (3, 2, 5), (2, 4, 5), (4, 1, 5), (3, 1, 6), (2, 3, 6), (4, 2, 6), (1, 4, 6)]
+    with open(path, "w") as fh:
+        fh.write("# contact point marker: octahedron of radius %g m\n" % r)
+        for x, y, z in v:
+            fh.write("v %.9g %.9g %.9g\n" % (x, y, z))
+        for a, b, c in f:
+            fh.write("f %d %d %d\n" % (a, b, c))
+
+
+def emit_derived_urdf(urdf_path: str, out_path: str, model: CompiledModel | None = None, point_radius: float = 1.0e-3,
+                      absolute_visual_paths: bool = True) -> str:
+    """Write ``out_path``: the reference URDF plus one ``<collision>`` mesh per contact candidate of ``model``.
+
+    The file is produced by the reference's own ``Urdf.to_string`` (tools/urdf_parsing.py:217) from the parsed
+    ``Urdf`` with ``GeometryMesh`` collision shapes added (tools/urdf_parsing.py:108-112, 359-369).  That serialiser
+    loses what its parser never read -- ``<mass value>`` (``:82`` parses 0.0), ``<dynamics damping>`` and the
+    ``effort`` / ``velocity`` limits -- so those attributes are patched back from the source file afterwards.
+    Each point is a ``point_radius`` octahedron (``contact_point.obj`` next to ``out_path``): against the floor it
+    touches ``point_radius`` lower than the candidate point itself (1 mm against a 20 mm breaking distance).
+    """
+    tools_dir = find_tools_dir(urdf_path)
+    up = load_urdf_parsing(tools_dir)
+    geo = up.geometry
+    with open(urdf_path, "r") as f:
+        text = f.read()
+    urdf = up.Urdf.from_string(text)
+    src = ElementTree.fromstring(text)
+    if model is None:
+        model = compile_model(urdf_path)
+    link_names = list(model.meta["link_names"])  # pybullet link order, entry 0 = base
+    cand_link = model.sections["full_cand_link"]
+    cand_local = model.sections["full_cand_local"].reshape(-1, 3)
+    inertial = {}
+    for ln in src.findall("link"):
+        org = ln.find("inertial/origin")
+        xyz = np.array([float(v) for v in org.get("xyz").split()]) if org is not None else np.zeros(3)
+        rpy = [float(v) for v in org.get("rpy").split()] if org is not None else [0.0, 0.0, 0.0]
+        inertial[ln.get("name")] = (xyz, Rotation.from_euler("xyz", rpy).as_matrix())
+    per_link = defaultdict(int)
+    for li, p in zip(cand_link, cand_local):
+        name = link_names[int(li) + 1]
+        cin, rin = inertial[name]
+        p_link = cin + rin @ p  # candidate points are stored in the link's inertial frame (Bullet's link frame)
+        urdf.links[name].collision_shapes.append(
+            geo.GeometryMesh(filename=CONTACT_POINT_MESH, origin=geo.Transform(translation=p_link)))
+        per_link[name] += 1
+    if absolute_visual_paths:  # keep the visuals loadable wherever the derived file is written
+        asset_dir = os.path.dirname(os.path.abspath(urdf_path))
+        for link in urdf.links.values():
+            for shape in link.visual_shapes:
+                if isinstance(shape, geo.GeometryMesh) and not os.path.isabs(shape.filename):
+                    shape.filename = os.path.join(asset_dir, shape.filename)
+    out = ElementTree.fromstring(urdf.to_string())  # the reference's serialiser
+    # patch back what the reference's parser drops (SURVEY.md section 0.5)
+    src_links = {ln.get("name"): ln for ln in src.findall("link")}
+    for ln in out.findall("link"):
+        m_src = src_links[ln.get("name")].find("inertial/mass")
+        m_out = ln.find("inertial/mass")
+        if m_src is not None and m_out is not None:
+            m_out.set("value", m_src.get("value"))
+    src_joints = {jn.get("name"): jn for jn in src.findall("joint")}
+    for jn in out.findall("joint"):
+        sj = src_joints[jn.get("name")]
+        dyn = sj.find("dynamics")
+        if dyn is not None and jn.find("dynamics") is None:
+            jn.append(ElementTree.Element("dynamics", dict(dyn.attrib)))
+        lim_s, lim_o = sj.find("limit"), jn.find("limit")
+        if lim_s is not None and lim_o is not None:
+            for k in ("effort", "velocity"):
+                if lim_s.get(k) is not None:
+                    lim_o.set(k, lim_s.get(k))
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)) or ".", exist_ok=True)
+    _write_contact_point_mesh(os.path.join(os.path.dirname(os.path.abspath(out_path)), CONTACT_POINT_MESH), point_radius)
+    from xml.dom import minidom
+
+    pretty = minidom.parseString(ElementTree.tostring(out, encoding="utf-8")).toprettyxml(indent="  ")
+    pretty = "\n".join(line for line in pretty.splitlines() if line.strip())
+    with open(out_path, "w") as f:
+        f.write(pretty + "\n")
+    return out_path
+
+
+# ---------------------------------------------------------------------------
 # Checked-in compiled model (the GPU box has no /root/reference)
 # ---------------------------------------------------------------------------
 DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
