@@ -10,7 +10,7 @@ python bench.py --workload c2 --steps 50 --warmup 5 --no-cpu-baseline > $out/${t
 python bench.py --workload standing --steps 20 --warmup 5 --no-cpu-baseline > $out/${tag}_bench_standing.json 2> $out/${tag}_bench_standing.err
 python bench.py --workload rollout --no-cpu-baseline > $out/${tag}_bench_rollout.json 2> $out/${tag}_bench_rollout.err                   # configs[3]
 : > $out/${tag}_bench_fallen_sweep.jsonl
-for n in 1 2 3 4 5 6 7 8; do                                                                                                            # configs[4]
-  python bench.py --workload fallen --substeps $n --steps 20 --warmup 5 --no-cpu-baseline >> $out/${tag}_bench_fallen_sweep.jsonl 2>> $out/${tag}_bench_fallen.err
+for n in 1 2 3 4 5 6 7 8; do   # configs[4]; 64 timed steps = one whole episode (reset step included), starting on an episode boundary
+  python bench.py --workload fallen --substeps $n --steps 64 --warmup 5 --preroll 59 --no-cpu-baseline >> $out/${tag}_bench_fallen_sweep.jsonl 2>> $out/${tag}_bench_fallen.err
 done
 python bench.py --no-contacts --steps 20 --warmup 5 --no-cpu-baseline --spread-steps 0 > $out/${tag}_bench_contact_free.json 2> $out/${tag}_bench_contact_free.err

@@ -14,14 +14,14 @@ struct Emu {
   trex::Uniform P;
   trex::WarpShared S;            // the slab of a lone warp
   trex::WarpShared slabs[4];     // the slabs of a 4-warp CTA (packed inward pass)
-  trex::HeavyShared heavy;       // shared memory of a solve_heavy warp
+  alignas(16) float scratch2[TREX_SOLVE2_SCRATCH];  // shared scratch of a solve2 warp
   int packed = 0;                // emu_step4 with n == 4: run the front phase as a 4-warp CTA (host threads)
   alignas(16) float work[4 * TREX_WORK_STRIDE];
   alignas(16) float workh[4 * TREX_HEAVY_STRIDE];
   alignas(16) float scratch[TREX_SOLVE_SCRATCH(TREX_KC)];
   int deferred = 1;
   int pack_reverse = 0;  // tests: fill the solver's lane groups from the top
-  long long solves[5] = {0, 0, 0, 0, 0};  // substeps finished in front_phase / by solve4<0> / by solve4<TREX_KC>; [3] substep rounds run as a 4-warp CTA; [4] substeps finished by solve_heavy
+  long long solves[5] = {0, 0, 0, 0, 0};  // substeps finished in front_phase / by solve4<0> / by solve4<TREX_KC>; [3] substep rounds run as a 4-warp CTA; [4] substeps finished by solve2
 };
 
 static_assert(trex::F_COUNT == 32, "field table");
@@ -55,7 +55,7 @@ void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, 
   memset(e->scratch, 0xff, sizeof(e->scratch));
   memset(e->work, 0xff, sizeof(e->work));
   memset(e->workh, 0xff, sizeof(e->workh));
-  memset(&e->heavy, 0xff, sizeof(e->heavy));
+  memset(e->scratch2, 0xff, sizeof(e->scratch2));
   return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
@@ -110,11 +110,18 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
         const int pending = e->pack_reverse ? (((1 << cnt[d]) - 1) << (4 - cnt[d])) : ((1 << cnt[d]) - 1);
         if (d == 0) trex::solve_phase<0>(e->P, e->scratch, e->work, rec, envs[0], pending);
         else if (d < TREX_CLASS_HEAVY) trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[d], pending);
-        else  // class 4: one environment per warp
+        else {  // class 5: two environments per warp (solve2), packed from the list like the kernel does
+          int hv[4], nh = 0;
           for (int g = 0; g < 4; g++)
-            if (pending & (1 << g))
-              trex::solve_heavy(e->P, mdli, e->heavy, e->work + envs[d][g] * TREX_WORK_STRIDE, e->workh + envs[d][g] * TREX_HEAVY_STRIDE,
-                                rec + envs[d][g] * TREX_STATE_STRIDE);
+            if (pending & (1 << g)) hv[nh++] = envs[d][g];
+          for (int i = 0; i < nh; i += 2) {
+            const bool two = i + 1 < nh;
+            int pair[2] = {hv[i], two ? hv[i + 1] : 0};
+            int pend = two ? 3 : 1;
+            if (e->pack_reverse && !two) { pair[1] = pair[0]; pair[0] = 0; pend = 2; }  // tests: a lone environment in the upper lane group
+            trex::heavy_phase(e->P, e->scratch2, e->work, e->workh, rec, pair, pend);
+          }
+        }
       }
     }
   }

@@ -173,6 +173,12 @@ TREX_FN vf shfl_group8(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++
 TREX_FN vf group8_sum(vf x) { for (int m = 4; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN vf group8_max(vf x) { for (int m = 4; m > 0; m >>= 1) x = vmax(x, shfl_xor(x, m)); return x; }
 
+TREX_FN vf shfl_group16(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~15) | (src & 15)]; return r; }
+TREX_FN vf group16_sum(vf x) { for (int m = 8; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
+TREX_FN void ld2(const float* p, const vi& idx, vf out[2]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 2; k++) out[k].v[l] = p[idx.v[l] + k]; }
+TREX_FN void st2_if(float* p, const vi& idx, const vf v[2], const vb& pred) {
+  for (int l = 0; l < 32; l++) if (pred.v[l]) for (int k = 0; k < 2; k++) p[idx.v[l] + k] = v[k].v[l];
+}
 TREX_FN void ld4(const float* p, const vi& idx, vf out[4]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 4; k++) out[k].v[l] = p[idx.v[l] + k]; }
 TREX_FN void ld4_if(const float* p, const vi& idx, const vb& pred, vf out[4]) {
   for (int l = 0; l < 32; l++) for (int k = 0; k < 4; k++) out[k].v[l] = pred.v[l] ? p[idx.v[l] + k] : 0.0f;

@@ -361,3 +361,46 @@ def test_four_environments_per_warp(model, action_limits):
             assert max(rel_err(a[sl], b[sl]) for sl in STATE_BLOCKS.values()) < 5e-3
     assert saw_contact and saw_free and saw_limit
     assert wp.env.packed_rounds() == 30 * 5 and w4.env.packed_rounds() == 0
+
+
+def test_two_heavy_environments_per_warp(model):
+    """solve2: environments with more than 8 contacts are solved two per warp, sixteen lanes each.  Three standing
+    environments (different poses: 12-16 contacts) step as one work unit -- two share a warp, the third runs alone in
+    the lower or (reverse packing) the upper lane group -- and every record equals, bit for bit, the record of the same
+    environment stepped on its own: the pairing never changes a result."""
+    from emu import EmuEnv, EmuWarp4
+
+    o = _oracle(model)
+    nc = o.num_candidates
+    hold = o.reset()[:25].copy()
+    w3 = EmuWarp4(model.blob(), n=3)
+    wr = EmuWarp4(model.blob(), n=3, deferred=3)
+    singles = [EmuEnv(model.blob()) for _ in range(3)]
+    w3.reset()
+    wr.reset()
+    rng = np.random.default_rng(5)
+    acts = np.stack([hold + rng.uniform(-0.02, 0.02, 25) * (e > 0) for e in range(3)]).astype(np.float32)
+    for e, s1 in enumerate(singles):
+        s1.reset()
+    heavy_steps = 0
+    for t in range(45):
+        pre = w3.rec.copy()
+        wr.rec[:] = pre
+        for e, s1 in enumerate(singles):
+            s1.rec[:] = pre[e]
+        w3.step(acts)
+        wr.step(acts)
+        for e, s1 in enumerate(singles):
+            s1.step(acts[e])
+            assert np.array_equal(s1.rec[:152], w3.rec[e, :152]), (t, e)
+        assert np.array_equal(wr.rec[:, :152], w3.rec[:, :152]), t
+        ks = [int(w3.aux[e, 7]) % 1000 for e in range(3)]
+        heavy_steps += all(k > 8 for k in ks)
+        if t == 44:
+            assert len(set(ks)) >= 1 and max(ks) >= 12
+    assert heavy_steps >= 10 and w3.env.heavy_solves() >= 3 * 5 * 10
+    # and the pair agrees with the oracle like a lone environment does
+    o.set_state(np.concatenate([pre[1, :88], pre[1, 88:88 + nc]]).astype(np.float64))
+    o.step(acts[1].astype(np.float64))
+    so, se = o.get_state(), w3.get_state(1, nc)
+    assert max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()) < 5e-3

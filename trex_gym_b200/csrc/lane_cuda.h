@@ -109,6 +109,18 @@ TREX_FN vf shfl_group8(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 8)
 TREX_FN vf group8_sum(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
 TREX_FN vf group8_max(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(TREX_FULL, x, m)); return x; }
 
+// width-16 lane groups (two environments per warp in solve2)
+TREX_FN vf shfl_group16(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 16); }
+TREX_FN vf group16_sum(vf x) { TREX_UNROLL for (int m = 8; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
+// 2 consecutive floats per lane (8-byte aligned offset): one 64-bit access
+TREX_FN void ld2(const float* p, vi idx, vf out[2]) {
+  const float2 t = *reinterpret_cast<const float2*>(p + idx);
+  out[0] = t.x; out[1] = t.y;
+}
+TREX_FN void st2_if(float* p, vi idx, const vf v[2], vb pred) {
+  if (pred) *reinterpret_cast<float2*>(p + idx) = make_float2(v[0], v[1]);
+}
+
 // 4 consecutive floats per lane (16-byte aligned offset): one 128-bit access
 TREX_FN void ld4(const float* p, vi idx, vf out[4]) {
   const float4 t = *reinterpret_cast<const float4*>(p + idx);

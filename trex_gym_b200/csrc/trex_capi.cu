@@ -130,21 +130,21 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   trex::solve_phase<KC>(P, scratch, work, state, envs, pending);
 }
 
-// one warp per environment of class 5 (more than TREX_KC contacts), a fixed grid striding over the list
+// one warp per TWO environments of class 5 (more than TREX_KC contacts; sixteen lanes each, see solve2), a fixed grid of
+// resident warps striding over the list
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
-trex_heavy_kernel(const trex::Uniform P, const int* __restrict__ mdli, float* __restrict__ state, const float* __restrict__ work,
-                  const float* __restrict__ workh,
+trex_heavy_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work, const float* __restrict__ workh,
                   const int* __restrict__ list, const int* __restrict__ list_count, const int* __restrict__ seen, int* __restrict__ hint) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  trex::HeavyShared* H = reinterpret_cast<trex::HeavyShared*>(smem_raw);
   const int warp = threadIdx.x >> 5;
+  float* scratch = reinterpret_cast<float*>(smem_raw) + warp * TREX_SOLVE2_SCRATCH;
   const int count = *list_count;
   if (blockIdx.x == 0 && threadIdx.x == 0) *hint = *seen;  // environments with > TREX_KC contacts in this round
-  for (int i = blockIdx.x * WARPS + warp; i < count; i += gridDim.x * WARPS) {
-    const int env = list[i];
-    trex::solve_heavy(P, mdli, H[warp], work + (size_t)env * TREX_WORK_STRIDE, workh + (size_t)env * TREX_HEAVY_STRIDE,
-                      state + (size_t)env * TREX_STATE_STRIDE);
+  for (int i = (blockIdx.x * WARPS + warp) * 2; i < count; i += gridDim.x * WARPS * 2) {
+    const bool two = i + 1 < count;
+    const int envs[2] = {list[i], two ? list[i + 1] : 0};
+    trex::heavy_phase(P, scratch, work, workh, state, envs, two ? 3 : 1);
     __syncwarp();
   }
 }
@@ -316,7 +316,7 @@ struct trex_handle {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int heavy_div = 0;            // > 0: class 5 goes to trex_heavy_kernel only while at most n_envs / heavy_div environments are in it (0: always)
-  int heavy_grid = 148 * 11;    // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
+  int heavy_grid = 148 * 7;     // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
   int64_t launches = 0;
   int64_t env_steps = 0;
 };
@@ -337,7 +337,7 @@ template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
   const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS,
-               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS, smem_h = sizeof(trex::HeavyShared);
+               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS, smem_h = sizeof(float) * TREX_SOLVE2_SCRATCH;
   // per template instance and device; handles may be created and stepped from different host threads
   static bool configured[16] = {false};
   static std::mutex configure_lock;
@@ -366,7 +366,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
         if (heavy) {  // class 5: more than TREX_KC contacts, one environment per warp, on the side stream
           CUDA_TRY(cudaEventRecord(h->ev_fork, st));
           CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-          trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, h->side>>>(h->P, h->d_mdli, h->d_state, h->d_work, h->d_workh,
+          trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, h->side>>>(h->P, h->d_state, h->d_work, h->d_workh,
                                                                       h->d_list + (size_t)TREX_CLASS_HEAVY * h->n_envs,
                                                                       h->d_list_count + 64 * TREX_CLASS_HEAVY + r,
                                                                       h->d_list_count + 64 * TREX_NCLASS + r,
@@ -476,12 +476,12 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   {
     // trex_heavy_kernel strides over its list with a fixed grid: exactly the CTAs that are resident at once (a larger
     // grid would run its surplus CTAs as a second wave after the first has walked the whole list)
-    int sms = 148, per_sm = 11;
+    int sms = 148, per_sm = 7;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(trex_heavy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(trex::HeavyShared));
+    cudaFuncSetAttribute(trex_heavy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * TREX_SOLVE2_SCRATCH));
     cudaFuncSetAttribute(trex_heavy_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trex_heavy_kernel<1>, 32, sizeof(trex::HeavyShared)) != cudaSuccess || per_sm < 1)
-      per_sm = 11;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trex_heavy_kernel<1>, 32, sizeof(float) * TREX_SOLVE2_SCRATCH) != cudaSuccess || per_sm < 1)
+      per_sm = 7;
     if (sms > 0) h->heavy_grid = sms * per_sm;
   }
   int rc;

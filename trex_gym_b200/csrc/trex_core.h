@@ -55,17 +55,17 @@
 #define TREX_WORK_STRIDE 2848
 static_assert(W_A4 + 12 * TREX_KC * TREX_KC <= TREX_WORK_STRIDE && (W_BT % 4) == 0 && (W_A4 % 4) == 0 && (TREX_WORK_STRIDE % 32) == 0,
               "work record layout");
-// environments with more contacts (class 4, solve_heavy) keep their contact rows in a record of their own, so the
+// environments with more contacts (class 5, solve2) keep their contact rows in a record of their own, so the
 // main records stay dense: same fields for up to TREX_KW contacts
 #define TREX_KW TREX_KMAX
 #define H_NC 0
 #define H_CS 8
 #define H_BT (H_CS + 16 * TREX_KW)
 #define H_A4 (H_BT + 96 * TREX_KW)
-#define TREX_HEAVY_STRIDE (((H_A4 + 12 * TREX_KW * TREX_KW) + 31) / 32 * 32)
+#define TREX_HEAVY_STRIDE (((H_A4 + 9 * TREX_KW * TREX_KW) + 31) / 32 * 32)  // A: [3*KW][3*KW], A[r][r'] = J_r' M^-1 J_r^T (symmetric)
 static_assert((H_BT % 4) == 0 && (H_A4 % 4) == 0 && TREX_KC <= TREX_KW, "heavy record layout");
 // deferred environments are listed by class so that the four environments of a solver warp have similar row counts
-#define TREX_NCLASS 6                      // 0: contact-free; 1: 1 contact, 2: 2, 3: 3-4, 4: 5-8 (solve4); 5: 9..KW (solve_heavy)
+#define TREX_NCLASS 6                      // 0: contact-free; 1: 1 contact, 2: 2, 3: 3-4, 4: 5-8 (solve4); 5: 9..KW (solve2)
 #define TREX_CLASS_HEAVY (TREX_NCLASS - 1)
 TREX_TOPO_FN int defer_class(int n_contacts) {
   return n_contacts <= 2 ? n_contacts : (n_contacts <= 4 ? 3 : (n_contacts <= TREX_KC ? 4 : TREX_CLASS_HEAVY));
@@ -120,7 +120,7 @@ struct Uniform {
   float r0[NB][3];  // static-index copy of F_R0 (body index, not lane)
   int iters, n_sub, max_episode_steps, head_lane, n_cand, n_rounds, contacts_on, reset_mode;
   int defer_contacts;     // 1: substeps with 1..TREX_KC contacts are also solved four environments per warp; 2: and those with
-                          // more contacts by solve_heavy (one environment per warp, contact rows in row space)
+                          // more contacts by solve2 (two environments per warp, sixteen lanes each)
   unsigned seed;
   long long env_offset;   // global id of environment 0 of this shard (keys the reset sampler)
   float reset_z_min, reset_z_max;  // reset_mode 1: base height range
@@ -972,8 +972,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
   // rows (the rows are then the 25 motors and the violated joint limits, all with unit Jacobians); with up to
   // TREX_KC contacts when P.defer_contacts.  The solver inputs go to the work record: M^-1, the per-joint row
   // scalars and -- below -- the contact rows.
-  // (workh: more than TREX_KC contacts go to solve_heavy; the caller passes it only while few environments are in that
-  // class -- solve_heavy wins by taking the long-running warps out of the front kernel, not by being faster per environment)
+  // (workh: more than TREX_KC contacts go to solve2, two environments per warp)
   const bool defer_c = work != nullptr && P.defer_contacts != 0 && n_act > 0 && n_act <= ((P.defer_contacts > 1 && workh != nullptr) ? TREX_KW : TREX_KC);
   if (work != nullptr && (n_act == 0 || defer_c)) {
     _Pragma("unroll 8") for (int gq = 0; gq < trex_topo::NDOF; gq++) st(work, lane + (W_COL + gq * 32), ld(S.col[gq], lane));
@@ -1080,10 +1079,9 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
       // 31 coordinates, so it needs the responses at the joints (B4), at the base (for the final update) and the
       // Delassus blocks A[r'][r] = J_r' M^-1 J_r^T between contact rows.
       warp_sync();
-      const bool heavy = n_act > TREX_KC;      // class 4: its own record, laid out for TREX_KW contacts
+      const bool heavy = n_act > TREX_KC;      // class 5: its own record, laid out for TREX_KW contacts
       float* cw = heavy ? workh : work;
       const int o_nc = heavy ? H_NC : W_NC, o_cs = heavy ? H_CS : W_CS, o_bt = heavy ? H_BT : W_BT, o_a4 = heavy ? H_A4 : W_A4;
-      const int kw = heavy ? TREX_KW : TREX_KC;
       {
         const vb own = lane < n_act;
         const vi ls = seli(own, lane, 0);
@@ -1098,21 +1096,28 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
         st_if(cw, vi(o_nc), vbroadcast((float)n_act), lane == 0);
       }
       TREX_ROLLED for (int r = 0; r < 3 * n_act; r++) st(cw, lane + (r * 32 + o_bt), ld(S.c.dV[r], lane));
-      const int n3 = 3 * n_act, nn = n3 * n3, recip = 1048576 / n3 + 1;  // idx / n3 == (idx * recip) >> 20 for idx < 2304
-      TREX_ROLLED for (int i0 = 0; i0 < nn; i0 += 32) {
-        const vi idx = lane + i0;
-        const vb valid = idx < nn;
-        const vi is = seli(valid, idx, 0);
-        const vi rp = (is * recip) >> 20;        // affected row (c', k')
-        const vi r = is - rp * n3;               // source row (c, k)
-        const vi cp = (rp * 43) >> 7, kp = rp - cp * 3;  // rp / 3, rp % 3 (rp < 48)
-        vf acc = 0.0f;
+      // Delassus blocks A[r'][r] = J_r' (M^-1 J_r^T): lane <-> affected row r' (its <= 11 Jacobian entries and their
+      // coordinates live in registers), uniform loop over the source row r -- every shared load of a response row is then
+      // a broadcast or hits distinct banks (the transposed mapping, lanes over r, put all 32 lanes on one bank)
+      const int n3 = 3 * n_act;
+      TREX_ROLLED for (int t0 = 0; t0 < n3; t0 += 32) {
+        const vi rp = lane + t0;                 // affected row (c', k')
+        const vb valid = rp < n3;
+        const vi rps = seli(valid, rp, 0);
+        const vi cp = (rps * 43) >> 7, kp = rps - cp * 3;  // rp / 3, rp % 3 (rp < 48)
+        vf jv[11];
+        vi dl[11];
         TREX_UNROLL for (int e = 0; e < 11; e++) {
-          const vf jv = ld(&S.c.Jc[0][0], rp * 12 + e);
-          const vi dl = ldb(&S.c.inv[0][0], cp * 16 + e);
-          acc = vfma(jv, ld(&S.c.dV[0][0], r * 32 + dl), acc);
+          jv[e] = ld(&S.c.Jc[0][0], rps * 12 + e);
+          dl[e] = ldb(&S.c.inv[0][0], cp * 16 + e);
         }
-        st_if(cw, (r * kw + cp) * 4 + kp + o_a4, acc, valid);
+        const vi dst = heavy ? rps + o_a4 : (cp * 4 + kp) + o_a4;
+        const int rstride = heavy ? 3 * TREX_KW : 4 * TREX_KC;
+        TREX_ROLLED for (int r = 0; r < n3; r++) {  // source row (c, k)
+          vf acc = 0.0f;
+          TREX_UNROLL for (int e = 0; e < 11; e++) acc = vfma(jv[e], ld(&S.c.dV[0][0], dl[e] + r * 32), acc);
+          st_if(cw, dst + r * rstride, acc, valid);
+        }
       }
       warp_sync();
       TREX_TICK(5)
@@ -1813,193 +1818,253 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
 }
 
 // ------------------------------------------------------------------------------------------
-// solve_heavy: projected Gauss-Seidel for ONE environment with many contacts (class 4: more than TREX_KC, e.g. a T-rex
-// standing on both feet: 14-16 points), one warp per environment, in its own kernel with its own shared-memory budget.
+// solve2: projected Gauss-Seidel for up to TWO environments with many contacts (class 5: more than TREX_KC and up to
+// TREX_KW = 16, e.g. a T-rex standing on both feet: 14-16 points) in one warp, SIXTEEN lanes per environment.
 //
-// Same sweep as the one-environment solver inside substep() -- lane = coordinate, motors in w-form with replicated
-// impulses, violated limits in order, normal rows, friction pairs -- except that the contact rows are carried in ROW
-// SPACE like in solve4: lane c owns contact c and tracks the velocity change u along its three rows, so a contact row
-// needs no reduction over the 31 coordinates (the one-environment sweep spends a 5-level butterfly per row and
-// iteration on that): joint rows add B[r][j] * d(impulse) to u, contact rows add the Delassus block A4 to every
-// owner's u and B[r][lane] * d(impulse) to the coordinates.  Inputs come from the work record written by front_phase.
+// The same row-space sweep as solve4<KC> with the lane group twice as wide: lane l of a group owns the joints at
+// positions 2l, 2l+1 of the solve order (g[2][25] = 50 registers instead of 100) and contact l (one contact per lane).
+// A motor sweep goes in 13 blocks of two private rows (one width-16 shuffle latency per two rows); the contact rows
+// read the Delassus matrix A (48 x 48, row r = the velocity change along every row per unit impulse of row r) and the
+// joint responses Bp (48 x 26, indexed by solve-order position) from the warp's shared scratch: 14.2 KB per
+// environment, which is what bounds the number of environments in flight per SM (14).
+// Row order, clamps, residual, rebuild period and integration are those of solve4.
 // ------------------------------------------------------------------------------------------
-struct alignas(16) HeavyShared {             // 18.7 KB: 12 warps per SM (M^-1 stays in the work record: read once for g, and by limit rows)
-  float A4[3 * TREX_KW][TREX_KW][4];      // A4[r][c'][k'] = J_{c',k'} M^-1 J_r^T
-  float Bt[3 * TREX_KW][33];              // row responses M^-1 J^T by lane, rows padded (conflict-free for "one row per owner")
-  float tmp[32];
-};
-
-TREX_FN void solve_heavy(const Uniform& P, const int* mdli, HeavyShared& H, const float* work, const float* workh, float* rec) {
-  const vi lane = lane_id();
-  const vb is_joint = lane < NJ;
-  const float max_imp = P.max_impulse, lim_hi = P.limit_max_impulse;
-  const int n_act = (int)ldu(workh, H_NC);
-  // ---- inputs: M^-1, per-joint row scalars, contact rows ---------------------------------------------------
-  const vf rhs_m = ld(work, lane + W_RHSM), jdi = ld(work, lane + W_JDI), dself = ld(work, lane + W_DSELF);
-  const vf rhs_l = ld(work, lane + W_RHSL), sigma = ld(work, lane + W_SIGMA);
-  const vb act_lo = is_joint && (sigma > 0.0f), act_hi = is_joint && (sigma < 0.0f);
-  const vf rhs_lo = rhs_l, rhs_hi = rhs_l;
-  const uint32_t mask_lo = vballot(act_lo), mask_hi = vballot(act_hi);
-  uint32_t lim_perm;
-  {
-    const vi pj = ldi(mdli, lane + IF_LIMIT_ORDER * 32);
-    lim_perm = vballot((lane < NJ) && ((((vi((int)(mask_lo | mask_hi))) >> pj) & 1) != 0));
-  }
-  const vb cown = lane < n_act;
-  const vi own = vmini(lane, TREX_KW - 1);  // lanes beyond the contacts shadow a row block; their u is never read
-  vf c_lam[3], c_rhs[3], c_jdi[3], c_dd[3], cu[3];
-  {
-    const vi sb = seli(cown, lane, 0) * 16 + H_CS;
-    TREX_UNROLL for (int k = 0; k < 3; k++) {
-      c_rhs[k] = ld_if(workh, sb + k, cown, 0.0f);
-      c_jdi[k] = ld_if(workh, sb + (3 + k), cown, 0.0f);
-      c_dd[k] = ld_if(workh, sb + (6 + k), cown, 0.0f);
-      c_lam[k] = 0.0f; cu[k] = 0.0f;
+#define TREX_S2_NR (3 * TREX_KW)                    // contact rows per environment (48)
+#define TREX_S2_BS 26                               // Bp row stride: 25 positions + 1, even (64-bit loads); 3 * 26 * c mod 32 is conflict-free over the 16 owners
+#define TREX_S2_ENV (TREX_S2_NR * TREX_S2_NR + TREX_S2_NR * TREX_S2_BS + 16)  // floats per environment: A, then Bp; + 16: the two groups' stashes are
+                                                                           // 16 banks apart, so their stride-3 reads of A never share a bank
+#define TREX_S2_LS (32 + 4 * TREX_KW)               // Lam per environment: net joint impulses by joint, then [KW][4] contact impulses
+#define TREX_S2_LIMIT_SLOTS 2
+#define TREX_SOLVE2_SCRATCH (2 * TREX_S2_ENV + 2 * TREX_S2_LS + 64 * TREX_S2_LIMIT_SLOTS)  // floats per warp
+template <int B, bool FWD>
+TREX_FN void s2_motor_block(vf (&w)[2], vf (&lam_m)[2], const vf (&g)[2][NJ], vf (&cu)[3], vi gl, vi bp_own, const float* Sc, float max_imp) {
+  constexpr int n = (2 * B + 2 <= NJ) ? 2 : NJ - 2 * B;
+  vf bk[3][2];  // responses of the owned contact's three rows at this block's joints
+  TREX_UNROLL for (int k = 0; k < 3; k++) ld2(Sc, bp_own + (k * TREX_S2_BS + 2 * B), bk[k]);
+  vf t[2], d[2];
+  TREX_UNROLL for (int i = 0; i < 2; i++) { t[i] = w[i]; d[i] = 0.0f; }
+  const vb own = gl == B;
+  TREX_UNROLL for (int ii = 0; ii < n; ii++) {  // the owner's private chain
+    const int i = FWD ? ii : n - 1 - ii;
+    const int j = trex_topo::noncontact_order(2 * B + i) - NJ;
+    const vf nl = vmin(vmax(t[i], -max_imp), max_imp);
+    d[i] = nl - lam_m[i];
+    lam_m[i] = sel(own, nl, lam_m[i]);
+    if (ii + 1 < n) {
+      const int i3 = FWD ? 1 : 0;
+      t[i3] = vfma(g[i3][j], d[i], t[i3]);
     }
-    c_lam[0] = ld_if(workh, sb + 9, cown, 0.0f);  // warm start
   }
-  const vi ccand = seli(cown, vf2i(ld_if(workh, seli(cown, lane, 0) * 16 + (H_CS + 10), cown, 0.0f)), 0);
-  TREX_ROLLED for (int r = 0; r < 3 * n_act; r++) {
-    st(H.Bt[r], lane, ld(workh, lane + (r * 32 + H_BT)));
-    vf a4[4];
-    const vb lo16 = lane < TREX_KW;
-    ld4_if(workh, seli(lo16, lane, 0) * 4 + (r * (4 * TREX_KW) + H_A4), lo16 && cown, a4);
-    st4_if(&H.A4[0][0][0], seli(lo16, lane, 0) * 4 + r * (4 * TREX_KW), a4, lo16);
+  TREX_UNROLL for (int ii = 0; ii < n; ii++) {  // publish: every lane applies the impulse changes of lane B
+    const int i = FWD ? ii : n - 1 - ii;
+    const int j = trex_topo::noncontact_order(2 * B + i) - NJ;
+    const vf db = shfl_group16(d[i], B);
+    TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(g[s][j], db, w[s]);
+    TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(bk[k][i], db, cu[k]);
+  }
+}
+
+// envs[g] = index (relative to work0 / workh0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
+TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const float* workh0, float* rec0, const int envs[2], int pending,
+                  float max_imp) {
+  constexpr int NR = TREX_S2_NR, BS = TREX_S2_BS, LS = TREX_S2_LS, AOFF = 0, BOFF = NR * NR;
+  const vi lane = lane_id();
+  const vi grp = lane >> 4, gl = lane & 15;
+  const vb gact = ((vi(pending) >> grp) & 1) != 0;
+  const vi genv = seli(grp == 0, vi(envs[0]), vi(envs[1]));
+  const vi es = seli(gact, genv, 0);
+  const vi woff = es * TREX_WORK_STRIDE, hoff = es * TREX_HEAVY_STRIDE, roff = es * TREX_STATE_STRIDE;
+  const float dt = P.dt;
+  float* Sc = scratch;                                 // [2][TREX_S2_ENV]: A, then Bp
+  float* Lam = Sc + 2 * TREX_S2_ENV;                   // [2][LS]
+  float* Lg = Lam + 2 * LS;                            // [TREX_S2_LIMIT_SLOTS][2][32]
+  const vi gb = grp * TREX_S2_ENV;                     // this group's stash
+  const vi a_own = gb + (AOFF + 3 * gl);               // column block of the owned contact in every row of A
+  const vi bp_own = gb + (BOFF + 3 * BS * gl);         // Bp rows of the owned contact
+  const vi bp_mine = gb + (BOFF + 2 * gl);             // the lane's two joints in every row of Bp
+
+  vi kk[2];
+  vb kv[2];
+  vf rhs_m[2], jdi[2], dself[2], rhs_l[2], sigma[2], njdi[2], g[2][NJ];
+  TREX_UNROLL for (int s = 0; s < 2; s++) {
+    kk[s] = 0;
+    TREX_UNROLL for (int l = 0; l < 13; l++)
+      if (2 * l + s < NJ) kk[s] = seli(gl == l, vi(trex_topo::noncontact_order(2 * l + s) - NJ), kk[s]);
+    kv[s] = gact && (gl * 2 + s < NJ);
+    rhs_m[s] = ld_if(work0, woff + kk[s] + W_RHSM, kv[s], 0.0f);
+    jdi[s] = ld_if(work0, woff + kk[s] + W_JDI, kv[s], 0.0f);
+    dself[s] = ld_if(work0, woff + kk[s] + W_DSELF, kv[s], 0.0f);
+    rhs_l[s] = ld_if(work0, woff + kk[s] + W_RHSL, kv[s], 0.0f);
+    sigma[s] = ld_if(work0, woff + kk[s] + W_SIGMA, kv[s], 0.0f);
+    njdi[s] = -jdi[s];
+    TREX_UNROLL for (int j4 = 0; j4 < 7; j4++) {  // row 6+k of the symmetric M^-1: seven 128-bit loads
+      vf c4[4];
+      ld4_if(work0, woff + kk[s] * 32 + (W_COL + 6 * 32 + 4 * j4), kv[s], c4);
+      TREX_UNROLL for (int e = 0; e < 4; e++)
+        if (4 * j4 + e < NJ) g[s][4 * j4 + e] = sel(kk[s] == 4 * j4 + e, 0.0f, -(jdi[s] * c4[e]));
+    }
+  }
+  // contact rows: scalars of the owned contact in registers, A / Bp of the group's environment into the stash
+  // (rows of absent contacts are zero: their updates then add exactly 0)
+  vf cu[3], cl[3], crhs[3], cjdi[3], cdd[3];
+  const vi nc = seli(gact, vf2i(ld(workh0, hoff + H_NC)), 0);
+  const int kmax = lane_value_i(warp_maxi(nc), 0);
+  const vb cown = gact && (gl < nc);
+  {
+    const vi sb = hoff + gl * 16 + H_CS;
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      crhs[k] = ld_if(workh0, sb + k, cown, 0.0f);
+      cjdi[k] = ld_if(workh0, sb + (3 + k), cown, 0.0f);
+      cdd[k] = ld_if(workh0, sb + (6 + k), cown, 0.0f);
+      cu[k] = 0.0f; cl[k] = 0.0f;
+    }
+    cl[0] = ld_if(workh0, sb + 9, cown, 0.0f);  // warm start
+  }
+  const vi ccand = seli(cown, vf2i(ld_if(workh0, hoff + gl * 16 + (H_CS + 10), cown, 0.0f)), 0);
+  {
+    const vi nr = nc * 3;
+    TREX_ROLLED for (int r = 0; r < 3 * kmax; r++) {
+      const vb rok = gact && (vi(r) < nr);
+      // A row r: 48 floats = 12 float4, lanes 0..11 of the group; columns of absent contacts read as zero
+      vf a4[4];
+      const vb al = gl < (NR / 4);
+      const vi gls = seli(al, gl, 0);
+      ld4_if(workh0, hoff + gls * 4 + (r * NR + H_A4), rok && al, a4);
+      TREX_UNROLL for (int e = 0; e < 4; e++) a4[e] = sel((gls * 4 + e) < nr, a4[e], 0.0f);
+      st4_if(Sc, gb + gls * 4 + (AOFF + r * NR), a4, al);
+      // Bp row r: the lane's own two joints (positions 2 gl, 2 gl + 1; the pad position 25 gets 0)
+      vf b2[2];
+      TREX_UNROLL for (int s = 0; s < 2; s++) b2[s] = ld_if(workh0, hoff + kk[s] + (r * 32 + H_BT), rok && kv[s], 0.0f);
+      st2_if(Sc, bp_mine + r * BS, b2, gl < 13);
+    }
   }
   warp_sync();
-  const float* Bt = &H.Bt[0][0];
-  const float* A4 = &H.A4[0][0][0];
-  const vi bt_own = own * 99;   // rows 3*own .. 3*own+2 of Bt (33 floats per row)
-  // warm-started normal impulses: velocity change of the coordinates and along the rows
-  vf dv = 0.0f;
-  TREX_ROLLED for (int c = 0; c < n_act; c++) {
-    const vf wc = vbroadcast(lane_value(c_lam[0], c));
-    dv = vfma(ld(Bt, lane + (3 * c) * 33), wc, dv);
-    vf a4[4];
-    ld4(A4, own * 4 + (3 * c) * (4 * TREX_KW), a4);
-    TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], wc, cu[k]);
+  // joints with a violated limit in either environment, in Bullet's limit-constraint order (bit p <=> position p)
+  static_assert(limit_order_matches_motor_order(), "solve2 assumes order[NJ + p] == order[p] - NJ");
+  uint32_t uperm = 0;
+  TREX_UNROLL for (int s = 0; s < 2; s++) {
+    const uint32_t b = vballot(kv[s] && (sigma[s] != 0.0f));
+    const uint32_t any = (b | (b >> 16)) & 0xffffu;  // bit l: lane l of either group
+    TREX_UNROLL for (int l = 0; l < 13; l++) uperm |= ((any >> l) & 1u) << (2 * l + s);
   }
-  // ---- projected Gauss-Seidel, Bullet's row order --------------------------------------------------------------
-  int it_done = 0;
-  const vf njdi = -jdi;
-  vf g[NJ];
-  TREX_UNROLL for (int j = 0; j < NJ; j++) {
-    const vf cj = ld(work, lane + (W_COL + (6 + j) * 32));
-    g[j] = sel(is_joint, sel(lane == j, 0.0f, njdi * cj), cj);  // base-coordinate lanes keep the raw coefficient
+  uint32_t cached = 0;
+  {
+    uint32_t m = uperm;
+    TREX_ROLLED for (int slot = 0; slot < TREX_S2_LIMIT_SLOTS && m != 0; slot++) {
+      const int pos = ctz_u(m);
+      m &= m - 1;
+      cached |= 1u << pos;
+      const int j = P.order[NJ + pos];
+      TREX_UNROLL for (int s = 0; s < 2; s++)
+        st(Lg, lane + (slot * 2 + s) * 32,
+           sel(kk[s] == j, 0.0f, njdi[s] * ld_if(work0, woff + kk[s] * 32 + (W_COL + 6 * 32 + j), kv[s], 0.0f)));
+    }
   }
-  vf lamr[NJ];  // motor impulses, replicated on every lane (uniform values)
-  TREX_UNROLL for (int j = 0; j < NJ; j++) lamr[j] = 0.0f;
-  vf lam_m = 0.0f, lam_lo = 0.0f, lam_hi = 0.0f;
-  vf dvo = dv, dvm = 0.0f, w = 0.0f;
+  warp_sync();
+
+  vf w[2], lam_m[2], lam_l[2];
+  TREX_UNROLL for (int s = 0; s < 2; s++) { w[s] = rhs_m[s]; lam_m[s] = 0.0f; lam_l[s] = 0.0f; }
+  const float lim_hi = P.limit_max_impulse;
+  vb alive = gact;
+  vi itd = 0;
+
+#define TREX_S2_LIMIT_SLOT(SJ)                                                                         \
+  {                                                                                                    \
+    const vf x = (lam_m[SJ] + rhs_m[SJ]) - w[SJ];              /* jdi * dv_j */                         \
+    const vf sum = lam_l[SJ] + (rhs_l[SJ] - sigma[SJ] * x);                                            \
+    const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                                       \
+    const vb own = alive && (gl == (pos >> 1)) && (sigma[SJ] != 0.0f);                                 \
+    const vf d = sel(own, (nl - lam_l[SJ]) * sigma[SJ], 0.0f);  /* change of the net joint impulse */   \
+    const vf db = shfl_group16(d, pos >> 1);                                                           \
+    lam_l[SJ] = sel(own, nl, lam_l[SJ]);                                                               \
+    TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(gj[s], db, w[s]);                              \
+    w[SJ] = w[SJ] - d;                                        /* self term: dv_j += D_j * d */         \
+    TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Sc, bp_own + (k * BS + pos)), db, cu[k]);  \
+  }
+#define TREX_S2_LIMITS(FORWARD)                                                                        \
+  {                                                                                                    \
+    uint32_t m = uperm;                                                                                \
+    while (m) {                                                                                        \
+      const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                            \
+      m &= ~(1u << pos);                                                                               \
+      const int j = P.order[NJ + pos];                                                                 \
+      vf gj[2];                                                                                        \
+      if ((cached >> pos) & 1u) {                                                                      \
+        const int slot = popc_u(cached & ((1u << pos) - 1u));                                          \
+        TREX_UNROLL for (int s = 0; s < 2; s++) gj[s] = ld(Lg, lane + (slot * 2 + s) * 32);            \
+      } else {                                                                                         \
+        TREX_UNROLL for (int s = 0; s < 2; s++)                                                        \
+          gj[s] = sel(kk[s] == j, 0.0f, njdi[s] * ld_if(work0, woff + kk[s] * 32 + (W_COL + 6 * 32 + j), kv[s], 0.0f)); \
+      }                                                                                                \
+      if (pos & 1) TREX_S2_LIMIT_SLOT(1) else TREX_S2_LIMIT_SLOT(0)                                    \
+    }                                                                                                  \
+  }
+#define MB_(b, fwd) s2_motor_block<b, fwd>(w, lam_m, g, cu, gl, bp_own, Sc, max_imp);
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
-    vf resid = 0.0f;
-    const vf lam_lo0 = lam_lo, lam_hi0 = lam_hi;
-#define TREX_H_MOTOR_ROW(K)                                                                            \
-    {                                                                                                  \
-      constexpr int j = trex_topo::noncontact_order(K) - NJ;                                           \
-      const vf nl = vmin(vmax(w, -max_imp), max_imp);   /* meaningful on lane j only */                \
-      const vf t = vfma(-g[j], lamr[j], w);                                                            \
-      const vf nlu = vbroadcast(lane_value(nl, j));     /* new impulse of motor j, on every lane */    \
-      const vf dj = nlu - lamr[j];                                                                     \
-      lamr[j] = nlu;                                                                                   \
-      w = vfma(g[j], nlu, t);                                                                          \
-      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bt, bt_own + (k * 33 + j)), dj, cu[k]);  \
+    // every 4th sweep (TREX_REBUILD_MASK) rebuild w and u exactly from the impulses (also the warm-started initial state):
+    // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j - jdi_k sum_r B[r][k] lambda_r
+    // u_r = sum_j B[r][j] Lambda_j + sum_r' A[r'][r] lambda_r'
+    if ((it & TREX_REBUILD_MASK) == 0) {
+      warp_sync();
+      TREX_UNROLL for (int s = 0; s < 2; s++) st_if(Lam, grp * LS + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+      TREX_UNROLL for (int k = 0; k < 3; k++) st(Lam, grp * LS + gl * 4 + (32 + k), cl[k]);
+      warp_sync();
+      vf acc[2], ua[3], bs[2];
+      TREX_UNROLL for (int s = 0; s < 2; s++) { acc[s] = rhs_m[s] - sigma[s] * lam_l[s]; bs[s] = 0.0f; }
+      TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = 0.0f;
+      TREX_UNROLL for (int j = 0; j < NJ; j++) {
+        const vf Lj = ld(Lam, grp * LS + j);
+        TREX_UNROLL for (int s = 0; s < 2; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
+        TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(ld(Sc, bp_own + (k * BS + motor_position(j))), Lj, ua[k]);
+      }
+      TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        TREX_UNROLL for (int k = 0; k < 3; k++) {
+          const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
+          vf b2[2];
+          ld2(Sc, bp_mine + (3 * c + k) * BS, b2);
+          TREX_UNROLL for (int s = 0; s < 2; s++) bs[s] = vfma(b2[s], Lr, bs[s]);
+          TREX_UNROLL for (int k2 = 0; k2 < 3; k2++) ua[k2] = vfma(ld(Sc, a_own + ((3 * c + k) * NR + k2)), Lr, ua[k2]);
+        }
+      }
+      TREX_UNROLL for (int s = 0; s < 2; s++) acc[s] = vfma(njdi[s], bs[s], acc[s]);
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = ua[k];
+      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = sel(alive, acc[s], w[s]);
     }
-#define TREX_H_REBUILD_DVM()                                                                           \
-    {                                                                                                  \
-      vf a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;                                                   \
-      TREX_UNROLL for (int j = 0; j + 3 < NJ; j += 4) {                                                \
-        a0 = vfma(g[j], lamr[j], a0);                                                                  \
-        a1 = vfma(g[j + 1], lamr[j + 1], a1);                                                          \
-        a2 = vfma(g[j + 2], lamr[j + 2], a2);                                                          \
-        a3 = vfma(g[j + 3], lamr[j + 3], a3);                                                          \
-      }                                                                                                \
-      TREX_UNROLL for (int j = NJ - (NJ % 4); j < NJ; j++) a0 = vfma(g[j], lamr[j], a0);               \
-      const vf Ssum = (a0 + a1) + (a2 + a3);                                                           \
-      warp_sync();                                                                                     \
-      TREX_UNROLL for (int j = 0; j < NJ; j++) st(H.tmp, vi(j), lamr[j]);                              \
-      warp_sync();                                                                                     \
-      const vf lam_new = sel(is_joint, ld(H.tmp, seli(is_joint, lane, 0)), 0.0f);                      \
-      const vf dm = (lam_new - lam_m) * dself;                                                         \
-      lam_m = lam_new;                                                                                 \
-      resid = sel(is_joint, dm * dm, 0.0f);                                                            \
-      dvm = sel(is_joint, dself * (lam_m - Ssum), Ssum);                                               \
-      dv = dvm + dvo;                                                                                  \
+    vf lam_m0[2], lam_l0[2];
+    vf cres = 0.0f;
+    TREX_UNROLL for (int s = 0; s < 2; s++) {
+      lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s];
+      w[s] = sel(alive, w[s], lam_m[s]);  // a finished environment is frozen: clamp(w) == its impulse, every row yields 0
     }
-#define TREX_H_LIMIT_BLOCK(FORWARD)                                                                    \
-    {                                                                                                  \
-      uint32_t m = lim_perm;                                                                           \
-      while (m) {                                                                                      \
-        const int pos = (FORWARD) ? ctz_u(m) : 31 - clz_u(m);                                          \
-        m &= ~(1u << pos);                                                                             \
-        const int j = P.order[NJ + pos];                                                               \
-        const vf cj = ld(work, lane + (W_COL + (6 + j) * 32));  /* limit rows are rare: from the record */ \
-        TREX_UNROLL for (int pass = 0; pass < 2; pass++) {                                             \
-          const bool do_lo = (pass == 0) == (FORWARD);                                                 \
-          if (do_lo && ((mask_lo >> j) & 1u)) {                                                        \
-            const vf sum = lam_lo + (rhs_lo - dv * jdi);                                               \
-            const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
-            const vf dl = vbroadcast(lane_value(nl - lam_lo, j));                                      \
-            lam_lo = sel(lane == j, nl, lam_lo);                                                       \
-            const vf t = cj * dl;                                                                      \
-            dv += t; dvo += t;                                                                         \
-            TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bt, bt_own + (k * 33 + j)), dl, cu[k]); \
-          }                                                                                            \
-          if (!do_lo && ((mask_hi >> j) & 1u)) {                                                       \
-            const vf sum = lam_hi + (rhs_hi + dv * jdi);                                               \
-            const vf nl = vmin(vmax(sum, 0.0f), lim_hi);                                               \
-            const vf dl = vbroadcast(lane_value(nl - lam_hi, j));                                      \
-            lam_hi = sel(lane == j, nl, lam_hi);                                                       \
-            const vf t = -(cj * dl);                                                                   \
-            dv += t; dvo += t;                                                                         \
-            TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bt, bt_own + (k * 33 + j)), -dl, cu[k]); \
-          }                                                                                            \
-        }                                                                                              \
-      }                                                                                                \
-    }
-#define M_(k) TREX_H_MOTOR_ROW(k)
     if (it & 1) {
-      w = lam_m + (rhs_m + njdi * dv);
-      M_(0) M_(1) M_(2) M_(3) M_(4) M_(5) M_(6) M_(7) M_(8) M_(9) M_(10) M_(11) M_(12) M_(13) M_(14) M_(15) M_(16)
-      M_(17) M_(18) M_(19) M_(20) M_(21) M_(22) M_(23) M_(24)
-      TREX_H_REBUILD_DVM()
-      TREX_H_LIMIT_BLOCK(true)
+      MB_(0, true) MB_(1, true) MB_(2, true) MB_(3, true) MB_(4, true) MB_(5, true) MB_(6, true) MB_(7, true) MB_(8, true) MB_(9, true)
+      MB_(10, true) MB_(11, true) MB_(12, true)
+      TREX_S2_LIMITS(true)
     } else {
-      TREX_H_LIMIT_BLOCK(false)
-      w = lam_m + (rhs_m + njdi * dv);
-      M_(24) M_(23) M_(22) M_(21) M_(20) M_(19) M_(18) M_(17) M_(16) M_(15) M_(14) M_(13) M_(12) M_(11) M_(10) M_(9) M_(8)
-      M_(7) M_(6) M_(5) M_(4) M_(3) M_(2) M_(1) M_(0)
-      TREX_H_REBUILD_DVM()
+      TREX_S2_LIMITS(false)
+      MB_(12, false) MB_(11, false) MB_(10, false) MB_(9, false) MB_(8, false) MB_(7, false) MB_(6, false) MB_(5, false) MB_(4, false)
+      MB_(3, false) MB_(2, false) MB_(1, false) MB_(0, false)
     }
-#undef M_
-#undef TREX_H_MOTOR_ROW
-#undef TREX_H_REBUILD_DVM
-#undef TREX_H_LIMIT_BLOCK
-    {
-      const vf dlo = (lam_lo - lam_lo0) * dself, dhi = (lam_hi - lam_hi0) * dself;
-      resid = sel(is_joint, vmax(resid, vmax(dlo * dlo, dhi * dhi)), 0.0f);
-    }
-    // normal rows: every lane evaluates its own contact from its tracked u, the owner of contact c publishes
-    TREX_ROLLED for (int c = 0; c < n_act; c++) {
-      const vf sum = c_lam[0] + (c_rhs[0] - cu[0] * c_jdi[0]);
+    // normal rows: every lane evaluates its own contact, the owner of contact c publishes
+    TREX_ROLLED for (int c = 0; c < kmax; c++) {
+      const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
       const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
-      const vf dl = nl - c_lam[0];
-      const vb ownr = lane == c;
-      const vf dlu = vbroadcast(lane_value(dl, c));
-      c_lam[0] = sel(ownr, nl, c_lam[0]);
-      const vf dvel = dl * c_dd[0];
-      resid = sel(ownr, vmax(resid, dvel * dvel), resid);
-      vf a4[4];
-      ld4(A4, own * 4 + (3 * c) * (4 * TREX_KW), a4);
-      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], dlu, cu[k]);
-      const vf t = ld(Bt, lane + (3 * c) * 33) * dlu;
-      dv += t; dvo += t;
+      const vb own = alive && (gl == c);
+      const vf dl = sel(own, nl - cl[0], 0.0f);
+      const vf d = shfl_group16(dl, c);
+      cl[0] = sel(own, nl, cl[0]);
+      const vf dvel = dl * cdd[0];
+      cres = vmax(cres, dvel * dvel);
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Sc, a_own + ((3 * c) * NR + k)), d, cu[k]);
+      vf b2[2];
+      ld2(Sc, bp_mine + (3 * c) * BS, b2);
+      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(b2[s], njdi[s] * d, w[s]);
     }
     // friction pairs, implicit cone; both rows read the velocities before either writes
-    TREX_ROLLED for (int c = 0; c < n_act; c++) {
-      const vf lim = P.mu * c_lam[0];
-      const vf sumB = c_lam[2] + (c_rhs[2] - cu[2] * c_jdi[2]);
-      const vf sumA = c_lam[1] + (c_rhs[1] - cu[1] * c_jdi[1]);
+    TREX_ROLLED for (int c = 0; c < kmax; c++) {
+      const vf lim = P.mu * cl[0];
+      const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
+      const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
       const vf n2 = sumA * sumA + sumB * sumB;
       const vb nz = n2 > 0.0f;
       const vf rn = vrsqrt(sel(nz, n2, 1.0f));
@@ -2007,32 +2072,115 @@ TREX_FN void solve_heavy(const Uniform& P, const int* mdli, HeavyShared& H, cons
       const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
       const vf nA = vmin(vmax(sumA, -clipA), clipA);
       const vf nB = vmin(vmax(sumB, -clipB), clipB);
-      const vf dA = nA - c_lam[1], dB = nB - c_lam[2];
-      const vb ownr = lane == c;
-      const vf dAu = vbroadcast(lane_value(dA, c)), dBu = vbroadcast(lane_value(dB, c));
-      c_lam[1] = sel(ownr, nA, c_lam[1]);
-      c_lam[2] = sel(ownr, nB, c_lam[2]);
-      const vf dvel = dA * c_dd[1] + dB * c_dd[2];
-      resid = sel(ownr, vmax(resid, dvel * dvel), resid);
-      vf aA[4], aB[4];
-      ld4(A4, own * 4 + (3 * c + 1) * (4 * TREX_KW), aA);
-      ld4(A4, own * 4 + (3 * c + 2) * (4 * TREX_KW), aB);
-      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
-      const vf t = ld(Bt, lane + (3 * c + 1) * 33) * dAu + ld(Bt, lane + (3 * c + 2) * 33) * dBu;
-      dv += t; dvo += t;
+      const vb own = alive && (gl == c);
+      const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
+      const vf dAu = shfl_group16(dA, c), dBu = shfl_group16(dB, c);
+      cl[1] = sel(own, nA, cl[1]);
+      cl[2] = sel(own, nB, cl[2]);
+      const vf dvel = dA * cdd[1] + dB * cdd[2];
+      cres = vmax(cres, dvel * dvel);
+      TREX_UNROLL for (int k = 0; k < 3; k++)
+        cu[k] = vfma(ld(Sc, a_own + ((3 * c + 1) * NR + k)), dAu, vfma(ld(Sc, a_own + ((3 * c + 2) * NR + k)), dBu, cu[k]));
+      vf bA[2], bB[2];
+      ld2(Sc, bp_mine + (3 * c + 1) * BS, bA);
+      ld2(Sc, bp_mine + (3 * c + 2) * BS, bB);
+      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
     }
-    it_done = it + 1;
-    const float rmax = lane_value(warp_max(resid), 0);
-    if (rmax <= P.resid_thresh || it >= P.iters - 1) break;
+    // residual per environment: max over its rows of (delta impulse / jacDiagABInv)^2
+    vf r = cres;
+    TREX_UNROLL for (int s = 0; s < 2; s++) {
+      const vf dm = (lam_m[s] - lam_m0[s]) * dself[s];
+      r = vmax(r, dm * dm);
+    }
+    if (uperm != 0u) {
+      TREX_UNROLL for (int s = 0; s < 2; s++) {
+        const vf dlm = (lam_l[s] - lam_l0[s]) * dself[s];
+        r = vmax(r, dlm * dlm);
+      }
+    }
+    const uint32_t over = vballot(alive && !(r <= P.resid_thresh));
+    itd = itd + seli(alive, vi(1), vi(0));
+    const vi ob = seli(grp == 0, vi((int)(over & 0xffffu)), vi((int)(over >> 16)));
+    alive = alive && (ob != 0) && (it < P.iters - 1);
+    if (over == 0u || it >= P.iters - 1) break;
   }
-  // ---- cached normal impulses, velocity update, integration -----------------------------------------------------
-  st_if(rec, ccand + ST_LAM, c_lam[0], cown);
-  EnvRegs R;
-  load_env_regs(rec, lane, R);
-  finish_substep(P, lane, R, sel(lane < 31, dv, 0.0f), lam_m);
-  store_env_regs(rec, lane, R);
+#undef MB_
+#undef TREX_S2_LIMIT_SLOT
+#undef TREX_S2_LIMITS
+
+  // ---- velocity change of every coordinate from the final impulses ------------------------------------
   warp_sync();
-  st_if(rec, vi(155), ld(rec, vi(155)) + (float)it_done, lane == 0);  // ST_ACC_ITERS (declared below)
+  TREX_UNROLL for (int s = 0; s < 2; s++) st_if(Lam, grp * LS + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
+  TREX_UNROLL for (int k = 0; k < 3; k++) st(Lam, grp * LS + gl * 4 + (32 + k), cl[k]);
+  warp_sync();
+  vf Ssum[2], bsum[2];
+  TREX_UNROLL for (int s = 0; s < 2; s++) { Ssum[s] = 0.0f; bsum[s] = 0.0f; }
+  TREX_UNROLL for (int j = 0; j < NJ; j++) {
+    const vf Lj = ld(Lam, grp * LS + j);
+    TREX_UNROLL for (int s = 0; s < 2; s++) Ssum[s] = vfma(g[s][j], Lj, Ssum[s]);
+  }
+  vf dvb[6];
+  TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = 0.0f;
+  TREX_UNROLL for (int s = 0; s < 2; s++) {
+    const vf Lk = lam_m[s] + sigma[s] * lam_l[s];
+    TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = vfma(ld_if(work0, woff + kk[s] + (W_COL + b * 32), kv[s], 0.0f), Lk, dvb[b]);
+  }
+  TREX_ROLLED for (int c = 0; c < kmax; c++)
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
+      vf b2[2];
+      ld2(Sc, bp_mine + (3 * c + k) * BS, b2);
+      TREX_UNROLL for (int s = 0; s < 2; s++) bsum[s] = vfma(b2[s], Lr, bsum[s]);
+    }
+  TREX_UNROLL for (int k = 0; k < 3; k++)
+    TREX_UNROLL for (int b = 0; b < 6; b++)
+      dvb[b] = vfma(ld_if(workh0, hoff + gl * 96 + (H_BT + k * 32 + 25 + b), cown, 0.0f), cl[k], dvb[b]);
+  st_if(rec0, roff + ccand + ST_LAM, cl[0], cown);  // cached normal impulse of the candidate (next substep's warm start)
+  TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = group16_sum(dvb[b]);
+
+  // ---- velocities += dv (clamped), applied motor torque, positions with the NEW velocities ----------------
+  TREX_UNROLL for (int s = 0; s < 2; s++) {
+    const vf Lk = lam_m[s] + sigma[s] * lam_l[s];
+    const vf dvk = dself[s] * (Lk - Ssum[s]) + bsum[s];
+    const vf qd0 = ld_if(rec0, roff + kk[s] + ST_QD, kv[s], 0.0f);
+    const vf q0 = ld_if(rec0, roff + kk[s] + ST_Q, kv[s], 0.0f);
+    const vf qd1 = clampv(qd0 + dvk, -P.maxvel, P.maxvel);
+    st_if(rec0, roff + kk[s] + ST_QD, qd1, kv[s]);
+    st_if(rec0, roff + kk[s] + ST_Q, q0 + dt * qd1, kv[s]);
+    st_if(rec0, roff + kk[s] + ST_TAU, vdiv(lam_m[s], dt), kv[s]);
+  }
+  {
+    vf om[3], vl[3], pos[3], qt[4];
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      om[k] = clampv(ld(rec0, roff + (ST_OM + k)) + dvb[k], -P.maxvel, P.maxvel);
+      vl[k] = clampv(ld(rec0, roff + (ST_VL + k)) + dvb[3 + k], -P.maxvel, P.maxvel);
+      pos[k] = ld(rec0, roff + (ST_POS + k)) + dt * vl[k];
+    }
+    TREX_UNROLL for (int k = 0; k < 4; k++) qt[k] = ld(rec0, roff + (ST_QUAT + k));
+    // btMultiBody::stepPositionsMultiDof: exponential map of the world angular velocity, q <- dq * q
+    vf fa = vsqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    fa = sel(fa * dt > 0.78539816339744831f, vbroadcast(0.78539816339744831f / dt), fa);
+    const vb small = fa < 0.001f;
+    const vf sc = sel(small, 0.5f * dt - (dt * dt * dt) * 0.020833333333f * fa * fa, vdiv(vsin(0.5f * fa * dt), sel(small, 1.0f, fa)));
+    const vf ax = om[0] * sc, ay = om[1] * sc, az = om[2] * sc, aw = vcos(fa * dt * 0.5f);
+    const vf nx = aw * qt[0] + ax * qt[3] + ay * qt[2] - az * qt[1];
+    const vf ny = aw * qt[1] - ax * qt[2] + ay * qt[3] + az * qt[0];
+    const vf nz = aw * qt[2] + ax * qt[1] - ay * qt[0] + az * qt[3];
+    const vf nw = aw * qt[3] - ax * qt[0] - ay * qt[1] - az * qt[2];
+    const vf inv = vdiv(1.0f, vsqrt(nx * nx + ny * ny + nz * nz + nw * nw));
+    warp_sync();
+    // one lane per field of the base block [pos3 quat4 om3 vl3]
+    vf val = 0.0f;
+    TREX_UNROLL for (int k = 0; k < 3; k++) {
+      val = sel(gl == ST_POS + k, pos[k], val);
+      val = sel(gl == ST_OM + k, om[k], val);
+      val = sel(gl == ST_VL + k, vl[k], val);
+    }
+    val = sel(gl == ST_QUAT, nx * inv, sel(gl == ST_QUAT + 1, ny * inv, sel(gl == ST_QUAT + 2, nz * inv, sel(gl == ST_QUAT + 3, nw * inv, val))));
+    st_if(rec0, roff + gl, val, gact && (gl < 13));
+  }
+  warp_sync();
+  return itd;
 }
 
 // reward (trex_env.py:186-196), termination (trex_env.py:183-184 + optional horizon / NaN guard) of one environment
@@ -2133,6 +2281,17 @@ TREX_FN void solve_phase(const Uniform& P, float* scratch, const float* work0, f
   const vi grp = lane >> 3;
   const vb wr = ((lane & 7) == 0) && ((((vi(pending)) >> grp) & 1) != 0);
   const vi genv = seli(grp == 0, vi(envs[0]), seli(grp == 1, vi(envs[1]), seli(grp == 2, vi(envs[2]), vi(envs[3]))));
+  const vi idx = seli(wr, genv * TREX_STATE_STRIDE + ST_ACC_ITERS, 0);
+  st_if(rec0, idx, ld(rec0, idx) + vi2f(itd), wr);
+}
+
+// heavy_phase: the deferred solves of up to two environments with more than TREX_KC contacts (any two)
+TREX_FN void heavy_phase(const Uniform& P, float* scratch, const float* work0, const float* workh0, float* rec0, const int envs[2], int pending) {
+  const vi lane = lane_id();
+  const vi itd = solve2(P, scratch, work0, workh0, rec0, envs, pending, P.max_impulse);
+  const vi grp = lane >> 4;
+  const vb wr = ((lane & 15) == 0) && ((((vi(pending)) >> grp) & 1) != 0);
+  const vi genv = seli(grp == 0, vi(envs[0]), vi(envs[1]));
   const vi idx = seli(wr, genv * TREX_STATE_STRIDE + ST_ACC_ITERS, 0);
   st_if(rec0, idx, ld(rec0, idx) + vi2f(itd), wr);
 }
