@@ -44,7 +44,12 @@ extern "C" {
  *   [13:38] joint position, pybullet link order  [38:63] joint velocity
  *   [63:88] applied motor torque of the last substep
  *   [88:152] cached normal impulse per contact candidate (solver warm start)
- *   [152] steps in the current episode  [153] episodes started  [154] NaN-guard resets  */
+ *   [152] steps in the current episode  [153] episodes started  [154] NaN-guard resets
+ *   [155:158] per-step accumulators (PGS iterations, contacts, contact overflow)
+ *   [158] active-set signature of the last env step: a 24-bit hash (stored as an exact float) over, per physics substep, the
+ *         contact candidates with rows, the limit rows / normal rows that ended with a positive impulse, the motors and
+ *         friction pairs that ended on their bounds and the PGS iterations executed -- equal signatures of kernel and
+ *         oracle mean both solved the same complementarity problem (tests/test_active_set_parity.py)  */
 
 #define TREX_OK 0
 #define TREX_ERR_INVALID (-1)

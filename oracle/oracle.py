@@ -54,6 +54,10 @@ def lib():
         L.trex_oracle_set_reward_weights.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 3
         L.trex_oracle_enable_contacts.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.trex_oracle_set_fixed_base.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.trex_oracle_signature.restype = ctypes.c_uint
+        L.trex_oracle_signature.argtypes = [ctypes.c_void_p]
+        L.trex_oracle_reset_signature.argtypes = [ctypes.c_void_p]
+        L.trex_oracle_signature_words.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint)]
         L.trex_oracle_reset.argtypes = [ctypes.c_void_p, dp]
         L.trex_oracle_step.argtypes = [ctypes.c_void_p, dp, dp, dp]
         L.trex_oracle_run.argtypes = [ctypes.c_void_p, dp, ctypes.c_int, dp, dp]
@@ -96,6 +100,16 @@ class Oracle:
 
     def set_fixed_base(self, on: bool) -> None:
         self._L.trex_oracle_set_fixed_base(self._h, int(bool(on)))
+
+    @property
+    def signature(self) -> int:
+        """Active-set signature of the last step (== record slot 158 of the kernels when both took the same branches)."""
+        return int(self._L.trex_oracle_signature(self._h))
+
+    def signature_words(self):
+        w = (ctypes.c_uint * 6)()
+        self._L.trex_oracle_signature_words(self._h, w)
+        return [int(x) for x in w]
 
     def get_state(self) -> np.ndarray:
         s = np.zeros(self.state_dim)

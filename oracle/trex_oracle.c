@@ -182,6 +182,7 @@ typedef struct {
   int fric_index; /* friction rows: index of the normal row */
   int cand;       /* contact rows: candidate index */
   int motor_dof;  /* motor rows: dof, else -1 */
+  int limit_dof;  /* joint-limit rows: dof, else -1 */
 } row_t;
 
 struct trex_oracle {
@@ -215,6 +216,8 @@ struct trex_oracle {
   long total_iters, total_substeps;
   double rterm[3];
   double resid_hist[512];
+  uint32_t sig;          /* running active-set signature (reset at the start of trex_oracle_step / on request) */
+  uint32_t sig_words[6]; /* the last substep's words: K lo, K hi, L, M, N | F << 16, iterations */
   row_t* rows;
 };
 
@@ -309,6 +312,9 @@ void trex_oracle_set_substeps(trex_oracle* o, int n) { o->n_sub = n < 1 ? 1 : n;
 void trex_oracle_set_reward_weights(trex_oracle* o, double d, double e, double k) { o->w_dist = d; o->w_energy = e; o->w_drift = k; }
 void trex_oracle_enable_contacts(trex_oracle* o, int on) { o->contacts_on = on; }
 void trex_oracle_set_fixed_base(trex_oracle* o, int on) { o->fixed_base = on; }
+unsigned trex_oracle_signature(const trex_oracle* o) { return o->sig; }
+void trex_oracle_reset_signature(trex_oracle* o) { o->sig = 0; }
+void trex_oracle_signature_words(const trex_oracle* o, unsigned* out6) { for (int i = 0; i < 6; i++) out6[i] = o->sig_words[i]; }
 int trex_oracle_last_iterations(const trex_oracle* o) { return o->last_iters; }
 int trex_oracle_last_num_contacts(const trex_oracle* o) { return o->last_contacts; }
 int trex_oracle_last_num_limit_rows(const trex_oracle* o) { return o->last_limits; }
@@ -626,7 +632,7 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
         row_t* r = &rows[n_nc++];
         memset(r->J, 0, sizeof(double) * nu);
         r->J[6 + k] = side == 0 ? 1.0 : -1.0;
-        r->motor_dof = -1; r->cand = -1; r->fric_index = -1;
+        r->motor_dof = -1; r->cand = -1; r->fric_index = -1; r->limit_dof = k;
         double rel = finish_row(o, r, u);
         r->lo = 0; r->hi = o->P[P_LIMIT_MAX_IMPULSE];
         /* btMultiBodyJointLimitConstraint::createConstraintRows [RECALL]: with split impulse on (the default),
@@ -648,7 +654,7 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
       row_t* r = &rows[n_nc++];
       memset(r->J, 0, sizeof(double) * nu);
       r->J[6 + k] = 1.0;
-      r->motor_dof = k; r->cand = -1; r->fric_index = -1;
+      r->motor_dof = k; r->cand = -1; r->fric_index = -1; r->limit_dof = -1;
       double rel = finish_row(o, r, u);
       double qd = o->qd[k];
       double vt = o->P[P_KP] * (target[k] - o->q[k]) / dt + qd + o->P[P_KD] * (0.0 - qd);
@@ -657,6 +663,7 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
     }
   }
   /* contacts: candidate points against the floor plane, normal (0,0,1), btPlaneSpace1 tangents */
+  uint32_t sig_k[2] = {0, 0}; /* active-set signature: the candidates with rows */
   int n_normal = 0;
   row_t* nrm = rows + n_nc;
   const v3 nz = {0, 0, 1}, t1 = {0, -1, 0}, t2 = {1, 0, 0};
@@ -687,10 +694,11 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
       v3 P;
       candidate_world(o, c, P);
       double dist = P[2] - o->P[P_FLOOR];
+      if (keep[c]) { if (c < 32) sig_k[0] |= 1u << c; else sig_k[1] |= 1u << (c - 32); }
       if (!keep[c]) { o->lam_cache[c] = 0; continue; }
       row_t* r = &nrm[n_normal++];
       point_jacobian(o, o->cand_link[c], P, nz, r->J);
-      r->cand = c; r->motor_dof = -1; r->fric_index = -1;
+      r->cand = c; r->motor_dof = -1; r->fric_index = -1; r->limit_dof = -1;
       double rel = finish_row(o, r, u);
       double pen = dist + o->P[P_LINEAR_SLOP];
       double poserr = 0, velerr = -rel; /* restitution 0 */
@@ -708,7 +716,7 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
     for (int d = 0; d < 2; d++) {
       row_t* r = &fr[2 * c + d];
       point_jacobian(o, o->cand_link[nrm[c].cand], P, d == 0 ? t1 : t2, r->J);
-      r->cand = nrm[c].cand; r->motor_dof = -1; r->fric_index = c;
+      r->cand = nrm[c].cand; r->motor_dof = -1; r->fric_index = c; r->limit_dof = -1;
       double rel = finish_row(o, r, u);
       r->rhs = -rel * r->jdi;
       r->mu = o->P[P_FRICTION];
@@ -749,6 +757,29 @@ void trex_oracle_substep(trex_oracle* o, const double* target, double max_impuls
     if (it < 512) o->resid_hist[it] = resid;
     it_done = it + 1;
     if (resid <= o->P[P_RESIDUAL] || it >= iters - 1) break;
+  }
+
+  { /* active-set signature of the step, folded per substep exactly like the kernels do (trex_core.h: StepStats):
+     * K (candidates with rows), then L (limit rows that ended with a positive impulse), M (motors that ended on their bound),
+     * N | F << 16 (contact slots with a positive normal impulse / with the friction pair on the cone), iterations */
+    uint32_t L = 0, M = 0, N = 0, F = 0, h = o->sig;
+    for (int j = 0; j < n_nc; j++) {
+      if (rows[j].limit_dof >= 0 && rows[j].lam > 0) L |= 1u << rows[j].limit_dof;
+      if (rows[j].motor_dof >= 0 && fabs(rows[j].lam) >= max_impulse) M |= 1u << rows[j].motor_dof;
+    }
+    for (int c = 0; c < n_normal; c++) {
+      if (!(nrm[c].lam > 0)) continue;
+      N |= 1u << c;
+      double lim = nrm[c].mu * nrm[c].lam, a = fr[2 * c].lam, b = fr[2 * c + 1].lam;
+      if (a * a + b * b >= 0.9999 * (lim * lim)) F |= 1u << c;
+    }
+#define SIG_MIX(h, w) (((h) ^ (uint32_t)(w)) * 16777619u)
+    h = SIG_MIX(SIG_MIX(h, sig_k[0]), sig_k[1]) & 0xffffffu;
+    h = SIG_MIX(SIG_MIX(SIG_MIX(SIG_MIX(h, L), M), N | (F << 16)), (uint32_t)it_done) & 0xffffffu;
+#undef SIG_MIX
+    o->sig = h;
+    o->sig_words[0] = sig_k[0]; o->sig_words[1] = sig_k[1]; o->sig_words[2] = L; o->sig_words[3] = M;
+    o->sig_words[4] = N | (F << 16); o->sig_words[5] = (uint32_t)it_done;
   }
 
   /* 7: velocities += dv (clamped); write back impulses */
@@ -838,6 +869,7 @@ void trex_oracle_step(trex_oracle* o, const double* action, double* obs, double*
     int d = o->obs_dof[k], link = o->dof_link[d];
     target[d] = clampd(action[k], o->lower[link], o->upper[link]);
   }
+  o->sig = 0;
   for (int s = 0; s < o->n_sub; s++) /* trex_env.py:148-150 ; max impulse = force*dt */
     trex_oracle_substep(o, target, o->P[P_MAX_TORQUE] * dt);
   observe(o, obs);

@@ -67,6 +67,13 @@ int trex_oracle_last_num_contacts(const trex_oracle* o); /* contact points with 
 int trex_oracle_last_num_limit_rows(const trex_oracle* o);
 long trex_oracle_total_iterations(const trex_oracle* o);
 long trex_oracle_total_substeps(const trex_oracle* o);
+/* Active-set signature of the last trex_oracle_step (24-bit hash over, per substep: the contact candidates with rows, the
+ * limit / normal rows that ended with a positive impulse, the motors / friction pairs that ended on their bound, the PGS
+ * iterations executed) -- defined exactly as record slot 158 of the kernels (trex_gym_b200/csrc/trex_core.h: StepStats), so
+ * equal signatures mean kernel and oracle solved the same complementarity problem.  words: the last substep's six words. */
+unsigned trex_oracle_signature(const trex_oracle* o);
+void trex_oracle_reset_signature(trex_oracle* o);
+void trex_oracle_signature_words(const trex_oracle* o, unsigned* out6);
 /* total linear momentum (3), angular momentum about world origin (3), kinetic energy (1), total mass (1), COM (3) */
 void trex_oracle_momentum(trex_oracle* o, double* out11);
 /* joint-space inverse mass matrix column via the unit-impulse pass (for tests): out[31] */

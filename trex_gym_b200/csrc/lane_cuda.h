@@ -77,7 +77,9 @@ TREX_FN float fadd_rn(float a, float b) { return __fadd_rn(a, b); }
 TREX_FN vf vmul_rn(vf a, vf b) { return __fmul_rn(a, b); }
 TREX_FN int ctz_u(uint32_t m) { return __ffs((int)m) - 1; }
 TREX_FN int clz_u(uint32_t m) { return __clz((int)m); }
-TREX_FN vf vrsqrt(vf x) { return rsqrtf(x); }
+// rsqrt.approx.ftz: one MUFU.RSQ (rsqrtf() adds a denormal pre/post-scaling pair around it; the solvers only take the
+// reciprocal root of a squared impulse norm already known to be > 0, where a denormal argument may flush)
+TREX_FN vf vrsqrt(vf x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 TREX_FN void stb(unsigned char* p, vi idx, vi v) { p[idx] = (unsigned char)v; }
 TREX_FN vi ldb(const unsigned char* p, vi idx) { return (int)p[idx]; }
 TREX_FN long long cycle_count() { return clock64(); }
@@ -109,6 +111,9 @@ TREX_FN vf shfl_group8(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 8)
 TREX_FN vf group8_sum(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
 TREX_FN vf group8_max(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(TREX_FULL, x, m)); return x; }
 
+// per-lane integer helpers of the active-set signature (trex_core.h: StepStats)
+TREX_FN vi shfl_xor_i(vi x, int m) { return __shfl_xor_sync(TREX_FULL, x, m); }
+TREX_FN vi sig_mix_v(vi h, vi w) { return (int)(((uint32_t)h ^ (uint32_t)w) * 16777619u); }
 // width-16 lane groups (two environments per warp in solve2)
 TREX_FN vf shfl_group16(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 16); }
 TREX_FN vf group16_sum(vf x) { TREX_UNROLL for (int m = 8; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }

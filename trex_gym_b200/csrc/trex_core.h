@@ -183,7 +183,18 @@ struct EnvRegs {
   float pos[3], quat[4], om[3], vl[3];  // floating base (uniform across lanes)
 };
 
+// Active-set signature of an env step (diagnostics for the parity tests: "did kernel and oracle solve the same
+// complementarity problem?").  A 24-bit FNV-style hash folded over the substeps, per substep over
+//   K  the contact candidates that got rows (two words: candidates 0..31, 32..63)        [front phase]
+//   L  joints whose limit row ended with a positive impulse, M  motors that ended on their impulse bound (bit = dof)
+//   NF bit c: contact slot c ended with a positive normal impulse; bit 16 + c: its friction pair ended on the cone
+//   it PGS iterations executed                                                              [solver]
+// kept as an exactly representable float in the environment record (ST_SIG).
+TREX_FN uint32_t sig_mix_u(uint32_t h, uint32_t w) { return (h ^ w) * 16777619u; }
+#define TREX_CONE_EDGE 0.9999f  // |lambda_t|^2 >= TREX_CONE_EDGE * (mu lambda_n)^2 counts as "on the cone"
+
 struct StepStats {
+  uint32_t sig;  // running active-set signature of the env step (see above)
   int iters;     // PGS iterations executed (summed over substeps)
   int contacts;  // active contact points (last substep)
   int overflow;  // contact points dropped because more than TREX_KMAX were active
@@ -967,6 +978,9 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
       n_act += popc_u(am[half]);
     }
     warp_sync();
+    stats.sig = sig_mix_u(sig_mix_u(stats.sig, am[0]), am[1]) & 0xffffffu;  // K: the candidates with rows
+  } else {
+    stats.sig = sig_mix_u(sig_mix_u(stats.sig, 0u), 0u) & 0xffffffu;
   }
   // Deferred solve: solve4() finishes this substep, four environments per warp.  Always when there are no contact
   // rows (the rows are then the 25 motors and the violated joint limits, all with unit Jacobians); with up to
@@ -1293,6 +1307,15 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
   TREX_TICK(6)
   stats.iters += it_done;
   stats.contacts = n_act;
+  {  // active-set signature of this substep's solve (see StepStats)
+    const uint32_t Lm = vballot(is_joint && ((lam_lo > 0.0f) || (lam_hi > 0.0f)));
+    const uint32_t Mm = vballot(is_joint && (vabs(lam_m) >= max_imp));
+    const vf lim = P.mu * c_lam[0];
+    const vb hasc = lane < n_act;
+    const uint32_t Nm = vballot(hasc && (c_lam[0] > 0.0f));
+    const uint32_t Fm = vballot(hasc && (c_lam[0] > 0.0f) && ((c_lam[1] * c_lam[1] + c_lam[2] * c_lam[2]) >= TREX_CONE_EDGE * (lim * lim)));
+    stats.sig = sig_mix_u(sig_mix_u(sig_mix_u(sig_mix_u(stats.sig, Lm), Mm), Nm | (Fm << 16)), (uint32_t)it_done) & 0xffffffu;
+  }
 
   // ---- 12-13. velocities += dv (clamped), motor torque, cached contact impulses, positions with the NEW velocities ----
   if (P.contacts_on) {
@@ -1309,7 +1332,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
 
 // environment record offsets (floats), see include/trex_b200.h
 enum { ST_POS = 0, ST_QUAT = 3, ST_OM = 7, ST_VL = 10, ST_Q = 13, ST_QD = 38, ST_TAU = 63, ST_LAM = 88,
-       ST_STEP = 152, ST_EPISODE = 153, ST_NANRESETS = 154 };
+       ST_STEP = 152, ST_EPISODE = 153, ST_NANRESETS = 154, ST_SIG = 158 };
 
 TREX_FN void load_env_regs(const float* rec, vi lane, EnvRegs& R) {
   const vb is_joint = lane < NJ;
@@ -1665,50 +1688,68 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       MB_(6, false) MB_(5, false) MB_(4, false) MB_(3, false) MB_(2, false) MB_(1, false) MB_(0, false)
     }
     if (KC > 0) {
-      // normal rows: every lane evaluates its own contact, the owner of contact c publishes
-      TREX_ROLLED for (int c = 0; c < kmax; c++) {
-        const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
-        const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
-        const vb own = alive && (gl == c);
-        const vf dl = sel(own, nl - cl[0], 0.0f);
-        const vf d = shfl_group8(dl, c);
-        cl[0] = sel(own, nl, cl[0]);
-        const vf dvel = dl * cdd[0];
-        cres = vmax(cres, dvel * dvel);
-        vf a4[4];
-        ld4(Bs, gb + glc * 4 + ((3 * c) * (4 * KC) + BT), a4);
-        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
-        vf b4[4];
-        ld4(Bs, gb + gl * 4 + (3 * c) * 36, b4);
-        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(b4[s], njdi[s] * d, w[s]);
+      // normal rows: every lane evaluates its own contact, the owner of contact c publishes.  The A4 / Bp rows a
+      // publication needs do not depend on the sweep's data: they are fetched one iteration ahead (software pipeline),
+      // so the shared-memory latency sits under the owner's clamp chain instead of behind the shuffle.
+      const vf cl0_0 = cl[0], cl1_0 = cl[1], cl2_0 = cl[2];
+      {
+        vf an[4], bn[4];
+        ld4(Bs, gb + glc * 4 + BT, an);
+        ld4(Bs, gb + gl * 4, bn);
+        TREX_ROLLED for (int c = 0; c < kmax; c++) {
+          vf a4[4], b4[4];
+          TREX_UNROLL for (int k = 0; k < 4; k++) { a4[k] = an[k]; b4[k] = bn[k]; }
+          const int cn = c + 1 < kmax ? c + 1 : c;
+          ld4(Bs, gb + glc * 4 + ((3 * cn) * (4 * KC) + BT), an);
+          ld4(Bs, gb + gl * 4 + (3 * cn) * 36, bn);
+          const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
+          const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
+          const vb own = alive && (gl == c);
+          const vf dl = sel(own, nl - cl[0], 0.0f);
+          const vf d = shfl_group8(dl, c);
+          cl[0] = sel(own, nl, cl[0]);
+          TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
+          TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(b4[s], njdi[s] * d, w[s]);
+        }
       }
       // friction pairs, implicit cone; both rows read the velocities before either writes
-      TREX_ROLLED for (int c = 0; c < kmax; c++) {
-        const vf lim = P.mu * cl[0];
-        const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
-        const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
-        const vf n2 = sumA * sumA + sumB * sumB;
-        const vb nz = n2 > 0.0f;
-        const vf rn = vrsqrt(sel(nz, n2, 1.0f));
-        const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
-        const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
-        const vf nA = vmin(vmax(sumA, -clipA), clipA);
-        const vf nB = vmin(vmax(sumB, -clipB), clipB);
-        const vb own = alive && (gl == c);
-        const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
-        const vf dAu = shfl_group8(dA, c), dBu = shfl_group8(dB, c);
-        cl[1] = sel(own, nA, cl[1]);
-        cl[2] = sel(own, nB, cl[2]);
-        const vf dvel = dA * cdd[1] + dB * cdd[2];
-        cres = vmax(cres, dvel * dvel);
-        vf aA[4], aB[4];
-        ld4(Bs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + BT), aA);
-        ld4(Bs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + BT), aB);
-        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
-        vf bA[4], bB[4];
-        ld4(Bs, gb + gl * 4 + (3 * c + 1) * 36, bA);
-        ld4(Bs, gb + gl * 4 + (3 * c + 2) * 36, bB);
-        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
+      {
+        vf aAn[4], aBn[4], bAn[4], bBn[4];
+        ld4(Bs, gb + glc * 4 + (4 * KC + BT), aAn);
+        ld4(Bs, gb + glc * 4 + (2 * 4 * KC + BT), aBn);
+        ld4(Bs, gb + gl * 4 + 36, bAn);
+        ld4(Bs, gb + gl * 4 + 2 * 36, bBn);
+        TREX_ROLLED for (int c = 0; c < kmax; c++) {
+          vf aA[4], aB[4], bA[4], bB[4];
+          TREX_UNROLL for (int k = 0; k < 4; k++) { aA[k] = aAn[k]; aB[k] = aBn[k]; bA[k] = bAn[k]; bB[k] = bBn[k]; }
+          const int cn = c + 1 < kmax ? c + 1 : c;
+          ld4(Bs, gb + glc * 4 + ((3 * cn + 1) * (4 * KC) + BT), aAn);
+          ld4(Bs, gb + glc * 4 + ((3 * cn + 2) * (4 * KC) + BT), aBn);
+          ld4(Bs, gb + gl * 4 + (3 * cn + 1) * 36, bAn);
+          ld4(Bs, gb + gl * 4 + (3 * cn + 2) * 36, bBn);
+          const vf lim = P.mu * cl[0];
+          const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
+          const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
+          const vf n2 = sumA * sumA + sumB * sumB;
+          const vb nz = n2 > 0.0f;
+          const vf rn = vrsqrt(sel(nz, n2, 1.0f));
+          const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
+          const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
+          const vf nA = vmin(vmax(sumA, -clipA), clipA);
+          const vf nB = vmin(vmax(sumB, -clipB), clipB);
+          const vb own = alive && (gl == c);
+          const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
+          const vf dAu = shfl_group8(dA, c), dBu = shfl_group8(dB, c);
+          cl[1] = sel(own, nA, cl[1]);
+          cl[2] = sel(own, nB, cl[2]);
+          TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
+          TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
+        }
+      }
+      {  // residual of the contact rows: every row is visited once per sweep, so its impulse change is end - start
+        const vf dn = (cl[0] - cl0_0) * cdd[0];
+        const vf dt2 = (cl[1] - cl1_0) * cdd[1] + (cl[2] - cl2_0) * cdd[2];
+        cres = vmax(dn * dn, dt2 * dt2);
       }
     }
     // residual per environment: max over its rows of (delta impulse / jacDiagABInv)^2
@@ -1812,6 +1853,25 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       val = sel(f == ST_QUAT, nx * inv, sel(f == ST_QUAT + 1, ny * inv, sel(f == ST_QUAT + 2, nz * inv, sel(f == ST_QUAT + 3, nw * inv, val))));
       st_if(rec0, rb + f, val, gact && (f < 13));
     }
+  }
+  {  // active-set signature of this substep's solve (StepStats), per environment: OR over the group's lanes, lane 0 folds
+    vi Lm = 0, Mm = 0;
+    TREX_UNROLL for (int s = 0; s < 4; s++) {
+      Lm = Lm | seli(kv[s] && (lam_l[s] > 0.0f), vi(1) << kk[s], vi(0));
+      Mm = Mm | seli(kv[s] && (vabs(lam_m[s]) >= max_imp), vi(1) << kk[s], vi(0));
+    }
+    vi NF = 0;
+    if (KC > 0) {
+      const vf lim = P.mu * cl[0];
+      const vb pos = cown && (cl[0] > 0.0f);
+      NF = seli(pos, vi(1) << gl, vi(0)) |
+           seli(pos && ((cl[1] * cl[1] + cl[2] * cl[2]) >= TREX_CONE_EDGE * (lim * lim)), vi(65536) << gl, vi(0));
+    }
+    TREX_UNROLL for (int m = 4; m > 0; m >>= 1) { Lm = Lm | shfl_xor_i(Lm, m); Mm = Mm | shfl_xor_i(Mm, m); NF = NF | shfl_xor_i(NF, m); }
+    const vb wr = gact && (gl == 0);
+    const vi si = seli(wr, roff + ST_SIG, 0);
+    const vi h = sig_mix_v(sig_mix_v(sig_mix_v(sig_mix_v(vf2i(ld(rec0, si)), Lm), Mm), NF), itd) & 0xffffff;
+    st_if(rec0, si, vi2f(h), wr);
   }
   warp_sync();
   return itd;
@@ -1923,7 +1983,7 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
   const vi ccand = seli(cown, vf2i(ld_if(workh0, hoff + gl * 16 + (H_CS + 10), cown, 0.0f)), 0);
   {
     const vi nr = nc * 3;
-    TREX_ROLLED for (int r = 0; r < 3 * kmax; r++) {
+    _Pragma("unroll 4") for (int r = 0; r < 3 * kmax; r++) {  // (several rows in flight: the copy is latency bound)
       const vb rok = gact && (vi(r) < nr);
       // A row r: 48 floats = 12 float4, lanes 0..11 of the group; columns of absent contacts read as zero
       vf a4[4];
@@ -2045,46 +2105,71 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
       MB_(12, false) MB_(11, false) MB_(10, false) MB_(9, false) MB_(8, false) MB_(7, false) MB_(6, false) MB_(5, false) MB_(4, false)
       MB_(3, false) MB_(2, false) MB_(1, false) MB_(0, false)
     }
-    // normal rows: every lane evaluates its own contact, the owner of contact c publishes
-    TREX_ROLLED for (int c = 0; c < kmax; c++) {
-      const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
-      const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
-      const vb own = alive && (gl == c);
-      const vf dl = sel(own, nl - cl[0], 0.0f);
-      const vf d = shfl_group16(dl, c);
-      cl[0] = sel(own, nl, cl[0]);
-      const vf dvel = dl * cdd[0];
-      cres = vmax(cres, dvel * dvel);
-      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Sc, a_own + ((3 * c) * NR + k)), d, cu[k]);
-      vf b2[2];
-      ld2(Sc, bp_mine + (3 * c) * BS, b2);
-      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(b2[s], njdi[s] * d, w[s]);
+    // normal rows: every lane evaluates its own contact, the owner of contact c publishes.  The rows of A and Bp a
+    // publication needs do not depend on the sweep's data: they are fetched one iteration ahead (software pipeline), so
+    // the shared-memory latency sits under the owner's clamp chain instead of behind the shuffle.
+    const vf cl0_0 = cl[0], cl1_0 = cl[1], cl2_0 = cl[2];
+    {
+      vf an[3], bn[2];
+      TREX_UNROLL for (int k = 0; k < 3; k++) an[k] = ld(Sc, a_own + k);
+      ld2(Sc, bp_mine, bn);
+      TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        vf a3[3], b2[2];
+        TREX_UNROLL for (int k = 0; k < 3; k++) a3[k] = an[k];
+        b2[0] = bn[0]; b2[1] = bn[1];
+        const int cn = c + 1 < kmax ? c + 1 : c;
+        TREX_UNROLL for (int k = 0; k < 3; k++) an[k] = ld(Sc, a_own + ((3 * cn) * NR + k));
+        ld2(Sc, bp_mine + (3 * cn) * BS, bn);
+        const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
+        const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
+        const vb own = alive && (gl == c);
+        const vf dl = sel(own, nl - cl[0], 0.0f);
+        const vf d = shfl_group16(dl, c);
+        cl[0] = sel(own, nl, cl[0]);
+        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a3[k], d, cu[k]);
+        TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(b2[s], njdi[s] * d, w[s]);
+      }
     }
     // friction pairs, implicit cone; both rows read the velocities before either writes
-    TREX_ROLLED for (int c = 0; c < kmax; c++) {
-      const vf lim = P.mu * cl[0];
-      const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
-      const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
-      const vf n2 = sumA * sumA + sumB * sumB;
-      const vb nz = n2 > 0.0f;
-      const vf rn = vrsqrt(sel(nz, n2, 1.0f));
-      const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
-      const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
-      const vf nA = vmin(vmax(sumA, -clipA), clipA);
-      const vf nB = vmin(vmax(sumB, -clipB), clipB);
-      const vb own = alive && (gl == c);
-      const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
-      const vf dAu = shfl_group16(dA, c), dBu = shfl_group16(dB, c);
-      cl[1] = sel(own, nA, cl[1]);
-      cl[2] = sel(own, nB, cl[2]);
-      const vf dvel = dA * cdd[1] + dB * cdd[2];
-      cres = vmax(cres, dvel * dvel);
-      TREX_UNROLL for (int k = 0; k < 3; k++)
-        cu[k] = vfma(ld(Sc, a_own + ((3 * c + 1) * NR + k)), dAu, vfma(ld(Sc, a_own + ((3 * c + 2) * NR + k)), dBu, cu[k]));
-      vf bA[2], bB[2];
-      ld2(Sc, bp_mine + (3 * c + 1) * BS, bA);
-      ld2(Sc, bp_mine + (3 * c + 2) * BS, bB);
-      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
+    {
+      vf aAn[3], aBn[3], bAn[2], bBn[2];
+      TREX_UNROLL for (int k = 0; k < 3; k++) { aAn[k] = ld(Sc, a_own + (NR + k)); aBn[k] = ld(Sc, a_own + (2 * NR + k)); }
+      ld2(Sc, bp_mine + BS, bAn);
+      ld2(Sc, bp_mine + 2 * BS, bBn);
+      TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        vf aA[3], aB[3], bA[2], bB[2];
+        TREX_UNROLL for (int k = 0; k < 3; k++) { aA[k] = aAn[k]; aB[k] = aBn[k]; }
+        TREX_UNROLL for (int s = 0; s < 2; s++) { bA[s] = bAn[s]; bB[s] = bBn[s]; }
+        const int cn = c + 1 < kmax ? c + 1 : c;
+        TREX_UNROLL for (int k = 0; k < 3; k++) {
+          aAn[k] = ld(Sc, a_own + ((3 * cn + 1) * NR + k));
+          aBn[k] = ld(Sc, a_own + ((3 * cn + 2) * NR + k));
+        }
+        ld2(Sc, bp_mine + (3 * cn + 1) * BS, bAn);
+        ld2(Sc, bp_mine + (3 * cn + 2) * BS, bBn);
+        const vf lim = P.mu * cl[0];
+        const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
+        const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
+        const vf n2 = sumA * sumA + sumB * sumB;
+        const vb nz = n2 > 0.0f;
+        const vf rn = vrsqrt(sel(nz, n2, 1.0f));
+        const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
+        const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
+        const vf nA = vmin(vmax(sumA, -clipA), clipA);
+        const vf nB = vmin(vmax(sumB, -clipB), clipB);
+        const vb own = alive && (gl == c);
+        const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
+        const vf dAu = shfl_group16(dA, c), dBu = shfl_group16(dB, c);
+        cl[1] = sel(own, nA, cl[1]);
+        cl[2] = sel(own, nB, cl[2]);
+        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
+        TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
+      }
+    }
+    {  // residual of the contact rows: every row is visited once per sweep, so its impulse change is end - start
+      const vf dn = (cl[0] - cl0_0) * cdd[0];
+      const vf dt2 = (cl[1] - cl1_0) * cdd[1] + (cl[2] - cl2_0) * cdd[2];
+      cres = vmax(dn * dn, dt2 * dt2);
     }
     // residual per environment: max over its rows of (delta impulse / jacDiagABInv)^2
     vf r = cres;
@@ -2179,6 +2264,25 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
     val = sel(gl == ST_QUAT, nx * inv, sel(gl == ST_QUAT + 1, ny * inv, sel(gl == ST_QUAT + 2, nz * inv, sel(gl == ST_QUAT + 3, nw * inv, val))));
     st_if(rec0, roff + gl, val, gact && (gl < 13));
   }
+  {  // active-set signature of this substep's solve (StepStats), per environment: OR over the group's lanes, lane 0 folds
+    vi Lm = 0, Mm = 0;
+    TREX_UNROLL for (int s = 0; s < 2; s++) {
+      Lm = Lm | seli(kv[s] && (lam_l[s] > 0.0f), vi(1) << kk[s], vi(0));
+      Mm = Mm | seli(kv[s] && (vabs(lam_m[s]) >= max_imp), vi(1) << kk[s], vi(0));
+    }
+    vi NF = 0;
+    {
+      const vf lim = P.mu * cl[0];
+      const vb pos = cown && (cl[0] > 0.0f);
+      NF = seli(pos, vi(1) << gl, vi(0)) |
+           seli(pos && ((cl[1] * cl[1] + cl[2] * cl[2]) >= TREX_CONE_EDGE * (lim * lim)), vi(65536) << gl, vi(0));
+    }
+    TREX_UNROLL for (int m = 8; m > 0; m >>= 1) { Lm = Lm | shfl_xor_i(Lm, m); Mm = Mm | shfl_xor_i(Mm, m); NF = NF | shfl_xor_i(NF, m); }
+    const vb wr = gact && (gl == 0);
+    const vi si = seli(wr, roff + ST_SIG, 0);
+    const vi h = sig_mix_v(sig_mix_v(sig_mix_v(sig_mix_v(vf2i(ld(rec0, si)), Lm), Mm), NF), itd) & 0xffffff;
+    st_if(rec0, si, vi2f(h), wr);
+  }
   warp_sync();
   return itd;
 }
@@ -2229,7 +2333,8 @@ TREX_FN void reward_and_done(const Uniform& P, const float* mdl, vi lane, WarpSh
 // cache (a fused kernel mixing the two solvers measured 7.6 no-instruction stalls per issue) and lets the
 // 4-environments-per-warp solver run at its own occupancy.
 // ------------------------------------------------------------------------------------------
-enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // per-step accumulators in the record
+enum { ST_ACC_ITERS = 155, ST_ACC_CONTACTS = 156, ST_ACC_OVERFLOW = 157 };  // per-step accumulators in the record (ST_SIG = 158 follows)
+static_assert(ST_SIG == ST_ACC_ITERS + 3, "front_phase stores the four accumulators as one block");
 
 // front_phase: one physics substep of ONE environment by one warp up to the solve: kinematics, bias forces,
 // articulated inertias, accelerations, velocity update, M^-1, row setup, contact detection.  With more than TREX_KC
@@ -2249,6 +2354,7 @@ TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, con
   R.tgt = vmin(vmax(a, MDL(F_LOWER)), MDL(F_UPPER));
   StepStats st;
   st.iters = 0; st.contacts = 0; st.overflow = 0;
+  st.sig = first_round ? 0u : (uint32_t)ldu(rec, ST_SIG);
 #ifdef TREX_PHASES
   for (int i = 0; i < 8; i++) st.phase[i] = 0.0f;
 #endif
@@ -2260,8 +2366,9 @@ TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, con
   acc = sel(lane == 0, vbroadcast(it0 + (float)st.iters), acc);
   acc = sel(lane == 1, vbroadcast((float)st.contacts), acc);
   acc = sel(lane == 2, vbroadcast(ov0 + (float)st.overflow), acc);
+  acc = sel(lane == 3, vbroadcast((float)(st.sig & 0xffffffu)), acc);
   warp_sync();
-  st_if(rec, lane + ST_ACC_ITERS, acc, lane < 3);
+  st_if(rec, lane + ST_ACC_ITERS, acc, lane < 4);  // ST_ACC_ITERS, ST_ACC_CONTACTS, ST_ACC_OVERFLOW, ST_SIG
 #ifdef TREX_PHASES
   {  // cycles per phase of this environment's front kernel work, summed over the substeps of the env step
     vf ph = 0.0f;
@@ -2340,7 +2447,7 @@ TREX_FN void tail_phase(const Uniform& P, const float* mdl, const int* mdli, con
     const float episode = ldu(rec, ST_EPISODE);
     reset_pose(P, mdl, lane, S, R, env_id, episode);
     StepStats rs;
-    rs.iters = 0; rs.contacts = 0; rs.overflow = 0;
+    rs.iters = 0; rs.contacts = 0; rs.overflow = 0; rs.sig = 0u;
 #ifdef TREX_PHASES
     for (int i = 0; i < 8; i++) rs.phase[i] = 0.0f;
 #endif
