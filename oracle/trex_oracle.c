@@ -195,6 +195,7 @@ struct trex_oracle {
   int obs_dof[MAXDOF], head_link;
   int ncand, cand_link[MAXC];
   v3 cand_local[MAXC];
+  double cand_r[MAXC]; /* sphere candidates (contact primitives): radius, 0 = a point */
   int n_order, nc_order[2 * MAXDOF];
   double P[P_COUNT];
   int n_sub, contacts_on;
@@ -282,6 +283,11 @@ trex_oracle* trex_oracle_create(const void* blob, size_t bytes) {
   if (o->ncand > MAXC) { snprintf(g_err, sizeof g_err, "too many contact candidates"); goto fail; }
   for (int i = 0; i < o->ncand; i++) o->cand_link[i] = ip[i];
   GETF("full_cand_local", f, c); memcpy(o->cand_local, f, sizeof(double) * 3 * o->ncand);
+  { /* optional section (older blobs have point candidates only) */
+    const void* d_; uint32_t c_;
+    if (blob_find(&b, "full_cand_r", 0, &d_, &c_) == 0 && (int)c_ == o->ncand) memcpy(o->cand_r, d_, sizeof(double) * o->ncand);
+    g_err[0] = 0;
+  }
   GETI("noncontact_order", ip, c); o->n_order = (int)c;
   for (uint32_t i = 0; i < c; i++) o->nc_order[i] = ip[i];
   o->n_sub = (int)o->P[P_NUM_SUBSTEPS];
@@ -548,7 +554,8 @@ static void candidate_world(const trex_oracle* o, int k, v3 P) {
   int b = o->cand_link[k] + 1;
   v3 t;
   m3tmulv(t, o->Rw[b], o->cand_local[k]);
-  v3set(P, o->comw[b][0] + t[0], o->comw[b][1] + t[1], o->comw[b][2] + t[2]);
+  /* a sphere candidate touches the floor with its lowest point: centre - r * (0,0,1), a world offset */
+  v3set(P, o->comw[b][0] + t[0], o->comw[b][1] + t[1], o->comw[b][2] + t[2] - o->cand_r[k]);
 }
 
 /* btMultiBodyConstraint::fillMultiBodyConstraint tail: unit-impulse response, jacDiagABInv, J.u */

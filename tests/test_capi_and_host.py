@@ -172,3 +172,71 @@ def test_replay_export_layout():
     assert d["joint_names"] == names and len(d["joint_positions"]) == 2 and len(d["joint_positions"][0]) == 25
     assert d["base_position"][0] == [0.0, 0.0, 3.0] and d["base_orientation_xyzw"][1] == [0.0, 0.0, 0.0, 1.0]
     assert abs(d["joint_positions"][0][3] - 0.03) < 1e-7
+
+
+def test_replay_host_fk_and_playback_with_a_fake_pybullet(tmp_path):
+    """The replay file is self-sufficient: host-side FK of a frame (replay.link_world_position) reproduces the golden head
+    position of the reset pose ((0.000, 3.100, 3.208)) and the oracle's head position at a bent
+    pose; play_in_pybullet drives a (fake) pybullet through the frames with the calls the reference side needs."""
+    import numpy as np
+
+    from oracle.oracle import Oracle
+    from trex_gym_b200.model_compiler import load_builtin
+    from trex_gym_b200.replay import ReplayRecorder, joint_names_in_state_order, link_world_position, play_in_pybullet
+
+    model = load_builtin()
+    names = joint_names_in_state_order(model)
+    q0 = np.zeros(25)
+    for k, v in model.meta["starting_configuration"].items():
+        q0[names.index(k)] = v
+    assert np.allclose(link_world_position(model, [0, 0, 3.0], [0, 0, 0, 1.0], q0), model.meta["golden"]["reset_head_position"], atol=1e-9)
+    o = Oracle(model.blob())
+    o.reset()
+    rng = np.random.default_rng(2)
+    for _ in range(12):
+        o.step(rng.uniform(-0.5, 0.5, 25))
+    s = o.get_state()
+    assert np.abs(link_world_position(model, s[0:3], s[3:7], s[13:38]) - o.head_position()).max() < 1e-9
+    # playback
+    rec = ReplayRecorder.__new__(ReplayRecorder)
+    rec.names, rec.dt = names, 0.01
+    f = np.zeros((1, 160), np.float32)
+    f[0, 0:3], f[0, 3:7], f[0, 13:38] = s[0:3], s[3:7], s[13:38]
+    rec.frames = [f, f, f]
+    path = rec.save(str(tmp_path / "replay.json"))
+
+    class FakePB:
+        GUI, DIRECT, URDF_USE_INERTIA_FROM_FILE = 1, 2, 2
+
+        def __init__(self):
+            self.calls = []
+            self.joint_names = list(model.meta["joint_names"])
+
+        def connect(self, mode):
+            self.calls.append(("connect", mode))
+
+        def loadURDF(self, path, flags=0):
+            self.calls.append(("loadURDF", path, flags))
+            return 7
+
+        def getNumJoints(self, body):
+            return len(self.joint_names)
+
+        def getJointInfo(self, body, i):
+            return (i, self.joint_names[i].encode())
+
+        def resetBasePositionAndOrientation(self, body, p, q):
+            self.calls.append(("base", tuple(p), tuple(q)))
+
+        def resetJointState(self, body, i, a):
+            self.calls.append(("joint", i, a))
+
+    pb = FakePB()
+    assert play_in_pybullet(path, "/ref/assets/trex.urdf", realtime=False, pb=pb, gui=False) == 3
+    assert pb.calls[0] == ("connect", FakePB.DIRECT) and pb.calls[1] == ("loadURDF", "/ref/assets/trex.urdf", 2)
+    joints = [c for c in pb.calls if c[0] == "joint"]
+    assert len(joints) == 3 * 25
+    # joint k of the record goes to the pybullet joint index of its URDF name (pybullet link order)
+    assert [c[1] for c in joints[:25]] == [model.meta["joint_names"].index(n) for n in names]
+    assert np.allclose([c[2] for c in joints[:25]], s[13:38], atol=1e-6)
+    assert len([c for c in pb.calls if c[0] == "base"]) == 3

@@ -404,3 +404,43 @@ def test_two_heavy_environments_per_warp(model):
     o.step(acts[1].astype(np.float64))
     so, se = o.get_state(), w3.get_state(1, nc)
     assert max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()) < 5e-3
+
+
+def test_contact_primitives_model_per_substep(model, action_limits):
+    """the contact model built from spheres / capsules fitted to the meshes (sphere candidates
+    with a radius: contact point = centre - r * normal).  The kernel source and the oracle read the same candidate table:
+    per-substep parity while the T-rex lands and stands on its toe capsules, and with random actions."""
+    from emu import EmuEnv
+
+    from trex_gym_b200.model_compiler import load_builtin, with_params
+
+    prim = with_params(load_builtin("primitives"), time_step=0.002, solver_iterations=60)
+    o = _oracle(prim, num_substeps=1)
+    e = EmuEnv(prim.blob(), num_substeps=1)
+    nc = o.num_candidates
+    assert nc == len(prim["mb_cand_r"]) > 48
+    lo, hi = action_limits
+    rng = np.random.default_rng(4)
+    hold = o.reset()[:25].copy()
+    e.reset()
+    errs, ks = [], []
+    for t in range(260):
+        a = hold if t < 180 else rng.uniform(lo, hi)
+        pre = e.get_state(nc)
+        o.set_state(pre)
+        o.step(a)
+        e.step(a)
+        so, se = o.get_state(), e.get_state(nc)
+        assert int(e.aux[7]) % 1000 == o.last_num_contacts
+        if o.last_num_contacts:
+            # (free fall with the pose held needs ~1e-3 N m of motor torque: that block is compared against a 1 N m floor)
+            errs.append(max(rel_err(so[sl], se[sl]) if k != "tau" else float(np.abs(so[sl] - se[sl]).max() / max(np.abs(so[sl]).max(), 1.0))
+                            for k, sl in STATE_BLOCKS.items()))
+            ks.append(o.last_num_contacts)
+            assert int(e.rec[158]) == o.signature or errs[-1] < 5e-3
+    errs = np.asarray(errs)
+    assert len(errs) > 100 and max(ks) >= 8
+    # sphere candidates rest on the floor at centre - r: the standing height is that of the capsules, not of the mesh vertices
+    zs = [o.candidate_position(k)[2] for k in range(nc)]
+    assert -0.03 < min(zs) < 0.03
+    assert np.percentile(errs, 50) < 5e-4 and np.percentile(errs, 99) < 2e-2, (np.percentile(errs, 50), errs.max())

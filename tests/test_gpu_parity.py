@@ -460,3 +460,51 @@ def test_heavy_contact_kernel_on_standing_batch(model):
     assert np.percentile(errs, 50) < 2e-3 and errs.max() < 2e-2, (np.percentile(errs, 50), errs.max())
     assert np.percentile(diffs, 50) < 3e-4 and diffs.max() < 1e-2, (np.percentile(diffs, 50), diffs.max())
     assert torch.isfinite(forced.get_state()).all().item()
+
+
+def test_contact_primitives_model_on_gpu(model):
+    """the contact model of spheres / capsules fitted to the meshes (62 sphere candidates with a
+    radius) through the CUDA path: a batch that lands and stands on its toe capsules, then flails with random actions,
+    per env step against the oracle on the same candidate table."""
+    import torch
+
+    from trex_gym_b200 import TrexVecEnv
+    from trex_gym_b200.model_compiler import load_builtin
+
+    prim = load_builtin("primitives")
+    n = 256
+    sim = _sim(prim, n)
+    o = _oracle(prim)
+    nc = o.num_candidates
+    assert nc == 62
+    names = list(prim.meta["obs_joint_names"])
+    hold = np.zeros(25, np.float32)
+    for k, v in prim.meta["starting_configuration"].items():
+        hold[names.index(k)] = v
+    a_hold = torch.tensor(hold, device="cuda").repeat(n, 1).contiguous()
+    errs, ks = [], []
+    for t in range(90):
+        act = a_hold if t < 60 else sim.random_actions(step=t, seed=6)
+        pre = sim.get_state().cpu().numpy()
+        sim.step(act)
+        post = sim.get_state().cpu().numpy()
+        a = act.cpu().numpy().astype(np.float64)
+        for e in (0, 100, 255):
+            o.set_state(_core(pre[e], nc))
+            o.step(a[e])
+            if o.last_num_contacts:
+                so = o.get_state()
+                errs.append(max(rel_err(so[sl], post[e, sl]) if k != "tau" else float(np.abs(so[sl] - post[e, sl]).max() / max(np.abs(so[sl]).max(), 1.0))
+                                for k, sl in STATE_BLOCKS.items()))
+                ks.append(o.last_num_contacts)
+    errs = np.asarray(errs)
+    print("contact primitives, per env step: n=%d p50 %.2e p99 %.2e max %.2e contacts up to %d" % (
+        len(errs), np.percentile(errs, 50), np.percentile(errs, 99), errs.max(), max(ks)))
+    assert len(errs) > 100 and max(ks) >= 8
+    assert np.percentile(errs, 50) < 5e-4 and np.percentile(errs, 95) < 2e-2
+    st = sim.stats()
+    assert st["nan_resets"] == 0 and st["contact_overflow"] == 0
+    # the gym surface takes the contact model by name
+    venv = TrexVecEnv(4, contact_model="primitives")
+    assert venv.sim.model.meta["contact_model"] == "primitives"
+    venv.close()

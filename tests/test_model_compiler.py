@@ -249,3 +249,99 @@ def test_derived_urdf_with_collision_elements(model, tmp_path):
     for k, a in model.sections.items():
         b = m2.sections[k]
         assert a.shape == b.shape and np.abs(a.astype(float) - b.astype(float)).max() < 1e-9, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Contact primitives from meshes (reference pattern: tools/mesh_primitives.py:323-402)
+# ---------------------------------------------------------------------------------------------------------------
+def _capsule_cloud(rng, radius, length, n=4000):
+    """Points on the surface of a capsule along z (length = distance of the end-sphere centres)."""
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    z = rng.uniform(-0.5 * length - radius, 0.5 * length + radius, n)
+    pts = np.zeros((n, 3))
+    cyl = np.abs(z) <= 0.5 * length
+    ang = rng.uniform(0, 2 * np.pi, n)
+    pts[cyl] = np.stack([radius * np.cos(ang[cyl]), radius * np.sin(ang[cyl]), z[cyl]], 1)
+    cap = ~cyl
+    pts[cap] = radius * d[cap]
+    pts[cap, 2] = np.abs(pts[cap, 2]) * np.sign(z[cap]) + np.sign(z[cap]) * 0.5 * length
+    return pts
+
+
+def test_fit_contact_primitives_recovers_a_capsule_and_a_sphere():
+    from scipy.spatial.transform import Rotation
+
+    from trex_gym_b200.model_compiler import fit_contact_primitives
+
+    rng = np.random.default_rng(0)
+    R = Rotation.from_euler("xyz", [0.4, -0.9, 1.3]).as_matrix()
+    t = np.array([0.3, -1.2, 0.7])
+    pts = _capsule_cloud(rng, 0.11, 0.8) @ R.T + t
+    (prim,) = fit_contact_primitives(pts, max_radius=1.0, max_divisions=0)
+    assert prim.kind == "capsule"
+    assert abs(prim.radius - 0.11) < 2e-3 and abs(prim.length - 0.8) < 5e-3
+    assert np.abs(prim.center - t).max() < 5e-3 and abs(abs(prim.axis @ R[:, 2]) - 1.0) < 1e-4
+    ends = sorted((c @ R[:, 2] for c, _ in prim.spheres()))
+    assert abs((ends[1] - ends[0]) - 0.8) < 5e-3
+    ball = rng.normal(size=(3000, 3))
+    ball = 0.25 * ball / np.linalg.norm(ball, axis=1, keepdims=True) + t
+    (sph,) = fit_contact_primitives(ball, max_radius=1.0, max_divisions=0)
+    assert sph.kind == "sphere" and abs(sph.radius - 0.25) < 5e-3 and np.abs(sph.center - t).max() < 5e-3
+    assert len(sph.spheres()) == 1
+
+
+def test_fit_contact_primitives_subdivides_by_octants():
+    """A fat box-shaped cloud: one primitive when the radius bound allows it, the 8 octants of the PCA frame when it does
+    not, 64 after two splits; octants with too few points are dropped; every piece respects the bound when it can."""
+    from trex_gym_b200.model_compiler import fit_contact_primitives
+
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-1, 1, size=(40000, 3)) * np.array([0.5, 0.7, 1.0])
+    assert len(fit_contact_primitives(pts, max_radius=10.0, max_divisions=4)) == 1
+    one = fit_contact_primitives(pts, max_radius=0.5, max_divisions=1)
+    assert len(one) == 8 and all(p.radius < 0.5 for p in one)
+    two = fit_contact_primitives(pts, max_radius=0.2, max_divisions=2)
+    assert len(two) == 64
+    assert len(fit_contact_primitives(pts, max_radius=0.5, max_divisions=0)) == 1  # no divisions allowed
+    # min_points: 7 of the 8 octants hold too few points and are dropped
+    lopsided = np.concatenate([np.abs(pts[:5000]), -np.abs(pts[:40])])
+    kept = fit_contact_primitives(lopsided, max_radius=0.2, max_divisions=1, min_points=100)
+    assert 1 <= len(kept) < 8
+    # the union of the pieces covers the cloud: every point is inside some primitive (inflated by 2 %)
+    def inside(p, prim):
+        d = p - prim.center
+        a = np.clip(d @ prim.axis, -0.5 * prim.length, 0.5 * prim.length)
+        return np.linalg.norm(d - np.outer(a, prim.axis), axis=1) <= 1.02 * prim.radius
+    cov = np.zeros(len(pts), bool)
+    for prim in one:
+        cov |= inside(pts, prim)
+    assert cov.mean() > 0.7  # (a capsule of radius = half the larger minor extent leaves the corners of a box outside)
+
+
+def test_primitives_model_candidates():
+    from trex_gym_b200.model_compiler import load_builtin
+
+    pts, prim = load_builtin(), load_builtin("primitives")
+    assert prim.meta["contact_model"] == "primitives"
+    r = prim["mb_cand_r"]
+    assert 32 <= len(r) <= 64 and (r > 0.04).all() and (r < 0.7).all() and len(prim["full_cand_r"]) == len(r)
+    assert (pts["mb_cand_r"] == 0).all()
+    # the same bodies carry candidates in both contact models, and nothing else differs between the two blobs
+    assert set(prim["mb_cand_body"].tolist()) == set(pts["mb_cand_body"].tolist())
+    for k in pts.sections:
+        if "cand" not in k:
+            assert np.array_equal(pts.sections[k], prim.sections[k]), k
+    # toes are capsules: two end spheres of equal radius per toe body
+    toe = prim.meta["body_root_links"].index("link_toe_03_a_left")
+    assert (prim["mb_cand_body"] == toe).sum() == 2 and len(set(r[prim["mb_cand_body"] == toe])) == 1
+
+
+@needs_ref
+def test_checked_in_primitives_blob_regenerates():
+    from trex_gym_b200.model_compiler import compile_model, load_builtin
+
+    fresh, stored = compile_model(URDF, contact_model="primitives"), load_builtin("primitives")
+    assert list(fresh.sections.keys()) == list(stored.sections.keys())
+    for k in fresh.sections:
+        assert fresh.sections[k].shape == stored.sections[k].shape and np.allclose(fresh.sections[k], stored.sections[k], rtol=0, atol=1e-12), k

@@ -11,6 +11,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -313,8 +314,9 @@ struct trex_handle {
   DevStats* d_stats = nullptr;
   // trex_heavy_kernel touches a handful of environments but each takes ~200 us: it runs on a side stream, hidden under the
   // two solve4 kernels of the same round (fork after the front kernel, join before the next one; no host synchronisation)
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  bool concurrent_solves = true;  // the contact-free solve kernel on a second side stream, under the contact solver
   int heavy_div = 0;            // > 0: class 5 goes to trex_heavy_kernel only while at most n_envs / heavy_div environments are in it (0: always)
   int heavy_grid = 148 * 7;     // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
   int64_t launches = 0;
@@ -362,9 +364,20 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (h->d_work) {
+        // The three solve kernels of a round work on disjoint lists of environments.  The two latency-bound ones go first:
+        // the contact solver on the caller's stream, the many-contact solver on a side stream; the contact-free solver
+        // (issue bound) runs on a second side stream and fills the issue slots they leave.  Fork / join by events only.
+        const bool contacts = h->P.defer_contacts && h->P.contacts_on;
         const bool heavy = h->P.defer_contacts > 1 && h->P.contacts_on && h->d_workh != nullptr;
-        if (heavy) {  // class 5: more than TREX_KC contacts, one environment per warp, on the side stream
-          CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+        const bool split = contacts && h->concurrent_solves && h->side2 != nullptr;
+        if (heavy || split) CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+        if (contacts) {
+          trex_solve_kernel<WS, TREX_KC><<<grid4 + 3, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
+                                                                            h->d_list_count + 64 + r, h->n_envs);
+          CUDA_TRY(cudaGetLastError());
+          h->launches++;
+        }
+        if (heavy) {  // class 5: more than TREX_KC contacts, two environments per warp
           CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
           trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, h->side>>>(h->P, h->d_state, h->d_work, h->d_workh,
                                                                       h->d_list + (size_t)TREX_CLASS_HEAVY * h->n_envs,
@@ -375,14 +388,14 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
           h->launches++;
           CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
         }
-        trex_solve_kernel<WS, 0><<<grid4, 32 * WS, smem_s, st>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r, h->n_envs);
+        cudaStream_t s0 = split ? h->side2 : st;
+        if (split) CUDA_TRY(cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
+        trex_solve_kernel<WS, 0><<<grid4, 32 * WS, smem_s, s0>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r, h->n_envs);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
-        if (h->P.defer_contacts && h->P.contacts_on) {
-          trex_solve_kernel<WS, TREX_KC><<<grid4 + 3, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
-                                                                            h->d_list_count + 64 + r, h->n_envs);
-          CUDA_TRY(cudaGetLastError());
-          h->launches++;
+        if (split) {
+          CUDA_TRY(cudaEventRecord(h->ev_join2, h->side2));
+          CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join2, 0));
         }
         if (heavy) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
       }
@@ -503,6 +516,9 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     CTRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     CTRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CTRY(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+    CTRY(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+    if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aid
   }
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
@@ -539,6 +555,8 @@ void trex_destroy(trex_handle* h) {
   if (h->host_copy) cudaStreamDestroy(h->host_copy);
   if (h->host_in) cudaStreamDestroy(h->host_in);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;

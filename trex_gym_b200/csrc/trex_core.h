@@ -935,7 +935,9 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
       // world point = xw + Rw^T p
       wpos[half][0] = ld(S.k.xw[0], bl) + ld(S.k.Rw[0], bl) * px + ld(S.k.Rw[3], bl) * py + ld(S.k.Rw[6], bl) * pz;
       wpos[half][1] = ld(S.k.xw[1], bl) + ld(S.k.Rw[1], bl) * px + ld(S.k.Rw[4], bl) * py + ld(S.k.Rw[7], bl) * pz;
-      wpos[half][2] = ld(S.k.xw[2], bl) + ld(S.k.Rw[2], bl) * px + ld(S.k.Rw[5], bl) * py + ld(S.k.Rw[8], bl) * pz;
+      // a sphere candidate (radius > 0, contact primitives fitted to the meshes) touches the floor with its lowest point:
+      // centre - r * normal, a WORLD offset (not body fixed), exactly what a sphere-plane manifold point is
+      wpos[half][2] = (ld(S.k.xw[2], bl) + ld(S.k.Rw[2], bl) * px + ld(S.k.Rw[5], bl) * py + ld(S.k.Rw[8], bl) * pz) - ldg_ro(cand_p, cis + 3 * TREX_NCAND_MAX);
       cbl[half] = bl;
       cact[half] = valid && ((wpos[half][2] - P.floor_z) < P.breaking);
       am[half] = vballot(cact[half]);
@@ -1688,63 +1690,49 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       MB_(6, false) MB_(5, false) MB_(4, false) MB_(3, false) MB_(2, false) MB_(1, false) MB_(0, false)
     }
     if (KC > 0) {
-      // normal rows: every lane evaluates its own contact, the owner of contact c publishes.  The A4 / Bp rows a
-      // publication needs do not depend on the sweep's data: they are fetched one iteration ahead (software pipeline),
-      // so the shared-memory latency sits under the owner's clamp chain instead of behind the shuffle.
+      // normal rows: every lane evaluates its own contact, the owner of contact c publishes
+      // (most warps of this kernel hold environments with 1-2 contacts: fetching the A4 / Bp rows one iteration ahead, as
+      // solve2 does for its 9-16 contacts, only adds loads here -- measured +30 % on the benchmark batch)
       const vf cl0_0 = cl[0], cl1_0 = cl[1], cl2_0 = cl[2];
-      {
-        vf an[4], bn[4];
-        ld4(Bs, gb + glc * 4 + BT, an);
-        ld4(Bs, gb + gl * 4, bn);
-        TREX_ROLLED for (int c = 0; c < kmax; c++) {
-          vf a4[4], b4[4];
-          TREX_UNROLL for (int k = 0; k < 4; k++) { a4[k] = an[k]; b4[k] = bn[k]; }
-          const int cn = c + 1 < kmax ? c + 1 : c;
-          ld4(Bs, gb + glc * 4 + ((3 * cn) * (4 * KC) + BT), an);
-          ld4(Bs, gb + gl * 4 + (3 * cn) * 36, bn);
-          const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
-          const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
-          const vb own = alive && (gl == c);
-          const vf dl = sel(own, nl - cl[0], 0.0f);
-          const vf d = shfl_group8(dl, c);
-          cl[0] = sel(own, nl, cl[0]);
-          TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
-          TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(b4[s], njdi[s] * d, w[s]);
-        }
+      TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
+        const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
+        const vb own = alive && (gl == c);
+        const vf dl = sel(own, nl - cl[0], 0.0f);
+        const vf d = shfl_group8(dl, c);
+        cl[0] = sel(own, nl, cl[0]);
+        vf a4[4];
+        ld4(Bs, gb + glc * 4 + ((3 * c) * (4 * KC) + BT), a4);
+        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
+        vf b4[4];
+        ld4(Bs, gb + gl * 4 + (3 * c) * 36, b4);
+        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(b4[s], njdi[s] * d, w[s]);
       }
       // friction pairs, implicit cone; both rows read the velocities before either writes
-      {
-        vf aAn[4], aBn[4], bAn[4], bBn[4];
-        ld4(Bs, gb + glc * 4 + (4 * KC + BT), aAn);
-        ld4(Bs, gb + glc * 4 + (2 * 4 * KC + BT), aBn);
-        ld4(Bs, gb + gl * 4 + 36, bAn);
-        ld4(Bs, gb + gl * 4 + 2 * 36, bBn);
-        TREX_ROLLED for (int c = 0; c < kmax; c++) {
-          vf aA[4], aB[4], bA[4], bB[4];
-          TREX_UNROLL for (int k = 0; k < 4; k++) { aA[k] = aAn[k]; aB[k] = aBn[k]; bA[k] = bAn[k]; bB[k] = bBn[k]; }
-          const int cn = c + 1 < kmax ? c + 1 : c;
-          ld4(Bs, gb + glc * 4 + ((3 * cn + 1) * (4 * KC) + BT), aAn);
-          ld4(Bs, gb + glc * 4 + ((3 * cn + 2) * (4 * KC) + BT), aBn);
-          ld4(Bs, gb + gl * 4 + (3 * cn + 1) * 36, bAn);
-          ld4(Bs, gb + gl * 4 + (3 * cn + 2) * 36, bBn);
-          const vf lim = P.mu * cl[0];
-          const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
-          const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
-          const vf n2 = sumA * sumA + sumB * sumB;
-          const vb nz = n2 > 0.0f;
-          const vf rn = vrsqrt(sel(nz, n2, 1.0f));
-          const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
-          const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
-          const vf nA = vmin(vmax(sumA, -clipA), clipA);
-          const vf nB = vmin(vmax(sumB, -clipB), clipB);
-          const vb own = alive && (gl == c);
-          const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
-          const vf dAu = shfl_group8(dA, c), dBu = shfl_group8(dB, c);
-          cl[1] = sel(own, nA, cl[1]);
-          cl[2] = sel(own, nB, cl[2]);
-          TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
-          TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
-        }
+      TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        const vf lim = P.mu * cl[0];
+        const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
+        const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
+        const vf n2 = sumA * sumA + sumB * sumB;
+        const vb nz = n2 > 0.0f;
+        const vf rn = vrsqrt(sel(nz, n2, 1.0f));
+        const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
+        const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
+        const vf nA = vmin(vmax(sumA, -clipA), clipA);
+        const vf nB = vmin(vmax(sumB, -clipB), clipB);
+        const vb own = alive && (gl == c);
+        const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
+        const vf dAu = shfl_group8(dA, c), dBu = shfl_group8(dB, c);
+        cl[1] = sel(own, nA, cl[1]);
+        cl[2] = sel(own, nB, cl[2]);
+        vf aA[4], aB[4];
+        ld4(Bs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + BT), aA);
+        ld4(Bs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + BT), aB);
+        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
+        vf bA[4], bB[4];
+        ld4(Bs, gb + gl * 4 + (3 * c + 1) * 36, bA);
+        ld4(Bs, gb + gl * 4 + (3 * c + 2) * 36, bB);
+        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
       }
       {  // residual of the contact rows: every row is visited once per sweep, so its impulse change is end - start
         const vf dn = (cl[0] - cl0_0) * cdd[0];
@@ -2109,63 +2097,70 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
     // publication needs do not depend on the sweep's data: they are fetched one iteration ahead (software pipeline), so
     // the shared-memory latency sits under the owner's clamp chain instead of behind the shuffle.
     const vf cl0_0 = cl[0], cl1_0 = cl[1], cl2_0 = cl[2];
+    // (two register sets alternate -- the loop is unrolled by two -- so the pipeline costs no register moves)
+#define TREX_S2_NORMAL(C, A3, B2, AN, BN)                                                                 \
+    {                                                                                                      \
+      const int cn = (C) + 1 < kmax ? (C) + 1 : (C);                                                       \
+      TREX_UNROLL for (int k = 0; k < 3; k++) AN[k] = ld(Sc, a_own + ((3 * cn) * NR + k));                 \
+      ld2(Sc, bp_mine + (3 * cn) * BS, BN);                                                                \
+      const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);                                                  \
+      const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);                                                        \
+      const vb own = alive && (gl == (C));                                                                 \
+      const vf dl = sel(own, nl - cl[0], 0.0f);                                                            \
+      const vf d = shfl_group16(dl, (C));                                                                  \
+      cl[0] = sel(own, nl, cl[0]);                                                                         \
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(A3[k], d, cu[k]);                               \
+      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(B2[s], njdi[s] * d, w[s]);                       \
+    }
     {
-      vf an[3], bn[2];
-      TREX_UNROLL for (int k = 0; k < 3; k++) an[k] = ld(Sc, a_own + k);
-      ld2(Sc, bp_mine, bn);
-      TREX_ROLLED for (int c = 0; c < kmax; c++) {
-        vf a3[3], b2[2];
-        TREX_UNROLL for (int k = 0; k < 3; k++) a3[k] = an[k];
-        b2[0] = bn[0]; b2[1] = bn[1];
-        const int cn = c + 1 < kmax ? c + 1 : c;
-        TREX_UNROLL for (int k = 0; k < 3; k++) an[k] = ld(Sc, a_own + ((3 * cn) * NR + k));
-        ld2(Sc, bp_mine + (3 * cn) * BS, bn);
-        const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
-        const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
-        const vb own = alive && (gl == c);
-        const vf dl = sel(own, nl - cl[0], 0.0f);
-        const vf d = shfl_group16(dl, c);
-        cl[0] = sel(own, nl, cl[0]);
-        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a3[k], d, cu[k]);
-        TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(b2[s], njdi[s] * d, w[s]);
+      vf a0[3], b0[2], a1[3], b1[2];
+      TREX_UNROLL for (int k = 0; k < 3; k++) a0[k] = ld(Sc, a_own + k);
+      ld2(Sc, bp_mine, b0);
+      TREX_ROLLED for (int c = 0; c < kmax; c += 2) {
+        TREX_S2_NORMAL(c, a0, b0, a1, b1)
+        if (c + 1 < kmax) TREX_S2_NORMAL(c + 1, a1, b1, a0, b0)
       }
     }
+#undef TREX_S2_NORMAL
     // friction pairs, implicit cone; both rows read the velocities before either writes
+#define TREX_S2_FRICTION(C, AA, AB, BA, BB, AAN, ABN, BAN, BBN)                                            \
+    {                                                                                                      \
+      const int cn = (C) + 1 < kmax ? (C) + 1 : (C);                                                       \
+      TREX_UNROLL for (int k = 0; k < 3; k++) {                                                            \
+        AAN[k] = ld(Sc, a_own + ((3 * cn + 1) * NR + k));                                                  \
+        ABN[k] = ld(Sc, a_own + ((3 * cn + 2) * NR + k));                                                  \
+      }                                                                                                    \
+      ld2(Sc, bp_mine + (3 * cn + 1) * BS, BAN);                                                           \
+      ld2(Sc, bp_mine + (3 * cn + 2) * BS, BBN);                                                           \
+      const vf lim = P.mu * cl[0];                                                                         \
+      const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);                                                 \
+      const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);                                                 \
+      const vf n2 = sumA * sumA + sumB * sumB;                                                             \
+      const vb nz = n2 > 0.0f;                                                                             \
+      const vf rn = vrsqrt(sel(nz, n2, 1.0f));                                                             \
+      const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);                                             \
+      const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));                                        \
+      const vf nA = vmin(vmax(sumA, -clipA), clipA);                                                       \
+      const vf nB = vmin(vmax(sumB, -clipB), clipB);                                                       \
+      const vb own = alive && (gl == (C));                                                                 \
+      const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);                           \
+      const vf dAu = shfl_group16(dA, (C)), dBu = shfl_group16(dB, (C));                                   \
+      cl[1] = sel(own, nA, cl[1]);                                                                         \
+      cl[2] = sel(own, nB, cl[2]);                                                                         \
+      TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(AA[k], dAu, vfma(AB[k], dBu, cu[k]));           \
+      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(njdi[s], vfma(BA[s], dAu, BB[s] * dBu), w[s]);   \
+    }
     {
-      vf aAn[3], aBn[3], bAn[2], bBn[2];
-      TREX_UNROLL for (int k = 0; k < 3; k++) { aAn[k] = ld(Sc, a_own + (NR + k)); aBn[k] = ld(Sc, a_own + (2 * NR + k)); }
-      ld2(Sc, bp_mine + BS, bAn);
-      ld2(Sc, bp_mine + 2 * BS, bBn);
-      TREX_ROLLED for (int c = 0; c < kmax; c++) {
-        vf aA[3], aB[3], bA[2], bB[2];
-        TREX_UNROLL for (int k = 0; k < 3; k++) { aA[k] = aAn[k]; aB[k] = aBn[k]; }
-        TREX_UNROLL for (int s = 0; s < 2; s++) { bA[s] = bAn[s]; bB[s] = bBn[s]; }
-        const int cn = c + 1 < kmax ? c + 1 : c;
-        TREX_UNROLL for (int k = 0; k < 3; k++) {
-          aAn[k] = ld(Sc, a_own + ((3 * cn + 1) * NR + k));
-          aBn[k] = ld(Sc, a_own + ((3 * cn + 2) * NR + k));
-        }
-        ld2(Sc, bp_mine + (3 * cn + 1) * BS, bAn);
-        ld2(Sc, bp_mine + (3 * cn + 2) * BS, bBn);
-        const vf lim = P.mu * cl[0];
-        const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
-        const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
-        const vf n2 = sumA * sumA + sumB * sumB;
-        const vb nz = n2 > 0.0f;
-        const vf rn = vrsqrt(sel(nz, n2, 1.0f));
-        const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
-        const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
-        const vf nA = vmin(vmax(sumA, -clipA), clipA);
-        const vf nB = vmin(vmax(sumB, -clipB), clipB);
-        const vb own = alive && (gl == c);
-        const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
-        const vf dAu = shfl_group16(dA, c), dBu = shfl_group16(dB, c);
-        cl[1] = sel(own, nA, cl[1]);
-        cl[2] = sel(own, nB, cl[2]);
-        TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
-        TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
+      vf aA0[3], aB0[3], bA0[2], bB0[2], aA1[3], aB1[3], bA1[2], bB1[2];
+      TREX_UNROLL for (int k = 0; k < 3; k++) { aA0[k] = ld(Sc, a_own + (NR + k)); aB0[k] = ld(Sc, a_own + (2 * NR + k)); }
+      ld2(Sc, bp_mine + BS, bA0);
+      ld2(Sc, bp_mine + 2 * BS, bB0);
+      TREX_ROLLED for (int c = 0; c < kmax; c += 2) {
+        TREX_S2_FRICTION(c, aA0, aB0, bA0, bB0, aA1, aB1, bA1, bB1)
+        if (c + 1 < kmax) TREX_S2_FRICTION(c + 1, aA1, aB1, bA1, bB1, aA0, aB0, bA0, bB0)
       }
     }
+#undef TREX_S2_FRICTION
     {  // residual of the contact rows: every row is visited once per sweep, so its impulse change is end - start
       const vf dn = (cl[0] - cl0_0) * cdd[0];
       const vf dt2 = (cl[1] - cl1_0) * cdd[1] + (cl[2] - cl2_0) * cdd[2];

@@ -77,7 +77,7 @@ struct ModelTables {
   std::vector<float> mdl;        // [F_COUNT][32]
   std::vector<int32_t> mdli;     // [IF_COUNT][32]
   std::vector<float> tasks;      // [rounds][4][32]  rx, ry, rz, mass
-  std::vector<float> cand_p;     // [3][64]
+  std::vector<float> cand_p;     // [4][64]: candidate point / sphere centre x, y, z in body coordinates, sphere radius (0 = point)
   std::vector<int32_t> cand_lane;  // [64]
   int n_rounds = 0, n_cand = 0, head_lane = 0;
   float head_p[3] = {0, 0, 0};
@@ -94,7 +94,7 @@ static inline bool build_tables(const void* blob, size_t bytes, ModelTables& T, 
   using namespace trex_topo;
   Blob B;
   if (!B.open(blob, bytes)) { T.err = B.err; return false; }
-  std::vector<double> pv, E0, r0, mass, mc, I, drot, lower, upper, jdamp, startq, headp, task_r, task_m, candp;
+  std::vector<double> pv, E0, r0, mass, mc, I, drot, lower, upper, jdamp, startq, headp, task_r, task_m, candp, candr;
   std::vector<int32_t> nbv, parent, headb, task_body, cand_body, obs_dof, order;
 #define NEED(x) if (!(x)) { T.err = B.err; return false; }
   NEED(B.f64("param_values", pv, P_COUNT));
@@ -112,6 +112,8 @@ static inline bool build_tables(const void* blob, size_t bytes, ModelTables& T, 
   NEED(B.f64("mb_start_q", startq, NB)); NEED(B.i32("mb_head_body", headb, 1)); NEED(B.f64("mb_head_p", headp, 3));
   NEED(B.i32("mb_task_body", task_body)); NEED(B.f64("mb_task_r", task_r)); NEED(B.f64("mb_task_m", task_m));
   NEED(B.i32("mb_cand_body", cand_body)); NEED(B.f64("mb_cand_p", candp));
+  if (!B.f64("mb_cand_r", candr)) { candr.assign(cand_body.size(), 0.0); B.err.clear(); }  // older blobs: point candidates
+  if (candr.size() != cand_body.size()) { T.err = "section mb_cand_r: unexpected size"; return false; }
   NEED(B.i32("obs_dof", obs_dof, NJ));
 #undef NEED
   for (int k = 0; k < NJ; k++)
@@ -226,11 +228,12 @@ static inline bool build_tables(const void* blob, size_t bytes, ModelTables& T, 
   // contact candidates
   T.n_cand = (int)cand_body.size();
   if (T.n_cand > 64) { T.err = "too many contact candidates"; return false; }
-  T.cand_p.assign(3 * 64, 0.0f);
+  T.cand_p.assign(4 * 64, 0.0f);
   T.cand_lane.assign(64, 25);
   for (int c = 0; c < T.n_cand; c++) {
     T.cand_lane[c] = body_lane(cand_body[c]);
     for (int k = 0; k < 3; k++) T.cand_p[(size_t)k * 64 + c] = (float)candp[3 * c + k];
+    T.cand_p[(size_t)3 * 64 + c] = (float)candr[c];
   }
   T.head_lane = body_lane(headb[0]);
   for (int k = 0; k < 3; k++) T.head_p[k] = (float)headp[k];

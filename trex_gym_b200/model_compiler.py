@@ -251,12 +251,94 @@ def _select_contact_points(world_pts: np.ndarray, count: int, mode: str) -> list
     return chosen
 
 
+# ---------------------------------------------------------------------------
+# Contact primitives from meshes.  The reference's tooling direction
+# (tools/mesh_primitives.py:323-402: PCA-aligned bounding box -> sphere or capsule, recursive octant subdivision while
+# the radius is too large) restated here for the model compiler: a body's visual-mesh vertex cloud becomes a few
+# spheres / capsules, and every sphere -- a capsule contributes its two end spheres -- is one floor-contact candidate.
+# ---------------------------------------------------------------------------
+@dataclasses.dataclass
+class ContactPrimitive:
+    kind: str            # "sphere" | "capsule"
+    center: np.ndarray   # in the frame of the input points
+    axis: np.ndarray     # unit vector of the capsule axis (the dominant PCA axis); unused for spheres
+    radius: float
+    length: float        # distance between the end-sphere centres (0 for spheres)
+
+    def spheres(self):
+        """(centre, radius) of the sphere(s) that can touch a plane: the sphere itself or the capsule's two end spheres."""
+        if self.kind == "sphere":
+            return [(self.center, self.radius)]
+        h = 0.5 * self.length * self.axis
+        return [(self.center - h, self.radius), (self.center + h, self.radius)]
+
+
+def _pca_box(points: np.ndarray):
+    """Oriented bounding box of a point cloud: axes = principal axes of the second moment about the centroid (columns
+    x, y, z with z the dominant one, right handed), centre and full extents in that frame
+    (cf. tools/mesh_primitives.py:323-344)."""
+    pts = np.asarray(points, float)
+    centroid = pts.mean(axis=0)
+    d = pts - centroid
+    u, _, _ = np.linalg.svd(d.T @ d)
+    z, y = u[:, 0], u[:, 1]
+    x = np.cross(y, z)
+    axes = np.stack([x, y, z], axis=1)
+    local = d @ axes
+    lo, hi = local.min(axis=0), local.max(axis=0)
+    return axes, centroid + axes @ (0.5 * (lo + hi)), hi - lo
+
+
+def _sphere_or_capsule(axes, center, size) -> ContactPrimitive:
+    """cf. tools/mesh_primitives.py:347-362: radius = half the larger minor extent; a capsule along the dominant axis when
+    the box is longer than one diameter, else a sphere."""
+    radius = 0.5 * float(max(size[0], size[1]))
+    length = float(size[2]) - 2.0 * radius
+    if length > 0.0:
+        return ContactPrimitive("capsule", center, axes[:, 2].copy(), radius, length)
+    return ContactPrimitive("sphere", center, axes[:, 2].copy(), radius, 0.0)
+
+
+def fit_contact_primitives(points: np.ndarray, max_radius: float, max_divisions: int = 4, min_points: int = 100, _depth: int = 0) -> list:
+    """Spheres / capsules covering ``points`` (N x 3): fit one primitive to the PCA box; while its radius exceeds
+    ``max_radius`` (and fewer than ``max_divisions`` splits were made) split the cloud into the octants of the box frame
+    -- octants with at most ``min_points`` points are dropped -- and recurse (cf. tools/mesh_primitives.py:296-402)."""
+    pts = np.asarray(points, float)
+    axes, center, size = _pca_box(pts)
+    prim = _sphere_or_capsule(axes, center, size)
+    if prim.radius > max_radius and _depth < max_divisions:
+        local = (pts - center) @ axes
+        out = []
+        sx, sy, sz = local[:, 0] >= 0, local[:, 1] >= 0, local[:, 2] >= 0
+        for mx in (sx, ~sx):
+            for my in (sy, ~sy):
+                for mz in (sz, ~sz):
+                    m = mx & my & mz
+                    if m.sum() > min_points:
+                        out.extend(fit_contact_primitives(pts[m], max_radius, max_divisions, min_points, _depth + 1))
+        if out:
+            return out
+    return [prim]
+
+
+# primitives per merged body for contact_model="primitives": (max_radius in metres, max_divisions); bodies as in CONTACT_POINT_PLAN
+CONTACT_PRIMITIVE_PLAN = {
+    "vertebrae_sacral": (0.45, 1),
+    "tibia": (1.0, 0), "tarsometatarsus": (1.0, 0),
+    "toe_02_a": (1.0, 0), "toe_02_b": (1.0, 0), "toe_03_a": (1.0, 0), "toe_03_c": (1.0, 0), "toe_04_a": (1.0, 0), "toe_04_d": (1.0, 0),
+    "vertebra_cervical_09": (1.0, 0), "vertebra_cervical_03": (1.0, 0),
+    "cranium": (0.35, 1),
+    "vertebra_caudal_02": (1.0, 0), "vertebra_caudal_10": (1.0, 0), "vertebra_caudal_24": (1.0, 0),
+}
+
+
 def compile_model(
     urdf_path: str,
     *,
     inertia_source: str = "urdf",
     with_contacts: bool = True,
     params: dict | None = None,
+    contact_model: str = "points",
 ) -> CompiledModel:
     """Compile ``urdf_path`` (normally ``<reference>/assets/trex.urdf``).
 
@@ -265,7 +347,14 @@ def compile_model(
     what pybullet does with default ``loadURDF`` flags on a link without a
     collision shape [RECALL, SURVEY.md H6 / Appendix A.1]: the diagonal becomes
     that of a box with half extents = the 0.001 m collision margin.
+
+    ``contact_model``: ``"points"`` (default) takes support points of each body's visual-mesh vertex cloud as floor
+    contact candidates (CONTACT_POINT_PLAN); ``"primitives"`` fits spheres / capsules to the clouds
+    (``fit_contact_primitives``, CONTACT_PRIMITIVE_PLAN) and every sphere / capsule end sphere is a candidate with a
+    radius (it touches the floor at centre - r * normal).
     """
+    if contact_model not in ("points", "primitives"):
+        raise ValueError("contact_model must be 'points' or 'primitives'")
     tools_dir = find_tools_dir(urdf_path)
     up = load_urdf_parsing(tools_dir)
     with open(urdf_path, "r") as f:
@@ -477,7 +566,7 @@ def compile_model(
     RW, XW = body_world_poses(start_q)
 
     # --- contact candidates -------------------------------------------------------
-    cand_body, cand_p, cand_link, cand_local = [], [], [], []
+    cand_body, cand_p, cand_link, cand_local, cand_r = [], [], [], [], []
     mesh_stats = {}
     asset_dir = os.path.dirname(os.path.abspath(urdf_path))
     lowest_vertex_z = None
@@ -519,10 +608,21 @@ def compile_model(
                 continue
             count, mode = CONTACT_POINT_PLAN[key]
             pts = np.concatenate(body_pts[b], axis=0)
+            if contact_model == "primitives":
+                max_radius, max_div = CONTACT_PRIMITIVE_PLAN[key]
+                spheres = [sp for prim in fit_contact_primitives(pts, max_radius, max_div) for sp in prim.spheres()]
+                # lowest-reaching spheres first (reset pose), as many as the point plan grants this body at most twice over
+                spheres.sort(key=lambda cr: float((RW[b] @ cr[0] + XW[b])[2] - cr[1]))
+                for centre, radius in spheres[: max(2, 2 * count)]:
+                    cand_body.append(b)
+                    cand_p.append(centre)
+                    cand_r.append(float(radius))
+                continue
             wpts = pts @ RW[b].T + XW[b]
             for idx in _select_contact_points(wpts, count, mode):
                 cand_body.append(b)
                 cand_p.append(pts[idx])
+                cand_r.append(0.0)
         if len(cand_body) > MAX_CONTACT_CANDIDATES:
             raise ValueError("too many contact candidates")
         # oracle view: attach each point to the body's root link, in that link's inertial frame
@@ -570,6 +670,7 @@ def compile_model(
     )
     S["full_cand_link"] = np.asarray(cand_link, np.int32).reshape(-1)
     S["full_cand_local"] = np.asarray(cand_local, np.float64).reshape(-1)
+    S["full_cand_r"] = np.asarray(cand_r, np.float64).reshape(-1)
     S["noncontact_order"] = noncontact_order
     S["obs_dof"] = obs_dof.astype(np.int32)
     S["mb_n_bodies"] = np.asarray([nb], np.int32)
@@ -592,6 +693,7 @@ def compile_model(
     S["mb_task_m"] = np.asarray(task_m)
     S["mb_cand_body"] = np.asarray(cand_body, np.int32).reshape(-1)
     S["mb_cand_p"] = np.asarray(cand_p, np.float64).reshape(-1)
+    S["mb_cand_r"] = np.asarray(cand_r, np.float64).reshape(-1)
 
     # golden numbers
     total_mass = float(full_mass.sum())
@@ -602,6 +704,7 @@ def compile_model(
     meta = {
         "urdf": os.path.basename(urdf_path),
         "inertia_source": inertia_source,
+        "contact_model": contact_model,
         "root_link": root,
         "n_links": n_links,
         "n_bodies": nb,
@@ -733,10 +836,16 @@ META_PATH = os.path.join(DATA_DIR, "trex_model.json")
 TOPOLOGY_HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "trex_topology.h")
 
 
-def load_builtin() -> CompiledModel:
-    with open(BLOB_PATH, "rb") as f:
+PRIMITIVES_BLOB_PATH = os.path.join(DATA_DIR, "trex_model_primitives.blob")
+PRIMITIVES_META_PATH = os.path.join(DATA_DIR, "trex_model_primitives.json")
+
+
+def load_builtin(contact_model: str = "points") -> CompiledModel:
+    """The checked-in compiled model: ``"points"`` (default) or ``"primitives"`` (spheres / capsules fitted to the meshes)."""
+    bp, mp = {"points": (BLOB_PATH, META_PATH), "primitives": (PRIMITIVES_BLOB_PATH, PRIMITIVES_META_PATH)}[contact_model]
+    with open(bp, "rb") as f:
         sections = model_blob.unpack(f.read())
-    with open(META_PATH, "r") as f:
+    with open(mp, "r") as f:
         meta = json.load(f)
     return CompiledModel(sections, meta)
 
@@ -806,12 +915,14 @@ def emit_topology_header(model: CompiledModel) -> str:
 
 def write_builtin(model: CompiledModel) -> None:
     os.makedirs(DATA_DIR, exist_ok=True)
-    with open(BLOB_PATH, "wb") as f:
+    primitives = model.meta.get("contact_model") == "primitives"
+    with open(PRIMITIVES_BLOB_PATH if primitives else BLOB_PATH, "wb") as f:
         f.write(model.blob())
-    with open(META_PATH, "w") as f:
+    with open(PRIMITIVES_META_PATH if primitives else META_PATH, "w") as f:
         json.dump(model.meta, f, indent=1, sort_keys=True)
-    with open(TOPOLOGY_HEADER, "w") as f:
-        f.write(emit_topology_header(model))
+    if not primitives:  # (the topology does not depend on the contact model)
+        with open(TOPOLOGY_HEADER, "w") as f:
+            f.write(emit_topology_header(model))
 
 
 if __name__ == "__main__":  # python -m trex_gym_b200.model_compiler [urdf]
@@ -822,3 +933,6 @@ if __name__ == "__main__":  # python -m trex_gym_b200.model_compiler [urdf]
     write_builtin(mdl)
     print(json.dumps(mdl.meta["golden"], indent=1))
     print("bodies", mdl.meta["n_bodies"], "links", mdl.meta["n_links"], "candidates", len(mdl["mb_cand_body"]))
+    prim = compile_model(path, contact_model="primitives")
+    write_builtin(prim)
+    print("contact primitives:", len(prim["mb_cand_body"]), "sphere candidates, radii %.3f..%.3f m" % (prim["mb_cand_r"].min(), prim["mb_cand_r"].max()))

@@ -56,14 +56,47 @@ class ReplayRecorder:
         return path
 
 
-def play_in_pybullet(path: str, urdf_path: str, realtime: bool = True):  # pragma: no cover - needs pybullet + a display
-    """Offline playback on the reference side: drives the reference's URDF in the pybullet GUI frame by frame."""
+def link_world_position(model: CompiledModel, base_position, base_orientation_xyzw, joint_positions, body: int | None = None,
+                        point=None) -> np.ndarray:
+    """Host-side forward kinematics of one exported frame on the merged model: world position of ``point`` (body
+    coordinates) of rigid body ``body``.  Defaults: the head link's COM -- what ``getLinkState(head)[0]`` returns in the
+    reference (trex_robot.py:330-335) and what the kernels report in ``aux[:, 0:3]``.  Lets a consumer of a replay file
+    check / place things without the GPU library."""
+    from scipy.spatial.transform import Rotation
+
+    S = model.sections
+    nb = int(S["mb_n_bodies"][0])
+    parent = S["mb_parent"]
+    E0 = S["mb_E0"].reshape(nb, 3, 3)
+    r0 = S["mb_r0"].reshape(nb, 3)
+    body = int(S["mb_head_body"][0]) if body is None else int(body)
+    point = S["mb_head_p"] if point is None else np.asarray(point, float)
+    q = np.concatenate([[0.0], np.asarray(joint_positions, float)])  # joint k moves body k + 1 (state order)
+    chain = []
+    b = body
+    while b > 0:
+        chain.append(b)
+        b = int(parent[b])
+    R = Rotation.from_quat(np.asarray(base_orientation_xyzw, float)).as_matrix()
+    x = np.asarray(base_position, float)
+    for b in reversed(chain):
+        c, s = np.cos(q[b]), np.sin(q[b])
+        x = x + R @ r0[b]
+        R = R @ E0[b] @ np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+    return x + R @ point
+
+
+def play_in_pybullet(path: str, urdf_path: str, realtime: bool = True, pb=None, gui: bool = True):
+    """Offline playback on the reference side: drives the reference's URDF in pybullet frame by frame (GUI by default;
+    ``gui=False`` for a headless check).  ``pb``: the pybullet module (injected by the tests, which have no pybullet).
+    Returns the number of frames played."""
     import time
 
-    import pybullet as pb
+    if pb is None:  # pragma: no cover - needs pybullet
+        import pybullet as pb
 
     rec = json.load(open(path))
-    pb.connect(pb.GUI)
+    pb.connect(pb.GUI if gui else pb.DIRECT)
     body = pb.loadURDF(urdf_path, flags=pb.URDF_USE_INERTIA_FROM_FILE)
     name_to_index = {pb.getJointInfo(body, i)[1].decode(): i for i in range(pb.getNumJoints(body))}
     ids = [name_to_index[n] for n in rec["joint_names"]]
@@ -73,3 +106,4 @@ def play_in_pybullet(path: str, urdf_path: str, realtime: bool = True):  # pragm
             pb.resetJointState(body, i, a)
         if realtime:
             time.sleep(rec["dt"])
+    return len(rec["base_position"])

@@ -27,18 +27,18 @@ RENDER_HEIGHT = 720
 RENDER_WIDTH = 960
 
 
-def _load_model(urdf_path) -> CompiledModel:
+def _load_model(urdf_path, contact_model="points") -> CompiledModel:
     """Compile ``urdf_path`` through the reference's ``tools/urdf_parsing`` when that checkout is
     reachable; otherwise fall back to the compiled model shipped with the package (generated from
     the reference's assets/trex.urdf by the same compiler)."""
     if urdf_path and os.path.isfile(urdf_path):
         try:
-            return compile_model(urdf_path)
+            return compile_model(urdf_path, contact_model=contact_model)
         except ReferenceToolsNotFound:
             pass
     if not os.path.isfile(BLOB_PATH):
         raise FileNotFoundError("no URDF at %r and no built-in model blob" % (urdf_path,))
-    return load_builtin()
+    return load_builtin(contact_model)
 
 
 class TrexBulletEnv(spaces.Env):
@@ -47,7 +47,7 @@ class TrexBulletEnv(spaces.Env):
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 50}
 
     def __init__(self, urdf_path=None, action_repeat=1, distance_weight=1.0, energy_weight=0.005, drift_weight=0.002,
-                 render=False, device=0, model=None, contacts=True):
+                 render=False, device=0, model=None, contacts=True, contact_model="points"):
         self._time_step = 0.01
         self._urdf_path = urdf_path
         self._action_repeat = action_repeat
@@ -67,7 +67,8 @@ class TrexBulletEnv(spaces.Env):
             "femur_L_joint": -0.6, "tibia_L_joint": 0.4, "tarsometatarsus_L_joint": -1.2,
             "femur_R_joint": -0.6, "tibia_R_joint": 0.4, "tarsometatarsus_R_joint": -1.2,
         }
-        mdl = model if model is not None else _load_model(urdf_path)
+        # contact_model: "points" (support points of the visual meshes) or "primitives" (spheres / capsules fitted to them)
+        mdl = model if model is not None else _load_model(urdf_path, contact_model)
         # dt = 0.01/NUM_SUBSTEPS and int(300/NUM_SUBSTEPS) iterations per physics step; the env step runs
         # action_repeat * NUM_SUBSTEPS physics steps (trex_env.py:148-150)
         self._sim = TrexBatchSim(1, device=device, model=mdl, num_substeps=NUM_SUBSTEPS,
@@ -131,8 +132,8 @@ class TrexVecEnv(object):
     ``VecNormalize`` -> ``ppo2.Runner`` call, trex_train.py:44-49), torch CUDA tensors in/out."""
 
     def __init__(self, num_envs, urdf_path=None, distance_weight=1.0, energy_weight=0.005, drift_weight=0.002,
-                 device=0, model=None, num_substeps=NUM_SUBSTEPS, max_episode_steps=0, contacts=True, seed=0):
-        mdl = model if model is not None else _load_model(urdf_path)
+                 device=0, model=None, num_substeps=NUM_SUBSTEPS, max_episode_steps=0, contacts=True, seed=0, contact_model="points"):
+        mdl = model if model is not None else _load_model(urdf_path, contact_model)
         self.sim = TrexBatchSim(num_envs, device=device, model=mdl, num_substeps=num_substeps,
                                 distance_weight=distance_weight, energy_weight=energy_weight, drift_weight=drift_weight,
                                 max_episode_steps=max_episode_steps, contacts=contacts, seed=seed)
