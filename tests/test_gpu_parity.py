@@ -429,8 +429,8 @@ def test_heavy_contact_kernel_on_standing_batch(model):
     for k, v in model.meta["starting_configuration"].items():
         hold[names.index(k)] = v
     a = torch.tensor(hold, device="cuda").repeat(n, 1).contiguous()
-    forced = _sim(model, n, heavy_share_div=1)
-    default = _sim(model, n)
+    forced = _sim(model, n)
+    default = _sim(model, n, heavy_solver=False)
     forced.reset()
     default.reset()
     o = _oracle(model)

@@ -102,8 +102,10 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
 }
 
 // one warp per FOUR deferred environments of one class, eight lanes per environment; KC = 0: the contact-free list,
-// KC = TREX_KC: the three lists of environments in contact (rows in row space, see solve4), warps assigned class by class
-template <int WARPS, int KC>
+// KC > 0: the lists of the contact classes CLO..CHI (rows in row space, see solve4), warps assigned class by class.
+// (A second instance with KC = 2 for the environments with 1-2 contacts -- 168 registers, 12 warps per SM -- was measured:
+// 70 spilled registers in the sweep, 9.3 instead of 8.1 ms per env step on the benchmark batch.  One instance serves 1-8.)
+template <int WARPS, int KC, int CLO, int CHI>
 __global__ void __launch_bounds__(32 * WARPS, (KC ? TREX_SOLVEC_MIN_BLOCKS : TREX_SOLVE_MIN_BLOCKS) / WARPS)
 trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
                   const int* __restrict__ list, const int* __restrict__ list_count, int n_envs) {
@@ -113,12 +115,12 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   int first = (blockIdx.x * WARPS + warp) * 4;
   int count = *list_count;
   if (KC > 0) {
-    // list / list_count point at class 1.  Warps are handed out heaviest class first (5-8 contacts, then 3-4, then 1-2):
+    // list / list_count point at class 0.  Warps are handed out heaviest class first (CHI, then down to CLO):
     // the longest-running warps start first instead of forming the tail of the launch.
-    list += (size_t)(TREX_CLASS_HEAVY - 2) * n_envs;   // the heaviest solve4 class
-    list_count += 64 * (TREX_CLASS_HEAVY - 2);
+    list += (size_t)CHI * n_envs;
+    list_count += 64 * CHI;
     count = *list_count;
-    for (int c = TREX_CLASS_HEAVY - 1; c > 1 && first >= ((count + 3) & ~3); c--) {
+    for (int c = CHI; c > CLO && first >= ((count + 3) & ~3); c--) {
       first -= (count + 3) & ~3;
       list -= n_envs;
       list_count -= 64;
@@ -347,8 +349,8 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
   if (!configured[h->device & 15]) {
     int rc;
     if ((rc = configure_kernel(trex_front_kernel<WF, WF == 4>, smem_f)) != TREX_OK) return rc;
-    if ((rc = configure_kernel(trex_solve_kernel<WS, 0>, smem_s)) != TREX_OK) return rc;
-    if ((rc = configure_kernel(trex_solve_kernel<WS, TREX_KC>, smem_c)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_solve_kernel<WS, 0, 0, 0>, smem_s)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1>, smem_c)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_heavy_kernel<1>, smem_h)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
@@ -372,8 +374,8 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
         const bool split = contacts && h->concurrent_solves && h->side2 != nullptr;
         if (heavy || split) CUDA_TRY(cudaEventRecord(h->ev_fork, st));
         if (contacts) {
-          trex_solve_kernel<WS, TREX_KC><<<grid4 + 3, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list + h->n_envs,
-                                                                            h->d_list_count + 64 + r, h->n_envs);
+          trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1><<<grid4 + 4, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list,
+                                                                                                     h->d_list_count + r, h->n_envs);
           CUDA_TRY(cudaGetLastError());
           h->launches++;
         }
@@ -390,7 +392,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
         }
         cudaStream_t s0 = split ? h->side2 : st;
         if (split) CUDA_TRY(cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
-        trex_solve_kernel<WS, 0><<<grid4, 32 * WS, smem_s, s0>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r, h->n_envs);
+        trex_solve_kernel<WS, 0, 0, 0><<<grid4, 32 * WS, smem_s, s0>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r, h->n_envs);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
         if (split) {
@@ -518,7 +520,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     CTRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CTRY(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
     CTRY(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
-    if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aid
+    if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aids
   }
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
