@@ -234,7 +234,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 WORKLOADS = {
     # name: (default envs/GPU, description)
-    "random": (65536, "random actions U(low,high) Philox-keyed by (seed,global env,step), 100-step pre-roll (BASELINE.json configs[2])"),
+    "random": (65536, "random actions U(low,high) Philox-keyed by (seed,global env,step), pre-rolled into the steady regime (BASELINE.json configs[2])"),
     "c2": (4096, "4,096 envs, random actions (BASELINE.json configs[1]: the parity-test batch)"),
     "standing": (65536, "every env holds the reset pose and stands on both feet (12-16 contacts each): the regime a trained policy produces"),
     "fallen": (65536, "fallen starts (reset_mode 1: base z U(0.3,3), uniform SO(3), joints U(limits)), horizon 64 with auto-reset, random actions (BASELINE.json configs[4])"),
@@ -296,10 +296,10 @@ def make_batch(workload, n, local, rank, args):
             sim.step(acts[0])
     else:
         acts = [sim.random_actions(step=t, seed=0, env_offset=env_offset) for t in range(ACTION_SETS)]
-        # untimed pre-roll: bring the batch from the reset pose (0.25 m above the floor) to its steady regime
+        # untimed pre-roll: bring the batch from the reset pose (0.25 m above the floor) to the steady regime of THIS action
+        # process (the 16 sets cycling: pre-rolling with other actions leaves a transient of ~50 steps in the timed region)
         for t in range(args.preroll):
-            sim.step(sim.random_actions(step=1_000_000 + t, seed=0, env_offset=env_offset, out=acts[0]))
-        acts[0] = sim.random_actions(step=0, seed=0, env_offset=env_offset, out=acts[0])
+            sim.step(acts[t % ACTION_SETS])
     return sim, acts
 
 
@@ -398,8 +398,9 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
 
     # ---- device-resident throughput ("value") -------------------------------------------------
+    phase0 = args.preroll if workload != "standing" else 0  # keep cycling where the pre-roll stopped
     for t in range(args.warmup):
-        sim.step(acts[t % ring])
+        sim.step(acts[(phase0 + t) % ring])
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -408,7 +409,7 @@ def run_ours(args):
     for k in range(args.steps):
         flush.fill_(float(k))  # L2 flush between timed steps (not timed)
         evs[k][0].record()
-        sim.step(acts[(args.warmup + k) % ring])
+        sim.step(acts[(phase0 + args.warmup + k) % ring])
         evs[k][1].record()
     barrier()
     launches = sim.kernel_launches - launches0
@@ -428,12 +429,12 @@ def run_ours(args):
         for k in range(args.spread_steps):
             flush.fill_(float(k))
             sevs[k][0].record()
-            sim.step(acts[(args.warmup + args.steps + k) % ring])
+            sim.step(acts[(phase0 + args.warmup + args.steps + k) % ring])
             sevs[k][1].record()
         barrier()
         ms = np.asarray([a.elapsed_time(b) for a, b in sevs])
         s2 = sim.stats()
-        spread = {"steps": int(args.spread_steps), "action_sets": ring, "ms_p10": float(np.percentile(ms, 10)), "ms_p50": float(np.percentile(ms, 50)),
+        spread = {"steps": int(args.spread_steps), "action_sets": ring, "ms_first10_mean": float(ms[:10].mean()), "ms_last10_mean": float(ms[-10:].mean()), "ms_p10": float(np.percentile(ms, 10)), "ms_p50": float(np.percentile(ms, 50)),
                   "ms_p90": float(np.percentile(ms, 90)), "ms_mean": float(ms.mean()), "ms_max": float(ms.max()),
                   "mean_contacts_per_env_at_end": s2["mean_contacts"], "nan_resets": s2["nan_resets"]}
 
@@ -489,7 +490,7 @@ def run_ours(args):
         cfg = {"workload": "%s: %d envs/GPU, %s%s" % (workload, n, WORKLOADS[workload][1], "" if not args.no_contacts else "; literal collision-less URDF (free fall)"),
                "envs_per_gpu": n, "num_substeps": sim.num_substeps, "solver_iterations": int(300 / sim.num_substeps),
                "mean_solver_iterations": it_sum, "mean_contacts_per_env": ct_sum, "horizon": args.horizon or (64 if workload == "fallen" else 0),
-               "preroll_steps": args.preroll, "action_sets": ring,
+               "preroll_steps": args.preroll, "action_sets": ring, "ms_timed_first": float(evs[0][0].elapsed_time(evs[0][1])), "ms_timed_last": float(evs[-1][0].elapsed_time(evs[-1][1])),
                "l2": "flushed between timed steps (256 MiB fill, untimed); steps timed individually with CUDA events",
                "parallelism": "envs sharded over %d GPU(s), no step-path collective" % world}
         if spread:
@@ -541,7 +542,7 @@ def main():
     ap.add_argument("--no-contacts", action="store_true", help="literal reference URDF (no collision shapes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warps-per-block", type=int, default=0)
-    ap.add_argument("--preroll", type=int, default=100, help="untimed env-steps from the reset state before warm-up, so the batch is in its steady regime (on the floor, in contact)")
+    ap.add_argument("--preroll", type=int, default=300, help="untimed env-steps from the reset state before warm-up, so the batch is in its steady regime (on the floor, in contact)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -37,14 +37,14 @@ def inner(workload):
     import bench
 
     n = bench.WORKLOADS[workload][0]
-    args = argparse.Namespace(no_contacts=False, substeps=5, warps_per_block=0, horizon=0, preroll=100 if workload != "standing" else 40)
+    args = argparse.Namespace(no_contacts=False, substeps=5, warps_per_block=0, horizon=0, preroll=300 if workload != "standing" else 40)
     sim, acts = bench.make_batch(workload, n, 0, 0, args)
     for t in range(3):
-        sim.step(acts[t % len(acts)])
+        sim.step(acts[(args.preroll + t) % len(acts)])
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     for t in range(K_STEPS):
-        sim.step(acts[(3 + t) % len(acts)])
+        sim.step(acts[(args.preroll + 3 + t) % len(acts)])
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     st = sim.stats()

@@ -200,8 +200,9 @@ def test_bucketed_contact_parity_gpu(model, n_sub):
 
 @pytest.mark.gpu
 def test_bench_batch_spot_check(model):
-    """The measured workload is the tested workload: the bench batch itself (65,536 envs after bench.py's 100-step
-    pre-roll, same action stream) with 64 sampled envs checked against the oracle for 5 steps, bucketed as above."""
+    """The measured workload is the tested workload: the bench batch itself (65,536 envs, bench.make_batch: the same 16
+    cycling action sets, pre-rolled 100 steps here -- bench.py's default is 300) with 64 sampled envs checked against the
+    oracle for 5 steps, bucketed as above."""
     import argparse
 
     import bench
@@ -215,9 +216,9 @@ def test_bench_batch_spot_check(model):
     sample = np.arange(0, 65536, 1024)
     for t in range(5):
         pre = sim.get_state()[sample].cpu().numpy().astype(np.float64)
-        sim.step(acts[t])
+        sim.step(acts[(100 + t) % len(acts)])
         post = sim.get_state()[sample].cpu().numpy().astype(np.float64)
-        a = acts[t][sample].cpu().numpy().astype(np.float64)
+        a = acts[(100 + t) % len(acts)][sample].cpu().numpy().astype(np.float64)
         for i in range(len(sample)):
             p = np.concatenate([pre[i, :88], pre[i, 88:88 + nc]])
             o.set_state(p)

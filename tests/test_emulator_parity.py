@@ -444,3 +444,35 @@ def test_contact_primitives_model_per_substep(model, action_limits):
     zs = [o.candidate_position(k)[2] for k in range(nc)]
     assert -0.03 < min(zs) < 0.03
     assert np.percentile(errs, 50) < 5e-4 and np.percentile(errs, 99) < 2e-2, (np.percentile(errs, 50), errs.max())
+
+
+def test_literal_reference_model(action_limits):
+    """What the reference's own pybullet calls simulate with the checked-in URDF [RECALL, SURVEY.md H6 / section 0.4]:
+    default-flag inertia (recomputed from the absent collision shapes: point masses) and no contact geometry at all.
+    Shipped as ``load_builtin("literal")`` / ``TrexBulletEnv(literal_reference=True)``; the animal free-falls, and kernel
+    source and oracle agree to the contact-free tolerance on it."""
+    from emu import EmuEnv
+
+    from trex_gym_b200.model_compiler import load_builtin
+
+    lit, std = load_builtin("literal"), load_builtin()
+    assert lit.meta["inertia_source"] == "bullet_default" and len(lit["mb_cand_body"]) == 0
+    I = lit["full_inertia"].reshape(-1, 3)
+    assert np.allclose(I[:, 0], lit["full_mass"] / 12.0 * 2 * 0.002 ** 2) and I.max() < 1e-2  # margin-sized boxes
+    assert np.array_equal(lit["full_mass"], std["full_mass"]) and np.array_equal(lit["mb_parent"], std["mb_parent"])
+    o = _oracle(lit, contacts=False)
+    e = EmuEnv(lit.blob(), contacts=False)
+    assert np.abs(o.reset() - e.reset()).max() < 1e-6
+    lo, hi = action_limits
+    rng = np.random.default_rng(0)
+    errs = []
+    for t in range(40):
+        a = rng.uniform(lo, hi)
+        pre = e.get_state(0)
+        o.set_state(pre)
+        o.step(a)
+        e.step(a)
+        so, se = o.get_state(), e.get_state(0)
+        errs.append(max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()))
+    assert max(errs) < 2e-5, max(errs)
+    assert o.get_state()[2] < 2.3  # free fall from z = 3: nothing holds the literal model up

@@ -202,3 +202,29 @@ def test_replay_frames_recorded_on_hardware(model, tmp_path):
     # the two environments were driven differently: the frames are really per environment
     a, b = rec.as_dict(0), rec.as_dict(1)
     assert np.abs(np.asarray(a["joint_positions"][-1]) - np.asarray(b["joint_positions"][-1])).max() > 1e-3
+
+
+def test_literal_reference_configuration(model):
+    """the default configuration (URDF inertia, derived floor contact) is not what the literal reference
+    simulates; ``literal_reference=True`` is -- default-flag inertia and no contact geometry -- and matches the oracle on the
+    same blob.  Both configurations ship and are tested."""
+    from oracle.oracle import Oracle
+    from trex_gym_b200 import TrexBulletEnv
+    from trex_gym_b200.model_compiler import load_builtin
+
+    env = TrexBulletEnv(literal_reference=True)
+    assert env._sim.model.meta["inertia_source"] == "bullet_default"
+    o = Oracle(load_builtin("literal").blob(), contacts=False)
+    assert np.abs(np.asarray(env.reset()) - o.reset()).max() < 1e-6
+    rng = np.random.default_rng(1)
+    for t in range(60):
+        a = rng.uniform(env.action_space.low, env.action_space.high).astype(np.float32)
+        obs, rew, done, info = env.step(a)
+        oobs, orew = o.step(a.astype(np.float64))
+    # free running for 60 steps, contact free: still close (1e-4 of the block magnitudes), and falling through the floor plane
+    assert np.abs(np.asarray(obs)[:25] - oobs[:25]).max() < 1e-3
+    assert env.model.get_base_position()[2] < 1.5 and not done
+    env.close()
+    std = TrexBulletEnv()
+    assert std._sim.model.meta["inertia_source"] == "urdf" and len(std._sim.model["mb_cand_body"]) == 48
+    std.close()

@@ -610,7 +610,8 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
     TREX_UNROLL for (int k = 0; k < 6; k++) bv[k] = shflv(v[k], dl);
     vf acc[6];
     TREX_UNROLL for (int k = 0; k < 6; k++) acc[k] = 0.0f;
-    TREX_ROLLED for (int rd = 0; rd < P.n_rounds; rd++) {
+    // (latency bound: four table loads feed ~25 dependent operations per round -- several rounds in flight)
+    _Pragma("unroll 5") for (int rd = 0; rd < P.n_rounds; rd++) {
       const float* t = tasks + rd * 4 * 32;
       const vf rx = ldg_ro(t, lane), ry = ldg_ro(t, lane + 32), rz = ldg_ro(t, lane + 64), m = ldg_ro(t, lane + 96);
       const vf cx = bv[3] + (bv[1] * rz - bv[2] * ry);
@@ -875,6 +876,17 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
 
   TREX_TICK(4)
   // ---- 10. constraint rows -------------------------------------------------------------------------
+  // the lane's two contact candidates (model constants): loaded here, ahead of the joint-row arithmetic, so that the two
+  // dependent global loads (body lane, then its pose from shared memory) are not exposed at the contact detection
+  vi c_bl[2];
+  vf c_px[2], c_py[2], c_pz[2], c_pr[2];
+  TREX_UNROLL for (int half = 0; half < 2; half++) {
+    const vi ci = lane + 32 * half;
+    const vi cis = seli(ci < P.n_cand, ci, 0);
+    c_bl[half] = ldi(cand_lane, cis);
+    c_px[half] = ldg_ro(cand_p, cis); c_py[half] = ldg_ro(cand_p, cis + TREX_NCAND_MAX);
+    c_pz[half] = ldg_ro(cand_p, cis + 2 * TREX_NCAND_MAX); c_pr[half] = ldg_ro(cand_p, cis + 3 * TREX_NCAND_MAX);
+  }
   // this lane's own velocity coordinate and diagonal of M^-1
   vf uown = R.qd;
   vf dself = 0.0f;
@@ -930,14 +942,14 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
       const vi ci = lane + 32 * half;
       const vb valid = ci < P.n_cand;
       const vi cis = seli(valid, ci, 0);
-      const vi bl = ldi(cand_lane, cis);
-      const vf px = ldg_ro(cand_p, cis), py = ldg_ro(cand_p, cis + TREX_NCAND_MAX), pz = ldg_ro(cand_p, cis + 2 * TREX_NCAND_MAX);
+      const vi bl = c_bl[half];
+      const vf px = c_px[half], py = c_py[half], pz = c_pz[half];
       // world point = xw + Rw^T p
       wpos[half][0] = ld(S.k.xw[0], bl) + ld(S.k.Rw[0], bl) * px + ld(S.k.Rw[3], bl) * py + ld(S.k.Rw[6], bl) * pz;
       wpos[half][1] = ld(S.k.xw[1], bl) + ld(S.k.Rw[1], bl) * px + ld(S.k.Rw[4], bl) * py + ld(S.k.Rw[7], bl) * pz;
       // a sphere candidate (radius > 0, contact primitives fitted to the meshes) touches the floor with its lowest point:
       // centre - r * normal, a WORLD offset (not body fixed), exactly what a sphere-plane manifold point is
-      wpos[half][2] = (ld(S.k.xw[2], bl) + ld(S.k.Rw[2], bl) * px + ld(S.k.Rw[5], bl) * py + ld(S.k.Rw[8], bl) * pz) - ldg_ro(cand_p, cis + 3 * TREX_NCAND_MAX);
+      wpos[half][2] = (ld(S.k.xw[2], bl) + ld(S.k.Rw[2], bl) * px + ld(S.k.Rw[5], bl) * py + ld(S.k.Rw[8], bl) * pz) - c_pr[half];
       cbl[half] = bl;
       cact[half] = valid && ((wpos[half][2] - P.floor_z) < P.breaking);
       am[half] = vballot(cact[half]);

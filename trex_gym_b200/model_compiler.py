@@ -838,11 +838,18 @@ TOPOLOGY_HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc
 
 PRIMITIVES_BLOB_PATH = os.path.join(DATA_DIR, "trex_model_primitives.blob")
 PRIMITIVES_META_PATH = os.path.join(DATA_DIR, "trex_model_primitives.json")
+LITERAL_BLOB_PATH = os.path.join(DATA_DIR, "trex_model_literal.blob")
+LITERAL_META_PATH = os.path.join(DATA_DIR, "trex_model_literal.json")
 
 
 def load_builtin(contact_model: str = "points") -> CompiledModel:
-    """The checked-in compiled model: ``"points"`` (default) or ``"primitives"`` (spheres / capsules fitted to the meshes)."""
-    bp, mp = {"points": (BLOB_PATH, META_PATH), "primitives": (PRIMITIVES_BLOB_PATH, PRIMITIVES_META_PATH)}[contact_model]
+    """The checked-in compiled model: ``"points"`` (default: URDF inertia tensors, derived floor-contact points),
+    ``"primitives"`` (the same with spheres / capsules fitted to the meshes as contact geometry) or ``"literal"`` -- what
+    the reference's own pybullet call does with the checked-in URDF [RECALL, SURVEY.md H6 and section 0.4]:
+    ``loadURDF`` without flags recomputes every link's inertia from its (absent) collision shape, and without any
+    ``<collision>`` element nothing ever touches the floor."""
+    bp, mp = {"points": (BLOB_PATH, META_PATH), "primitives": (PRIMITIVES_BLOB_PATH, PRIMITIVES_META_PATH),
+              "literal": (LITERAL_BLOB_PATH, LITERAL_META_PATH)}[contact_model]
     with open(bp, "rb") as f:
         sections = model_blob.unpack(f.read())
     with open(mp, "r") as f:
@@ -916,11 +923,13 @@ def emit_topology_header(model: CompiledModel) -> str:
 def write_builtin(model: CompiledModel) -> None:
     os.makedirs(DATA_DIR, exist_ok=True)
     primitives = model.meta.get("contact_model") == "primitives"
-    with open(PRIMITIVES_BLOB_PATH if primitives else BLOB_PATH, "wb") as f:
+    literal = model.meta.get("inertia_source") == "bullet_default"
+    bp, mp = (LITERAL_BLOB_PATH, LITERAL_META_PATH) if literal else ((PRIMITIVES_BLOB_PATH, PRIMITIVES_META_PATH) if primitives else (BLOB_PATH, META_PATH))
+    with open(bp, "wb") as f:
         f.write(model.blob())
-    with open(PRIMITIVES_META_PATH if primitives else META_PATH, "w") as f:
+    with open(mp, "w") as f:
         json.dump(model.meta, f, indent=1, sort_keys=True)
-    if not primitives:  # (the topology does not depend on the contact model)
+    if not primitives and not literal:  # (the topology does not depend on the contact model or the inertia source)
         with open(TOPOLOGY_HEADER, "w") as f:
             f.write(emit_topology_header(model))
 
@@ -936,3 +945,6 @@ if __name__ == "__main__":  # python -m trex_gym_b200.model_compiler [urdf]
     prim = compile_model(path, contact_model="primitives")
     write_builtin(prim)
     print("contact primitives:", len(prim["mb_cand_body"]), "sphere candidates, radii %.3f..%.3f m" % (prim["mb_cand_r"].min(), prim["mb_cand_r"].max()))
+    lit = compile_model(path, inertia_source="bullet_default", with_contacts=False)
+    write_builtin(lit)
+    print("literal reference model: bullet-default inertia, %d contact candidates" % len(lit["mb_cand_body"]))

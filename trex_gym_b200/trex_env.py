@@ -47,7 +47,7 @@ class TrexBulletEnv(spaces.Env):
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 50}
 
     def __init__(self, urdf_path=None, action_repeat=1, distance_weight=1.0, energy_weight=0.005, drift_weight=0.002,
-                 render=False, device=0, model=None, contacts=True, contact_model="points"):
+                 render=False, device=0, model=None, contacts=True, contact_model="points", literal_reference=False):
         self._time_step = 0.01
         self._urdf_path = urdf_path
         self._action_repeat = action_repeat
@@ -67,8 +67,16 @@ class TrexBulletEnv(spaces.Env):
             "femur_L_joint": -0.6, "tibia_L_joint": 0.4, "tarsometatarsus_L_joint": -1.2,
             "femur_R_joint": -0.6, "tibia_R_joint": 0.4, "tarsometatarsus_R_joint": -1.2,
         }
-        # contact_model: "points" (support points of the visual meshes) or "primitives" (spheres / capsules fitted to them)
-        mdl = model if model is not None else _load_model(urdf_path, contact_model)
+        # contact_model: "points" (support points of the visual meshes) or "primitives" (spheres / capsules fitted to them).
+        # literal_reference=True reproduces what the reference's own pybullet calls do with the checked-in URDF [RECALL]:
+        # inertia recomputed from the (absent) collision shapes and no floor contact at all (the URDF has no <collision>:
+        # the animal free-falls).  The DEFAULT is the physically meaningful configuration -- inertia tensors from the file
+        # and floor contact on derived geometry -- which is NOT what the literal reference simulates.
+        if literal_reference:
+            contacts = False
+            mdl = model if model is not None else load_builtin("literal")
+        else:
+            mdl = model if model is not None else _load_model(urdf_path, contact_model)
         # dt = 0.01/NUM_SUBSTEPS and int(300/NUM_SUBSTEPS) iterations per physics step; the env step runs
         # action_repeat * NUM_SUBSTEPS physics steps (trex_env.py:148-150)
         self._sim = TrexBatchSim(1, device=device, model=mdl, num_substeps=NUM_SUBSTEPS,
@@ -132,8 +140,13 @@ class TrexVecEnv(object):
     ``VecNormalize`` -> ``ppo2.Runner`` call, trex_train.py:44-49), torch CUDA tensors in/out."""
 
     def __init__(self, num_envs, urdf_path=None, distance_weight=1.0, energy_weight=0.005, drift_weight=0.002,
-                 device=0, model=None, num_substeps=NUM_SUBSTEPS, max_episode_steps=0, contacts=True, seed=0, contact_model="points"):
-        mdl = model if model is not None else _load_model(urdf_path, contact_model)
+                 device=0, model=None, num_substeps=NUM_SUBSTEPS, max_episode_steps=0, contacts=True, seed=0, contact_model="points",
+                 literal_reference=False):
+        if literal_reference:  # see TrexBulletEnv
+            contacts = False
+            mdl = model if model is not None else load_builtin("literal")
+        else:
+            mdl = model if model is not None else _load_model(urdf_path, contact_model)
         self.sim = TrexBatchSim(num_envs, device=device, model=mdl, num_substeps=num_substeps,
                                 distance_weight=distance_weight, energy_weight=energy_weight, drift_weight=drift_weight,
                                 max_episode_steps=max_episode_steps, contacts=contacts, seed=seed)
