@@ -88,7 +88,10 @@ typedef struct trex_config {
   int32_t heavy_share_div;   /* > 0: environments with 9-16 contacts go to trex_heavy_kernel only while at most
                                 n_envs / heavy_share_div of the batch were in that class in the previous substep (1 = always);
                                 0 = default: always (the routing then depends on the environment alone, never on its batch) */
-  int32_t reserved[11];      /* must be zero */
+  int32_t pipelines;         /* the batch is stepped as this many independent groups of environments, each a chain of kernels on
+                                its own stream, so that one group's latency-bound solvers overlap another group's issue-bound
+                                dynamics kernel (results do not depend on it): 1..4; 0 = default (2 from 8,192 environments) */
+  int32_t reserved[10];      /* must be zero */
 } trex_config;
 
 typedef struct trex_stats {

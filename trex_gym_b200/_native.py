@@ -42,7 +42,8 @@ class TrexConfig(ctypes.Structure):
         ("warps_per_block", ctypes.c_int32),
         ("solver_placement", ctypes.c_int32),
         ("heavy_share_div", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 11),
+        ("pipelines", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 10),
     ]
 
 

@@ -311,13 +311,24 @@ struct trex_handle {
   cudaStream_t host_main = nullptr, host_copy = nullptr, host_in = nullptr;
   cudaEvent_t ev_step_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr}, ev_in_done[2] = {nullptr, nullptr};
   int host_slot = 0;
-  int* d_list = nullptr;        // [TREX_NCLASS][n_envs] environments whose solve was deferred in the current substep round, by class
-  int* d_list_count = nullptr;  // [TREX_NCLASS][64] one counter per class and substep round
   DevStats* d_stats = nullptr;
-  // trex_heavy_kernel touches a handful of environments but each takes ~200 us: it runs on a side stream, hidden under the
-  // two solve4 kernels of the same round (fork after the front kernel, join before the next one; no host synchronisation)
-  cudaStream_t side = nullptr, side2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  // Environments are independent, so the batch is stepped as `n_pipes` groups, each with its own chain
+  // front -> solves -> front -> ... -> tail on its own stream.  The groups' kernels overlap freely: while one group's
+  // solvers (latency bound, few warps per SM) drain, another group's front kernel (issue bound) fills the issue slots --
+  // the hardware block scheduler interleaves their CTAs.  Within a group the three solve kernels of a round also run
+  // concurrently (caller-side stream + two side streams).  Fork / join by events only: no host synchronisation, and the
+  // whole step stays capturable into a CUDA graph from the caller's stream.
+  static constexpr int MAX_PIPES = 4;
+  struct Pipe {
+    int first = 0, count = 0;     // environments [first, first + count)
+    cudaStream_t main = nullptr;  // pipe 0 runs on the caller's stream instead
+    cudaStream_t side = nullptr, side2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_done = nullptr;
+    int* d_list = nullptr;        // [TREX_NCLASS][count] environments whose solve was deferred in the current substep round, by class
+    int* d_list_count = nullptr;  // [TREX_NCLASS + 2][64] one counter per class and substep round (+ heavy seen / hint)
+  } pipe[MAX_PIPES];
+  int n_pipes = 0;              // 0 until trex_create decides (config / default)
+  cudaEvent_t ev_start = nullptr;
   bool concurrent_solves = true;  // the contact-free solve kernel on a second side stream, under the contact solver
   int heavy_div = 0;            // > 0: class 5 goes to trex_heavy_kernel only while at most n_envs / heavy_div environments are in it (0: always)
   int heavy_grid = 148 * 7;     // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
@@ -355,58 +366,82 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
     if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
   }
-  const int grid1 = (h->n_envs + WF - 1) / WF;            // one warp per environment
-  const int grid4 = (h->n_envs + 4 * WS - 1) / (4 * WS);  // one warp per four environments
-  if (mode == 0) {
-    if (h->d_work) CUDA_TRY(cudaMemsetAsync(h->d_list_count, 0, 64 * (TREX_NCLASS + 1) * sizeof(int), st));  // (not the hint behind them)  // one counter per list and substep round
-    for (int r = 0; r < h->P.n_sub; r++) {
-      trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
-                                                           h->d_state, h->d_work, h->d_workh, action, h->d_list, h->d_list_count + r,
-                                                           h->d_list_count + 64 * (TREX_NCLASS + 1), h->heavy_div, h->n_envs, r == 0);
+  if (h->n_pipes > 1) CUDA_TRY(cudaEventRecord(h->ev_start, st));
+  trex::Uniform Pp[trex_handle::MAX_PIPES];
+  cudaStream_t sp[trex_handle::MAX_PIPES];
+  for (int p = 0; p < h->n_pipes; p++) {
+    trex_handle::Pipe& q = h->pipe[p];
+    Pp[p] = h->P;
+    Pp[p].env_offset = h->P.env_offset + q.first;  // the reset sampler is keyed by the global environment id
+    sp[p] = p == 0 ? st : q.main;
+    if (p > 0) CUDA_TRY(cudaStreamWaitEvent(sp[p], h->ev_start, 0));
+    if (mode == 0 && h->d_work) CUDA_TRY(cudaMemsetAsync(q.d_list_count, 0, 64 * (TREX_NCLASS + 1) * sizeof(int), sp[p]));  // (not the hint behind them)
+  }
+  const int n_rounds = mode == 0 ? h->P.n_sub : 0;
+  for (int r = 0; r < n_rounds; r++) {
+    for (int p = 0; p < h->n_pipes; p++) {
+      trex_handle::Pipe& q = h->pipe[p];
+      cudaStream_t s = sp[p];
+      const size_t e0 = (size_t)q.first;
+      const int grid1 = (q.count + WF - 1) / WF;            // one warp per environment
+      const int grid4 = (q.count + 4 * WS - 1) / (4 * WS);  // one warp per four environments
+      float* state = h->d_state + e0 * TREX_STATE_STRIDE;
+      float* work = h->d_work ? h->d_work + e0 * TREX_WORK_STRIDE : nullptr;
+      float* workh = h->d_workh ? h->d_workh + e0 * TREX_HEAVY_STRIDE : nullptr;
+      trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, s>>>(Pp[p], h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+                                                          state, work, workh, action + e0 * trex::NJ, q.d_list, q.d_list_count + r,
+                                                          q.d_list_count + 64 * (TREX_NCLASS + 1), h->heavy_div, q.count, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
-      if (h->d_work) {
-        // The three solve kernels of a round work on disjoint lists of environments.  The two latency-bound ones go first:
-        // the contact solver on the caller's stream, the many-contact solver on a side stream; the contact-free solver
-        // (issue bound) runs on a second side stream and fills the issue slots they leave.  Fork / join by events only.
-        const bool contacts = h->P.defer_contacts && h->P.contacts_on;
-        const bool heavy = h->P.defer_contacts > 1 && h->P.contacts_on && h->d_workh != nullptr;
-        const bool split = contacts && h->concurrent_solves && h->side2 != nullptr;
-        if (heavy || split) CUDA_TRY(cudaEventRecord(h->ev_fork, st));
-        if (contacts) {
-          trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1><<<grid4 + 4, 32 * WS, smem_c, st>>>(h->P, h->d_state, h->d_work, h->d_list,
-                                                                                                     h->d_list_count + r, h->n_envs);
-          CUDA_TRY(cudaGetLastError());
-          h->launches++;
-        }
-        if (heavy) {  // class 5: more than TREX_KC contacts, two environments per warp
-          CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-          trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, h->side>>>(h->P, h->d_state, h->d_work, h->d_workh,
-                                                                      h->d_list + (size_t)TREX_CLASS_HEAVY * h->n_envs,
-                                                                      h->d_list_count + 64 * TREX_CLASS_HEAVY + r,
-                                                                      h->d_list_count + 64 * TREX_NCLASS + r,
-                                                                      h->d_list_count + 64 * (TREX_NCLASS + 1));
-          CUDA_TRY(cudaGetLastError());
-          h->launches++;
-          CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
-        }
-        cudaStream_t s0 = split ? h->side2 : st;
-        if (split) CUDA_TRY(cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
-        trex_solve_kernel<WS, 0, 0, 0><<<grid4, 32 * WS, smem_s, s0>>>(h->P, h->d_state, h->d_work, h->d_list, h->d_list_count + r, h->n_envs);
+      if (!h->d_work) continue;
+      // The three solve kernels of a round work on disjoint lists of environments.  The two latency-bound ones go first:
+      // the contact solver on the group's stream, the many-contact solver on a side stream; the contact-free solver
+      // (issue bound) runs on a second side stream and fills the issue slots they leave.
+      const bool contacts = h->P.defer_contacts && h->P.contacts_on;
+      const bool heavy = h->P.defer_contacts > 1 && h->P.contacts_on && workh != nullptr;
+      const bool split = contacts && h->concurrent_solves && q.side2 != nullptr;
+      if (heavy || split) CUDA_TRY(cudaEventRecord(q.ev_fork, s));
+      if (contacts) {
+        trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1><<<grid4 + 4, 32 * WS, smem_c, s>>>(Pp[p], state, work, q.d_list, q.d_list_count + r, q.count);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
-        if (split) {
-          CUDA_TRY(cudaEventRecord(h->ev_join2, h->side2));
-          CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join2, 0));
-        }
-        if (heavy) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
       }
+      if (heavy) {  // class 5: more than TREX_KC contacts, two environments per warp
+        CUDA_TRY(cudaStreamWaitEvent(q.side, q.ev_fork, 0));
+        trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, q.side>>>(Pp[p], state, work, workh, q.d_list + (size_t)TREX_CLASS_HEAVY * q.count,
+                                                                   q.d_list_count + 64 * TREX_CLASS_HEAVY + r, q.d_list_count + 64 * TREX_NCLASS + r,
+                                                                   q.d_list_count + 64 * (TREX_NCLASS + 1));
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        CUDA_TRY(cudaEventRecord(q.ev_join, q.side));
+      }
+      cudaStream_t s0 = split ? q.side2 : s;
+      if (split) CUDA_TRY(cudaStreamWaitEvent(q.side2, q.ev_fork, 0));
+      trex_solve_kernel<WS, 0, 0, 0><<<grid4, 32 * WS, smem_s, s0>>>(Pp[p], state, work, q.d_list, q.d_list_count + r, q.count);
+      CUDA_TRY(cudaGetLastError());
+      h->launches++;
+      if (split) {
+        CUDA_TRY(cudaEventRecord(q.ev_join2, q.side2));
+        CUDA_TRY(cudaStreamWaitEvent(s, q.ev_join2, 0));
+      }
+      if (heavy) CUDA_TRY(cudaStreamWaitEvent(s, q.ev_join, 0));
     }
   }
-  trex_tail_kernel<WF><<<grid1, 32 * WF, smem_f, st>>>(h->P, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane, h->d_state,
-                                                      obs, reward, done, h->d_aux, mask, h->n_envs, mode);
-  CUDA_TRY(cudaGetLastError());
-  h->launches++;
+  for (int p = 0; p < h->n_pipes; p++) {
+    trex_handle::Pipe& q = h->pipe[p];
+    const size_t e0 = (size_t)q.first;
+    const int grid1 = (q.count + WF - 1) / WF;
+    trex_tail_kernel<WF><<<grid1, 32 * WF, smem_f, sp[p]>>>(Pp[p], h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+                                                           h->d_state + e0 * TREX_STATE_STRIDE, obs ? obs + e0 * 3 * trex::NJ : nullptr,
+                                                           reward ? reward + e0 : nullptr, done ? done + e0 : nullptr,
+                                                           h->d_aux + e0 * TREX_AUX_STRIDE, mask ? mask + e0 : nullptr, q.count, mode);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (p > 0) {
+      CUDA_TRY(cudaEventRecord(q.ev_done, sp[p]));
+      CUDA_TRY(cudaStreamWaitEvent(st, q.ev_done, 0));
+    }
+  }
   return TREX_OK;
 }
 
@@ -476,7 +511,12 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
       return fail(TREX_ERR_INVALID, "trex_config.heavy_share_div must be >= 0%s");
     }
     h->heavy_div = cfg->heavy_share_div;
-    for (int i = 0; i < 11; i++)
+    if (cfg->pipelines < 0 || cfg->pipelines > trex_handle::MAX_PIPES) {
+      delete h;
+      return fail(TREX_ERR_INVALID, "trex_config.pipelines must be 0 (default) .. 4%s");
+    }
+    h->n_pipes = cfg->pipelines;
+    for (int i = 0; i < 10; i++)
       if (cfg->reserved[i] != 0) {
         delete h;
         return fail(TREX_ERR_INVALID, "trex_config.reserved must be zero%s");
@@ -487,6 +527,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     delete h;
     return rc_;
   }
+  if (h->n_pipes <= 0) h->n_pipes = n_envs >= 8192 ? 2 : 1;  // small batches: one group fills the machine no better split
   trex_host::fill_uniform(h->T, h->C, h->P);
   {
     // trex_heavy_kernel strides over its list with a fixed grid: exactly the CTAs that are resident at once (a larger
@@ -513,21 +554,35 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   CTRY(cudaMalloc((void**)&h->d_state, N * TREX_STATE_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_state, 0, N * TREX_STATE_STRIDE * sizeof(float)));
   if (h->deferred_solve) CTRY(cudaMalloc((void**)&h->d_work, N * TREX_WORK_STRIDE * sizeof(float)));
-  if (h->deferred_solve && h->C.defer_contacts > 1 && h->C.enable_contacts) {
-    CTRY(cudaMalloc((void**)&h->d_workh, N * TREX_HEAVY_STRIDE * sizeof(float)));
-    CTRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    CTRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CTRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    CTRY(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
-    CTRY(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
-    if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aids
+  const bool with_heavy = h->deferred_solve && h->C.defer_contacts > 1 && h->C.enable_contacts;
+  if (with_heavy) CTRY(cudaMalloc((void**)&h->d_workh, N * TREX_HEAVY_STRIDE * sizeof(float)));
+  if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aids
+  if (const char* e = getenv("TREX_PIPES")) { const int v = atoi(e); if (v >= 1 && v <= trex_handle::MAX_PIPES) h->n_pipes = v; }
+  if (h->n_pipes > n_envs) h->n_pipes = 1;
+  CTRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  for (int p = 0; p < h->n_pipes; p++) {
+    trex_handle::Pipe& q = h->pipe[p];
+    // groups of (almost) equal size, boundaries on multiples of four environments (the solvers' work unit)
+    const int per = ((n_envs + h->n_pipes - 1) / h->n_pipes + 3) & ~3;
+    q.first = p * per < n_envs ? p * per : n_envs;
+    q.count = (q.first + per <= n_envs) ? per : n_envs - q.first;
+    if (p > 0) CTRY(cudaStreamCreateWithFlags(&q.main, cudaStreamNonBlocking));
+    if (with_heavy) {
+      CTRY(cudaStreamCreateWithFlags(&q.side, cudaStreamNonBlocking));
+      CTRY(cudaStreamCreateWithFlags(&q.side2, cudaStreamNonBlocking));
+      CTRY(cudaEventCreateWithFlags(&q.ev_fork, cudaEventDisableTiming));
+      CTRY(cudaEventCreateWithFlags(&q.ev_join, cudaEventDisableTiming));
+      CTRY(cudaEventCreateWithFlags(&q.ev_join2, cudaEventDisableTiming));
+    }
+    CTRY(cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming));
+    CTRY(cudaMalloc((void**)&q.d_list, (size_t)TREX_NCLASS * (q.count > 0 ? q.count : 1) * sizeof(int)));
+    CTRY(cudaMalloc((void**)&q.d_list_count, 64 * (TREX_NCLASS + 2) * sizeof(int)));
+    CTRY(cudaMemset(q.d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int)));
   }
+  while (h->n_pipes > 1 && h->pipe[h->n_pipes - 1].count <= 0) h->n_pipes--;
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
   // (the staging buffers of the host-buffer entry points are allocated on first use: ensure_host_path)
-  CTRY(cudaMalloc((void**)&h->d_list, TREX_NCLASS * N * sizeof(int)));
-  CTRY(cudaMalloc((void**)&h->d_list_count, 64 * (TREX_NCLASS + 2) * sizeof(int)));
-  CTRY(cudaMemset(h->d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int)));
   CTRY(cudaMalloc((void**)&h->d_stats, sizeof(DevStats)));
 #undef CTRY
   // all environments start from the reference reset (TrexBulletEnv.__init__ calls reset(), trex_env.py:92)
@@ -545,7 +600,7 @@ void trex_destroy(trex_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_mdl); cudaFree(h->d_mdli); cudaFree(h->d_tasks); cudaFree(h->d_cand_p); cudaFree(h->d_cand_lane);
-  cudaFree(h->d_work); cudaFree(h->d_workh); cudaFree(h->d_list); cudaFree(h->d_list_count);
+  cudaFree(h->d_work); cudaFree(h->d_workh);
   cudaFree(h->d_lower); cudaFree(h->d_upper); cudaFree(h->d_state); cudaFree(h->d_aux); cudaFree(h->d_stats);
   for (int b = 0; b < 2; b++) {
     cudaFree(h->d_action[b]); cudaFree(h->d_obs[b]); cudaFree(h->d_reward[b]); cudaFree(h->d_done[b]);
@@ -556,11 +611,18 @@ void trex_destroy(trex_handle* h) {
   if (h->host_main) cudaStreamDestroy(h->host_main);
   if (h->host_copy) cudaStreamDestroy(h->host_copy);
   if (h->host_in) cudaStreamDestroy(h->host_in);
-  if (h->side) cudaStreamDestroy(h->side);
-  if (h->side2) cudaStreamDestroy(h->side2);
-  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (int p = 0; p < trex_handle::MAX_PIPES; p++) {
+    trex_handle::Pipe& q = h->pipe[p];
+    cudaFree(q.d_list); cudaFree(q.d_list_count);
+    if (q.main) cudaStreamDestroy(q.main);
+    if (q.side) cudaStreamDestroy(q.side);
+    if (q.side2) cudaStreamDestroy(q.side2);
+    if (q.ev_fork) cudaEventDestroy(q.ev_fork);
+    if (q.ev_join) cudaEventDestroy(q.ev_join);
+    if (q.ev_join2) cudaEventDestroy(q.ev_join2);
+    if (q.ev_done) cudaEventDestroy(q.ev_done);
+  }
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
   delete h;
 }
 
