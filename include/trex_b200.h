@@ -62,6 +62,9 @@ typedef struct trex_handle trex_handle;
 #define TREX_SOLVE_FRONT 1
 #define TREX_SOLVE_FREE_ONLY 2
 #define TREX_SOLVE_NO_HEAVY 3
+#define TREX_HEAVY_BOTH 0
+#define TREX_HEAVY_SHARED 1
+#define TREX_HEAVY_TENSOR 2
 
 typedef struct trex_config {
   int32_t num_substeps;      /* trex_env.py:18 NUM_SUBSTEPS (5); dt = 0.01/n, iterations = int(300/n)  (:71-73) */
@@ -91,7 +94,12 @@ typedef struct trex_config {
   int32_t pipelines;         /* the batch is stepped as this many independent groups of environments, each a chain of kernels on
                                 its own stream, so that one group's latency-bound solvers overlap another group's issue-bound
                                 dynamics kernel (results do not depend on it): 1..4; 0 = default (2 from 8,192 environments) */
-  int32_t reserved[10];      /* must be zero */
+  int32_t heavy_memory;      /* where the many-contact solver (9-16 contacts, two environments per warp) keeps its 48 x 48 Delassus
+                                matrices: TREX_HEAVY_BOTH (default) runs two kernel instances concurrently on one task list -- one with
+                                the matrices in TENSOR MEMORY (tcgen05.st / tcgen05.ld as a per-lane scratchpad, 8 warps per SM), one
+                                with them in shared memory (fills the shared memory left: 4 more warps per SM);
+                                TREX_HEAVY_SHARED / TREX_HEAVY_TENSOR run one of them alone.  Results are bit-identical. */
+  int32_t reserved[9];       /* must be zero */
 } trex_config;
 
 typedef struct trex_stats {

@@ -15,6 +15,8 @@ struct Emu {
   trex::WarpShared S;            // the slab of a lone warp
   trex::WarpShared slabs[4];     // the slabs of a 4-warp CTA (packed inward pass)
   alignas(16) float scratch2[TREX_SOLVE2_SCRATCH];  // shared scratch of a solve2 warp
+  float tmem[32][512];           // tensor memory of a solve2<true> warp (32 lanes x 512 columns)
+  int heavy_tmem = 0;            // solve2 with the Delassus matrices in (emulated) tensor memory
   int packed = 0;                // emu_step4 with n == 4: run the front phase as a 4-warp CTA (host threads)
   alignas(16) float work[4 * TREX_WORK_STRIDE];
   alignas(16) float workh[4 * TREX_HEAVY_STRIDE];
@@ -56,6 +58,7 @@ void* emu_create(const void* blob, size_t bytes, int n_sub, float wd, float we, 
   memset(e->work, 0xff, sizeof(e->work));
   memset(e->workh, 0xff, sizeof(e->workh));
   memset(e->scratch2, 0xff, sizeof(e->scratch2));
+  memset(e->tmem, 0xff, sizeof(e->tmem));
   return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
@@ -119,7 +122,9 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
             int pair[2] = {hv[i], two ? hv[i + 1] : 0};
             int pend = two ? 3 : 1;
             if (e->pack_reverse && !two) { pair[1] = pair[0]; pair[0] = 0; pend = 2; }  // tests: a lone environment in the upper lane group
-            trex::heavy_phase(e->P, e->scratch2, e->work, e->workh, rec, pair, pend);
+            tmem_t tm = {e->tmem};
+            if (e->heavy_tmem) trex::heavy_phase<true>(e->P, e->scratch2, tm, e->work, e->workh, rec, pair, pend);
+            else trex::heavy_phase<false>(e->P, e->scratch2, tm, e->work, e->workh, rec, pair, pend);
           }
         }
       }
@@ -137,6 +142,7 @@ void emu_step(void* h, float* rec, const float* action, float* obs, float* rewar
 void emu_solve_counts(void* h, long long* out) { for (int i = 0; i < 5; i++) out[i] = ((Emu*)h)->solves[i]; }
 void emu_set_deferred(void* h, int on) {  // bit 0 deferral on, bit 1 reverse packing, bit 2 contact-free substeps only, bit 3 front phase as a 4-warp CTA, bit 4 more than TREX_KC contacts stay in the front phase
   Emu* e = (Emu*)h;
+  e->heavy_tmem = (on >> 5) & 1;  // bit 5: solve2 keeps the Delassus matrices in tensor memory
   e->deferred = on & 1; e->pack_reverse = (on >> 1) & 1; e->P.defer_contacts = ((on >> 2) & 1) ? 0 : (((on >> 4) & 1) ? 1 : 2); e->packed = (on >> 3) & 1;
 }
 }

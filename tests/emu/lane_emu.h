@@ -173,6 +173,14 @@ TREX_FN vf shfl_group8(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++
 TREX_FN vf group8_sum(vf x) { for (int m = 4; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN vf group8_max(vf x) { for (int m = 4; m > 0; m >>= 1) x = vmax(x, shfl_xor(x, m)); return x; }
 
+// tensor memory as a per-lane scratchpad (device: tcgen05.st / tcgen05.ld 32x32b.x4): here 32 lanes x 512 columns of host memory
+struct tmem_t { float (*m)[512]; };
+TREX_FN void tmem_st4(tmem_t t, int col, const vf& a, const vf& b, const vf& c, const vf& d) {
+  for (int l = 0; l < 32; l++) { t.m[l][col] = a.v[l]; t.m[l][col + 1] = b.v[l]; t.m[l][col + 2] = c.v[l]; t.m[l][col + 3] = d.v[l]; }
+}
+TREX_FN void tmem_st_wait() {}
+TREX_FN void tmem_ld4(tmem_t t, int col, vf (&out)[4]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 4; k++) out[k].v[l] = t.m[l][col + k]; }
+TREX_FN void tmem_wait4(vf (&)[4]) {}
 TREX_FN vi shfl_xor_i(const vi& x, int m) { vi r; for (int l = 0; l < 32; l++) r.v[l] = x.v[l ^ m]; return r; }
 TREX_FN vi sig_mix_v(const vi& h, const vi& w) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)(((uint32_t)h.v[l] ^ (uint32_t)w.v[l]) * 16777619u); return r; }
 TREX_FN vf shfl_group16(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~15) | (src & 15)]; return r; }

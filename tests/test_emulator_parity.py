@@ -476,3 +476,24 @@ def test_literal_reference_model(action_limits):
         errs.append(max(rel_err(so[sl], se[sl]) for sl in STATE_BLOCKS.values()))
     assert max(errs) < 2e-5, max(errs)
     assert o.get_state()[2] < 2.3  # free fall from z = 3: nothing holds the literal model up
+
+
+def test_solve2_with_the_delassus_matrix_in_tensor_memory(model):
+    """solve2<true> keeps the Delassus matrices of its two environments in tensor memory (device: tcgen05.st / tcgen05.ld,
+    a per-lane scratchpad; here an emulated 32 x 512 array) instead of shared memory.  The arithmetic is untouched: records
+    are bit-identical with the shared-memory instance, so the two kernel instances can share one list of environments."""
+    from emu import EmuWarp4
+
+    o = _oracle(model)
+    hold = o.reset()[:25].copy()
+    a = EmuWarp4(model.blob(), n=3)
+    b = EmuWarp4(model.blob(), n=3, deferred=1 | 32)
+    a.reset()
+    b.reset()
+    rng = np.random.default_rng(6)
+    acts = np.stack([hold + rng.uniform(-0.02, 0.02, 25) * (e > 0) for e in range(3)]).astype(np.float32)
+    for t in range(40):
+        a.step(acts)
+        b.step(acts)
+        assert np.array_equal(a.rec[:, :160], b.rec[:, :160]), t
+    assert b.env.heavy_solves() >= 3 * 5 * 8 and int(b.aux[0, 7]) % 1000 >= 12

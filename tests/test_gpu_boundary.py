@@ -104,7 +104,7 @@ def test_named_config_fields_are_validated(model):
 
     assert create()[0] == 0
     assert create(warps_per_block=4, solver_placement=_native.SOLVE_NO_HEAVY, env_offset=1 << 40)[0] == 0
-    for bad in (dict(warps_per_block=3), dict(solver_placement=7), dict(heavy_share_div=-1), dict(pipelines=9), dict(reserved0=1)):
+    for bad in (dict(warps_per_block=3), dict(solver_placement=7), dict(heavy_share_div=-1), dict(pipelines=9), dict(heavy_memory=3), dict(reserved0=1)):
         rc, msg = create(**bad)
         assert rc == -1 and list(bad)[0].rstrip("0") in msg, (bad, rc, msg)
 

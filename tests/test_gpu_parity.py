@@ -508,3 +508,33 @@ def test_contact_primitives_model_on_gpu(model):
     venv = TrexVecEnv(4, contact_model="primitives")
     assert venv.sim.model.meta["contact_model"] == "primitives"
     venv.close()
+
+
+def test_solve2_tensor_memory_and_shared_memory_instances_agree(model):
+    """The many-contact solver runs as two kernel instances on one task list: Delassus matrices in TENSOR MEMORY
+    (tcgen05.st / tcgen05.ld as a per-lane scratchpad) and in shared memory.  Alone or together, with one or two groups of
+    environments, they give bit-identical records on a batch where every environment stands on both feet (12-16 contacts)
+    next to environments flailing with random actions."""
+    import torch
+
+    from trex_gym_b200 import _native
+
+    n = 4096 + 6
+    names = list(model.meta["obs_joint_names"])
+    hold = torch.zeros(25, device="cuda")
+    for k, v in model.meta["starting_configuration"].items():
+        hold[names.index(k)] = v
+    sims = [_sim(model, n, heavy_memory=m, pipelines=p) for m, p in ((_native.HEAVY_SHARED, 1), (_native.HEAVY_TENSOR, 1),
+                                                                     (_native.HEAVY_BOTH, 1), (_native.HEAVY_BOTH, 2))]
+    for t in range(45):
+        a = sims[0].random_actions(step=t, seed=7)
+        a[: n - 500] = hold
+        for s in sims:
+            s.step(a)
+    st = [s.get_state() for s in sims]
+    for x in st[1:]:
+        assert torch.equal(st[0], x)
+    stats = sims[0].stats()
+    assert stats["mean_contacts"] > 10 and stats["nan_resets"] == 0 and stats["contact_overflow"] >= 0
+    k = (sims[0].aux()[:, 7] % 1000)
+    assert (k > 8).float().mean().item() > 0.8  # the batch really is in the many-contact class

@@ -43,11 +43,13 @@ class TrexConfig(ctypes.Structure):
         ("solver_placement", ctypes.c_int32),
         ("heavy_share_div", ctypes.c_int32),
         ("pipelines", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 10),
+        ("heavy_memory", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 9),
     ]
 
 
 SOLVE_DEFAULT, SOLVE_FRONT, SOLVE_FREE_ONLY, SOLVE_NO_HEAVY = 0, 1, 2, 3  # trex_config.solver_placement
+HEAVY_BOTH, HEAVY_SHARED, HEAVY_TENSOR = 0, 1, 2  # trex_config.heavy_memory
 
 
 class TrexStats(ctypes.Structure):

@@ -126,6 +126,42 @@ TREX_FN void st2_if(float* p, vi idx, const vf v[2], vb pred) {
   if (pred) *reinterpret_cast<float2*>(p + idx) = make_float2(v[0], v[1]);
 }
 
+// Tensor memory (TMEM, 256 KB per SM on sm_100a) as a software-managed per-lane scratchpad: `tcgen05.st/ld ... 32x32b.x4`
+// moves four consecutive 32-bit columns between registers and the TMEM lane of each thread of the warp (a warp reaches the
+// 32 lanes 32 * (warp % 4) ..).  solve2 keeps the Delassus matrix of its two environments there: lane c' holds its own
+// three entries of every row r in columns 4 r .. 4 r + 2.  Loads are asynchronous: tmem_wait4 passes the registers
+// through `tcgen05.wait::ld`, so no use can be scheduled ahead of it.
+struct tmem_t { uint32_t base; };  // TMEM address of column 0 of this warp's lane slice
+TREX_FN void tmem_st4(tmem_t t, int col, vf a, vf b, vf c, vf d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t.base + (uint32_t)col), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// one warp of the CTA allocates `cols` columns (power of two >= 32) and publishes the address through shared memory; every thread
+// of the CTA calls this (it contains a CTA barrier); the same warp frees them at the end (tmem_free_cta, after a CTA barrier)
+template <int COLS>
+__device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t* smem_slot) {
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *smem_slot;
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free_cta(uint32_t base) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+TREX_FN void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+TREX_FN void tmem_ld4(tmem_t t, int col, vf (&out)[4]) {  // (results land asynchronously: read them only after tmem_wait4(out))
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3]) : "r"(t.base + (uint32_t)col));
+}
+TREX_FN void tmem_wait4(vf (&v)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])::"memory");
+}
+
 // 4 consecutive floats per lane (16-byte aligned offset): one 128-bit access
 TREX_FN void ld4(const float* p, vi idx, vf out[4]) {
   const float4 t = *reinterpret_cast<const float4*>(p + idx);

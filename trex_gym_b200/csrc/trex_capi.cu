@@ -133,23 +133,39 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   trex::solve_phase<KC>(P, scratch, work, state, envs, pending);
 }
 
-// one warp per TWO environments of class 5 (more than TREX_KC contacts; sixteen lanes each, see solve2), a fixed grid of
-// resident warps striding over the list
-template <int WARPS>
+// one warp per TWO environments of class 5 (more than TREX_KC contacts; sixteen lanes each, see solve2).  Persistent warps pull
+// pairs of environments from a shared task counter.  Two instances run CONCURRENTLY on the same list, because the number of
+// environments in flight per SM is what bounds this solver and each instance is bounded by a different memory:
+//   TM = true : 4-warp CTAs, the Delassus matrices in TENSOR MEMORY (256 columns per CTA: 2 CTAs = 8 warps per SM),
+//               11.4 KB of shared memory per warp
+//   TM = false: 1-warp CTAs, the Delassus matrices in shared memory (29.8 KB per warp): they fill the shared memory left
+template <int WARPS, bool TM>
 __global__ void __launch_bounds__(32 * WARPS)
 trex_heavy_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work, const float* __restrict__ workh,
-                  const int* __restrict__ list, const int* __restrict__ list_count, const int* __restrict__ seen, int* __restrict__ hint) {
+                  const int* __restrict__ list, const int* __restrict__ list_count, const int* __restrict__ seen, int* __restrict__ hint,
+                  int* __restrict__ next_task) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  float* scratch = reinterpret_cast<float*>(smem_raw) + warp * TREX_SOLVE2_SCRATCH;
+  float* scratch = reinterpret_cast<float*>(smem_raw) + warp * (TM ? TREX_SOLVE2_SCRATCH_TM : TREX_SOLVE2_SCRATCH);
   const int count = *list_count;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *hint = *seen;  // environments with > TREX_KC contacts in this round
-  for (int i = (blockIdx.x * WARPS + warp) * 2; i < count; i += gridDim.x * WARPS * 2) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hint != nullptr) *hint = *seen;  // environments with > TREX_KC contacts in this round
+  tmem_t tm = {0u};
+  __shared__ uint32_t tmem_slot;
+  if (TM) {
+    if (count == 0) return;  // (uniform over the CTA: nobody allocates)
+    tm.base = tmem_alloc_cta<TREX_S2_TMEM_COLS>(&tmem_slot) + ((uint32_t)(warp & 3) << 21);  // lane 32 * (warp % 4) in bits 31:16
+  }
+  for (;;) {
+    int i = 0;
+    if ((threadIdx.x & 31) == 0) i = atomicAdd(next_task, 2);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= count) break;
     const bool two = i + 1 < count;
     const int envs[2] = {list[i], two ? list[i + 1] : 0};
-    trex::heavy_phase(P, scratch, work, workh, state, envs, two ? 3 : 1);
+    trex::heavy_phase<TM>(P, scratch, tm, work, workh, state, envs, two ? 3 : 1);
     __syncwarp();
   }
+  if (TM) tmem_free_cta<TREX_S2_TMEM_COLS>(tm.base - ((uint32_t)(warp & 3) << 21));
 }
 
 // one warp per environment: reward / done / auto-reset / observations (mode 0), or reset only (mode 1, optional mask)
@@ -322,16 +338,19 @@ struct trex_handle {
   struct Pipe {
     int first = 0, count = 0;     // environments [first, first + count)
     cudaStream_t main = nullptr;  // pipe 0 runs on the caller's stream instead
-    cudaStream_t side = nullptr, side2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_done = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr, ev_done = nullptr;
     int* d_list = nullptr;        // [TREX_NCLASS][count] environments whose solve was deferred in the current substep round, by class
-    int* d_list_count = nullptr;  // [TREX_NCLASS + 2][64] one counter per class and substep round (+ heavy seen / hint)
+    int* d_list_count = nullptr;  // [TREX_NCLASS + 3][64] one counter per class and substep round, + heavy seen, solve2 task counters, hint
   } pipe[MAX_PIPES];
   int n_pipes = 0;              // 0 until trex_create decides (config / default)
   cudaEvent_t ev_start = nullptr;
   bool concurrent_solves = true;  // the contact-free solve kernel on a second side stream, under the contact solver
   int heavy_div = 0;            // > 0: class 5 goes to trex_heavy_kernel only while at most n_envs / heavy_div environments are in it (0: always)
-  int heavy_grid = 148 * 7;     // CTAs of trex_heavy_kernel (one warp each): every SM full, the list is strided over
+  int heavy_grid = 148 * 7;     // CTAs of trex_heavy_kernel<1, false> alone (one warp each): every SM full
+  int heavy_grid_tm = 148 * 2;  // CTAs of trex_heavy_kernel<4, true> (tensor-memory instance: 256 of the 512 columns each)
+  int heavy_grid_mixed = 148 * 4;  // CTAs of the shared-memory instance next to the tensor-memory one
+  int heavy_mode = 0;           // 0: both instances concurrently; 1: shared memory only; 2: tensor memory only (TREX_HEAVY_MODE, measurement aid)
   int64_t launches = 0;
   int64_t env_steps = 0;
 };
@@ -352,7 +371,7 @@ template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
   const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS,
-               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS, smem_h = sizeof(float) * TREX_SOLVE2_SCRATCH;
+               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS, smem_h = sizeof(float) * TREX_SOLVE2_SCRATCH, smem_ht = sizeof(float) * TREX_SOLVE2_SCRATCH_TM * 4;
   // per template instance and device; handles may be created and stepped from different host threads
   static bool configured[16] = {false};
   static std::mutex configure_lock;
@@ -362,7 +381,8 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
     if ((rc = configure_kernel(trex_front_kernel<WF, WF == 4>, smem_f)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, 0, 0, 0>, smem_s)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1>, smem_c)) != TREX_OK) return rc;
-    if ((rc = configure_kernel(trex_heavy_kernel<1>, smem_h)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_heavy_kernel<1, false>, smem_h)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_heavy_kernel<4, true>, smem_ht)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
   }
@@ -375,7 +395,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
     Pp[p].env_offset = h->P.env_offset + q.first;  // the reset sampler is keyed by the global environment id
     sp[p] = p == 0 ? st : q.main;
     if (p > 0) CUDA_TRY(cudaStreamWaitEvent(sp[p], h->ev_start, 0));
-    if (mode == 0 && h->d_work) CUDA_TRY(cudaMemsetAsync(q.d_list_count, 0, 64 * (TREX_NCLASS + 1) * sizeof(int), sp[p]));  // (not the hint behind them)
+    if (mode == 0 && h->d_work) CUDA_TRY(cudaMemsetAsync(q.d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int), sp[p]));  // class counters, heavy seen, solve2 task counters (not the hint behind them)
   }
   const int n_rounds = mode == 0 ? h->P.n_sub : 0;
   for (int r = 0; r < n_rounds; r++) {
@@ -390,7 +410,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       float* workh = h->d_workh ? h->d_workh + e0 * TREX_HEAVY_STRIDE : nullptr;
       trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, s>>>(Pp[p], h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
                                                           state, work, workh, action + e0 * trex::NJ, q.d_list, q.d_list_count + r,
-                                                          q.d_list_count + 64 * (TREX_NCLASS + 1), h->heavy_div, q.count, r == 0);
+                                                          q.d_list_count + 64 * (TREX_NCLASS + 2), h->heavy_div, q.count, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (!h->d_work) continue;
@@ -406,13 +426,29 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
         CUDA_TRY(cudaGetLastError());
         h->launches++;
       }
-      if (heavy) {  // class 5: more than TREX_KC contacts, two environments per warp
+      if (heavy) {  // class 5: more than TREX_KC contacts, two environments per warp; two instances share the task counter
+        int* next_task = q.d_list_count + 64 * (TREX_NCLASS + 1) + r;
+        const int* cnt = q.d_list_count + 64 * TREX_CLASS_HEAVY + r;
+        const int* lst = q.d_list + (size_t)TREX_CLASS_HEAVY * q.count;
+        int* hint = q.d_list_count + 64 * (TREX_NCLASS + 2);
         CUDA_TRY(cudaStreamWaitEvent(q.side, q.ev_fork, 0));
-        trex_heavy_kernel<1><<<h->heavy_grid, 32, smem_h, q.side>>>(Pp[p], state, work, workh, q.d_list + (size_t)TREX_CLASS_HEAVY * q.count,
-                                                                   q.d_list_count + 64 * TREX_CLASS_HEAVY + r, q.d_list_count + 64 * TREX_NCLASS + r,
-                                                                   q.d_list_count + 64 * (TREX_NCLASS + 1));
-        CUDA_TRY(cudaGetLastError());
-        h->launches++;
+        if (h->heavy_mode != 1) {  // the tensor-memory instance first: its CTAs take their two slots per SM ...
+          trex_heavy_kernel<4, true><<<h->heavy_grid_tm, 128, smem_ht, q.side>>>(Pp[p], state, work, workh, lst, cnt, q.d_list_count + 64 * TREX_NCLASS + r, hint, next_task);
+          CUDA_TRY(cudaGetLastError());
+          h->launches++;
+        }
+        if (h->heavy_mode != 2) {  // ... and the shared-memory instance fills what is left of the shared memory
+          cudaStream_t sh = h->heavy_mode == 0 ? q.side3 : q.side;
+          if (h->heavy_mode == 0) CUDA_TRY(cudaStreamWaitEvent(q.side3, q.ev_fork, 0));
+          trex_heavy_kernel<1, false><<<h->heavy_mode == 0 ? h->heavy_grid_mixed : h->heavy_grid, 32, smem_h, sh>>>(
+              Pp[p], state, work, workh, lst, cnt, q.d_list_count + 64 * TREX_NCLASS + r, h->heavy_mode == 0 ? nullptr : hint, next_task);
+          CUDA_TRY(cudaGetLastError());
+          h->launches++;
+          if (h->heavy_mode == 0) {
+            CUDA_TRY(cudaEventRecord(q.ev_join3, q.side3));
+            CUDA_TRY(cudaStreamWaitEvent(q.side, q.ev_join3, 0));
+          }
+        }
         CUDA_TRY(cudaEventRecord(q.ev_join, q.side));
       }
       cudaStream_t s0 = split ? q.side2 : s;
@@ -516,7 +552,12 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
       return fail(TREX_ERR_INVALID, "trex_config.pipelines must be 0 (default) .. 4%s");
     }
     h->n_pipes = cfg->pipelines;
-    for (int i = 0; i < 10; i++)
+    if (cfg->heavy_memory < TREX_HEAVY_BOTH || cfg->heavy_memory > TREX_HEAVY_TENSOR) {
+      delete h;
+      return fail(TREX_ERR_INVALID, "trex_config.heavy_memory must be one of TREX_HEAVY_*%s");
+    }
+    h->heavy_mode = cfg->heavy_memory;
+    for (int i = 0; i < 9; i++)
       if (cfg->reserved[i] != 0) {
         delete h;
         return fail(TREX_ERR_INVALID, "trex_config.reserved must be zero%s");
@@ -528,17 +569,30 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     return rc_;
   }
   if (h->n_pipes <= 0) h->n_pipes = n_envs >= 8192 ? 2 : 1;  // small batches: one group fills the machine no better split
+  if (const char* e = getenv("TREX_PIPES")) { const int v = atoi(e); if (v >= 1 && v <= trex_handle::MAX_PIPES) h->n_pipes = v; }  // measurement aid
+  if (h->n_pipes > n_envs) h->n_pipes = 1;
   trex_host::fill_uniform(h->T, h->C, h->P);
   {
     // trex_heavy_kernel strides over its list with a fixed grid: exactly the CTAs that are resident at once (a larger
     // grid would run its surplus CTAs as a second wave after the first has walked the whole list)
     int sms = 148, per_sm = 7;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(trex_heavy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * TREX_SOLVE2_SCRATCH));
-    cudaFuncSetAttribute(trex_heavy_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trex_heavy_kernel<1>, 32, sizeof(float) * TREX_SOLVE2_SCRATCH) != cudaSuccess || per_sm < 1)
+    cudaFuncSetAttribute(trex_heavy_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * TREX_SOLVE2_SCRATCH));
+    cudaFuncSetAttribute(trex_heavy_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trex_heavy_kernel<1, false>, 32, sizeof(float) * TREX_SOLVE2_SCRATCH) != cudaSuccess || per_sm < 1)
       per_sm = 7;
-    if (sms > 0) h->heavy_grid = sms * per_sm;
+    if (sms > 0) {
+      h->heavy_grid = sms * per_sm;
+      const int np = h->n_pipes > 0 ? h->n_pipes : 1;  // the groups' solvers run concurrently and share the SM's tensor memory
+      int tm_per_sm = (512 / TREX_S2_TMEM_COLS) / np;
+      if (tm_per_sm < 1) tm_per_sm = 1;
+      h->heavy_grid_tm = sms * tm_per_sm;
+      // shared memory left next to the tensor-memory CTAs (4 warps x 11.4 KB + 1 KB each), in one-warp CTAs of 29.8 + 1 KB
+      const int left = 227 * 1024 - (512 / TREX_S2_TMEM_COLS) * ((int)(sizeof(float) * TREX_SOLVE2_SCRATCH_TM * 4) + 1024);
+      const int fit = left / ((int)(sizeof(float) * TREX_SOLVE2_SCRATCH) + 1024);
+      h->heavy_grid_mixed = sms * ((fit / np) > 0 ? fit / np : 1);
+    }
+    if (const char* e = getenv("TREX_HEAVY_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 2) h->heavy_mode = v; }
   }
   int rc;
 #define TRY(x) if ((rc = (x)) != TREX_OK) { trex_destroy(h); return rc; }
@@ -557,8 +611,6 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   const bool with_heavy = h->deferred_solve && h->C.defer_contacts > 1 && h->C.enable_contacts;
   if (with_heavy) CTRY(cudaMalloc((void**)&h->d_workh, N * TREX_HEAVY_STRIDE * sizeof(float)));
   if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aids
-  if (const char* e = getenv("TREX_PIPES")) { const int v = atoi(e); if (v >= 1 && v <= trex_handle::MAX_PIPES) h->n_pipes = v; }
-  if (h->n_pipes > n_envs) h->n_pipes = 1;
   CTRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   for (int p = 0; p < h->n_pipes; p++) {
     trex_handle::Pipe& q = h->pipe[p];
@@ -570,14 +622,16 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     if (with_heavy) {
       CTRY(cudaStreamCreateWithFlags(&q.side, cudaStreamNonBlocking));
       CTRY(cudaStreamCreateWithFlags(&q.side2, cudaStreamNonBlocking));
+      CTRY(cudaStreamCreateWithFlags(&q.side3, cudaStreamNonBlocking));
+      CTRY(cudaEventCreateWithFlags(&q.ev_join3, cudaEventDisableTiming));
       CTRY(cudaEventCreateWithFlags(&q.ev_fork, cudaEventDisableTiming));
       CTRY(cudaEventCreateWithFlags(&q.ev_join, cudaEventDisableTiming));
       CTRY(cudaEventCreateWithFlags(&q.ev_join2, cudaEventDisableTiming));
     }
     CTRY(cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming));
     CTRY(cudaMalloc((void**)&q.d_list, (size_t)TREX_NCLASS * (q.count > 0 ? q.count : 1) * sizeof(int)));
-    CTRY(cudaMalloc((void**)&q.d_list_count, 64 * (TREX_NCLASS + 2) * sizeof(int)));
-    CTRY(cudaMemset(q.d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int)));
+    CTRY(cudaMalloc((void**)&q.d_list_count, 64 * (TREX_NCLASS + 3) * sizeof(int)));
+    CTRY(cudaMemset(q.d_list_count, 0, 64 * (TREX_NCLASS + 3) * sizeof(int)));
   }
   while (h->n_pipes > 1 && h->pipe[h->n_pipes - 1].count <= 0) h->n_pipes--;
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
@@ -617,6 +671,8 @@ void trex_destroy(trex_handle* h) {
     if (q.main) cudaStreamDestroy(q.main);
     if (q.side) cudaStreamDestroy(q.side);
     if (q.side2) cudaStreamDestroy(q.side2);
+    if (q.side3) cudaStreamDestroy(q.side3);
+    if (q.ev_join3) cudaEventDestroy(q.ev_join3);
     if (q.ev_fork) cudaEventDestroy(q.ev_fork);
     if (q.ev_join) cudaEventDestroy(q.ev_join);
     if (q.ev_join2) cudaEventDestroy(q.ev_join2);

@@ -1896,6 +1896,23 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
 #define TREX_S2_LS (32 + 4 * TREX_KW)               // Lam per environment: net joint impulses by joint, then [KW][4] contact impulses
 #define TREX_S2_LIMIT_SLOTS 2
 #define TREX_SOLVE2_SCRATCH (2 * TREX_S2_ENV + 2 * TREX_S2_LS + 64 * TREX_S2_LIMIT_SLOTS)  // floats per warp
+// solve2<true>: the Delassus matrix lives in TENSOR MEMORY (lane c' holds its own three entries of row r in TMEM columns
+// 4 r .. 4 r + 2 of its lane: 192 of the 256 columns a 4-warp CTA allocates), the shared scratch shrinks to Bp + the small parts
+#define TREX_S2_ENV_TM (TREX_S2_NR * TREX_S2_BS + 16)
+#define TREX_SOLVE2_SCRATCH_TM (2 * TREX_S2_ENV_TM + 2 * TREX_S2_LS + 64 * TREX_S2_LIMIT_SLOTS)
+#define TREX_S2_TMEM_COLS 256
+// rows of the Delassus matrix for the lane's own contact: from the shared stash (three 32-bit loads, a[3] unused) or from TMEM
+template <bool TM>
+TREX_FN void s2_fetch_a(const float* Sc, vi a_own, tmem_t tm, int row, vf (&a)[4]) {
+  if (TM) {
+    tmem_ld4(tm, 4 * row, a);
+  } else {
+    TREX_UNROLL for (int k = 0; k < 3; k++) a[k] = ld(Sc, a_own + (row * TREX_S2_NR + k));
+  }
+}
+template <bool TM>
+TREX_FN void s2_ready_a(vf (&a)[4]) { if (TM) tmem_wait4(a); }
+
 template <int B, bool FWD>
 TREX_FN void s2_motor_block(vf (&w)[2], vf (&lam_m)[2], const vf (&g)[2][NJ], vf (&cu)[3], vi gl, vi bp_own, const float* Sc, float max_imp) {
   constexpr int n = (2 * B + 2 <= NJ) ? 2 : NJ - 2 * B;
@@ -1925,9 +1942,11 @@ TREX_FN void s2_motor_block(vf (&w)[2], vf (&lam_m)[2], const vf (&g)[2][NJ], vf
 }
 
 // envs[g] = index (relative to work0 / workh0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
-TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const float* workh0, float* rec0, const int envs[2], int pending,
-                  float max_imp) {
-  constexpr int NR = TREX_S2_NR, BS = TREX_S2_BS, LS = TREX_S2_LS, AOFF = 0, BOFF = NR * NR;
+template <bool TM>
+TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work0, const float* workh0, float* rec0, const int envs[2],
+                  int pending, float max_imp) {
+  constexpr int NR = TREX_S2_NR, BS = TREX_S2_BS, LS = TREX_S2_LS, AOFF = 0, BOFF = TM ? 0 : NR * NR;
+  constexpr int ENV = TM ? TREX_S2_ENV_TM : TREX_S2_ENV;
   const vi lane = lane_id();
   const vi grp = lane >> 4, gl = lane & 15;
   const vb gact = ((vi(pending) >> grp) & 1) != 0;
@@ -1935,10 +1954,10 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
   const vi es = seli(gact, genv, 0);
   const vi woff = es * TREX_WORK_STRIDE, hoff = es * TREX_HEAVY_STRIDE, roff = es * TREX_STATE_STRIDE;
   const float dt = P.dt;
-  float* Sc = scratch;                                 // [2][TREX_S2_ENV]: A, then Bp
-  float* Lam = Sc + 2 * TREX_S2_ENV;                   // [2][LS]
+  float* Sc = scratch;                                 // [2][ENV]: A (unless in TMEM), then Bp
+  float* Lam = Sc + 2 * ENV;                           // [2][LS]
   float* Lg = Lam + 2 * LS;                            // [TREX_S2_LIMIT_SLOTS][2][32]
-  const vi gb = grp * TREX_S2_ENV;                     // this group's stash
+  const vi gb = grp * ENV;                             // this group's stash
   const vi a_own = gb + (AOFF + 3 * gl);               // column block of the owned contact in every row of A
   const vi bp_own = gb + (BOFF + 3 * BS * gl);         // Bp rows of the owned contact
   const vi bp_mine = gb + (BOFF + 2 * gl);             // the lane's two joints in every row of Bp
@@ -1985,18 +2004,26 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
     const vi nr = nc * 3;
     _Pragma("unroll 4") for (int r = 0; r < 3 * kmax; r++) {  // (several rows in flight: the copy is latency bound)
       const vb rok = gact && (vi(r) < nr);
-      // A row r: 48 floats = 12 float4, lanes 0..11 of the group; columns of absent contacts read as zero
-      vf a4[4];
-      const vb al = gl < (NR / 4);
-      const vi gls = seli(al, gl, 0);
-      ld4_if(workh0, hoff + gls * 4 + (r * NR + H_A4), rok && al, a4);
-      TREX_UNROLL for (int e = 0; e < 4; e++) a4[e] = sel((gls * 4 + e) < nr, a4[e], 0.0f);
-      st4_if(Sc, gb + gls * 4 + (AOFF + r * NR), a4, al);
+      if (TM) {
+        // A row r -> tensor memory: every lane stores its own three entries A[r][3 gl .. 3 gl + 2] (zero for absent contacts)
+        vf a3[3];
+        TREX_UNROLL for (int k = 0; k < 3; k++) a3[k] = ld_if(workh0, hoff + gl * 3 + (r * NR + H_A4 + k), rok && ((gl * 3 + k) < nr), 0.0f);
+        tmem_st4(tm, 4 * r, a3[0], a3[1], a3[2], vf(0.0f));
+      } else {
+        // A row r: 48 floats = 12 float4, lanes 0..11 of the group; columns of absent contacts read as zero
+        vf a4[4];
+        const vb al = gl < (NR / 4);
+        const vi gls = seli(al, gl, 0);
+        ld4_if(workh0, hoff + gls * 4 + (r * NR + H_A4), rok && al, a4);
+        TREX_UNROLL for (int e = 0; e < 4; e++) a4[e] = sel((gls * 4 + e) < nr, a4[e], 0.0f);
+        st4_if(Sc, gb + gls * 4 + (AOFF + r * NR), a4, al);
+      }
       // Bp row r: the lane's own two joints (positions 2 gl, 2 gl + 1; the pad position 25 gets 0)
       vf b2[2];
       TREX_UNROLL for (int s = 0; s < 2; s++) b2[s] = ld_if(workh0, hoff + kk[s] + (r * 32 + H_BT), rok && kv[s], 0.0f);
       st2_if(Sc, bp_mine + r * BS, b2, gl < 13);
     }
+    if (TM) tmem_st_wait();
   }
   warp_sync();
   // joints with a violated limit in either environment, in Bullet's limit-constraint order (bit p <=> position p)
@@ -2078,12 +2105,15 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
         TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(ld(Sc, bp_own + (k * BS + motor_position(j))), Lj, ua[k]);
       }
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        vf ar[3][4];
+        TREX_UNROLL for (int k = 0; k < 3; k++) s2_fetch_a<TM>(Sc, a_own, tm, 3 * c + k, ar[k]);
+        TREX_UNROLL for (int k = 0; k < 3; k++) s2_ready_a<TM>(ar[k]);
         TREX_UNROLL for (int k = 0; k < 3; k++) {
           const vf Lr = ld(Lam, grp * LS + (32 + c * 4 + k));
           vf b2[2];
           ld2(Sc, bp_mine + (3 * c + k) * BS, b2);
           TREX_UNROLL for (int s = 0; s < 2; s++) bs[s] = vfma(b2[s], Lr, bs[s]);
-          TREX_UNROLL for (int k2 = 0; k2 < 3; k2++) ua[k2] = vfma(ld(Sc, a_own + ((3 * c + k) * NR + k2)), Lr, ua[k2]);
+          TREX_UNROLL for (int k2 = 0; k2 < 3; k2++) ua[k2] = vfma(ar[k][k2], Lr, ua[k2]);
         }
       }
       TREX_UNROLL for (int s = 0; s < 2; s++) acc[s] = vfma(njdi[s], bs[s], acc[s]);
@@ -2113,7 +2143,8 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
 #define TREX_S2_NORMAL(C, A3, B2, AN, BN)                                                                 \
     {                                                                                                      \
       const int cn = (C) + 1 < kmax ? (C) + 1 : (C);                                                       \
-      TREX_UNROLL for (int k = 0; k < 3; k++) AN[k] = ld(Sc, a_own + ((3 * cn) * NR + k));                 \
+      s2_ready_a<TM>(A3);                                                                                  \
+      s2_fetch_a<TM>(Sc, a_own, tm, 3 * cn, AN);                                                           \
       ld2(Sc, bp_mine + (3 * cn) * BS, BN);                                                                \
       const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);                                                  \
       const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);                                                        \
@@ -2125,23 +2156,24 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
       TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(B2[s], njdi[s] * d, w[s]);                       \
     }
     {
-      vf a0[3], b0[2], a1[3], b1[2];
-      TREX_UNROLL for (int k = 0; k < 3; k++) a0[k] = ld(Sc, a_own + k);
+      vf a0[4], b0[2], a1[4], b1[2];
+      s2_fetch_a<TM>(Sc, a_own, tm, 0, a0);
       ld2(Sc, bp_mine, b0);
       TREX_ROLLED for (int c = 0; c < kmax; c += 2) {
         TREX_S2_NORMAL(c, a0, b0, a1, b1)
-        if (c + 1 < kmax) TREX_S2_NORMAL(c + 1, a1, b1, a0, b0)
+        if (c + 1 < kmax) TREX_S2_NORMAL(c + 1, a1, b1, a0, b0) else s2_ready_a<TM>(a1);
       }
+      if ((kmax & 1) == 0) s2_ready_a<TM>(a0);  /* (the last prefetch is never used: retire it) */
     }
 #undef TREX_S2_NORMAL
     // friction pairs, implicit cone; both rows read the velocities before either writes
 #define TREX_S2_FRICTION(C, AA, AB, BA, BB, AAN, ABN, BAN, BBN)                                            \
     {                                                                                                      \
       const int cn = (C) + 1 < kmax ? (C) + 1 : (C);                                                       \
-      TREX_UNROLL for (int k = 0; k < 3; k++) {                                                            \
-        AAN[k] = ld(Sc, a_own + ((3 * cn + 1) * NR + k));                                                  \
-        ABN[k] = ld(Sc, a_own + ((3 * cn + 2) * NR + k));                                                  \
-      }                                                                                                    \
+      s2_ready_a<TM>(AA);                                                                                  \
+      s2_ready_a<TM>(AB);                                                                                  \
+      s2_fetch_a<TM>(Sc, a_own, tm, 3 * cn + 1, AAN);                                                      \
+      s2_fetch_a<TM>(Sc, a_own, tm, 3 * cn + 2, ABN);                                                      \
       ld2(Sc, bp_mine + (3 * cn + 1) * BS, BAN);                                                           \
       ld2(Sc, bp_mine + (3 * cn + 2) * BS, BBN);                                                           \
       const vf lim = P.mu * cl[0];                                                                         \
@@ -2163,14 +2195,16 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, const float* work0, const fl
       TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(njdi[s], vfma(BA[s], dAu, BB[s] * dBu), w[s]);   \
     }
     {
-      vf aA0[3], aB0[3], bA0[2], bB0[2], aA1[3], aB1[3], bA1[2], bB1[2];
-      TREX_UNROLL for (int k = 0; k < 3; k++) { aA0[k] = ld(Sc, a_own + (NR + k)); aB0[k] = ld(Sc, a_own + (2 * NR + k)); }
+      vf aA0[4], aB0[4], bA0[2], bB0[2], aA1[4], aB1[4], bA1[2], bB1[2];
+      s2_fetch_a<TM>(Sc, a_own, tm, 1, aA0);
+      s2_fetch_a<TM>(Sc, a_own, tm, 2, aB0);
       ld2(Sc, bp_mine + BS, bA0);
       ld2(Sc, bp_mine + 2 * BS, bB0);
       TREX_ROLLED for (int c = 0; c < kmax; c += 2) {
         TREX_S2_FRICTION(c, aA0, aB0, bA0, bB0, aA1, aB1, bA1, bB1)
-        if (c + 1 < kmax) TREX_S2_FRICTION(c + 1, aA1, aB1, bA1, bB1, aA0, aB0, bA0, bB0)
+        if (c + 1 < kmax) TREX_S2_FRICTION(c + 1, aA1, aB1, bA1, bB1, aA0, aB0, bA0, bB0) else { s2_ready_a<TM>(aA1); s2_ready_a<TM>(aB1); }
       }
+      if ((kmax & 1) == 0) { s2_ready_a<TM>(aA0); s2_ready_a<TM>(aB0); }
     }
 #undef TREX_S2_FRICTION
     {  // residual of the contact rows: every row is visited once per sweep, so its impulse change is end - start
@@ -2400,9 +2434,11 @@ TREX_FN void solve_phase(const Uniform& P, float* scratch, const float* work0, f
 }
 
 // heavy_phase: the deferred solves of up to two environments with more than TREX_KC contacts (any two)
-TREX_FN void heavy_phase(const Uniform& P, float* scratch, const float* work0, const float* workh0, float* rec0, const int envs[2], int pending) {
+template <bool TM = false>
+TREX_FN void heavy_phase(const Uniform& P, float* scratch, tmem_t tm, const float* work0, const float* workh0, float* rec0, const int envs[2],
+                         int pending) {
   const vi lane = lane_id();
-  const vi itd = solve2(P, scratch, work0, workh0, rec0, envs, pending, P.max_impulse);
+  const vi itd = solve2<TM>(P, scratch, tm, work0, workh0, rec0, envs, pending, P.max_impulse);
   const vi grp = lane >> 4;
   const vb wr = ((lane & 15) == 0) && ((((vi(pending)) >> grp) & 1) != 0);
   const vi genv = seli(grp == 0, vi(envs[0]), vi(envs[1]));
