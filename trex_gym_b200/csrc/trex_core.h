@@ -16,9 +16,10 @@
 //   concurrently, one per lane, reading the per-body data as shared-memory broadcasts).
 //   M^-1 is symmetric, so lane d ends up holding exactly the coefficients it needs to
 //   update "its" velocity coordinate in the projected Gauss-Seidel sweep;
-// * the constraint solve (projected Gauss-Seidel in Bullet's row order) of every substep with at most 8 contacts is
-//   deferred to solve4(): four environments per warp, eight lanes each, contact rows carried in row space; only
-//   substeps with more contacts (and the reset step) use the one-environment sweep inside substep().
+// * the constraint solve (projected Gauss-Seidel in Bullet's row order) is deferred to kernels of its own: substeps with at
+//   most 8 contacts to solve4() (four environments per warp, eight lanes each, contact rows carried in row space), substeps
+//   with 9..16 contacts to solve2() (two environments per warp, sixteen lanes each, the Delassus matrix in tensor memory
+//   or shared memory); only the reset step uses the one-environment sweep inside substep().
 //
 // Written against the lane vocabulary of lane_cuda.h (device) / tests/emu/lane_emu.h
 // (host emulation for the CPU test-suite).  All control flow is warp-uniform.
