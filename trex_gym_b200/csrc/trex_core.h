@@ -1502,6 +1502,9 @@ TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf
 #ifndef TREX_REBUILD_MASK
 #define TREX_REBUILD_MASK 3  // exact rebuild of w (and u) every 4th sweep (every 8th: the 2e-5 per-env-step parity bound is exceeded, 2.1e-5)
 #endif
+#ifndef TREX_REBUILD_MASK_C
+#define TREX_REBUILD_MASK_C 3  // ... with contact rows (KC > 0)
+#endif
 #define TREX_LIMIT_SLOTS(KC) ((KC) > 4 ? 2 : 6)
 #define TREX_SOLVE_SCRATCH(KC) (4 * TREX_GC_STRIDE(KC) + 4 * (32 + 4 * (KC)) + 128 * TREX_LIMIT_SLOTS(KC))  // floats
 // envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
@@ -1656,7 +1659,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     // every 4th sweep (TREX_REBUILD_MASK) rebuild w (and u) exactly from the impulses (bounds the FP32 drift of the incremental updates):
     // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j - jdi_k sum_r B[r][k] lambda_r
     // u_r = sum_j B[r][j] Lambda_j + sum_r' A[r][r'] lambda_r'         (also the warm-started initial state)
-    if ((it & TREX_REBUILD_MASK) == 0 && (KC > 0 || it > 0)) {
+    if ((it & (KC > 0 ? TREX_REBUILD_MASK_C : TREX_REBUILD_MASK)) == 0 && (KC > 0 || it > 0)) {
       warp_sync();
       TREX_UNROLL for (int s = 0; s < 4; s++) st_if(Lam, grp * LS + kk[s], lam_m[s] + sigma[s] * lam_l[s], kv[s]);
       if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) st_if(Lam, grp * LS + glc * 4 + (32 + k), cl[k], gl < KC);
