@@ -1142,10 +1142,19 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
         }
         const vi dst = heavy ? rps + o_a4 : (cp * 4 + kp) + o_a4;
         const int rstride = heavy ? 3 * TREX_KW : 4 * TREX_KC;
-        TREX_ROLLED for (int r = 0; r < n3; r++) {  // source row (c, k)
-          vf acc = 0.0f;
-          TREX_UNROLL for (int e = 0; e < 11; e++) acc = vfma(jv[e], ld(&S.c.dV[0][0], dl[e] + r * 32), acc);
-          st_if(cw, dst + r * rstride, acc, valid);
+        // (n3 is a multiple of 3: three source rows per trip share the eleven per-lane base addresses, the loads take immediate offsets)
+        const float* dVb = &S.c.dV[0][0];
+        TREX_ROLLED for (int r = 0; r < n3; r += 3) {  // source rows (c, 0..2)
+          vf acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+          TREX_UNROLL for (int e = 0; e < 11; e++) {
+            const vi a = dl[e] + r * 32;
+            acc0 = vfma(jv[e], ld(dVb, a), acc0);
+            acc1 = vfma(jv[e], ld(dVb, a + 32), acc1);
+            acc2 = vfma(jv[e], ld(dVb, a + 64), acc2);
+          }
+          st_if(cw, dst + r * rstride, acc0, valid);
+          st_if(cw, dst + (r + 1) * rstride, acc1, valid);
+          st_if(cw, dst + (r + 2) * rstride, acc2, valid);
         }
       }
       warp_sync();
