@@ -122,6 +122,22 @@ TREX_FN vf vabs(const vf& x) { vf r; for (int l = 0; l < 32; l++) r.v[l] = fabsf
 TREX_FN vf vmin(const vf& a, const vf& b) { vf r; for (int l = 0; l < 32; l++) r.v[l] = fminf(a.v[l], b.v[l]); return r; }
 TREX_FN vf vmax(const vf& a, const vf& b) { vf r; for (int l = 0; l < 32; l++) r.v[l] = fmaxf(a.v[l], b.v[l]); return r; }
 TREX_FN vf vmin(const vf& a, float b) { return vmin(a, vf(b)); }
+TREX_FN vf vclamp_sym(const vf& x, const vf& m) {  // min.xorsign.abs: min(|x|, |m|) with sign(x) ^ sign(m)
+  vf r;
+  for (int l = 0; l < 32; l++) r.v[l] = (signbit(x.v[l]) != signbit(m.v[l]) ? -1.0f : 1.0f) * fminf(fabsf(x.v[l]), fabsf(m.v[l]));
+  return r;
+}
+// packed FP32 pairs (device: fma.rn.f32x2 / mul.rn.f32x2, the same bits as two scalar operations)
+TREX_FN void vfma2s(vf& c0, vf& c1, const vf& a0, const vf& a1, const vf& s) {
+  for (int l = 0; l < 32; l++) { c0.v[l] = fmaf(a0.v[l], s.v[l], c0.v[l]); c1.v[l] = fmaf(a1.v[l], s.v[l], c1.v[l]); }
+}
+TREX_FN void vfma2v(vf& c0, vf& c1, const vf& a0, const vf& a1, const vf& b0, const vf& b1) {
+  for (int l = 0; l < 32; l++) { c0.v[l] = fmaf(a0.v[l], b0.v[l], c0.v[l]); c1.v[l] = fmaf(a1.v[l], b1.v[l], c1.v[l]); }
+}
+TREX_FN void vmul2s(vf& r0, vf& r1, const vf& a0, const vf& a1, const vf& s) {
+  for (int l = 0; l < 32; l++) { r0.v[l] = a0.v[l] * s.v[l]; r1.v[l] = a1.v[l] * s.v[l]; }
+}
+TREX_FN vf vclamp_sym(const vf& x, float m) { return vclamp_sym(x, vf(m)); }
 TREX_FN vf vmax(const vf& a, float b) { return vmax(a, vf(b)); }
 TREX_FN vf vsin(const vf& x) { vf r; for (int l = 0; l < 32; l++) r.v[l] = sinf(x.v[l]); return r; }
 TREX_FN vf vcos(const vf& x) { vf r; for (int l = 0; l < 32; l++) r.v[l] = cosf(x.v[l]); return r; }
@@ -170,6 +186,7 @@ TREX_FN vi vmini(const vi& a, int b) { vi r; for (int l = 0; l < 32; l++) r.v[l]
 TREX_FN vi vf2i(const vf& x) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)x.v[l]; return r; }
 TREX_FN vi warp_maxi(const vi& x) { int m = x.v[0]; for (int l = 1; l < 32; l++) m = x.v[l] > m ? x.v[l] : m; return vi(m); }
 TREX_FN vf shfl_group8(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~7) | (src & 7)]; return r; }
+TREX_FN vf shflv_group8(const vf& x, const vi& src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~7) | (src.v[l] & 7)]; return r; }
 TREX_FN vf group8_sum(vf x) { for (int m = 4; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN vf group8_max(vf x) { for (int m = 4; m > 0; m >>= 1) x = vmax(x, shfl_xor(x, m)); return x; }
 
@@ -184,6 +201,7 @@ TREX_FN void tmem_wait4(vf (&)[4]) {}
 TREX_FN vi shfl_xor_i(const vi& x, int m) { vi r; for (int l = 0; l < 32; l++) r.v[l] = x.v[l ^ m]; return r; }
 TREX_FN vi sig_mix_v(const vi& h, const vi& w) { vi r; for (int l = 0; l < 32; l++) r.v[l] = (int)(((uint32_t)h.v[l] ^ (uint32_t)w.v[l]) * 16777619u); return r; }
 TREX_FN vf shfl_group16(const vf& x, int src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~15) | (src & 15)]; return r; }
+TREX_FN vf shflv_group16(const vf& x, const vi& src) { vf r; for (int l = 0; l < 32; l++) r.v[l] = x.v[(l & ~15) | (src.v[l] & 15)]; return r; }
 TREX_FN vf group16_sum(vf x) { for (int m = 8; m > 0; m >>= 1) x = x + shfl_xor(x, m); return x; }
 TREX_FN void ld2(const float* p, const vi& idx, vf out[2]) { for (int l = 0; l < 32; l++) for (int k = 0; k < 2; k++) out[k].v[l] = p[idx.v[l] + k]; }
 TREX_FN void st2_if(float* p, const vi& idx, const vf v[2], const vb& pred) {

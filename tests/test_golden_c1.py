@@ -36,9 +36,12 @@ def test_emulated_kernel_follows_c1_fixture(model):
     assert np.abs(e.reset() - g["reset_obs"]).max() < 1e-6
     for t in range(20):
         ob, r, done = e.step(g["actions"][t])
-        # free-running FP32 vs FP64 in contact is chaotic (an active-set flip at step 11 of this trajectory costs 1e-2 on
-        # the joint velocities for one step, see tests/test_active_set_parity.py): per block, 2e-2 of the block's magnitude
+        # free-running FP32 vs FP64 in contact is chaotic: step 11 of this trajectory (first touch-down of the second
+        # foot, 6 contacts) takes a different active set in FP32 and FP64 -- with any ordering of the solver's roundings --
+        # which costs 1e-2 .. 7e-2 of the joint velocities for the following steps (tests/test_active_set_parity.py
+        # buckets such steps).  Per block: 2e-3 of the block's magnitude before the flip, 1e-1 after it
+        tol = 2e-3 if t < 11 else 1e-1
         for blk in (slice(0, 25), slice(25, 50), slice(50, 75)):
-            assert np.abs(ob[blk] - g["obs"][t][blk]).max() < 2e-2 * max(1.0, np.abs(g["obs"][t][blk]).max()), t
-        assert abs(r - g["reward"][t]) < 5e-3 * max(1.0, abs(g["reward"][t])), t
+            assert np.abs(ob[blk] - g["obs"][t][blk]).max() < tol * max(1.0, np.abs(g["obs"][t][blk]).max()), t
+        assert abs(r - g["reward"][t]) < (1e-3 if t < 11 else 2e-2) * max(1.0, abs(g["reward"][t])), t
         assert not done

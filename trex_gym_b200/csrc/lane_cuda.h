@@ -59,6 +59,24 @@ TREX_FN vf vsqrt(vf x) { return sqrtf(x); }
 TREX_FN vf vabs(vf x) { return fabsf(x); }
 TREX_FN vf vmin(vf a, vf b) { return fminf(a, b); }
 TREX_FN vf vmax(vf a, vf b) { return fmaxf(a, b); }
+// symmetric clamp min(max(x, -m), m) for m >= 0 as ONE instruction: FMNMX.XORSIGN takes min(|x|, |m|) with the sign bit
+// sign(x) ^ sign(m) (half the latency of the FMNMX pair on the Gauss-Seidel chain; same bits for every non-NaN x)
+TREX_FN vf vclamp_sym(vf x, vf m) { float r; asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(m)); return r; }
+// Packed FP32 pairs (Blackwell FFMA2 / FMUL2: `fma.rn.f32x2`, one issue slot for two IEEE fused multiply-adds on an aligned
+// register pair -- the same bits as two FFMAs).  The solvers are issue bound; their impulse publications update two or four
+// accumulators with one scalar.  (c0, c1) += (a0, a1) * s / (c0, c1) += (a0, a1) * (b0, b1) / (r0, r1) = (a0, a1) * s
+TREX_FN void vfma2s(vf& c0, vf& c1, vf a0, vf a1, vf s) {
+  asm("{\n .reg .b64 ra, rs, rc;\n mov.b64 ra, {%2, %3};\n mov.b64 rs, {%4, %4};\n mov.b64 rc, {%0, %1};\n"
+      " fma.rn.f32x2 rc, ra, rs, rc;\n mov.b64 {%0, %1}, rc;\n}" : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(s));
+}
+TREX_FN void vfma2v(vf& c0, vf& c1, vf a0, vf a1, vf b0, vf b1) {
+  asm("{\n .reg .b64 ra, rb, rc;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%0, %1};\n"
+      " fma.rn.f32x2 rc, ra, rb, rc;\n mov.b64 {%0, %1}, rc;\n}" : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+TREX_FN void vmul2s(vf& r0, vf& r1, vf a0, vf a1, vf s) {
+  asm("{\n .reg .b64 ra, rs, rr;\n mov.b64 ra, {%2, %3};\n mov.b64 rs, {%4, %4};\n"
+      " mul.rn.f32x2 rr, ra, rs;\n mov.b64 {%0, %1}, rr;\n}" : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(s));
+}
 TREX_FN vf vsin(vf x) { return sinf(x); }
 TREX_FN vf vcos(vf x) { return cosf(x); }
 TREX_FN vf vdiv(vf a, vf b) { return a / b; }
@@ -108,6 +126,7 @@ TREX_FN vi warp_maxi(vi x) {
 }
 // width-8 lane groups (four environments per warp in solve4)
 TREX_FN vf shfl_group8(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 8); }
+TREX_FN vf shflv_group8(vf x, vi src) { return __shfl_sync(TREX_FULL, x, src, 8); }  // per-lane source (uniform within a group)
 TREX_FN vf group8_sum(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
 TREX_FN vf group8_max(vf x) { TREX_UNROLL for (int m = 4; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(TREX_FULL, x, m)); return x; }
 
@@ -116,6 +135,7 @@ TREX_FN vi shfl_xor_i(vi x, int m) { return __shfl_xor_sync(TREX_FULL, x, m); }
 TREX_FN vi sig_mix_v(vi h, vi w) { return (int)(((uint32_t)h ^ (uint32_t)w) * 16777619u); }
 // width-16 lane groups (two environments per warp in solve2)
 TREX_FN vf shfl_group16(vf x, int src) { return __shfl_sync(TREX_FULL, x, src, 16); }
+TREX_FN vf shflv_group16(vf x, vi src) { return __shfl_sync(TREX_FULL, x, src, 16); }
 TREX_FN vf group16_sum(vf x) { TREX_UNROLL for (int m = 8; m > 0; m >>= 1) x += __shfl_xor_sync(TREX_FULL, x, m); return x; }
 // 2 consecutive floats per lane (8-byte aligned offset): one 64-bit access
 TREX_FN void ld2(const float* p, vi idx, vf out[2]) {

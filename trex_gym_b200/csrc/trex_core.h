@@ -1195,7 +1195,7 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
 #define TREX_MOTOR_ROW(K)                                                                              \
     {                                                                                                  \
       constexpr int j = trex_topo::noncontact_order(K) - NJ;                                           \
-      const vf nl = vmin(vmax(w, -max_imp), max_imp);   /* meaningful on lane j only */                \
+      const vf nl = vclamp_sym(w, max_imp);              /* meaningful on lane j only */                \
       const vf t = vfma(-g[j], lamr[j], w);             /* off the critical path */                    \
       const vf nlu = vbroadcast(lane_value(nl, j));     /* new impulse of motor j, on every lane */    \
       lamr[j] = nlu;                                                                                   \
@@ -1310,8 +1310,8 @@ TREX_FN int substep(const Uniform& P, const float* mdl, const int* mdli, const f
       const vf rn = vrsqrt(sel(nz, n2, 1.0f));
       const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
       const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
-      const vf nA = vmin(vmax(sumA, -clipA), clipA);
-      const vf nB = vmin(vmax(sumB, -clipB), clipB);
+      const vf nA = vclamp_sym(sumA, clipA);
+      const vf nB = vclamp_sym(sumB, clipB);
       dA = nA - c_lam[1];
       dB = nB - c_lam[2];
       const vb own = lane == c;
@@ -1470,33 +1470,63 @@ TREX_TOPO_FN bool limit_order_matches_motor_order() {
     if (trex_topo::noncontact_order(NJ + p) != trex_topo::noncontact_order(p) - NJ) return false;
   return true;
 }
+#ifndef TREX_S4_PRESUB
+#define TREX_S4_PRESUB(KC) 0  // (measured: no gain in either solve4 instance -- they are issue bound, not chain bound)
+#endif
 template <int B, bool FWD, int KC>
-TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf (&cu)[3], vi gl, vi bt_own, const float* Bs,
+TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf (&cu)[3], vi glx, vi dead, vi bt_own, const float* Bs,
                             float max_imp) {
   constexpr int n = (4 * B + 4 <= NJ) ? 4 : NJ - 4 * B;
   vf bk[3][4];  // responses of the owned contact's three rows at this block's four joints
   if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) ld4(Bs, bt_own + (k * 36 + 4 * B), bk[k]);
-  vf t[4], d[4];
-  TREX_UNROLL for (int i = 0; i < 4; i++) { t[i] = w[i]; d[i] = 0.0f; }
-  const vb own = gl == B;
-  // the owner's private chain (the other lanes compute on their own registers and discard)
-  TREX_UNROLL for (int ii = 0; ii < n; ii++) {
-    const int i = FWD ? ii : n - 1 - ii;
-    const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
-    const vf nl = vmin(vmax(t[i], -max_imp), max_imp);
-    d[i] = nl - lam_m[i];
-    lam_m[i] = sel(own, nl, lam_m[i]);
-    TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
-      const int i3 = FWD ? i2 : n - 1 - i2;
-      t[i3] = vfma(g[i3][j], d[i], t[i3]);
+  vf t[4], d[4], nl[4];
+  TREX_UNROLL for (int i = 0; i < 4; i++) { t[i] = w[i]; d[i] = 0.0f; nl[i] = 0.0f; }
+  // the owner's private chain (the other lanes compute on their own registers and discard); the clamp is one FMNMX.XORSIGN.
+  if (TREX_S4_PRESUB(KC)) {
+    // Row i's target is w_i + sum_{earlier rows e of the block} g[i][e] (new_e - old_e): the old impulses are taken out
+    // BEFORE the chain, so that a row costs a clamp and one FMA of dependent latency (10 cycles instead of 14; six more
+    // FMAs per block off the chain).  Pays in the contact solver (two warps per scheduler: latency bound); the contact-free
+    // solver is issue bound (three warps per scheduler), there it costs 1 % and one more rounding per row
+    TREX_UNROLL for (int ii = 0; ii < n; ii++) {
+      const int i = FWD ? ii : n - 1 - ii;
+      const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
+      TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
+        const int i3 = FWD ? i2 : n - 1 - i2;
+        t[i3] = vfma(-g[i3][j], lam_m[i], t[i3]);
+      }
+    }
+    TREX_UNROLL for (int ii = 0; ii < n; ii++) {
+      const int i = FWD ? ii : n - 1 - ii;
+      const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
+      nl[i] = vclamp_sym(t[i], max_imp);
+      TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
+        const int i3 = FWD ? i2 : n - 1 - i2;
+        t[i3] = vfma(g[i3][j], nl[i], t[i3]);
+      }
+    }
+  } else {
+    TREX_UNROLL for (int ii = 0; ii < n; ii++) {
+      const int i = FWD ? ii : n - 1 - ii;
+      const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
+      nl[i] = vclamp_sym(t[i], max_imp);
+      const vf di = nl[i] - lam_m[i];
+      TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
+        const int i3 = FWD ? i2 : n - 1 - i2;
+        t[i3] = vfma(g[i3][j], di, t[i3]);
+      }
     }
   }
+  const vb own = glx == B;  // (glx = -1 in a finished environment: it keeps its impulses ...)
+  const vi src = dead | B;  // (... and publishes the zeros of its group's idle last lane: dead = 7)
   // publish: every lane applies the four impulse changes of lane B
   TREX_UNROLL for (int ii = 0; ii < n; ii++) {
     const int i = FWD ? ii : n - 1 - ii;
     const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
-    const vf db = shfl_group8(d[i], B);
-    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(g[s][j], db, w[s]);
+    d[i] = nl[i] - lam_m[i];
+    lam_m[i] = sel(own, nl[i], lam_m[i]);
+    const vf db = shflv_group8(d[i], src);
+    vfma2s(w[0], w[1], g[0][j], g[1][j], db);  // (two FFMA2 instead of four FFMA: the solvers are issue bound)
+    vfma2s(w[2], w[3], g[2][j], g[3][j], db);
     if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(bk[k][i], db, cu[k]);
   }
 }
@@ -1635,7 +1665,8 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     const vf d = sel(own, (nl - lam_l[SJ]) * sigma[SJ], 0.0f);  /* change of the net joint impulse */   \
     const vf db = shfl_group8(d, pos >> 2);                                                            \
     lam_l[SJ] = sel(own, nl, lam_l[SJ]);                                                               \
-    TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(gj[s], db, w[s]);                              \
+    vfma2s(w[0], w[1], gj[0], gj[1], db);                                                              \
+    vfma2s(w[2], w[3], gj[2], gj[3], db);                                                              \
     w[SJ] = w[SJ] - d;                                        /* self term: dv_j += D_j * d */         \
     if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Bs, bt_own + (k * 36 + pos)), db, cu[k]); \
   }
@@ -1663,7 +1694,8 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       }                                                                                                \
     }                                                                                                  \
   }
-#define MB_(b, fwd) s4_motor_block<b, fwd, KC>(w, lam_m, g, cu, gl, bt_own, Bs, max_imp);
+#define MB_(b, fwd) s4_motor_block<b, fwd, KC>(w, lam_m, g, cu, glx, dead, bt_own, Bs, max_imp);
+  vf mu_l = P.mu;
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
     // every 4th sweep (TREX_REBUILD_MASK) rebuild w (and u) exactly from the impulses (bounds the FP32 drift of the incremental updates):
     // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j - jdi_k sum_r B[r][k] lambda_r
@@ -1678,7 +1710,8 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = 0.0f;
       TREX_UNROLL for (int j = 0; j < NJ; j++) {
         const vf Lj = ld(Lam, grp * LS + j);
-        TREX_UNROLL for (int s = 0; s < 4; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
+        vfma2s(acc[0], acc[1], g[0][j], g[1][j], Lj);
+        vfma2s(acc[2], acc[3], g[2][j], g[3][j], Lj);
         if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(ld(Bs, bt_own + (k * 36 + motor_position(j))), Lj, ua[k]);
       }
       if (KC > 0) {
@@ -1702,11 +1735,11 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
     }
     vf lam_m0[4], lam_l0[4];
     vf cres = 0.0f;
-    TREX_UNROLL for (int s = 0; s < 4; s++) {
-      lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s];
-      // an environment that has finished (converged) is frozen: clamp(w) == its impulse, so every row yields 0
-      w[s] = sel(alive, w[s], lam_m[s]);
-    }
+    TREX_UNROLL for (int s = 0; s < 4; s++) { lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s]; }
+    // an environment that has finished (converged) is frozen without a select on the dependent chain: it owns no motor row
+    // (glx = -1) and publishes the zeros of its group's idle lane 7 (dead = 7); its contact rows have jdi = rhs = 0 and an
+    // unbounded cone (below), so they reproduce their impulses exactly
+    const vi glx = seli(alive, gl, vi(-1)), dead = seli(alive, vi(0), vi(7));
     if (it & 1) {
       MB_(0, true) MB_(1, true) MB_(2, true) MB_(3, true) MB_(4, true) MB_(5, true) MB_(6, true)
       TREX_S4_LIMITS(true)
@@ -1715,41 +1748,44 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       MB_(6, false) MB_(5, false) MB_(4, false) MB_(3, false) MB_(2, false) MB_(1, false) MB_(0, false)
     }
     if (KC > 0) {
-      // normal rows: every lane evaluates its own contact, the owner of contact c publishes
+      // normal rows: every lane evaluates its own contact, the owner of contact c publishes.  Dependent chain per row:
+      // FFMA, FMNMX, FADD, SHFL, FFMA (the impulse + rhs sum is taken before the loop; Bullet's upper bound 1e10 cannot bind
+      // on a state that passes the NaN / overflow guard; no select: rows of absent contacts and of finished environments
+      // have jdi = rhs = 0 and reproduce their impulse)
       // (most warps of this kernel hold environments with 1-2 contacts: fetching the A4 / Bp rows one iteration ahead, as
       // solve2 does for its 9-16 contacts, only adds loads here -- measured +30 % on the benchmark batch)
       const vf cl0_0 = cl[0], cl1_0 = cl[1], cl2_0 = cl[2];
+      const vf pre0 = cl[0] + crhs[0];
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
-        const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);
-        const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);
-        const vb own = alive && (gl == c);
-        const vf dl = sel(own, nl - cl[0], 0.0f);
-        const vf d = shfl_group8(dl, c);
-        cl[0] = sel(own, nl, cl[0]);
+        const vf nl = vmax(vfma(-cu[0], cjdi[0], pre0), 0.0f);
+        const vf d = shfl_group8(nl - cl[0], c);
+        cl[0] = sel(gl == c, nl, cl[0]);
         vf a4[4];
         ld4(Bs, gb + glc * 4 + ((3 * c) * (4 * KC) + BT), a4);
         TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
         vf b4[4];
         ld4(Bs, gb + gl * 4 + (3 * c) * 36, b4);
-        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(b4[s], njdi[s] * d, w[s]);
+        vf nd[4];
+        vmul2s(nd[0], nd[1], njdi[0], njdi[1], d);
+        vmul2s(nd[2], nd[3], njdi[2], njdi[3], d);
+        vfma2v(w[0], w[1], b4[0], b4[1], nd[0], nd[1]);
+        vfma2v(w[2], w[3], b4[2], b4[3], nd[2], nd[3]);
       }
-      // friction pairs, implicit cone; both rows read the velocities before either writes
+      // friction pairs, implicit cone; both rows read the velocities before either writes.  |lim sin|, |lim cos| of
+      // atan2(sumA, sumB) = lim |sum| / sqrt(sumA^2 + sumB^2); at sumA = sumB = 0 both clips multiply a zero, which is
+      // what the reference's clamp of a zero sum gives
+      const vf lim = mu_l * cl[0];
+      const vf preA = cl[1] + crhs[1], preB = cl[2] + crhs[2];
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
-        const vf lim = P.mu * cl[0];
-        const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);
-        const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);
-        const vf n2 = sumA * sumA + sumB * sumB;
-        const vb nz = n2 > 0.0f;
-        const vf rn = vrsqrt(sel(nz, n2, 1.0f));
-        const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);
-        const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));
-        const vf nA = vmin(vmax(sumA, -clipA), clipA);
-        const vf nB = vmin(vmax(sumB, -clipB), clipB);
-        const vb own = alive && (gl == c);
-        const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);
-        const vf dAu = shfl_group8(dA, c), dBu = shfl_group8(dB, c);
-        cl[1] = sel(own, nA, cl[1]);
-        cl[2] = sel(own, nB, cl[2]);
+        const vf sumB = vfma(-cu[2], cjdi[2], preB);
+        const vf sumA = vfma(-cu[1], cjdi[1], preA);
+        const vf rn = vrsqrt(vmax(sumA * sumA + sumB * sumB, 1.0e-30f));
+        const vf nA = vclamp_sym(sumA, lim * vabs(sumA * rn));
+        const vf nB = vclamp_sym(sumB, lim * vabs(sumB * rn));
+        const vf dAu = shfl_group8(nA - cl[1], c), dBu = shfl_group8(nB - cl[2], c);
+        const vb mine = gl == c;
+        cl[1] = sel(mine, nA, cl[1]);
+        cl[2] = sel(mine, nB, cl[2]);
         vf aA[4], aB[4];
         ld4(Bs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + BT), aA);
         ld4(Bs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + BT), aB);
@@ -1757,7 +1793,13 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         vf bA[4], bB[4];
         ld4(Bs, gb + gl * 4 + (3 * c + 1) * 36, bA);
         ld4(Bs, gb + gl * 4 + (3 * c + 2) * 36, bB);
-        TREX_UNROLL for (int s = 0; s < 4; s++) w[s] = vfma(njdi[s], vfma(bA[s], dAu, bB[s] * dBu), w[s]);
+        vf tb[4];
+        vmul2s(tb[0], tb[1], bB[0], bB[1], dBu);
+        vmul2s(tb[2], tb[3], bB[2], bB[3], dBu);
+        vfma2s(tb[0], tb[1], bA[0], bA[1], dAu);
+        vfma2s(tb[2], tb[3], bA[2], bA[3], dAu);
+        vfma2v(w[0], w[1], njdi[0], njdi[1], tb[0], tb[1]);
+        vfma2v(w[2], w[3], njdi[2], njdi[3], tb[2], tb[3]);
       }
       {  // residual of the contact rows: every row is visited once per sweep, so its impulse change is end - start
         const vf dn = (cl[0] - cl0_0) * cdd[0];
@@ -1784,6 +1826,10 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
                        seli(grp == 2, vi((int)((over >> 16) & 0xffu)), vi((int)(over >> 24)))));
     alive = alive && (ob != 0) && (it < P.iters - 1);
     if (over == 0u || it >= P.iters - 1) break;
+    if (KC > 0) {  // freeze the contact rows of an environment that has just finished
+      TREX_UNROLL for (int k = 0; k < 3; k++) { crhs[k] = sel(alive, crhs[k], 0.0f); cjdi[k] = sel(alive, cjdi[k], 0.0f); }
+      mu_l = sel(alive, mu_l, 1.0e30f);
+    }
   }
 #undef MB_
 #undef TREX_S4_LIMIT_SLOT
@@ -1798,7 +1844,8 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
   TREX_UNROLL for (int s = 0; s < 4; s++) { Ssum[s] = 0.0f; bsum[s] = 0.0f; }
   TREX_UNROLL for (int j = 0; j < NJ; j++) {
     const vf Lj = ld(Lam, grp * LS + j);
-    TREX_UNROLL for (int s = 0; s < 4; s++) Ssum[s] = vfma(g[s][j], Lj, Ssum[s]);
+    vfma2s(Ssum[0], Ssum[1], g[0][j], g[1][j], Lj);
+    vfma2s(Ssum[2], Ssum[3], g[2][j], g[3][j], Lj);
   }
   vf dvb[6];
   TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = 0.0f;
@@ -1932,29 +1979,25 @@ template <bool TM>
 TREX_FN void s2_ready_a(vf (&a)[4]) { if (TM) tmem_wait4(a); }
 
 template <int B, bool FWD>
-TREX_FN void s2_motor_block(vf (&w)[2], vf (&lam_m)[2], const vf (&g)[2][NJ], vf (&cu)[3], vi gl, vi bp_own, const float* Sc, float max_imp) {
+TREX_FN void s2_motor_block(vf (&w)[2], vf (&lam_m)[2], const vf (&g)[2][NJ], vf (&cu)[3], vi glx, vi dead, vi bp_own, const float* Sc, float max_imp) {
   constexpr int n = (2 * B + 2 <= NJ) ? 2 : NJ - 2 * B;
   vf bk[3][2];  // responses of the owned contact's three rows at this block's joints
   TREX_UNROLL for (int k = 0; k < 3; k++) ld2(Sc, bp_own + (k * TREX_S2_BS + 2 * B), bk[k]);
-  vf t[2], d[2];
-  TREX_UNROLL for (int i = 0; i < 2; i++) { t[i] = w[i]; d[i] = 0.0f; }
-  const vb own = gl == B;
-  TREX_UNROLL for (int ii = 0; ii < n; ii++) {  // the owner's private chain
-    const int i = FWD ? ii : n - 1 - ii;
-    const int j = trex_topo::noncontact_order(2 * B + i) - NJ;
-    const vf nl = vmin(vmax(t[i], -max_imp), max_imp);
-    d[i] = nl - lam_m[i];
-    lam_m[i] = sel(own, nl, lam_m[i]);
-    if (ii + 1 < n) {
-      const int i3 = FWD ? 1 : 0;
-      t[i3] = vfma(g[i3][j], d[i], t[i3]);
-    }
-  }
+  constexpr int i0 = FWD ? 0 : n - 1, i1 = FWD ? 1 : 0;  // first / second row of the block in visiting order
+  constexpr int j0 = trex_topo::noncontact_order(2 * B + i0) - NJ;
+  vf nl[2];
+  nl[0] = 0.0f; nl[1] = 0.0f;
+  // the owner's private chain: clamp (one FMNMX.XORSIGN), difference, FMA, clamp
+  nl[i0] = vclamp_sym(w[i0], max_imp);
+  if (n == 2) nl[i1] = vclamp_sym(vfma(g[i1][j0], nl[i0] - lam_m[i0], w[i1]), max_imp);
+  const vb own = glx == B;  // (a finished environment owns nothing and publishes the zeros of its idle lane 15)
+  const vi src = dead | B;
   TREX_UNROLL for (int ii = 0; ii < n; ii++) {  // publish: every lane applies the impulse changes of lane B
     const int i = FWD ? ii : n - 1 - ii;
     const int j = trex_topo::noncontact_order(2 * B + i) - NJ;
-    const vf db = shfl_group16(d[i], B);
-    TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(g[s][j], db, w[s]);
+    const vf db = shflv_group16(nl[i] - lam_m[i], src);
+    lam_m[i] = sel(own, nl[i], lam_m[i]);
+    vfma2s(w[0], w[1], g[0][j], g[1][j], db);
     TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(bk[k][i], db, cu[k]);
   }
 }
@@ -2082,7 +2125,7 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
     const vf d = sel(own, (nl - lam_l[SJ]) * sigma[SJ], 0.0f);  /* change of the net joint impulse */   \
     const vf db = shfl_group16(d, pos >> 1);                                                           \
     lam_l[SJ] = sel(own, nl, lam_l[SJ]);                                                               \
-    TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(gj[s], db, w[s]);                              \
+    vfma2s(w[0], w[1], gj[0], gj[1], db);                                                              \
     w[SJ] = w[SJ] - d;                                        /* self term: dv_j += D_j * d */         \
     TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(ld(Sc, bp_own + (k * BS + pos)), db, cu[k]);  \
   }
@@ -2104,7 +2147,8 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
       if (pos & 1) TREX_S2_LIMIT_SLOT(1) else TREX_S2_LIMIT_SLOT(0)                                    \
     }                                                                                                  \
   }
-#define MB_(b, fwd) s2_motor_block<b, fwd>(w, lam_m, g, cu, gl, bp_own, Sc, max_imp);
+#define MB_(b, fwd) s2_motor_block<b, fwd>(w, lam_m, g, cu, glx, dead, bp_own, Sc, max_imp);
+  vf mu_l = P.mu;
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
     // every 16th sweep (TREX_S2_REBUILD_MASK) rebuild w and u exactly from the impulses (also the warm-started initial state):
     // w_k = rhs_m,k - sigma_k lam_l,k + sum_j g[k][j] Lambda_j - jdi_k sum_r B[r][k] lambda_r
@@ -2119,7 +2163,7 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
       TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = 0.0f;
       TREX_UNROLL for (int j = 0; j < NJ; j++) {
         const vf Lj = ld(Lam, grp * LS + j);
-        TREX_UNROLL for (int s = 0; s < 2; s++) acc[s] = vfma(g[s][j], Lj, acc[s]);
+        vfma2s(acc[0], acc[1], g[0][j], g[1][j], Lj);
         TREX_UNROLL for (int k = 0; k < 3; k++) ua[k] = vfma(ld(Sc, bp_own + (k * BS + motor_position(j))), Lj, ua[k]);
       }
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
@@ -2140,10 +2184,10 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
     }
     vf lam_m0[2], lam_l0[2];
     vf cres = 0.0f;
-    TREX_UNROLL for (int s = 0; s < 2; s++) {
-      lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s];
-      w[s] = sel(alive, w[s], lam_m[s]);  // a finished environment is frozen: clamp(w) == its impulse, every row yields 0
-    }
+    TREX_UNROLL for (int s = 0; s < 2; s++) { lam_m0[s] = lam_m[s]; lam_l0[s] = lam_l[s]; }
+    // a finished environment is frozen without a select on the dependent chain (see solve4): no motor row of its own, the
+    // zeros of its idle lane 15 published, contact rows with jdi = rhs = 0 and an unbounded cone
+    const vi glx = seli(alive, gl, vi(-1)), dead = seli(alive, vi(0), vi(15));
     if (it & 1) {
       MB_(0, true) MB_(1, true) MB_(2, true) MB_(3, true) MB_(4, true) MB_(5, true) MB_(6, true) MB_(7, true) MB_(8, true) MB_(9, true)
       MB_(10, true) MB_(11, true) MB_(12, true)
@@ -2164,15 +2208,15 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
       s2_ready_a<TM>(A3);                                                                                  \
       s2_fetch_a<TM>(Sc, a_own, tm, 3 * cn, AN);                                                           \
       ld2(Sc, bp_mine + (3 * cn) * BS, BN);                                                                \
-      const vf sum = cl[0] + (crhs[0] - cu[0] * cjdi[0]);                                                  \
-      const vf nl = vmin(vmax(sum, 0.0f), 1.0e10f);                                                        \
-      const vb own = alive && (gl == (C));                                                                 \
-      const vf dl = sel(own, nl - cl[0], 0.0f);                                                            \
-      const vf d = shfl_group16(dl, (C));                                                                  \
-      cl[0] = sel(own, nl, cl[0]);                                                                         \
+      const vf nl = vmax(vfma(-cu[0], cjdi[0], pre0), 0.0f);  /* chain: FFMA, FMNMX, FADD, SHFL, FFMA */  \
+      const vf d = shfl_group16(nl - cl[0], (C));                                                          \
+      cl[0] = sel(gl == (C), nl, cl[0]);                                                                   \
       TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(A3[k], d, cu[k]);                               \
-      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(B2[s], njdi[s] * d, w[s]);                       \
+      vf nd[2];                                                                                            \
+      vmul2s(nd[0], nd[1], njdi[0], njdi[1], d);                                                           \
+      vfma2v(w[0], w[1], B2[0], B2[1], nd[0], nd[1]);                                                      \
     }
+    const vf pre0 = cl[0] + crhs[0];
     {
       vf a0[4], b0[2], a1[4], b1[2];
       s2_fetch_a<TM>(Sc, a_own, tm, 0, a0);
@@ -2194,24 +2238,23 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
       s2_fetch_a<TM>(Sc, a_own, tm, 3 * cn + 2, ABN);                                                      \
       ld2(Sc, bp_mine + (3 * cn + 1) * BS, BAN);                                                           \
       ld2(Sc, bp_mine + (3 * cn + 2) * BS, BBN);                                                           \
-      const vf lim = P.mu * cl[0];                                                                         \
-      const vf sumB = cl[2] + (crhs[2] - cu[2] * cjdi[2]);                                                 \
-      const vf sumA = cl[1] + (crhs[1] - cu[1] * cjdi[1]);                                                 \
-      const vf n2 = sumA * sumA + sumB * sumB;                                                             \
-      const vb nz = n2 > 0.0f;                                                                             \
-      const vf rn = vrsqrt(sel(nz, n2, 1.0f));                                                             \
-      const vf clipA = sel(nz, vabs(lim * (sumA * rn)), 0.0f);                                             \
-      const vf clipB = sel(nz, vabs(lim * (sumB * rn)), vabs(lim));                                        \
-      const vf nA = vmin(vmax(sumA, -clipA), clipA);                                                       \
-      const vf nB = vmin(vmax(sumB, -clipB), clipB);                                                       \
-      const vb own = alive && (gl == (C));                                                                 \
-      const vf dA = sel(own, nA - cl[1], 0.0f), dB = sel(own, nB - cl[2], 0.0f);                           \
-      const vf dAu = shfl_group16(dA, (C)), dBu = shfl_group16(dB, (C));                                   \
-      cl[1] = sel(own, nA, cl[1]);                                                                         \
-      cl[2] = sel(own, nB, cl[2]);                                                                         \
+      const vf sumB = vfma(-cu[2], cjdi[2], preB);                                                         \
+      const vf sumA = vfma(-cu[1], cjdi[1], preA);                                                         \
+      const vf rn = vrsqrt(vmax(sumA * sumA + sumB * sumB, 1.0e-30f));                                     \
+      const vf nA = vclamp_sym(sumA, lim * vabs(sumA * rn));                                               \
+      const vf nB = vclamp_sym(sumB, lim * vabs(sumB * rn));                                               \
+      const vf dAu = shfl_group16(nA - cl[1], (C)), dBu = shfl_group16(nB - cl[2], (C));                   \
+      const vb mine = gl == (C);                                                                           \
+      cl[1] = sel(mine, nA, cl[1]);                                                                        \
+      cl[2] = sel(mine, nB, cl[2]);                                                                        \
       TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(AA[k], dAu, vfma(AB[k], dBu, cu[k]));           \
-      TREX_UNROLL for (int s = 0; s < 2; s++) w[s] = vfma(njdi[s], vfma(BA[s], dAu, BB[s] * dBu), w[s]);   \
+      vf tb[2];                                                                                            \
+      vmul2s(tb[0], tb[1], BB[0], BB[1], dBu);                                                             \
+      vfma2s(tb[0], tb[1], BA[0], BA[1], dAu);                                                             \
+      vfma2v(w[0], w[1], njdi[0], njdi[1], tb[0], tb[1]);                                                  \
     }
+    const vf lim = mu_l * cl[0];
+    const vf preA = cl[1] + crhs[1], preB = cl[2] + crhs[2];
     {
       vf aA0[4], aB0[4], bA0[2], bB0[2], aA1[4], aB1[4], bA1[2], bB1[2];
       s2_fetch_a<TM>(Sc, a_own, tm, 1, aA0);
@@ -2247,6 +2290,9 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
     const vi ob = seli(grp == 0, vi((int)(over & 0xffffu)), vi((int)(over >> 16)));
     alive = alive && (ob != 0) && (it < P.iters - 1);
     if (over == 0u || it >= P.iters - 1) break;
+    // freeze the contact rows of an environment that has just finished
+    TREX_UNROLL for (int k = 0; k < 3; k++) { crhs[k] = sel(alive, crhs[k], 0.0f); cjdi[k] = sel(alive, cjdi[k], 0.0f); }
+    mu_l = sel(alive, mu_l, 1.0e30f);
   }
 #undef MB_
 #undef TREX_S2_LIMIT_SLOT
@@ -2261,7 +2307,7 @@ TREX_FN vi solve2(const Uniform& P, float* scratch, tmem_t tm, const float* work
   TREX_UNROLL for (int s = 0; s < 2; s++) { Ssum[s] = 0.0f; bsum[s] = 0.0f; }
   TREX_UNROLL for (int j = 0; j < NJ; j++) {
     const vf Lj = ld(Lam, grp * LS + j);
-    TREX_UNROLL for (int s = 0; s < 2; s++) Ssum[s] = vfma(g[s][j], Lj, Ssum[s]);
+    vfma2s(Ssum[0], Ssum[1], g[0][j], g[1][j], Lj);
   }
   vf dvb[6];
   TREX_UNROLL for (int b = 0; b < 6; b++) dvb[b] = 0.0f;
