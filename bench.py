@@ -483,7 +483,8 @@ def run_ours(args):
         _native.check(_native.lib().trex_measure_fp32_peak(local, _native.ctypes.byref(tf)), "trex_measure_fp32_peak")
         fp32_peak = float(tf.value)
         kernel_ms = dev_ms / args.steps  # all kernels of one env step (rank 0's own device time)
-        traffic, traffic_note = lookup_traffic(workload, n, sim.num_substeps)
+        traffic, traffic_note = (lookup_traffic(workload, n, sim.num_substeps) if not args.no_contacts and not os.environ.get("TREX_CHUNK")
+                                 else (None, "profiles/traffic.json has no entry for this configuration"))
         flops = f_alg(sim.num_substeps, it_sum, ct_sum) * n
         achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
         hbm_gbs = B_ALG * n / (kernel_ms * 1e-3) / 1e9

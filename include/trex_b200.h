@@ -65,6 +65,8 @@ typedef struct trex_handle trex_handle;
 #define TREX_HEAVY_BOTH 0
 #define TREX_HEAVY_SHARED 1
 #define TREX_HEAVY_TENSOR 2
+#define TREX_CONTACT_TENSOR 0
+#define TREX_CONTACT_SHARED 1
 
 typedef struct trex_config {
   int32_t num_substeps;      /* trex_env.py:18 NUM_SUBSTEPS (5); dt = 0.01/n, iterations = int(300/n)  (:71-73) */
@@ -93,13 +95,23 @@ typedef struct trex_config {
                                 0 = default: always (the routing then depends on the environment alone, never on its batch) */
   int32_t pipelines;         /* the batch is stepped as this many independent groups of environments, each a chain of kernels on
                                 its own stream, so that one group's latency-bound solvers overlap another group's issue-bound
-                                dynamics kernel (results do not depend on it): 1..4; 0 = default (2 from 8,192 environments) */
+                                dynamics kernel (results do not depend on it): 1..8; 0 = default (2 from 8,192 environments) */
   int32_t heavy_memory;      /* where the many-contact solver (9-16 contacts, two environments per warp) keeps its 48 x 48 Delassus
                                 matrices: TREX_HEAVY_BOTH (default) runs two kernel instances concurrently on one task list -- one with
                                 the matrices in TENSOR MEMORY (tcgen05.st / tcgen05.ld as a per-lane scratchpad, 8 warps per SM), one
                                 with them in shared memory (fills the shared memory left: 4 more warps per SM);
                                 TREX_HEAVY_SHARED / TREX_HEAVY_TENSOR run one of them alone.  Results are bit-identical. */
-  int32_t reserved[9];       /* must be zero */
+  int32_t chunk_envs;        /* L2-resident work records: every group of `pipelines` walks its share of the batch in chunks of this many
+                                environments (multiple of 4) -- all substeps of a chunk before the next one -- and reuses the same
+                                work-record slots, so the 4.6-11.4 KB per environment and substep that the dynamics kernel hands to
+                                the solvers stay in the 126 MB L2 instead of crossing HBM twice (results do not depend on it).
+                                0 or -1 = off (default: one chunk per group; measured 6 % faster, HBM is at 7 % of its bandwidth either way) */
+  int32_t contact_memory;    /* where the contact solver (1-8 contacts, four environments per warp) keeps its Delassus blocks and the
+                                responses of each lane's own contact along the sweep: TREX_CONTACT_TENSOR (default) in TENSOR MEMORY
+                                (persistent 4-warp CTAs, tcgen05.ld 32x32b as a lane-private scratchpad: the shared-memory instance
+                                runs at 69 % of the shared-memory data pipe's wavefront peak), TREX_CONTACT_SHARED in shared memory.
+                                Results are bit-identical. */
+  int32_t reserved[7];       /* must be zero */
 } trex_config;
 
 typedef struct trex_stats {

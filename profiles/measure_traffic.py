@@ -28,7 +28,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 K_STEPS = 2
-WORKLOADS = ("random", "standing", "c2")
+# (name, bench workload, extra environment, ncu --cache-control): "all" = ncu flushes the caches before every kernel (the cold-cache
+# upper bound, comparable with earlier rounds); "none" = caches keep their contents between the (serialised) kernels, which is
+# what the L2-resident work records of trex_config.chunk_envs need to show up
+WORKLOADS = (
+    ("random", "random", {}, "all"),
+    ("standing", "standing", {}, "all"),
+    ("c2", "c2", {}, "all"),
+    ("random_warm", "random", {}, "none"),
+    ("random_chunk8192_warm", "random", {"TREX_CHUNK": "8192", "TREX_PIPES": "2"}, "none"),
+    ("random_chunk4096_warm", "random", {"TREX_CHUNK": "4096", "TREX_PIPES": "2"}, "none"),
+)
 
 
 def inner(workload):
@@ -57,11 +67,11 @@ def outer():
     out = {"source_hash": bench.source_hash(), "how": "ncu dram__bytes_read.sum + dram__bytes_write.sum over every kernel of %d env steps / %d (profiles/measure_traffic.py)" % (K_STEPS, K_STEPS),
            "workloads": {}}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    for w in WORKLOADS:
+    for w, bench_w, extra_env, cache in WORKLOADS:
         log = os.path.join(ROOT, "gpurun_out", "traffic_%s.csv" % w)
         cmd = ["ncu", "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
-               "--csv", "--log-file", log, sys.executable, os.path.abspath(__file__), "--inner", w]
-        p = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+               "--cache-control", cache, "--csv", "--log-file", log, sys.executable, os.path.abspath(__file__), "--inner", bench_w]
+        p = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **extra_env))
         meta = None
         for line in p.stdout.splitlines():
             if line.startswith("INNER "):
@@ -86,7 +96,7 @@ def outer():
                                "bytes_per_env_step_batch": int(total / K_STEPS), "bytes_per_env_step": total / K_STEPS / meta["envs"],
                                "kernel_launches_per_step": launches / K_STEPS,
                                "per_kernel_bytes_per_step": {k: int(v) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
-                               "capture": "gpurun_out/traffic_%s.csv" % w}
+                               "ncu_cache_control": cache, "environment": extra_env, "capture": "gpurun_out/traffic_%s.csv" % w}
         print(w, "%.3f GB per env step of %d envs" % (total / K_STEPS / 1e9, meta["envs"]), flush=True)
     with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
         json.dump(out, f, indent=1)

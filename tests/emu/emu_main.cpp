@@ -17,6 +17,7 @@ struct Emu {
   alignas(16) float scratch2[TREX_SOLVE2_SCRATCH];  // shared scratch of a solve2 warp
   float tmem[32][512];           // tensor memory of a solve2<true> warp (32 lanes x 512 columns)
   int heavy_tmem = 0;            // solve2 with the Delassus matrices in (emulated) tensor memory
+  int solve_tmem = 0;            // solve4<TREX_KC, true>: Delassus blocks and sweep responses in (emulated) tensor memory
   int packed = 0;                // emu_step4 with n == 4: run the front phase as a 4-warp CTA (host threads)
   alignas(16) float work[4 * TREX_WORK_STRIDE];
   alignas(16) float workh[4 * TREX_HEAVY_STRIDE];
@@ -112,6 +113,7 @@ void emu_step4(void* h, int n, float* rec, const float* action, float* obs, floa
         if (!cnt[d]) continue;
         const int pending = e->pack_reverse ? (((1 << cnt[d]) - 1) << (4 - cnt[d])) : ((1 << cnt[d]) - 1);
         if (d == 0) trex::solve_phase<0>(e->P, e->scratch, e->work, rec, envs[0], pending);
+        else if (d < TREX_CLASS_HEAVY && e->solve_tmem) { tmem_t tm4 = {e->tmem}; trex::solve_phase<TREX_KC, true>(e->P, e->scratch, e->work, rec, envs[d], pending, tm4); }
         else if (d < TREX_CLASS_HEAVY) trex::solve_phase<TREX_KC>(e->P, e->scratch, e->work, rec, envs[d], pending);
         else {  // class 5: two environments per warp (solve2), packed from the list like the kernel does
           int hv[4], nh = 0;
@@ -143,6 +145,7 @@ void emu_solve_counts(void* h, long long* out) { for (int i = 0; i < 5; i++) out
 void emu_set_deferred(void* h, int on) {  // bit 0 deferral on, bit 1 reverse packing, bit 2 contact-free substeps only, bit 3 front phase as a 4-warp CTA, bit 4 more than TREX_KC contacts stay in the front phase
   Emu* e = (Emu*)h;
   e->heavy_tmem = (on >> 5) & 1;  // bit 5: solve2 keeps the Delassus matrices in tensor memory
+  e->solve_tmem = (on >> 6) & 1;  // bit 6: solve4 keeps its Delassus blocks and sweep responses in tensor memory
   e->deferred = on & 1; e->pack_reverse = (on >> 1) & 1; e->P.defer_contacts = ((on >> 2) & 1) ? 0 : (((on >> 4) & 1) ? 1 : 2); e->packed = (on >> 3) & 1;
 }
 }

@@ -497,3 +497,26 @@ def test_solve2_with_the_delassus_matrix_in_tensor_memory(model):
         b.step(acts)
         assert np.array_equal(a.rec[:, :160], b.rec[:, :160]), t
     assert b.env.heavy_solves() >= 3 * 5 * 8 and int(b.aux[0, 7]) % 1000 >= 12
+
+
+def test_solve4_with_delassus_blocks_and_sweep_responses_in_tensor_memory(model, action_limits):
+    """solve4<8, TM = true> (the tensor-memory instance of the contact solver, 1-8 contacts) keeps the Delassus blocks A4 and the
+    responses of every lane's own contact along the sweep in tensor memory (device: tcgen05.st / tcgen05.ld 32x32b, lane-private
+    columns; here an emulated 32 x 512 array) instead of shared memory -- that kernel is bound by the shared-memory data
+    pipe.  The arithmetic is untouched: records are bit-identical with the shared-memory instance."""
+    from emu import EmuWarp4
+
+    lo, hi = action_limits
+    a = EmuWarp4(model.blob(), n=4)
+    b = EmuWarp4(model.blob(), n=4, deferred=1 | 64)
+    a.reset()
+    b.reset()
+    rng = np.random.default_rng(16)
+    seen = set()
+    for t in range(60):
+        acts = rng.uniform(lo, hi, size=(4, 25)).astype(np.float32)
+        a.step(acts)
+        b.step(acts)
+        assert np.array_equal(a.rec[:, :160], b.rec[:, :160]), t
+        seen.update(int(k) % 1000 for k in b.aux[:, 7])
+    assert len([k for k in seen if 1 <= k <= 8]) >= 3, seen  # several contact counts went through the tensor-memory instance

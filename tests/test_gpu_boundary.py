@@ -104,7 +104,8 @@ def test_named_config_fields_are_validated(model):
 
     assert create()[0] == 0
     assert create(warps_per_block=4, solver_placement=_native.SOLVE_NO_HEAVY, env_offset=1 << 40)[0] == 0
-    for bad in (dict(warps_per_block=3), dict(solver_placement=7), dict(heavy_share_div=-1), dict(pipelines=9), dict(heavy_memory=3), dict(reserved0=1)):
+    for bad in (dict(warps_per_block=3), dict(solver_placement=7), dict(heavy_share_div=-1), dict(pipelines=9), dict(heavy_memory=3), dict(chunk_envs=6), dict(contact_memory=2),
+                dict(reserved0=1)):
         rc, msg = create(**bad)
         assert rc == -1 and list(bad)[0].rstrip("0") in msg, (bad, rc, msg)
 
@@ -238,6 +239,10 @@ def test_pipelined_groups_do_not_change_results(model):
 
     n = 9998  # not a multiple of anything convenient
     sims = [_sim(model, n, pipelines=p, reset_mode=1, max_episode_steps=7, seed=4, env_offset=123) for p in (1, 2, 3, 4)]
+    # ... and walked chunk by chunk (trex_config.chunk_envs: all substeps of a chunk before the next one, every chunk of a group in
+    # the same work-record slots, so that the records stay in L2), with the last chunk short
+    sims += [_sim(model, n, pipelines=p, chunk_envs=c, reset_mode=1, max_episode_steps=7, seed=4, env_offset=123)
+             for p, c in ((1, 4096), (2, 1024), (3, 2500))]
     ref = sims[0]
     for t in range(16):
         a = ref.random_actions(step=t, seed=2, env_offset=123)

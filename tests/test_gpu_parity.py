@@ -538,3 +538,25 @@ def test_solve2_tensor_memory_and_shared_memory_instances_agree(model):
     assert stats["mean_contacts"] > 10 and stats["nan_resets"] == 0 and stats["contact_overflow"] >= 0
     k = (sims[0].aux()[:, 7] % 1000)
     assert (k > 8).float().mean().item() > 0.8  # the batch really is in the many-contact class
+
+
+def test_contact_solver_tensor_memory_and_shared_memory_instances_agree(model):
+    """trex_config.contact_memory: the contact solver (1-8 contacts, four environments per warp) with its Delassus blocks and
+    sweep responses in TENSOR MEMORY (persistent 4-warp CTAs pulling tasks from a counter; default) and in shared memory
+    (one-warp CTAs, static assignment) give bit-identical records on a flailing batch, with one or two groups in flight."""
+    import torch
+
+    from trex_gym_b200 import _native
+
+    n = 8192 + 10
+    sims = [_sim(model, n, contact_memory=m, pipelines=p, seed=3) for m, p in ((_native.CONTACT_SHARED, 1), (_native.CONTACT_TENSOR, 1),
+                                                                               (_native.CONTACT_TENSOR, 2))]
+    for t in range(120):
+        a = sims[0].random_actions(step=t, seed=5)
+        for s in sims:
+            s.step(a)
+    st = [s.get_state() for s in sims]
+    for x in st[1:]:
+        assert torch.equal(st[0], x)
+    k = (sims[0].aux()[:, 7] % 1000)
+    assert ((k >= 1) & (k <= 8)).float().mean().item() > 0.2 and sims[0].stats()["nan_resets"] == 0  # the contact classes are populated

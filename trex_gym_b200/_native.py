@@ -44,12 +44,15 @@ class TrexConfig(ctypes.Structure):
         ("heavy_share_div", ctypes.c_int32),
         ("pipelines", ctypes.c_int32),
         ("heavy_memory", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 9),
+        ("chunk_envs", ctypes.c_int32),
+        ("contact_memory", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 7),
     ]
 
 
 SOLVE_DEFAULT, SOLVE_FRONT, SOLVE_FREE_ONLY, SOLVE_NO_HEAVY = 0, 1, 2, 3  # trex_config.solver_placement
 HEAVY_BOTH, HEAVY_SHARED, HEAVY_TENSOR = 0, 1, 2  # trex_config.heavy_memory
+CONTACT_TENSOR, CONTACT_SHARED = 0, 1  # trex_config.contact_memory
 
 
 class TrexStats(ctypes.Structure):

@@ -30,6 +30,8 @@
 #define TREX_STR(x) TREX_STR2(x)
 
 #ifndef TREX_PHASES
+#define TREX_S4_TMEM_COLS 256
+static_assert(S4_TM_COLS(TREX_KC) <= TREX_S4_TMEM_COLS, "tensor-memory columns of solve4");
 static_assert(TREX_STATE_DIM == TREX_STATE_STRIDE, "state record size");
 static_assert(TREX_AUX_DIM == TREX_AUX_STRIDE, "aux record size");
 #endif
@@ -105,6 +107,10 @@ trex_front_kernel(const trex::Uniform P, const float* __restrict__ mdl, const in
 // KC > 0: the lists of the contact classes CLO..CHI (rows in row space, see solve4), warps assigned class by class.
 // (A second instance with KC = 2 for the environments with 1-2 contacts -- 168 registers, 12 warps per SM -- was measured:
 // 70 spilled registers in the sweep, 9.3 instead of 8.1 ms per env step on the benchmark batch.  One instance serves 1-8.)
+// (Round 2 also measured both instances with the coefficient rows g in a lane-private shared-memory copy instead of 100
+// registers per thread -- 16 instead of 12 warps per SM contact-free, 12 instead of 8 for a 1-2-contact instance: +11 % and
+// +30 % step time.  And the contact instance held to 6 / 4 warps per SM by extra shared memory: +1 % / +10 %.  These kernels
+// are not bound by the number of resident warps.)
 template <int WARPS, int KC, int CLO, int CHI>
 __global__ void __launch_bounds__(32 * WARPS, (KC ? TREX_SOLVEC_MIN_BLOCKS : TREX_SOLVE_MIN_BLOCKS) / WARPS)
 trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
@@ -131,6 +137,42 @@ trex_solve_kernel(const trex::Uniform P, float* __restrict__ state, const float*
   int envs[4] = {0, 0, 0, 0}, pending = 0;
   for (int e = 0; e < 4 && first + e < count; e++) { envs[e] = list[first + e]; pending |= 1 << e; }
   trex::solve_phase<KC>(P, scratch, work, state, envs, pending);
+}
+
+// The contact solver with its Delassus blocks and sweep responses in TENSOR MEMORY (solve4<TREX_KC, true>): persistent 4-warp
+// CTAs (the four warps of a CTA reach the four 32-lane quarters of its tensor-memory columns), 256 columns per CTA, two CTAs =
+// 8 warps per SM.  Warps pull tasks (four environments of one class, heaviest class first) from a counter.
+template <int CLO, int CHI>
+__global__ void __launch_bounds__(128, 2)
+trex_solve_tm_kernel(const trex::Uniform P, float* __restrict__ state, const float* __restrict__ work,
+                     const int* __restrict__ list, const int* __restrict__ list_count, int* __restrict__ next_task, int n_envs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  float* scratch = reinterpret_cast<float*>(smem_raw) + warp * TREX_SOLVE_SCRATCH_TM(TREX_KC);
+  int tasks_of[CHI + 1], total = 0;
+#pragma unroll
+  for (int c = CHI; c >= CLO; c--) { tasks_of[c] = (list_count[64 * c] + 3) >> 2; total += tasks_of[c]; }
+  if (total == 0) return;  // (uniform over the CTA: nobody allocates)
+  __shared__ uint32_t tmem_slot;
+  tmem_t tm;
+  tm.base = tmem_alloc_cta<TREX_S4_TMEM_COLS>(&tmem_slot) + ((uint32_t)(warp & 3) << 21);  // lane 32 * (warp % 4) in bits 31:16
+  for (;;) {
+    int t = 0;
+    if ((threadIdx.x & 31) == 0) t = atomicAdd(next_task, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= total) break;
+    int c = CHI;
+#pragma unroll
+    for (int cc = CHI; cc > CLO; cc--)
+      if (c == cc && t >= tasks_of[cc]) { t -= tasks_of[cc]; c = cc - 1; }
+    const int* lst = list + (size_t)c * n_envs;
+    const int count = list_count[64 * c], first = 4 * t;
+    int envs[4] = {0, 0, 0, 0}, pending = 0;
+    for (int e = 0; e < 4 && first + e < count; e++) { envs[e] = lst[first + e]; pending |= 1 << e; }
+    trex::solve_phase<TREX_KC, true>(P, scratch, work, state, envs, pending, tm);
+    __syncwarp();
+  }
+  tmem_free_cta<TREX_S4_TMEM_COLS>(tm.base - ((uint32_t)(warp & 3) << 21));
 }
 
 // one warp per TWO environments of class 5 (more than TREX_KC contacts; sixteen lanes each, see solve2).  Persistent warps pull
@@ -308,6 +350,10 @@ trex_stats_kernel(const float* __restrict__ state, const float* __restrict__ aux
 
 }  // namespace
 
+#ifndef TREX_DEFAULT_CHUNK_PIPES
+#define TREX_DEFAULT_CHUNK_PIPES 2
+#endif
+
 struct trex_handle {
   int device = 0;
   int n_envs = 0;
@@ -334,14 +380,24 @@ struct trex_handle {
   // the hardware block scheduler interleaves their CTAs.  Within a group the three solve kernels of a round also run
   // concurrently (caller-side stream + two side streams).  Fork / join by events only: no host synchronisation, and the
   // whole step stays capturable into a CUDA graph from the caller's stream.
-  static constexpr int MAX_PIPES = 4;
+  //
+  // L2-resident work records (trex_config.chunk_envs): every group walks its share of the batch CHUNK by chunk -- all
+  // substeps of a chunk (front -> solves -> ... -> tail) before the next chunk starts -- and all chunks of a group use the
+  // same work-record slots.  The records written by the front kernel (M^-1, row scalars, contact rows: 4.6 .. 11.4 KB per
+  // environment and substep) are then read back by the solvers out of the 126 MB L2 and overwritten in place by the next
+  // substep / chunk: they never travel to HBM, and the state record of an environment crosses HBM once per env step
+  // instead of once per substep.  Footprint in flight: groups x chunk x ~6 KB.
+  static constexpr int MAX_PIPES = 8;
+  int chunk = 0;                // environments per chunk (multiple of 4); 0: one chunk per group (records in HBM)
+  int n_chunks = 0;             // chunk c = environments [c * chunk, ...) goes to group c % n_pipes
   struct Pipe {
-    int first = 0, count = 0;     // environments [first, first + count)
+    int first = 0, count = 0;     // environments [first, first + count) (unchunked: the group's whole share)
+    size_t work_slot = 0;         // first work-record slot of this group (chunked: p * chunk; else == first)
     cudaStream_t main = nullptr;  // pipe 0 runs on the caller's stream instead
     cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr, ev_done = nullptr;
     int* d_list = nullptr;        // [TREX_NCLASS][count] environments whose solve was deferred in the current substep round, by class
-    int* d_list_count = nullptr;  // [TREX_NCLASS + 3][64] one counter per class and substep round, + heavy seen, solve2 task counters, hint
+    int* d_list_count = nullptr;  // [TREX_NCLASS + 4][64] one counter per class and substep round, + heavy seen, solve2 task counters, hint, solve4-TM task counters
   } pipe[MAX_PIPES];
   int n_pipes = 0;              // 0 until trex_create decides (config / default)
   cudaEvent_t ev_start = nullptr;
@@ -350,6 +406,8 @@ struct trex_handle {
   int heavy_grid = 148 * 7;     // CTAs of trex_heavy_kernel<1, false> alone (one warp each): every SM full
   int heavy_grid_tm = 148 * 2;  // CTAs of trex_heavy_kernel<4, true> (tensor-memory instance: 256 of the 512 columns each)
   int heavy_grid_mixed = 148 * 4;  // CTAs of the shared-memory instance next to the tensor-memory one
+  bool solve_tm = true;         // contact solver (1-8 contacts) with its Delassus blocks / sweep responses in tensor memory (trex_config.contact_memory)
+  int solve_tm_grid = 148 * 2;
   int heavy_mode = 0;           // 0: both instances concurrently; 1: shared memory only; 2: tensor memory only (TREX_HEAVY_MODE, measurement aid)
   int64_t launches = 0;
   int64_t env_steps = 0;
@@ -370,8 +428,11 @@ int configure_kernel(K kernel, size_t smem) {
 template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
                 int mode, cudaStream_t st) {
-  const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS,
-               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS, smem_h = sizeof(float) * TREX_SOLVE2_SCRATCH, smem_ht = sizeof(float) * TREX_SOLVE2_SCRATCH_TM * 4;
+  static const size_t extra_c = getenv("TREX_SOLVEC_EXTRA_SMEM") ? (size_t)atoi(getenv("TREX_SOLVEC_EXTRA_SMEM")) : 0;  // measurement aid: fewer resident warps
+  static const size_t extra_s = getenv("TREX_SOLVE_EXTRA_SMEM") ? (size_t)atoi(getenv("TREX_SOLVE_EXTRA_SMEM")) : 0;
+  const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS + extra_s,
+               smem_c = sizeof(float) * TREX_SOLVE_SCRATCH(TREX_KC) * WS + extra_c, smem_h = sizeof(float) * TREX_SOLVE2_SCRATCH, smem_ht = sizeof(float) * TREX_SOLVE2_SCRATCH_TM * 4,
+               smem_ct = sizeof(float) * TREX_SOLVE_SCRATCH_TM(TREX_KC) * 4;
   // per template instance and device; handles may be created and stepped from different host threads
   static bool configured[16] = {false};
   static std::mutex configure_lock;
@@ -381,36 +442,44 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
     if ((rc = configure_kernel(trex_front_kernel<WF, WF == 4>, smem_f)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, 0, 0, 0>, smem_s)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1>, smem_c)) != TREX_OK) return rc;
+    if ((rc = configure_kernel(trex_solve_tm_kernel<1, TREX_CLASS_HEAVY - 1>, smem_ct)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_heavy_kernel<1, false>, smem_h)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_heavy_kernel<4, true>, smem_ht)) != TREX_OK) return rc;
     if ((rc = configure_kernel(trex_tail_kernel<WF>, smem_f)) != TREX_OK) return rc;
     configured[h->device & 15] = true;
   }
   if (h->n_pipes > 1) CUDA_TRY(cudaEventRecord(h->ev_start, st));
-  trex::Uniform Pp[trex_handle::MAX_PIPES];
   cudaStream_t sp[trex_handle::MAX_PIPES];
   for (int p = 0; p < h->n_pipes; p++) {
-    trex_handle::Pipe& q = h->pipe[p];
-    Pp[p] = h->P;
-    Pp[p].env_offset = h->P.env_offset + q.first;  // the reset sampler is keyed by the global environment id
-    sp[p] = p == 0 ? st : q.main;
+    sp[p] = p == 0 ? st : h->pipe[p].main;
     if (p > 0) CUDA_TRY(cudaStreamWaitEvent(sp[p], h->ev_start, 0));
-    if (mode == 0 && h->d_work) CUDA_TRY(cudaMemsetAsync(q.d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int), sp[p]));  // class counters, heavy seen, solve2 task counters (not the hint behind them)
   }
   const int n_rounds = mode == 0 ? h->P.n_sub : 0;
-  for (int r = 0; r < n_rounds; r++) {
-    for (int p = 0; p < h->n_pipes; p++) {
-      trex_handle::Pipe& q = h->pipe[p];
-      cudaStream_t s = sp[p];
-      const size_t e0 = (size_t)q.first;
-      const int grid1 = (q.count + WF - 1) / WF;            // one warp per environment
-      const int grid4 = (q.count + 4 * WS - 1) / (4 * WS);  // one warp per four environments
-      float* state = h->d_state + e0 * TREX_STATE_STRIDE;
-      float* work = h->d_work ? h->d_work + e0 * TREX_WORK_STRIDE : nullptr;
-      float* workh = h->d_workh ? h->d_workh + e0 * TREX_HEAVY_STRIDE : nullptr;
-      trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, s>>>(Pp[p], h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+  // chunk c of the batch belongs to group c % n_pipes; the host issues the chains of the groups' k-th chunks one after
+  // the other (the streams run them concurrently)
+  for (int c = 0; c < h->n_chunks; c++) {
+    const int p = c % h->n_pipes;
+    trex_handle::Pipe& q = h->pipe[p];
+    cudaStream_t s = sp[p];
+    const int first = h->chunk > 0 ? c * h->chunk : q.first;
+    const int count = h->chunk > 0 ? (first + h->chunk <= h->n_envs ? h->chunk : h->n_envs - first) : q.count;
+    if (count <= 0) continue;
+    trex::Uniform Pc = h->P;
+    Pc.env_offset = h->P.env_offset + first;  // the reset sampler is keyed by the global environment id
+    if (mode == 0 && h->d_work) {
+      CUDA_TRY(cudaMemsetAsync(q.d_list_count, 0, 64 * (TREX_NCLASS + 2) * sizeof(int), s));  // class counters, heavy seen, solve2 task counters (not the hint behind them)
+      if (h->solve_tm) CUDA_TRY(cudaMemsetAsync(q.d_list_count + 64 * (TREX_NCLASS + 3), 0, 64 * sizeof(int), s));  // task counters of the tensor-memory contact solver
+    }
+    const size_t e0 = (size_t)first;
+    const int grid1 = (count + WF - 1) / WF;            // one warp per environment
+    const int grid4 = (count + 4 * WS - 1) / (4 * WS);  // one warp per four environments
+    float* state = h->d_state + e0 * TREX_STATE_STRIDE;
+    float* work = h->d_work ? h->d_work + q.work_slot * TREX_WORK_STRIDE : nullptr;
+    float* workh = h->d_workh ? h->d_workh + q.work_slot * TREX_HEAVY_STRIDE : nullptr;
+    for (int r = 0; r < n_rounds; r++) {
+      trex_front_kernel<WF, WF == 4><<<grid1, 32 * WF, smem_f, s>>>(Pc, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
                                                           state, work, workh, action + e0 * trex::NJ, q.d_list, q.d_list_count + r,
-                                                          q.d_list_count + 64 * (TREX_NCLASS + 2), h->heavy_div, q.count, r == 0);
+                                                          q.d_list_count + 64 * (TREX_NCLASS + 2), h->heavy_div, count, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (!h->d_work) continue;
@@ -421,19 +490,24 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       const bool heavy = h->P.defer_contacts > 1 && h->P.contacts_on && workh != nullptr;
       const bool split = contacts && h->concurrent_solves && q.side2 != nullptr;
       if (heavy || split) CUDA_TRY(cudaEventRecord(q.ev_fork, s));
-      if (contacts) {
-        trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1><<<grid4 + 4, 32 * WS, smem_c, s>>>(Pp[p], state, work, q.d_list, q.d_list_count + r, q.count);
+      if (contacts && h->solve_tm) {
+        trex_solve_tm_kernel<1, TREX_CLASS_HEAVY - 1><<<h->solve_tm_grid, 128, smem_ct, s>>>(Pc, state, work, q.d_list, q.d_list_count + r,
+                                                                                         q.d_list_count + 64 * (TREX_NCLASS + 3) + r, count);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+      } else if (contacts) {
+        trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1><<<grid4 + 4, 32 * WS, smem_c, s>>>(Pc, state, work, q.d_list, q.d_list_count + r, count);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
       }
       if (heavy) {  // class 5: more than TREX_KC contacts, two environments per warp; two instances share the task counter
         int* next_task = q.d_list_count + 64 * (TREX_NCLASS + 1) + r;
         const int* cnt = q.d_list_count + 64 * TREX_CLASS_HEAVY + r;
-        const int* lst = q.d_list + (size_t)TREX_CLASS_HEAVY * q.count;
+        const int* lst = q.d_list + (size_t)TREX_CLASS_HEAVY * count;
         int* hint = q.d_list_count + 64 * (TREX_NCLASS + 2);
         CUDA_TRY(cudaStreamWaitEvent(q.side, q.ev_fork, 0));
         if (h->heavy_mode != 1) {  // the tensor-memory instance first: its CTAs take their two slots per SM ...
-          trex_heavy_kernel<4, true><<<h->heavy_grid_tm, 128, smem_ht, q.side>>>(Pp[p], state, work, workh, lst, cnt, q.d_list_count + 64 * TREX_NCLASS + r, hint, next_task);
+          trex_heavy_kernel<4, true><<<h->heavy_grid_tm, 128, smem_ht, q.side>>>(Pc, state, work, workh, lst, cnt, q.d_list_count + 64 * TREX_NCLASS + r, hint, next_task);
           CUDA_TRY(cudaGetLastError());
           h->launches++;
         }
@@ -441,7 +515,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
           cudaStream_t sh = h->heavy_mode == 0 ? q.side3 : q.side;
           if (h->heavy_mode == 0) CUDA_TRY(cudaStreamWaitEvent(q.side3, q.ev_fork, 0));
           trex_heavy_kernel<1, false><<<h->heavy_mode == 0 ? h->heavy_grid_mixed : h->heavy_grid, 32, smem_h, sh>>>(
-              Pp[p], state, work, workh, lst, cnt, q.d_list_count + 64 * TREX_NCLASS + r, h->heavy_mode == 0 ? nullptr : hint, next_task);
+              Pc, state, work, workh, lst, cnt, q.d_list_count + 64 * TREX_NCLASS + r, h->heavy_mode == 0 ? nullptr : hint, next_task);
           CUDA_TRY(cudaGetLastError());
           h->launches++;
           if (h->heavy_mode == 0) {
@@ -453,7 +527,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       }
       cudaStream_t s0 = split ? q.side2 : s;
       if (split) CUDA_TRY(cudaStreamWaitEvent(q.side2, q.ev_fork, 0));
-      trex_solve_kernel<WS, 0, 0, 0><<<grid4, 32 * WS, smem_s, s0>>>(Pp[p], state, work, q.d_list, q.d_list_count + r, q.count);
+      trex_solve_kernel<WS, 0, 0, 0><<<grid4, 32 * WS, smem_s, s0>>>(Pc, state, work, q.d_list, q.d_list_count + r, count);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
       if (split) {
@@ -462,21 +536,16 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       }
       if (heavy) CUDA_TRY(cudaStreamWaitEvent(s, q.ev_join, 0));
     }
-  }
-  for (int p = 0; p < h->n_pipes; p++) {
-    trex_handle::Pipe& q = h->pipe[p];
-    const size_t e0 = (size_t)q.first;
-    const int grid1 = (q.count + WF - 1) / WF;
-    trex_tail_kernel<WF><<<grid1, 32 * WF, smem_f, sp[p]>>>(Pp[p], h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
-                                                           h->d_state + e0 * TREX_STATE_STRIDE, obs ? obs + e0 * 3 * trex::NJ : nullptr,
-                                                           reward ? reward + e0 : nullptr, done ? done + e0 : nullptr,
-                                                           h->d_aux + e0 * TREX_AUX_STRIDE, mask ? mask + e0 : nullptr, q.count, mode);
+    trex_tail_kernel<WF><<<grid1, 32 * WF, smem_f, s>>>(Pc, h->d_mdl, h->d_mdli, h->d_tasks, h->d_cand_p, h->d_cand_lane,
+                                                        h->d_state + e0 * TREX_STATE_STRIDE, obs ? obs + e0 * 3 * trex::NJ : nullptr,
+                                                        reward ? reward + e0 : nullptr, done ? done + e0 : nullptr,
+                                                        h->d_aux + e0 * TREX_AUX_STRIDE, mask ? mask + e0 : nullptr, count, mode);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
-    if (p > 0) {
-      CUDA_TRY(cudaEventRecord(q.ev_done, sp[p]));
-      CUDA_TRY(cudaStreamWaitEvent(st, q.ev_done, 0));
-    }
+  }
+  for (int p = 1; p < h->n_pipes; p++) {
+    CUDA_TRY(cudaEventRecord(h->pipe[p].ev_done, sp[p]));
+    CUDA_TRY(cudaStreamWaitEvent(st, h->pipe[p].ev_done, 0));
   }
   return TREX_OK;
 }
@@ -549,15 +618,25 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     h->heavy_div = cfg->heavy_share_div;
     if (cfg->pipelines < 0 || cfg->pipelines > trex_handle::MAX_PIPES) {
       delete h;
-      return fail(TREX_ERR_INVALID, "trex_config.pipelines must be 0 (default) .. 4%s");
+      return fail(TREX_ERR_INVALID, "trex_config.pipelines must be 0 (default) .. 8%s");
     }
     h->n_pipes = cfg->pipelines;
+    if (cfg->chunk_envs < -1 || (cfg->chunk_envs > 0 && (cfg->chunk_envs & 3))) {
+      delete h;
+      return fail(TREX_ERR_INVALID, "trex_config.chunk_envs must be -1 (off), 0 (default) or a positive multiple of 4%s");
+    }
+    h->chunk = cfg->chunk_envs;
+    if (cfg->contact_memory < TREX_CONTACT_TENSOR || cfg->contact_memory > TREX_CONTACT_SHARED) {
+      delete h;
+      return fail(TREX_ERR_INVALID, "trex_config.contact_memory must be one of TREX_CONTACT_*%s");
+    }
+    h->solve_tm = cfg->contact_memory == TREX_CONTACT_TENSOR;
     if (cfg->heavy_memory < TREX_HEAVY_BOTH || cfg->heavy_memory > TREX_HEAVY_TENSOR) {
       delete h;
       return fail(TREX_ERR_INVALID, "trex_config.heavy_memory must be one of TREX_HEAVY_*%s");
     }
     h->heavy_mode = cfg->heavy_memory;
-    for (int i = 0; i < 9; i++)
+    for (int i = 0; i < 7; i++)
       if (cfg->reserved[i] != 0) {
         delete h;
         return fail(TREX_ERR_INVALID, "trex_config.reserved must be zero%s");
@@ -568,9 +647,19 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     delete h;
     return rc_;
   }
-  if (h->n_pipes <= 0) h->n_pipes = n_envs >= 8192 ? 2 : 1;  // small batches: one group fills the machine no better split
-  if (const char* e = getenv("TREX_PIPES")) { const int v = atoi(e); if (v >= 1 && v <= trex_handle::MAX_PIPES) h->n_pipes = v; }  // measurement aid
+  if (const char* e = getenv("TREX_CHUNK")) { const int v = atoi(e); if (v == -1 || (v > 0 && !(v & 3))) h->chunk = v; }  // measurement aids
+  if (const char* e = getenv("TREX_PIPES")) { const int v = atoi(e); if (v >= 1 && v <= trex_handle::MAX_PIPES) h->n_pipes = v; }
+  // default: off.  Measured on the benchmark batch (65,536 environments, one B200): chunks of 8,192 on 2 streams cost 6 % of
+  // step time (8.37 vs 7.89 ms), 4,096 on 4 streams 8 % -- the small launches pay their tails and launch gaps, and HBM is at 7 %
+  // of its bandwidth without them -- while the DRAM traffic per env step falls from 3.5 GB to the figure in DESIGN.md.
+  if (h->chunk > 0 && h->chunk >= n_envs) h->chunk = -1;
+  if (h->chunk < 0) h->chunk = 0;
+  if (h->n_pipes <= 0) h->n_pipes = h->chunk > 0 ? TREX_DEFAULT_CHUNK_PIPES : (n_envs >= 8192 ? 2 : 1);  // small batches: one group fills the machine no better split
   if (h->n_pipes > n_envs) h->n_pipes = 1;
+  if (h->chunk > 0) {
+    h->n_chunks = (n_envs + h->chunk - 1) / h->chunk;
+    if (h->n_pipes > h->n_chunks) h->n_pipes = h->n_chunks;
+  }
   trex_host::fill_uniform(h->T, h->C, h->P);
   {
     // trex_heavy_kernel strides over its list with a fixed grid: exactly the CTAs that are resident at once (a larger
@@ -593,6 +682,9 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
       h->heavy_grid_mixed = sms * ((fit / np) > 0 ? fit / np : 1);
     }
     if (const char* e = getenv("TREX_HEAVY_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 2) h->heavy_mode = v; }
+    if (const char* e = getenv("TREX_SOLVE_TM")) h->solve_tm = e[0] == '1';  // measurement aid
+    if (sms > 0) h->solve_tm_grid = sms * 2;  // persistent CTAs, two per SM (255 registers); measured best also with two groups in flight
+    if (const char* e = getenv("TREX_SOLVE_TM_GRID")) { const int v = atoi(e); if (v > 0) h->solve_tm_grid = v; }
   }
   int rc;
 #define TRY(x) if ((rc = (x)) != TREX_OK) { trex_destroy(h); return rc; }
@@ -607,9 +699,11 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   const size_t N = (size_t)n_envs;
   CTRY(cudaMalloc((void**)&h->d_state, N * TREX_STATE_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_state, 0, N * TREX_STATE_STRIDE * sizeof(float)));
-  if (h->deferred_solve) CTRY(cudaMalloc((void**)&h->d_work, N * TREX_WORK_STRIDE * sizeof(float)));
+  // work records: one slot per environment, or (chunked) one slot per environment of the chunks in flight
+  const size_t work_slots = h->chunk > 0 ? (size_t)h->n_pipes * (size_t)h->chunk : N;
+  if (h->deferred_solve) CTRY(cudaMalloc((void**)&h->d_work, work_slots * TREX_WORK_STRIDE * sizeof(float)));
   const bool with_heavy = h->deferred_solve && h->C.defer_contacts > 1 && h->C.enable_contacts;
-  if (with_heavy) CTRY(cudaMalloc((void**)&h->d_workh, N * TREX_HEAVY_STRIDE * sizeof(float)));
+  if (with_heavy) CTRY(cudaMalloc((void**)&h->d_workh, work_slots * TREX_HEAVY_STRIDE * sizeof(float)));
   if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aids
   CTRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   for (int p = 0; p < h->n_pipes; p++) {
@@ -618,6 +712,8 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
     const int per = ((n_envs + h->n_pipes - 1) / h->n_pipes + 3) & ~3;
     q.first = p * per < n_envs ? p * per : n_envs;
     q.count = (q.first + per <= n_envs) ? per : n_envs - q.first;
+    q.work_slot = h->chunk > 0 ? (size_t)p * (size_t)h->chunk : (size_t)q.first;
+    const int list_cap = h->chunk > 0 ? h->chunk : (q.count > 0 ? q.count : 1);
     if (p > 0) CTRY(cudaStreamCreateWithFlags(&q.main, cudaStreamNonBlocking));
     if (with_heavy) {
       CTRY(cudaStreamCreateWithFlags(&q.side, cudaStreamNonBlocking));
@@ -629,11 +725,12 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
       CTRY(cudaEventCreateWithFlags(&q.ev_join2, cudaEventDisableTiming));
     }
     CTRY(cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming));
-    CTRY(cudaMalloc((void**)&q.d_list, (size_t)TREX_NCLASS * (q.count > 0 ? q.count : 1) * sizeof(int)));
-    CTRY(cudaMalloc((void**)&q.d_list_count, 64 * (TREX_NCLASS + 3) * sizeof(int)));
-    CTRY(cudaMemset(q.d_list_count, 0, 64 * (TREX_NCLASS + 3) * sizeof(int)));
+    CTRY(cudaMalloc((void**)&q.d_list, (size_t)TREX_NCLASS * list_cap * sizeof(int)));
+    CTRY(cudaMalloc((void**)&q.d_list_count, 64 * (TREX_NCLASS + 4) * sizeof(int)));
+    CTRY(cudaMemset(q.d_list_count, 0, 64 * (TREX_NCLASS + 4) * sizeof(int)));
   }
-  while (h->n_pipes > 1 && h->pipe[h->n_pipes - 1].count <= 0) h->n_pipes--;
+  while (h->chunk == 0 && h->n_pipes > 1 && h->pipe[h->n_pipes - 1].count <= 0) h->n_pipes--;
+  if (h->chunk == 0) h->n_chunks = h->n_pipes;
   CTRY(cudaMalloc((void**)&h->d_aux, N * TREX_AUX_STRIDE * sizeof(float)));
   CTRY(cudaMemset(h->d_aux, 0, N * TREX_AUX_STRIDE * sizeof(float)));
   // (the staging buffers of the host-buffer entry points are allocated on first use: ensure_host_path)

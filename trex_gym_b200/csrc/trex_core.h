@@ -1473,59 +1473,44 @@ TREX_TOPO_FN bool limit_order_matches_motor_order() {
 #ifndef TREX_S4_PRESUB
 #define TREX_S4_PRESUB(KC) 0  // (measured: no gain in either solve4 instance -- they are issue bound, not chain bound)
 #endif
-template <int B, bool FWD, int KC>
+// tensor-memory columns of solve4<KC, TM = true> (per lane, lane-private): the lane's own block of every Delassus row
+// A4[r][own contact][0..3] at 4 r, then the responses of the lane's own contact at every solve-order position,
+// B[3 own + k][pos] at S4_TM_BK + 28 k + pos
+#define S4_TM_BK(KC) (12 * (KC))
+#define S4_TM_COLS(KC) (S4_TM_BK(KC) + 84)
+template <int B, bool FWD, int KC, bool TM>
 TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf (&cu)[3], vi glx, vi dead, vi bt_own, const float* Bs,
-                            float max_imp) {
+                            tmem_t tm, float max_imp) {
   constexpr int n = (4 * B + 4 <= NJ) ? 4 : NJ - 4 * B;
   vf bk[3][4];  // responses of the owned contact's three rows at this block's four joints
-  if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) ld4(Bs, bt_own + (k * 36 + 4 * B), bk[k]);
+  if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) {
+    if (TM) tmem_ld4(tm, S4_TM_BK(KC) + k * 28 + 4 * B, bk[k]);  // (asynchronous: retired below, after the private chain)
+    else ld4(Bs, bt_own + (k * 36 + 4 * B), bk[k]);
+  }
   vf t[4], d[4], nl[4];
   TREX_UNROLL for (int i = 0; i < 4; i++) { t[i] = w[i]; d[i] = 0.0f; nl[i] = 0.0f; }
-  // the owner's private chain (the other lanes compute on their own registers and discard); the clamp is one FMNMX.XORSIGN.
-  if (TREX_S4_PRESUB(KC)) {
-    // Row i's target is w_i + sum_{earlier rows e of the block} g[i][e] (new_e - old_e): the old impulses are taken out
-    // BEFORE the chain, so that a row costs a clamp and one FMA of dependent latency (10 cycles instead of 14; six more
-    // FMAs per block off the chain).  Pays in the contact solver (two warps per scheduler: latency bound); the contact-free
-    // solver is issue bound (three warps per scheduler), there it costs 1 % and one more rounding per row
-    TREX_UNROLL for (int ii = 0; ii < n; ii++) {
-      const int i = FWD ? ii : n - 1 - ii;
-      const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
-      TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
-        const int i3 = FWD ? i2 : n - 1 - i2;
-        t[i3] = vfma(-g[i3][j], lam_m[i], t[i3]);
-      }
-    }
-    TREX_UNROLL for (int ii = 0; ii < n; ii++) {
-      const int i = FWD ? ii : n - 1 - ii;
-      const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
-      nl[i] = vclamp_sym(t[i], max_imp);
-      TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
-        const int i3 = FWD ? i2 : n - 1 - i2;
-        t[i3] = vfma(g[i3][j], nl[i], t[i3]);
-      }
-    }
-  } else {
-    TREX_UNROLL for (int ii = 0; ii < n; ii++) {
-      const int i = FWD ? ii : n - 1 - ii;
-      const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
-      nl[i] = vclamp_sym(t[i], max_imp);
-      const vf di = nl[i] - lam_m[i];
-      TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
-        const int i3 = FWD ? i2 : n - 1 - i2;
-        t[i3] = vfma(g[i3][j], di, t[i3]);
-      }
+  // the owner's private chain (the other lanes compute on their own registers and discard): per row one symmetric clamp
+  // (FMNMX.XORSIGN), the difference and one FMA into each later row of the block
+  TREX_UNROLL for (int ii = 0; ii < n; ii++) {
+    const int i = FWD ? ii : n - 1 - ii;
+    const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
+    nl[i] = vclamp_sym(t[i], max_imp);
+    d[i] = nl[i] - lam_m[i];
+    TREX_UNROLL for (int i2 = ii + 1; i2 < n; i2++) {
+      const int i3 = FWD ? i2 : n - 1 - i2;
+      t[i3] = vfma(g[i3][j], d[i], t[i3]);
     }
   }
   const vb own = glx == B;  // (glx = -1 in a finished environment: it keeps its impulses ...)
   const vi src = dead | B;  // (... and publishes the zeros of its group's idle last lane: dead = 7)
+  if (KC > 0 && TM) TREX_UNROLL for (int k = 0; k < 3; k++) tmem_wait4(bk[k]);
   // publish: every lane applies the four impulse changes of lane B
   TREX_UNROLL for (int ii = 0; ii < n; ii++) {
     const int i = FWD ? ii : n - 1 - ii;
     const int j = trex_topo::noncontact_order(4 * B + i) - NJ;
-    d[i] = nl[i] - lam_m[i];
     lam_m[i] = sel(own, nl[i], lam_m[i]);
     const vf db = shflv_group8(d[i], src);
-    vfma2s(w[0], w[1], g[0][j], g[1][j], db);  // (two FFMA2 instead of four FFMA: the solvers are issue bound)
+    vfma2s(w[0], w[1], g[0][j], g[1][j], db);  // (two FFMA2 instead of four FFMA)
     vfma2s(w[2], w[3], g[2][j], g[3][j], db);
     if (KC > 0) TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(bk[k][i], db, cu[k]);
   }
@@ -1542,15 +1527,24 @@ TREX_FN void s4_motor_block(vf (&w)[4], vf (&lam_m)[4], const vf (&g)[4][NJ], vf
 #define TREX_REBUILD_MASK 3  // exact rebuild of w (and u) every 4th sweep (every 8th: the 2e-5 per-env-step parity bound is exceeded, 2.1e-5)
 #endif
 #ifndef TREX_REBUILD_MASK_C
-#define TREX_REBUILD_MASK_C 3  // ... with contact rows (KC > 0)
+#define TREX_REBUILD_MASK_C 15  // ... with contact rows (KC > 0): every 16th sweep (the parity with the oracle is set by the conditioning of
+                                // the step there, as in solve2; every 4th: +3.6 % step time -- the kernel is bound by shared-memory wavefronts)
 #endif
 #define TREX_LIMIT_SLOTS(KC) ((KC) > 4 ? 2 : 6)
 #define TREX_SOLVE_SCRATCH(KC) (4 * TREX_GC_STRIDE(KC) + 4 * (32 + 4 * (KC)) + 128 * TREX_LIMIT_SLOTS(KC))  // floats
+// TM = true (tensor-memory instance of the contact solver): the Delassus blocks A4 and the responses of the lane's own contact
+// along the sweep ("bk") live in TENSOR MEMORY -- both are lane-private read patterns, i.e. what tcgen05.ld 32x32b offers --
+// and only the responses at the lane's own joints ("b4") stay in shared memory.  solve4<8> is bound by the shared-memory
+// data pipe (69 % of the LSU wavefront peak at 48 % issue utilisation: 84 + 24 kmax wavefronts per sweep); the tensor-memory
+// loads do not go through it.
+#define TREX_SOLVE_SCRATCH_TM(KC) (4 * TREX_BT_SIZE(KC) + 4 * (32 + 4 * (KC)) + 128 * TREX_LIMIT_SLOTS(KC))
 // envs[g] = index (relative to work0 / rec0) of the environment served by lane group g, valid when pending bit g is set.
-template <int KC>
-TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending, float max_imp) {
+template <int KC, bool TM = false>
+TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending, float max_imp,
+                  tmem_t tm = tmem_t()) {
   static_assert((KC == 0 || KC == 1 || KC == 2 || KC == 4 || KC == 8) && KC <= TREX_KC, "one contact per lane of a group");
-  constexpr int GC = TREX_GC_STRIDE(KC), LS = 32 + 4 * KC;
+  static_assert(!TM || KC == TREX_KC, "the tensor-memory instance serves all contact classes of solve4");
+  constexpr int GC = TM ? TREX_BT_SIZE(KC) : TREX_GC_STRIDE(KC), LS = 32 + 4 * KC;
   const vi lane = lane_id();
   const vi grp = lane >> 3, gl = lane & 7;
   const vb gact = ((vi(pending) >> grp) & 1) != 0;
@@ -1619,8 +1613,27 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       }
       TREX_UNROLL for (int k = 0; k < 3; k++) {
         st4_if(Bs, gb + gl * 4 + (3 * c + k) * 36, b4[k], gl < 8);
-        st4_if(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4[k], gl < KC);
+        if (TM) tmem_st4(tm, 4 * (3 * c + k), a4[k][0], a4[k][1], a4[k][2], a4[k][3]);
+        else st4_if(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4[k], gl < KC);
       }
+    }
+    if (TM) {
+      // the three response rows of the lane's OWN contact over all joints, in solve-order position: 7 x 128 bits per row from the
+      // record (indexed by joint), permuted in registers, into the lane's tensor-memory columns
+      TREX_UNROLL for (int k = 0; k < 3; k++) {
+        vf row[28];
+        TREX_UNROLL for (int j4 = 0; j4 < 7; j4++) {
+          vf c4[4];
+          ld4_if(work0, woff + glc * 96 + (W_BT + k * 32 + 4 * j4), cown, c4);
+          TREX_UNROLL for (int e = 0; e < 4; e++) row[4 * j4 + e] = c4[e];
+        }
+        TREX_UNROLL for (int b = 0; b < 7; b++) {
+          vf q[4];
+          TREX_UNROLL for (int e = 0; e < 4; e++) q[e] = (4 * b + e < NJ) ? row[trex_topo::noncontact_order(4 * b + e < NJ ? 4 * b + e : 0) - NJ] : vf(0.0f);
+          tmem_st4(tm, S4_TM_BK(KC) + k * 28 + 4 * b, q[0], q[1], q[2], q[3]);
+        }
+      }
+      tmem_st_wait();
     }
   }
   warp_sync();
@@ -1694,7 +1707,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       }                                                                                                \
     }                                                                                                  \
   }
-#define MB_(b, fwd) s4_motor_block<b, fwd, KC>(w, lam_m, g, cu, glx, dead, bt_own, Bs, max_imp);
+#define MB_(b, fwd) s4_motor_block<b, fwd, KC, TM>(w, lam_m, g, cu, glx, dead, bt_own, Bs, tm, max_imp);
   vf mu_l = P.mu;
   TREX_ROLLED for (int it = 0; it < P.iters; it++) {
     // every 4th sweep (TREX_REBUILD_MASK) rebuild w (and u) exactly from the impulses (bounds the FP32 drift of the incremental updates):
@@ -1724,7 +1737,8 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
             ld4(Bs, gb + gl * 4 + (3 * c + k) * 36, b4);
             TREX_UNROLL for (int s = 0; s < 4; s++) bs[s] = vfma(b4[s], Lr, bs[s]);
             vf a4[4];
-            ld4(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4);
+            if (TM) { tmem_ld4(tm, 4 * (3 * c + k), a4); tmem_wait4(a4); }
+            else ld4(Bs, gb + glc * 4 + ((3 * c + k) * (4 * KC) + BT), a4);
             TREX_UNROLL for (int k2 = 0; k2 < 3; k2++) ua[k2] = vfma(a4[k2], Lr, ua[k2]);
           }
         }
@@ -1757,11 +1771,13 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       const vf cl0_0 = cl[0], cl1_0 = cl[1], cl2_0 = cl[2];
       const vf pre0 = cl[0] + crhs[0];
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        vf a4[4];
+        if (TM) tmem_ld4(tm, 4 * (3 * c), a4);  // (in flight under the clamp chain and the shuffle)
+        else ld4(Bs, gb + glc * 4 + ((3 * c) * (4 * KC) + BT), a4);
         const vf nl = vmax(vfma(-cu[0], cjdi[0], pre0), 0.0f);
         const vf d = shfl_group8(nl - cl[0], c);
         cl[0] = sel(gl == c, nl, cl[0]);
-        vf a4[4];
-        ld4(Bs, gb + glc * 4 + ((3 * c) * (4 * KC) + BT), a4);
+        if (TM) tmem_wait4(a4);
         TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(a4[k], d, cu[k]);
         vf b4[4];
         ld4(Bs, gb + gl * 4 + (3 * c) * 36, b4);
@@ -1777,6 +1793,14 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
       const vf lim = mu_l * cl[0];
       const vf preA = cl[1] + crhs[1], preB = cl[2] + crhs[2];
       TREX_ROLLED for (int c = 0; c < kmax; c++) {
+        vf aA[4], aB[4];
+        if (TM) {
+          tmem_ld4(tm, 4 * (3 * c + 1), aA);
+          tmem_ld4(tm, 4 * (3 * c + 2), aB);
+        } else {
+          ld4(Bs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + BT), aA);
+          ld4(Bs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + BT), aB);
+        }
         const vf sumB = vfma(-cu[2], cjdi[2], preB);
         const vf sumA = vfma(-cu[1], cjdi[1], preA);
         const vf rn = vrsqrt(vmax(sumA * sumA + sumB * sumB, 1.0e-30f));
@@ -1786,9 +1810,7 @@ TREX_FN vi solve4(const Uniform& P, float* scratch, const float* work0, float* r
         const vb mine = gl == c;
         cl[1] = sel(mine, nA, cl[1]);
         cl[2] = sel(mine, nB, cl[2]);
-        vf aA[4], aB[4];
-        ld4(Bs, gb + glc * 4 + ((3 * c + 1) * (4 * KC) + BT), aA);
-        ld4(Bs, gb + glc * 4 + ((3 * c + 2) * (4 * KC) + BT), aB);
+        if (TM) { tmem_wait4(aA); tmem_wait4(aB); }
         TREX_UNROLL for (int k = 0; k < 3; k++) cu[k] = vfma(aA[k], dAu, vfma(aB[k], dBu, cu[k]));
         vf bA[4], bB[4];
         ld4(Bs, gb + gl * 4 + (3 * c + 1) * 36, bA);
@@ -2485,10 +2507,11 @@ TREX_FN int front_phase(const Uniform& P, const float* mdl, const int* mdli, con
 }
 
 // solve_phase: the deferred solves of up to four environments (any four: the groups are independent)
-template <int KC>
-TREX_FN void solve_phase(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending) {
+template <int KC, bool TM = false>
+TREX_FN void solve_phase(const Uniform& P, float* scratch, const float* work0, float* rec0, const int envs[4], int pending,
+                         tmem_t tm = tmem_t()) {
   const vi lane = lane_id();
-  const vi itd = solve4<KC>(P, scratch, work0, rec0, envs, pending, P.max_impulse);
+  const vi itd = solve4<KC, TM>(P, scratch, work0, rec0, envs, pending, P.max_impulse, tm);
   // iterations executed per environment -> its accumulator (lane 8e holds group e's count)
   const vi grp = lane >> 3;
   const vb wr = ((lane & 7) == 0) && ((((vi(pending)) >> grp) & 1) != 0);

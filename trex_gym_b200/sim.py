@@ -27,7 +27,7 @@ class TrexBatchSim:
                  drift_weight: float = 0.002, max_episode_steps: int = 0, contacts: bool = True,
                  seed: int = 0, warps_per_block: int | None = None, reset_mode: int = 0, env_offset: int = 0,
                  deferred_solve: bool = True, defer_contacts: bool = True, heavy_solver: bool = True,
-                 heavy_share_div: int = 0, pipelines: int = 0, heavy_memory: int = 0):
+                 heavy_share_div: int = 0, pipelines: int = 0, heavy_memory: int = 0, chunk_envs: int = 0, contact_memory: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("trex_gym_b200 needs a CUDA device (no CPU fallback)")
         dev = torch.device(device if not isinstance(device, int) else "cuda:%d" % device)
@@ -56,6 +56,8 @@ class TrexBatchSim:
         cfg.warps_per_block = int(warps_per_block or 0)
         cfg.heavy_memory = int(heavy_memory)  # _native.HEAVY_BOTH / HEAVY_SHARED / HEAVY_TENSOR: where solve2 keeps its Delassus matrices
         cfg.pipelines = int(pipelines)  # 0 = default; independent groups of environments on separate streams
+        cfg.contact_memory = int(contact_memory)  # _native.CONTACT_TENSOR (default) / CONTACT_SHARED: where solve4 keeps its contact stash
+        cfg.chunk_envs = int(chunk_envs)  # 0 = default; L2-resident work records (include/trex_b200.h), -1 = off
         blob = self.model.blob()
         h = ctypes.c_void_p()
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
