@@ -508,7 +508,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak if fp32_peak else None,
                          "traffic": traffic, "traffic_source": traffic_note,
-                         "kernel": "one env step = %d x (trex_front_kernel; then concurrently trex_solve_kernel<8> (1-8 contacts), trex_solve_kernel<0> (contact free), trex_heavy_kernel x 2 (9-16 contacts: tensor-memory and shared-memory instance)) + trex_tail_kernel, per group of environments; shares of the device time in profiles/r2j_launches_random.txt" % sim.num_substeps,
+                         "kernel": "one env step = %d x (trex_front_kernel; then concurrently trex_solve_tm_kernel (1-8 contacts, contact stash in tensor memory), trex_solve_kernel<0> (contact free), trex_heavy_kernel x 2 (9-16 contacts: tensor-memory and shared-memory instance)) + trex_tail_kernel, per group of environments; shares of the device time in profiles/r2t_launches_random.txt" % sim.num_substeps,
                          "kernel_ms": kernel_ms,
                          "peak_source": "measured in this run: register-resident FFMA microbenchmark (trex_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                          "flops_per_env_step": f_alg(sim.num_substeps, it_sum, ct_sum),
