@@ -490,16 +490,9 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
       const bool heavy = h->P.defer_contacts > 1 && h->P.contacts_on && workh != nullptr;
       const bool split = contacts && h->concurrent_solves && q.side2 != nullptr;
       if (heavy || split) CUDA_TRY(cudaEventRecord(q.ev_fork, s));
-      if (contacts && h->solve_tm) {
-        trex_solve_tm_kernel<1, TREX_CLASS_HEAVY - 1><<<h->solve_tm_grid, 128, smem_ct, s>>>(Pc, state, work, q.d_list, q.d_list_count + r,
-                                                                                         q.d_list_count + 64 * (TREX_NCLASS + 3) + r, count);
-        CUDA_TRY(cudaGetLastError());
-        h->launches++;
-      } else if (contacts) {
-        trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1><<<grid4 + 4, 32 * WS, smem_c, s>>>(Pc, state, work, q.d_list, q.d_list_count + r, count);
-        CUDA_TRY(cudaGetLastError());
-        h->launches++;
-      }
+      // launch order: the many-contact solver first (few environments, the longest latency: its CTAs must not queue behind the
+      // persistent contact solver, whose two CTAs per SM take the whole register file), then the contact solver, then the
+      // contact-free one (measured: 7.47 vs 7.49-7.59 ms per step with the contact solver first)
       if (heavy) {  // class 5: more than TREX_KC contacts, two environments per warp; two instances share the task counter
         int* next_task = q.d_list_count + 64 * (TREX_NCLASS + 1) + r;
         const int* cnt = q.d_list_count + 64 * TREX_CLASS_HEAVY + r;
@@ -524,6 +517,16 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
           }
         }
         CUDA_TRY(cudaEventRecord(q.ev_join, q.side));
+      }
+      if (contacts && h->solve_tm) {
+        trex_solve_tm_kernel<1, TREX_CLASS_HEAVY - 1><<<h->solve_tm_grid, 128, smem_ct, s>>>(Pc, state, work, q.d_list, q.d_list_count + r,
+                                                                                         q.d_list_count + 64 * (TREX_NCLASS + 3) + r, count);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+      } else if (contacts) {
+        trex_solve_kernel<WS, TREX_KC, 1, TREX_CLASS_HEAVY - 1><<<grid4 + 4, 32 * WS, smem_c, s>>>(Pc, state, work, q.d_list, q.d_list_count + r, count);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
       }
       cudaStream_t s0 = split ? q.side2 : s;
       if (split) CUDA_TRY(cudaStreamWaitEvent(q.side2, q.ev_fork, 0));
