@@ -228,13 +228,20 @@ def test_random_actions_keyed_by_global_env(model, action_limits):
     assert np.abs(a.mean(0) - (lo + hi) / 2).max() < 0.6
 
 
-def test_step_host_equals_device_step(model):
-    s1, s2 = _sim(model, 96), _sim(model, 96)
-    for t in range(3):
+@pytest.mark.parametrize("n", [96, 9000])
+def test_step_host_equals_device_step(model, n):
+    """trex_step_host == trex_step bit for bit: with one group of environments (one copy in, the step, one copy out) and with
+    two (from 8,192 environments: every group's copies ride on its own stream and the second group starts behind the first
+    group's first dynamics kernel, so the first group's copy out runs under the second group's last solve)."""
+    s1, s2 = _sim(model, n), _sim(model, n)
+    for t in range(4):
         act = s1.random_actions(step=t)
         obs, rew, done = s1.step(act)
         hobs, hrew, hdone = s2.step_host(act.cpu().numpy())
         assert (obs.cpu().numpy() == hobs).all() and (rew.cpu().numpy() == hrew).all() and (done.cpu().numpy() == hdone).all()
+    import torch
+
+    assert torch.equal(s1.get_state(), s2.get_state())
 
 
 def test_gym_surface(model):

@@ -400,7 +400,7 @@ struct trex_handle {
     int* d_list_count = nullptr;  // [TREX_NCLASS + 4][64] one counter per class and substep round, + heavy seen, solve2 task counters, hint, solve4-TM task counters
   } pipe[MAX_PIPES];
   int n_pipes = 0;              // 0 until trex_create decides (config / default)
-  cudaEvent_t ev_start = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stagger = nullptr;
   bool concurrent_solves = true;  // the contact-free solve kernel on a second side stream, under the contact solver
   int heavy_div = 0;            // > 0: class 5 goes to trex_heavy_kernel only while at most n_envs / heavy_div environments are in it (0: always)
   int heavy_grid = 148 * 7;     // CTAs of trex_heavy_kernel<1, false> alone (one warp each): every SM full
@@ -425,9 +425,20 @@ int configure_kernel(K kernel, size_t smem) {
 // mode 0: one env step (n_sub front/solve rounds + tail); mode 1: reset (tail only).
 // WF: warps per CTA of the front / tail kernels (one environment per warp; 2 gives 16 resident warps per SM),
 // WS: warps per CTA of the solve kernels (four environments per warp; 1 with the default WF = 2: finest scheduling grain).
+// host buffers of a group-staged step (trex_step_host): every group's action rows are copied in on the group's own stream right
+// before its kernels and its observation / reward / done rows copied out right behind its tail kernel; the second group
+// starts behind the first group's first dynamics kernel, so it also ends later and the first group's copy out runs under its
+// last solve (measured without the stagger: the groups finish together and nothing overlaps)
+struct HostIO {
+  const float* action;
+  float* obs;
+  float* reward;
+  uint8_t* done;
+};
+
 template <int WF, int WS>
 int launch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
-                int mode, cudaStream_t st) {
+                int mode, cudaStream_t st, const HostIO* io = nullptr) {
   static const size_t extra_c = getenv("TREX_SOLVEC_EXTRA_SMEM") ? (size_t)atoi(getenv("TREX_SOLVEC_EXTRA_SMEM")) : 0;  // measurement aid: fewer resident warps
   static const size_t extra_s = getenv("TREX_SOLVE_EXTRA_SMEM") ? (size_t)atoi(getenv("TREX_SOLVE_EXTRA_SMEM")) : 0;
   const size_t smem_f = sizeof(trex::WarpShared) * WF, smem_s = sizeof(float) * TREX_SOLVE_SCRATCH(0) * WS + extra_s,
@@ -464,6 +475,10 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
     const int first = h->chunk > 0 ? c * h->chunk : q.first;
     const int count = h->chunk > 0 ? (first + h->chunk <= h->n_envs ? h->chunk : h->n_envs - first) : q.count;
     if (count <= 0) continue;
+    const bool stagger = io != nullptr && h->n_chunks == 2 && h->n_pipes == 2;
+    if (io) CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(action) + (size_t)first * trex::NJ, io->action + (size_t)first * trex::NJ,
+                                     (size_t)count * trex::NJ * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (stagger && c == 1) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_stagger, 0));
     trex::Uniform Pc = h->P;
     Pc.env_offset = h->P.env_offset + first;  // the reset sampler is keyed by the global environment id
     if (mode == 0 && h->d_work) {
@@ -482,6 +497,7 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
                                                           q.d_list_count + 64 * (TREX_NCLASS + 2), h->heavy_div, count, r == 0);
       CUDA_TRY(cudaGetLastError());
       h->launches++;
+      if (stagger && c == 0 && r == 0) CUDA_TRY(cudaEventRecord(h->ev_stagger, s));
       if (!h->d_work) continue;
       // The three solve kernels of a round work on disjoint lists of environments.  The two latency-bound ones go first:
       // the contact solver on the group's stream, the many-contact solver on a side stream; the contact-free solver
@@ -545,6 +561,11 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
                                                         h->d_aux + e0 * TREX_AUX_STRIDE, mask ? mask + e0 : nullptr, count, mode);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    if (io) {
+      if (io->obs) CUDA_TRY(cudaMemcpyAsync(io->obs + e0 * 3 * trex::NJ, obs + e0 * 3 * trex::NJ, (size_t)count * 3 * trex::NJ * sizeof(float), cudaMemcpyDeviceToHost, s));
+      if (io->reward) CUDA_TRY(cudaMemcpyAsync(io->reward + e0, reward + e0, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, s));
+      if (io->done) CUDA_TRY(cudaMemcpyAsync(io->done + e0, done + e0, (size_t)count, cudaMemcpyDeviceToHost, s));
+    }
   }
   for (int p = 1; p < h->n_pipes; p++) {
     CUDA_TRY(cudaEventRecord(h->pipe[p].ev_done, sp[p]));
@@ -554,11 +575,11 @@ int launch_step(trex_handle* h, const float* action, float* obs, float* reward, 
 }
 
 int dispatch_step(trex_handle* h, const float* action, float* obs, float* reward, uint8_t* done, const uint8_t* mask,
-                  int mode, cudaStream_t st) {
+                  int mode, cudaStream_t st, const HostIO* io = nullptr) {
   switch (h->warps_per_block) {
-    case 1: return launch_step<1, 2>(h, action, obs, reward, done, mask, mode, st);
-    case 2: return launch_step<2, 1>(h, action, obs, reward, done, mask, mode, st);
-    case 4: return launch_step<4, 4>(h, action, obs, reward, done, mask, mode, st);
+    case 1: return launch_step<1, 2>(h, action, obs, reward, done, mask, mode, st, io);
+    case 2: return launch_step<2, 1>(h, action, obs, reward, done, mask, mode, st, io);
+    case 4: return launch_step<4, 4>(h, action, obs, reward, done, mask, mode, st, io);
     default: return fail(TREX_ERR_INVALID, "warps_per_block must be 1, 2 or 4%s");
   }
 }
@@ -709,6 +730,7 @@ int trex_create(const void* model_blob, size_t bytes, int32_t n_envs, int32_t de
   if (with_heavy) CTRY(cudaMalloc((void**)&h->d_workh, work_slots * TREX_HEAVY_STRIDE * sizeof(float)));
   if (const char* e = getenv("TREX_SERIAL_SOLVES")) h->concurrent_solves = !(e[0] == '1');  // measurement aids
   CTRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  CTRY(cudaEventCreateWithFlags(&h->ev_stagger, cudaEventDisableTiming));
   for (int p = 0; p < h->n_pipes; p++) {
     trex_handle::Pipe& q = h->pipe[p];
     // groups of (almost) equal size, boundaries on multiples of four environments (the solvers' work unit)
@@ -779,6 +801,7 @@ void trex_destroy(trex_handle* h) {
     if (q.ev_done) cudaEventDestroy(q.ev_done);
   }
   if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_stagger) cudaEventDestroy(h->ev_stagger);
   delete h;
 }
 
@@ -859,8 +882,25 @@ int trex_host_wait(trex_handle* h) {
 }
 
 int trex_step_host(trex_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host) {
-  const int rc = trex_step_host_async(h, action_host, obs_host, reward_host, done_host);
-  return rc != TREX_OK ? rc : trex_host_wait(h);
+  if (!h) return fail(TREX_ERR_INVALID, "handle is NULL%s");
+  if (!action_host) return fail(TREX_ERR_INVALID, "action is NULL%s");
+  static const bool staged_off = getenv("TREX_HOST_STAGED") && getenv("TREX_HOST_STAGED")[0] == '0';  // measurement aid
+  if (h->n_pipes < 2 || staged_off) {  // one group: one copy in, the step, one copy out
+    const int rc = trex_step_host_async(h, action_host, obs_host, reward_host, done_host);
+    return rc != TREX_OK ? rc : trex_host_wait(h);
+  }
+  // group-staged (see HostIO): the copies ride on the groups' own streams
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = ensure_host_path(h);
+  if (rc != TREX_OK) return rc;
+  rc = trex_host_wait(h);  // (a pipelined step may still be in flight)
+  if (rc != TREX_OK) return rc;
+  const HostIO io = {action_host, obs_host, reward_host, done_host};
+  rc = dispatch_step(h, h->d_action[0], h->d_obs[0], h->d_reward[0], h->d_done[0], nullptr, 0, h->host_main, &io);
+  if (rc != TREX_OK) return rc;
+  h->env_steps += h->n_envs;
+  CUDA_TRY(cudaStreamSynchronize(h->host_main));
+  return TREX_OK;
 }
 
 int trex_reset_host(trex_handle* h, float* obs_host) {
