@@ -2,7 +2,7 @@
 # One bench line per BASELINE.json configuration (run on a B200 box from the repository root):
 #   bash profiles/run_workloads.sh <tag>        ->  gpurun_out/<tag>_bench_<workload>.json
 # Copy the lines worth keeping to profiles/ (profiles/README.md lists them).
-tag=${1:-r2}
+tag=${1:-r2x}
 out=gpurun_out
 mkdir -p $out
 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_random.json 2> $out/${tag}_bench_random.err                                   # configs[2], the headline
