@@ -1470,9 +1470,6 @@ TREX_TOPO_FN bool limit_order_matches_motor_order() {
     if (trex_topo::noncontact_order(NJ + p) != trex_topo::noncontact_order(p) - NJ) return false;
   return true;
 }
-#ifndef TREX_S4_PRESUB
-#define TREX_S4_PRESUB(KC) 0  // (measured: no gain in either solve4 instance -- they are issue bound, not chain bound)
-#endif
 // tensor-memory columns of solve4<KC, TM = true> (per lane, lane-private): the lane's own block of every Delassus row
 // A4[r][own contact][0..3] at 4 r, then the responses of the lane's own contact at every solve-order position,
 // B[3 own + k][pos] at S4_TM_BK + 28 k + pos
