@@ -399,8 +399,12 @@ def run_ours(args):
 
     # ---- device-resident throughput ("value") -------------------------------------------------
     phase0 = args.preroll if workload != "standing" else 0  # keep cycling where the pre-roll stopped
+    step_fn = sim.step
+    if getattr(args, "graph", False):
+        sim.capture_graph()
+        step_fn = sim.step_graph
     for t in range(args.warmup):
-        sim.step(acts[(phase0 + t) % ring])
+        step_fn(acts[(phase0 + t) % ring])
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -409,7 +413,7 @@ def run_ours(args):
     for k in range(args.steps):
         flush.fill_(float(k))  # L2 flush between timed steps (not timed)
         evs[k][0].record()
-        sim.step(acts[(phase0 + args.warmup + k) % ring])
+        step_fn(acts[(phase0 + args.warmup + k) % ring])
         evs[k][1].record()
     barrier()
     launches = sim.kernel_launches - launches0
@@ -429,7 +433,7 @@ def run_ours(args):
         for k in range(args.spread_steps):
             flush.fill_(float(k))
             sevs[k][0].record()
-            sim.step(acts[(phase0 + args.warmup + args.steps + k) % ring])
+            step_fn(acts[(phase0 + args.warmup + args.steps + k) % ring])
             sevs[k][1].record()
         barrier()
         ms = np.asarray([a.elapsed_time(b) for a, b in sevs])
@@ -543,6 +547,7 @@ def main():
     ap.add_argument("--no-contacts", action="store_true", help="literal reference URDF (no collision shapes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warps-per-block", type=int, default=0)
+    ap.add_argument("--graph", action="store_true", help="device-resident value through the CUDA-graph replay of the step (TrexBatchSim.step_graph)")
     ap.add_argument("--preroll", type=int, default=300, help="untimed env-steps from the reset state before warm-up, so the batch is in its steady regime (on the floor, in contact)")
     args = ap.parse_args()
     if args.warmup < 3:

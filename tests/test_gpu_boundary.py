@@ -177,6 +177,21 @@ def test_cuda_graph_capture_of_a_step(model):
     assert eager.stats()["mean_contacts"] > 4.0  # half the batch stands on both feet
 
 
+def test_step_graph_replays_the_step(model):
+    """TrexBatchSim.capture_graph / step_graph: the whole env step (kernels, fork / join events, counter resets of the persistent
+    solvers) captured once into a CUDA graph with simulator-owned buffers and replayed per step -- bit-identical to ``step``."""
+    import torch
+
+    n = 4096
+    a, b = _sim(model, n, seed=1), _sim(model, n, seed=1)
+    for t in range(30):
+        act = a.random_actions(step=t)
+        o1, r1, d1 = a.step(act)
+        o2, r2, d2 = b.step_graph(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+    assert torch.equal(a.get_state()[:, :152], b.get_state()[:, :152]) and a.stats()["mean_contacts"] > 0.05
+
+
 def test_replay_frames_recorded_on_hardware(model, tmp_path):
     """SURVEY.md section 8f row 4 on the GPU: record 20 real frames of two environments while the batch is stepped, then
     recompute the head position on the HOST from each exported frame (base pose + joint angles only) and compare it with

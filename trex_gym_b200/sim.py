@@ -122,6 +122,39 @@ class TrexBatchSim:
             "trex_step")
         return self.obs, self.reward, self.done
 
+    # -- CUDA-graph replay of the step (small batches are launch bound: 26 launches + events per group and env step) --------
+    def capture_graph(self):
+        """Capture one ``trex_step`` (every kernel, fork / join event and counter reset of the step) into a CUDA graph with
+        simulator-owned static buffers; afterwards ``step_graph(action)`` copies the action in and replays the graph.  The step
+        is capturable because the library forks from and joins back into the caller's stream by events only
+        (``include/trex_b200.h``).  State is untouched by the capture.  Results are bit-identical to ``step``."""
+        if getattr(self, "_graph", None) is not None:
+            return
+        self._g_action = torch.zeros(self.num_envs, _native.NUM_JOINTS, device=self.device, dtype=torch.float32)
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            pre = self.get_state().clone()
+            self.step(self._g_action)          # warm-up on the capture stream (kernel attributes get configured here)
+            self.set_state(pre)
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                self.step(self._g_action)
+        torch.cuda.synchronize(self.device)
+        self.set_state(pre)                    # (capture does not execute, the warm-up step is undone)
+        torch.cuda.synchronize(self.device)
+        self._graph = g
+
+    def step_graph(self, action: torch.Tensor):
+        """``step`` through the captured graph: one device-to-device copy of the actions + one graph launch."""
+        if getattr(self, "_graph", None) is None:
+            self.capture_graph()
+        self._check_tensor(action, (self.num_envs, _native.NUM_JOINTS), torch.float32, "action")
+        self._g_action.copy_(action, non_blocking=True)
+        self._graph.replay()
+        return self.obs, self.reward, self.done
+
     def step_into(self, action: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
         """Step writing into caller-provided buffers (e.g. slices of a rollout buffer)."""
         self._check_tensor(action, (self.num_envs, _native.NUM_JOINTS), torch.float32, "action")
